@@ -1,0 +1,753 @@
+// phox_engine.cu : host side of libphox.so - the context object behind the C ABI of include/phox.h.
+//
+// Plays the role of CSGOptiX (launch driver, CSGOptiX/CSGOptiX.cc:1122-1198), QSim::simulate
+// (per-event loop with genstep slicing, qudarap/QSim.cc:428-617), QEvt (event buffers, genstep
+// upload, hit gathering: qudarap/QEvt.cc:332-441, 934-963, 1113-1133), QBnd/QScint texture setup
+// (qudarap/QBnd.cc:130-194, QTex.cc:260-275, QScint.cc:84-120) and CSGFoundry::upload
+// (CSG/CSGFoundry.cc:3377-3405) for the one path this library covers.
+//
+// Design: one context = one GPU = one stream.  Geometry, BVH and tables are uploaded once and stay
+// resident.  Event buffers grow on demand and are reused.  A launch is: (prefix of
+// genstep.numphoton) -> k_simulate -> k_hit_offsets -> [sync: read hit total] -> k_hit_compact.
+// There is no CPU fallback: without a CUDA device phox_create fails.
+#include "../../include/phox.h"
+#include "phox_kernels.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace phox;
+
+namespace {
+thread_local std::string g_create_error;
+
+double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;          // elements
+    cudaError_t reserve(size_t n, bool keep = false, cudaStream_t st = 0) {
+        if (n <= cap) return cudaSuccess;
+        size_t want = keep ? std::max(n, cap + cap / 2) : n;
+        T* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, want * sizeof(T));
+        if (e != cudaSuccess) return e;
+        if (keep && p && cap) {
+            e = cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) { cudaFree(q); return e; }
+        }
+        if (p) cudaFree(p);
+        p = q; cap = want;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+}  // namespace
+
+struct phox_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    std::string description;
+    phox_config cfg;
+    size_t vram_total = 0;
+
+    // geometry
+    bool have_geometry = false;
+    DevBuf<float4> d_node, d_plan, d_itra, d_prim;
+    DevBuf<InstanceRec> d_inst;
+    DevBuf<BvhNode> d_bvh;
+    DevBuf<float> d_boxes;
+    BvhScratch bvh_scratch;
+    int nprim = 0, nnode = 0, nplan = 0, nitra = 0, ninst = 0, nsolid = 0;
+    int tlas_root = 0;
+    int build_kernels = 0;
+
+    // tables
+    bool have_tables = false;
+    cudaArray_t bnd_array = nullptr, icdf_array = nullptr;
+    cudaTextureObject_t bnd_tex = 0, icdf_tex = 0;
+    DevBuf<uint4> d_optical;
+    unsigned nx = 0, ny = 0;
+    float nm0 = 60.f, nms = 1.f;
+    unsigned hd_factor = 0;
+
+    // event
+    DevBuf<Genstep> d_genstep;
+    DevBuf<unsigned long long> d_prefix;
+    DevBuf<Photon> d_input, d_photon, d_record, d_hit;
+    DevBuf<Seq> d_seq;
+    DevBuf<Prd> d_prd;
+    DevBuf<unsigned> d_block_hits;
+    DevBuf<unsigned long long> d_block_off;
+    DevBuf<unsigned long long> d_counters;     // [0] rays, [1] hit total of the launch
+    unsigned long long* h_counters = nullptr;  // pinned mirror
+    std::vector<Photon> h_photon;              // concatenated per-launch arrays in debug modes
+    std::vector<Photon> h_record;
+    std::vector<Seq> h_seq;
+    std::vector<Prd> h_prd;
+    int64_t num_photon = 0, num_hit = 0;
+    int event_max_record = 0;
+    bool have_event = false;
+    phox_stats stats;
+
+    int fail(int code, const std::string& m) { err = m; return code; }
+    int cuda_fail(cudaError_t e, const char* what) {
+        err = std::string(what) + ": " + cudaGetErrorString(e);
+        return PHOX_E_CUDA;
+    }
+};
+
+#define CK(call)                                                   \
+    do {                                                           \
+        cudaError_t _e = (call);                                   \
+        if (_e != cudaSuccess) return ctx->cuda_fail(_e, #call);   \
+    } while (0)
+
+extern "C" void phox_default_config(phox_config* c) {
+    if (!c) return;
+    std::memset(c, 0, sizeof(*c));
+    c->max_bounce = 31;
+    c->event_mode = PHOX_MODE_MINIMAL;
+    c->max_record = 32;
+    c->rng_mode = PHOX_RNG_DEBUG_TAG;
+    c->accel = PHOX_ACCEL_BVH;
+    c->hit_mask = F_SURFACE_DETECT;
+    c->epsilon0_mask = F_TORCH | F_CERENKOV | F_SCINTILLATION | F_BULK_SCATTER | F_BULK_REEMIT;
+    c->propagate_refine = 0;
+    c->propagate_epsilon = 0.05f;
+    c->propagate_epsilon0 = 0.05f;
+    c->refine_distance = 5000.f;
+    c->tmax = 1000000.f;
+    c->max_time = 1.e27f;
+    c->rng_seed = 0;
+    c->rng_offset = 0;
+    c->skipahead_event_offset = 100000;
+    c->max_slot = 0;
+}
+
+extern "C" phox_context* phox_create(int device) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("phox_create: no CUDA device (") + cudaGetErrorString(e) + "); this engine has no CPU path";
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) {
+        g_create_error = "phox_create: device index out of range";
+        return nullptr;
+    }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) { g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return nullptr; }
+    phox_context* ctx = new phox_context();
+    ctx->device = device;
+    phox_default_config(&ctx->cfg);
+    std::memset(&ctx->stats, 0, sizeof(ctx->stats));
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_counters, 4 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = ctx->d_counters.reserve(4);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("phox_create: ") + cudaGetErrorString(e);
+        delete ctx;
+        return nullptr;
+    }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    size_t free_b = 0;
+    cudaMemGetInfo(&free_b, &ctx->vram_total);
+    char buf[256];
+    std::snprintf(buf, sizeof(buf), "phox: B200-native simulate engine on device %d (%s, sm_%d%d, %d SMs, %.1f GB)", device, prop.name,
+                  prop.major, prop.minor, prop.multiProcessorCount, ctx->vram_total / 1e9);
+    ctx->description = buf;
+    return ctx;
+}
+
+static void free_tables(phox_context* ctx) {
+    if (ctx->bnd_tex) cudaDestroyTextureObject(ctx->bnd_tex);
+    if (ctx->icdf_tex) cudaDestroyTextureObject(ctx->icdf_tex);
+    if (ctx->bnd_array) cudaFreeArray(ctx->bnd_array);
+    if (ctx->icdf_array) cudaFreeArray(ctx->icdf_array);
+    ctx->bnd_tex = ctx->icdf_tex = 0;
+    ctx->bnd_array = ctx->icdf_array = nullptr;
+    ctx->have_tables = false;
+}
+
+extern "C" void phox_destroy(phox_context* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    free_tables(ctx);
+    ctx->d_node.release(); ctx->d_plan.release(); ctx->d_itra.release(); ctx->d_prim.release();
+    ctx->d_inst.release(); ctx->d_bvh.release(); ctx->d_boxes.release(); ctx->d_optical.release();
+    ctx->d_genstep.release(); ctx->d_prefix.release(); ctx->d_input.release(); ctx->d_photon.release();
+    ctx->d_record.release(); ctx->d_hit.release(); ctx->d_seq.release(); ctx->d_prd.release();
+    ctx->d_block_hits.release(); ctx->d_block_off.release(); ctx->d_counters.release();
+    bvh_scratch_free(ctx->bvh_scratch);
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* phox_last_error(const phox_context* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+extern "C" const char* phox_desc(const phox_context* ctx) { return ctx ? ctx->description.c_str() : "phox: no context"; }
+
+// ---- geometry -----------------------------------------------------------------------------------
+static bool invert_affine(const float* m, double* inv) {
+    // m : qat4 row-vector convention, rows 0..2 = linear part, row 3 = translation ; v' = v*M
+    double a[3][3];
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) a[r][c] = m[4 * r + c];
+    double det = a[0][0] * (a[1][1] * a[2][2] - a[1][2] * a[2][1]) - a[0][1] * (a[1][0] * a[2][2] - a[1][2] * a[2][0]) +
+                 a[0][2] * (a[1][0] * a[2][1] - a[1][1] * a[2][0]);
+    if (det == 0.0 || !std::isfinite(det)) return false;
+    double id = 1.0 / det;
+    double b[3][3];
+    b[0][0] = (a[1][1] * a[2][2] - a[1][2] * a[2][1]) * id;
+    b[0][1] = (a[0][2] * a[2][1] - a[0][1] * a[2][2]) * id;
+    b[0][2] = (a[0][1] * a[1][2] - a[0][2] * a[1][1]) * id;
+    b[1][0] = (a[1][2] * a[2][0] - a[1][0] * a[2][2]) * id;
+    b[1][1] = (a[0][0] * a[2][2] - a[0][2] * a[2][0]) * id;
+    b[1][2] = (a[0][2] * a[1][0] - a[0][0] * a[1][2]) * id;
+    b[2][0] = (a[1][0] * a[2][1] - a[1][1] * a[2][0]) * id;
+    b[2][1] = (a[0][1] * a[2][0] - a[0][0] * a[2][1]) * id;
+    b[2][2] = (a[0][0] * a[1][1] - a[0][1] * a[1][0]) * id;
+    double t[3] = {m[12], m[13], m[14]};
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) inv[4 * r + c] = b[r][c];
+    for (int c = 0; c < 3; c++) inv[12 + c] = -(t[0] * b[0][c] + t[1] * b[1][c] + t[2] * b[2][c]);
+    inv[3] = inv[7] = inv[11] = 0.0;
+    inv[15] = 1.0;
+    return true;
+}
+
+extern "C" int phox_set_geometry(phox_context* ctx, const void* solid_, int64_t nsolid, const void* prim_, int64_t nprim, const void* node_,
+                                 int64_t nnode, const void* plan_, int64_t nplan, const void* itra_, int64_t nitra, const void* inst_,
+                                 int64_t ninst) {
+    if (!ctx) return PHOX_E_ARG;
+    if (!solid_ || !prim_ || !node_ || nsolid <= 0 || nprim <= 0 || nnode <= 0) return ctx->fail(PHOX_E_ARG, "phox_set_geometry: solid/prim/node arrays are required");
+    if ((nitra > 0 && !itra_) || (nplan > 0 && !plan_)) return ctx->fail(PHOX_E_ARG, "phox_set_geometry: null itra/plan with non-zero count");
+    if (nprim > 0xffff + 1) { /* globalPrimIdx is truncated to 16 bits in prd, like the reference (CSGOptiX7.cu:899) */ }
+    CK(cudaSetDevice(ctx->device));
+    const Solid* solid = (const Solid*)solid_;
+    const Prim* prim = (const Prim*)prim_;
+    const Node* node = (const Node*)node_;
+    const Qat4* inst = (const Qat4*)inst_;
+
+    // validate the index structure before anything reaches the device
+    for (int64_t s = 0; s < nsolid; s++) {
+        if (solid[s].num_prim < 0 || solid[s].prim_offset < 0 || (int64_t)solid[s].prim_offset + solid[s].num_prim > nprim)
+            return ctx->fail(PHOX_E_ARG, "phox_set_geometry: solid prim range outside prim array");
+    }
+    for (int64_t p = 0; p < nprim; p++) {
+        int nn = prim[p].num_node(), no = prim[p].node_offset();
+        if (nn <= 0 || no < 0 || (int64_t)no + nn > nnode) return ctx->fail(PHOX_E_ARG, "phox_set_geometry: prim node range outside node array");
+    }
+    for (int64_t n = 0; n < nnode; n++) {
+        unsigned ti = node[n].transform_idx();
+        if (ti > (unsigned)nitra) return ctx->fail(PHOX_E_ARG, "phox_set_geometry: node transform index outside itra array");
+        if (node[n].typecode() == CSG_CONVEXPOLYHEDRON && (int64_t)node[n].u[0] + node[n].u[1] > nplan)
+            return ctx->fail(PHOX_E_ARG, "phox_set_geometry: convexpolyhedron planes outside plan array");
+    }
+
+    // instances: default to one identity instance of solid 0 (what CSGFoundry::addInstance does for
+    // the global remainder solid, sysrap/stree.h:6737-6747)
+    std::vector<Qat4> inst_default;
+    if (ninst <= 0 || !inst) {
+        Qat4 q; std::memset(&q, 0, sizeof(q));
+        q.f[0] = q.f[5] = q.f[10] = 1.f; q.f[15] = 1.f;
+        q.i[3] = 0; q.i[7] = 0; q.i[11] = 0; q.i[15] = 0;
+        inst_default.push_back(q);
+        inst = inst_default.data();
+        ninst = 1;
+    }
+
+    ctx->have_geometry = false;
+    ctx->nsolid = (int)nsolid; ctx->nprim = (int)nprim; ctx->nnode = (int)nnode; ctx->nplan = (int)nplan; ctx->nitra = (int)nitra; ctx->ninst = (int)ninst;
+
+    CK(ctx->d_node.reserve((size_t)nnode * 4));
+    CK(ctx->d_prim.reserve((size_t)nprim * 4));
+    CK(ctx->d_plan.reserve(std::max<size_t>(1, (size_t)nplan)));
+    CK(ctx->d_itra.reserve(std::max<size_t>(4, (size_t)nitra * 4)));
+    CK(cudaMemcpyAsync(ctx->d_node.p, node_, (size_t)nnode * 64, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_prim.p, prim_, (size_t)nprim * 64, cudaMemcpyHostToDevice, ctx->stream));
+    if (nplan > 0) CK(cudaMemcpyAsync(ctx->d_plan.p, plan_, (size_t)nplan * 16, cudaMemcpyHostToDevice, ctx->stream));
+    if (nitra > 0) {
+        // the 4th column of a transform may carry identity ints (sqat4.h) : clear it, it multiplies w = 0
+        std::vector<Qat4> it((const Qat4*)itra_, (const Qat4*)itra_ + nitra);
+        for (auto& q : it) { q.f[3] = 0.f; q.f[7] = 0.f; q.f[11] = 0.f; q.f[15] = 1.f; }
+        CK(cudaMemcpyAsync(ctx->d_itra.p, it.data(), (size_t)nitra * 64, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+
+    // boxes: per-prim boxes straight from CSGPrim, per-solid union, per-instance world boxes
+    std::vector<float> boxes((size_t)(nprim + ninst) * 6);
+    for (int64_t p = 0; p < nprim; p++) for (int k = 0; k < 6; k++) boxes[6 * p + k] = prim[p].f[8 + k];
+    std::vector<float> solid_box((size_t)nsolid * 6);
+    for (int64_t s = 0; s < nsolid; s++) {
+        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int k = 0; k < solid[s].num_prim; k++) {
+            const float* b = &boxes[6 * (size_t)(solid[s].prim_offset + k)];
+            for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], b[a]); hi[a] = std::max(hi[a], b[a + 3]); }
+        }
+        for (int a = 0; a < 3; a++) { solid_box[6 * s + a] = lo[a]; solid_box[6 * s + 3 + a] = hi[a]; }
+    }
+
+    // node pool layout: [instance tree : max(ninst-1,1)] [solid s tree : max(numPrim-1,1)] ...
+    std::vector<int> solid_root(nsolid);
+    int pool = std::max<int>((int)ninst - 1, 1);
+    ctx->tlas_root = 0;
+    for (int64_t s = 0; s < nsolid; s++) { solid_root[s] = pool; pool += std::max(solid[s].num_prim - 1, 1); }
+
+    std::vector<InstanceRec> recs(ninst);
+    for (int64_t i = 0; i < ninst; i++) {
+        const Qat4& q = inst[i];
+        int gas = q.i[7];
+        if (gas < 0 || gas >= nsolid) return ctx->fail(PHOX_E_ARG, "phox_set_geometry: instance gas_idx outside solid array");
+        float m[16];
+        std::memcpy(m, q.f, 64);
+        m[3] = m[7] = m[11] = 0.f; m[15] = 1.f;
+        static const float ident[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+        bool is_ident = std::memcmp(m, ident, 64) == 0;
+        double inv[16];
+        if (!invert_affine(m, inv)) return ctx->fail(PHOX_E_ARG, "phox_set_geometry: singular instance transform");
+        InstanceRec& r = recs[i];
+        std::memset(&r, 0, sizeof(r));
+        for (int k = 0; k < 4; k++) r.inv[k] = make_float4((float)inv[4 * k], (float)inv[4 * k + 1], (float)inv[4 * k + 2], (float)inv[4 * k + 3]);
+        r.solid = gas;
+        r.identity = q.i[11];
+        r.is_identity = is_ident ? 1 : 0;
+        r.bvh_root = solid_root[gas];
+        r.prim_offset = solid[gas].prim_offset;
+        r.num_prim = solid[gas].num_prim;
+        // world box of the instance = box of the 8 transformed corners of the solid box
+        const float* sb = &solid_box[6 * (size_t)gas];
+        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int c = 0; c < 8; c++) {
+            float v[3] = {(c & 1) ? sb[3] : sb[0], (c & 2) ? sb[4] : sb[1], (c & 4) ? sb[5] : sb[2]};
+            for (int a = 0; a < 3; a++) {
+                float w = m[a] * v[0] + m[4 + a] * v[1] + m[8 + a] * v[2] + m[12 + a];
+                lo[a] = std::min(lo[a], w); hi[a] = std::max(hi[a], w);
+            }
+        }
+        float* ib = &boxes[6 * (size_t)(nprim + i)];
+        for (int a = 0; a < 3; a++) {
+            float pad = 1e-4f * std::max(1.f, std::max(std::fabs(lo[a]), std::fabs(hi[a])));   // rounding of the corner transform
+            ib[a] = lo[a] - pad; ib[a + 3] = hi[a] + pad;
+        }
+    }
+
+    CK(ctx->d_inst.reserve((size_t)ninst));
+    CK(ctx->d_boxes.reserve(boxes.size()));
+    CK(ctx->d_bvh.reserve((size_t)pool));
+    CK(cudaMemcpyAsync(ctx->d_inst.p, recs.data(), recs.size() * sizeof(InstanceRec), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_boxes.p, boxes.data(), boxes.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+
+    ctx->build_kernels = 0;
+    CK(bvh_build(ctx->d_boxes.p + 6 * (size_t)nprim, (int)ninst, 0, ctx->d_bvh.p + ctx->tlas_root, ctx->bvh_scratch, ctx->stream, &ctx->build_kernels));
+    for (int64_t s = 0; s < nsolid; s++) {
+        if (solid[s].num_prim == 0) continue;
+        CK(bvh_build(ctx->d_boxes.p + 6 * (size_t)solid[s].prim_offset, solid[s].num_prim, solid[s].prim_offset, ctx->d_bvh.p + solid_root[s],
+                     ctx->bvh_scratch, ctx->stream, &ctx->build_kernels));
+        CK(cudaStreamSynchronize(ctx->stream));     // scratch is reused by the next build
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->have_geometry = true;
+    return PHOX_OK;
+}
+
+// ---- tables -------------------------------------------------------------------------------------
+static cudaError_t make_tex(cudaArray_t* arr, cudaTextureObject_t* tex, const void* src, size_t width, size_t height, int channels) {
+    cudaChannelFormatDesc desc = channels == 4 ? cudaCreateChannelDesc<float4>() : cudaCreateChannelDesc<float>();
+    cudaError_t e = cudaMallocArray(arr, &desc, width, height);
+    if (e != cudaSuccess) return e;
+    size_t pitch = width * sizeof(float) * channels;
+    e = cudaMemcpy2DToArray(*arr, 0, 0, src, pitch, pitch, height, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return e;
+    cudaResourceDesc res;
+    std::memset(&res, 0, sizeof(res));
+    res.resType = cudaResourceTypeArray;
+    res.res.array.array = *arr;
+    cudaTextureDesc td;
+    std::memset(&td, 0, sizeof(td));
+    td.addressMode[0] = cudaAddressModeWrap;        // qudarap/QTex.cc:260-275
+    td.addressMode[1] = cudaAddressModeWrap;
+    td.filterMode = cudaFilterModeLinear;
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 1;
+    return cudaCreateTextureObject(tex, &res, &td, nullptr);
+}
+
+extern "C" int phox_set_tables(phox_context* ctx, const float* bnd, int64_t nbnd, int64_t nwl, float domain_low, float domain_step,
+                               const int32_t* optical, const float* icdf, int64_t icdf_ny, int64_t icdf_nx, int32_t hd_factor) {
+    if (!ctx) return PHOX_E_ARG;
+    if (!bnd || !optical || nbnd <= 0 || nwl <= 1) return ctx->fail(PHOX_E_ARG, "phox_set_tables: bnd and optical are required");
+    if (nbnd * 8 > 65536) return ctx->fail(PHOX_E_ARG, "phox_set_tables: more than 8192 boundaries do not fit one 2D texture");
+    if (!(domain_step > 0.f)) return ctx->fail(PHOX_E_ARG, "phox_set_tables: domain_step must be positive");
+    if (icdf && (icdf_ny != 3 || icdf_nx < 2)) return ctx->fail(PHOX_E_ARG, "phox_set_tables: icdf must be 3 rows (hd layers) x nx");
+    if (icdf && hd_factor != 0 && hd_factor != 10 && hd_factor != 20) return ctx->fail(PHOX_E_ARG, "phox_set_tables: hd_factor must be 0, 10 or 20");
+    CK(cudaSetDevice(ctx->device));
+    free_tables(ctx);
+    ctx->nx = (unsigned)nwl; ctx->ny = (unsigned)(nbnd * 8);
+    ctx->nm0 = domain_low; ctx->nms = domain_step;
+    CK(make_tex(&ctx->bnd_array, &ctx->bnd_tex, bnd, (size_t)nwl, (size_t)nbnd * 8, 4));
+    if (icdf) {
+        CK(make_tex(&ctx->icdf_array, &ctx->icdf_tex, icdf, (size_t)icdf_nx, (size_t)icdf_ny, 1));
+        ctx->hd_factor = (unsigned)hd_factor;
+    }
+    CK(ctx->d_optical.reserve((size_t)nbnd * 4));
+    CK(cudaMemcpy(ctx->d_optical.p, optical, (size_t)nbnd * 4 * 16, cudaMemcpyHostToDevice));
+    ctx->have_tables = true;
+    return PHOX_OK;
+}
+
+extern "C" int phox_set_config(phox_context* ctx, const phox_config* cfg) {
+    if (!ctx || !cfg) return PHOX_E_ARG;
+    if (cfg->max_bounce < 0) return ctx->fail(PHOX_E_ARG, "phox_set_config: max_bounce < 0");
+    if (cfg->max_record < 0 || cfg->max_record > 32) return ctx->fail(PHOX_E_ARG, "phox_set_config: max_record must be 0..32 (sseq::SLOTS)");
+    if (cfg->event_mode < PHOX_MODE_MINIMAL || cfg->event_mode > PHOX_MODE_DEBUGHEAVY) return ctx->fail(PHOX_E_ARG, "phox_set_config: unknown event_mode");
+    if (cfg->max_slot < 0) return ctx->fail(PHOX_E_ARG, "phox_set_config: max_slot < 0");
+    ctx->cfg = *cfg;
+    return PHOX_OK;
+}
+
+extern "C" int phox_get_config(const phox_context* ctx, phox_config* cfg) {
+    if (!ctx || !cfg) return PHOX_E_ARG;
+    *cfg = ctx->cfg;
+    return PHOX_OK;
+}
+
+// ---- events ---------------------------------------------------------------------------------------
+static int64_t effective_max_slot(const phox_context* ctx) {
+    if (ctx->cfg.max_slot > 0) return ctx->cfg.max_slot;
+    // SEventConfig::HeuristicMaxSlot : 0.87*VRAM / (64 B * 1.75)   (sysrap/SEventConfig.cc:1897-1903)
+    double v = 0.87 * (double)ctx->vram_total / (64.0 * 1.75);
+    int64_t s = (int64_t)v;
+    return std::min<int64_t>(s, 0xffffff00ll);      // one launch indexes slots with 32 bits
+}
+
+struct Slice { int64_t gs_start, gs_stop, ph_offset, ph_count; };
+
+// SGenstep::GetGenstepSlices (sysrap/SGenstep.h:249-323): greedy, whole gensteps, in order.
+static void make_slices(std::vector<Slice>& out, const Genstep* gs, int64_t n, int64_t max_slot) {
+    Slice sl = {0, 0, 0, 0};
+    for (int64_t i = 0; i < n; i++) {
+        int64_t num = gs[i].numphoton();
+        if (sl.ph_count + num <= max_slot) { sl.gs_stop = i + 1; sl.ph_count += num; }
+        else {
+            sl.gs_stop = i;
+            out.push_back(sl);
+            sl.ph_count = num; sl.gs_start = i; sl.gs_stop = i + 1;
+        }
+        if (i == n - 1) out.push_back(sl);
+    }
+    int64_t off = 0;
+    for (auto& s : out) { s.ph_offset = off; off += s.ph_count; }
+}
+
+static bool mode_keeps_photon(int m) { return m != PHOX_MODE_MINIMAL; }
+static bool mode_keeps_seq(int m) { return m == PHOX_MODE_HITPHOTONSEQ || m == PHOX_MODE_DEBUGLITE || m == PHOX_MODE_DEBUGHEAVY; }
+static bool mode_keeps_record(int m) { return m == PHOX_MODE_DEBUGLITE || m == PHOX_MODE_DEBUGHEAVY; }
+static bool mode_keeps_prd(int m) { return m == PHOX_MODE_DEBUGHEAVY; }
+
+// one launch over slots [0,n) ; gensteps + prefix already on the device
+static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned long long* d_prefix, int ngs, const Photon* d_input,
+                      unsigned long long input_base, unsigned long long photon_offset, int64_t n, int event_id) {
+    const int T = 128;
+    int nblock = (int)((n + T - 1) / T);
+    const phox_config& c = ctx->cfg;
+    int mode = c.event_mode;
+    bool dbg = mode_keeps_seq(mode) || mode_keeps_record(mode) || mode_keeps_prd(mode);
+
+    CK(ctx->d_photon.reserve((size_t)n));
+    CK(ctx->d_block_hits.reserve((size_t)nblock));
+    CK(ctx->d_block_off.reserve((size_t)nblock));
+    if (mode_keeps_seq(mode)) CK(ctx->d_seq.reserve((size_t)n));
+    if (mode_keeps_record(mode)) CK(ctx->d_record.reserve((size_t)n * c.max_record));
+    if (mode_keeps_prd(mode)) CK(ctx->d_prd.reserve((size_t)n * c.max_record));
+
+    SimParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.scene.geo.node = ctx->d_node.p; P.scene.geo.plan = ctx->d_plan.p; P.scene.geo.itra = ctx->d_itra.p;
+    P.scene.prim = ctx->d_prim.p; P.scene.nodes = ctx->d_bvh.p; P.scene.inst = ctx->d_inst.p;
+    P.scene.ninst = ctx->ninst; P.scene.tlas_root = ctx->tlas_root; P.scene.accel = c.accel;
+    P.tables.bnd_tex = ctx->bnd_tex; P.tables.icdf_tex = ctx->icdf_tex; P.tables.optical = ctx->d_optical.p;
+    P.tables.nx = ctx->nx; P.tables.ny = ctx->ny; P.tables.nm0 = ctx->nm0; P.tables.nms = ctx->nms; P.tables.hd_factor = ctx->hd_factor;
+    P.genstep = d_gs; P.gs_prefix = d_prefix; P.num_genstep = ngs;
+    P.input_photon = d_input; P.input_base = input_base; P.photon_offset = photon_offset;
+    P.num_photon = (unsigned)n; P.event_index = event_id;
+    P.photon = ctx->d_photon.p;
+    P.seq = mode_keeps_seq(mode) ? ctx->d_seq.p : nullptr;
+    P.record = mode_keeps_record(mode) ? ctx->d_record.p : nullptr;
+    P.prd = mode_keeps_prd(mode) ? ctx->d_prd.p : nullptr;
+    P.max_record = c.max_record;
+    P.block_hits = ctx->d_block_hits.p;
+    P.counters = ctx->d_counters.p;
+    P.max_bounce = c.max_bounce;
+    P.tmin = c.propagate_epsilon; P.tmin0 = c.propagate_epsilon0; P.tmax = c.tmax; P.max_time = c.max_time;
+    P.refine_distance = c.refine_distance; P.eps0_mask = c.epsilon0_mask; P.hit_mask = c.hit_mask; P.refine = c.propagate_refine;
+    P.seed = c.rng_seed; P.rng_offset = c.rng_offset; P.skipahead = c.skipahead_event_offset;
+    P.burn = c.rng_mode == PHOX_RNG_DEBUG_TAG ? 1 : 0;
+
+    if (dbg) k_simulate<true><<<nblock, T, 0, ctx->stream>>>(P);
+    else k_simulate<false><<<nblock, T, 0, ctx->stream>>>(P);
+    CK(cudaGetLastError());
+    k_hit_offsets<<<1, 1024, 0, ctx->stream>>>(ctx->d_block_hits.p, nblock, ctx->d_block_off.p, ctx->d_counters.p + 1);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    int64_t nhit = (int64_t)ctx->h_counters[1];
+    ctx->stats.num_kernel += 2;
+    if (nhit > 0) {
+        CK(ctx->d_hit.reserve((size_t)(ctx->num_hit + nhit), true, ctx->stream));
+        k_hit_compact<<<nblock, T, 0, ctx->stream>>>(ctx->d_photon.p, (unsigned)n, c.hit_mask, ctx->d_block_off.p, ctx->d_hit.p + ctx->num_hit);
+        CK(cudaGetLastError());
+        ctx->stats.num_kernel += 1;
+    }
+    ctx->num_hit += nhit;
+    ctx->stats.num_launch += 1;
+    return PHOX_OK;
+}
+
+static int gather_debug(phox_context* ctx, int64_t n) {
+    int mode = ctx->cfg.event_mode;
+    int mr = ctx->cfg.max_record;
+    if (mode_keeps_photon(mode)) {
+        size_t o = ctx->h_photon.size();
+        ctx->h_photon.resize(o + n);
+        CK(cudaMemcpyAsync(ctx->h_photon.data() + o, ctx->d_photon.p, (size_t)n * 64, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (mode_keeps_seq(mode)) {
+        size_t o = ctx->h_seq.size();
+        ctx->h_seq.resize(o + n);
+        CK(cudaMemcpyAsync(ctx->h_seq.data() + o, ctx->d_seq.p, (size_t)n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (mode_keeps_record(mode)) {
+        size_t o = ctx->h_record.size();
+        ctx->h_record.resize(o + (size_t)n * mr);
+        CK(cudaMemcpyAsync(ctx->h_record.data() + o, ctx->d_record.p, (size_t)n * mr * 64, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (mode_keeps_prd(mode)) {
+        size_t o = ctx->h_prd.size();
+        ctx->h_prd.resize(o + (size_t)n * mr);
+        CK(cudaMemcpyAsync(ctx->h_prd.data() + o, ctx->d_prd.p, (size_t)n * mr * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PHOX_OK;
+}
+
+static int begin_event(phox_context* ctx) {
+    if (!ctx->have_geometry) return ctx->fail(PHOX_E_STATE, "phox_simulate: geometry not set");
+    if (!ctx->have_tables) return ctx->fail(PHOX_E_STATE, "phox_simulate: tables not set");
+    CK(cudaSetDevice(ctx->device));
+    ctx->num_photon = 0; ctx->num_hit = 0;
+    ctx->h_photon.clear(); ctx->h_record.clear(); ctx->h_seq.clear(); ctx->h_prd.clear();
+    std::memset(&ctx->stats, 0, sizeof(ctx->stats));
+    ctx->event_max_record = ctx->cfg.max_record;
+    CK(cudaMemsetAsync(ctx->d_counters.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    ctx->have_event = false;
+    return PHOX_OK;
+}
+
+static int check_gensteps(phox_context* ctx, const Genstep* gs, int64_t ngs, int64_t ninput, bool have_input) {
+    int64_t n_input_gs = 0;
+    for (int64_t i = 0; i < ngs; i++) {
+        int code = gs[i].gencode();
+        if ((code == GS_SCINTILLATION || code == GS_DsG4Scintillation_r4695) && !ctx->icdf_tex)
+            return ctx->fail(PHOX_E_STATE, "phox_simulate: scintillation genstep but no icdf table was set");
+        if (code == GS_INPUT_PHOTON) {
+            n_input_gs++;
+            if (!have_input) return ctx->fail(PHOX_E_ARG, "phox_simulate: INPUT_PHOTON genstep without input photons");
+            if ((int64_t)gs[i].numphoton() != ninput || ngs != 1)
+                return ctx->fail(PHOX_E_ARG, "phox_simulate: input photons ride on exactly one INPUT_PHOTON genstep with numphoton == ninput");
+        }
+    }
+    (void)n_input_gs;
+    return PHOX_OK;
+}
+
+extern "C" int phox_simulate(phox_context* ctx, const void* genstep_, int64_t ngs, const void* input_photon, int64_t ninput, int32_t event_id,
+                             uint64_t photon_offset, double* launch_seconds) {
+    if (!ctx) return PHOX_E_ARG;
+    if (!genstep_ || ngs <= 0) return ctx->fail(PHOX_E_ARG, "phox_simulate: no gensteps");       // QSim::simulate returns -1. here
+    int rc = begin_event(ctx);
+    if (rc) return rc;
+    const Genstep* gs = (const Genstep*)genstep_;
+    rc = check_gensteps(ctx, gs, ngs, ninput, input_photon != nullptr);
+    if (rc) return rc;
+
+    double t0 = now_s();
+    std::vector<Slice> slices;
+    int64_t max_slot = effective_max_slot(ctx);
+    for (int64_t i = 0; i < ngs; i++)
+        if ((int64_t)gs[i].numphoton() > max_slot) return ctx->fail(PHOX_E_NOMEM, "phox_simulate: one genstep exceeds max_slot; split it (photon_offset lets callers shard input photons)");
+    make_slices(slices, gs, ngs, max_slot);
+
+    CK(ctx->d_genstep.reserve((size_t)ngs));
+    CK(ctx->d_prefix.reserve((size_t)ngs + 1));
+    CK(cudaMemcpyAsync(ctx->d_genstep.p, gs, (size_t)ngs * sizeof(Genstep), cudaMemcpyHostToDevice, ctx->stream));
+    if (input_photon) {
+        CK(ctx->d_input.reserve((size_t)ninput));
+        CK(cudaMemcpyAsync(ctx->d_input.p, input_photon, (size_t)ninput * 64, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    std::vector<unsigned long long> prefix;
+    double t_up = now_s() - t0, t_launch = 0., t_gather = 0.;
+    for (const Slice& sl : slices) {
+        if (sl.ph_count == 0) continue;
+        double ta = now_s();
+        int n = (int)(sl.gs_stop - sl.gs_start);
+        prefix.assign((size_t)n + 1, 0ull);
+        for (int k = 0; k < n; k++) prefix[k + 1] = prefix[k] + gs[sl.gs_start + k].numphoton();
+        CK(cudaMemcpyAsync(ctx->d_prefix.p, prefix.data(), prefix.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        double tb = now_s();
+        rc = run_launch(ctx, ctx->d_genstep.p + sl.gs_start, ctx->d_prefix.p, n, input_photon ? ctx->d_input.p : nullptr,
+                        photon_offset, photon_offset + (uint64_t)sl.ph_offset, sl.ph_count, event_id);
+        if (rc) return rc;
+        double tc = now_s();
+        if (mode_keeps_photon(ctx->cfg.event_mode)) { rc = gather_debug(ctx, sl.ph_count); if (rc) return rc; }
+        double td = now_s();
+        t_up += tb - ta; t_launch += tc - tb; t_gather += td - tc;
+        ctx->num_photon += sl.ph_count;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(ctx->h_counters, ctx->d_counters.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    ctx->stats.num_photon = (uint64_t)ctx->num_photon; ctx->stats.num_hit = (uint64_t)ctx->num_hit; ctx->stats.num_ray = ctx->h_counters[0];
+    ctx->stats.launch_seconds = t_launch; ctx->stats.upload_seconds = t_up; ctx->stats.gather_seconds = t_gather;
+    if (launch_seconds) *launch_seconds = t_launch;
+    ctx->have_event = true;
+    return PHOX_OK;
+}
+
+extern "C" int phox_simulate_device(phox_context* ctx, const void* d_genstep, int64_t ngs, const void* d_input_photon, int64_t ninput,
+                                    int32_t event_id, uint64_t photon_offset, double* launch_seconds) {
+    if (!ctx) return PHOX_E_ARG;
+    if (!d_genstep || ngs <= 0) return ctx->fail(PHOX_E_ARG, "phox_simulate_device: no gensteps");
+    int rc = begin_event(ctx);
+    if (rc) return rc;
+    double t0 = now_s();
+    CK(ctx->d_prefix.reserve((size_t)ngs + 1));
+    k_genstep_prefix<<<1, 1024, 0, ctx->stream>>>((const Genstep*)d_genstep, (int)ngs, ctx->d_prefix.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ctx->h_counters + 2, ctx->d_prefix.p + ngs, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    int64_t n = (int64_t)ctx->h_counters[2];
+    ctx->stats.num_kernel += 1;
+    if (n <= 0) return ctx->fail(PHOX_E_ARG, "phox_simulate_device: gensteps hold no photons");
+    if (n > effective_max_slot(ctx)) return ctx->fail(PHOX_E_NOMEM, "phox_simulate_device: event exceeds max_slot; the device-resident path is single-launch");
+    (void)ninput;
+    rc = run_launch(ctx, (const Genstep*)d_genstep, ctx->d_prefix.p, (int)ngs, (const Photon*)d_input_photon, photon_offset, photon_offset, n, event_id);
+    if (rc) return rc;
+    if (mode_keeps_photon(ctx->cfg.event_mode)) { rc = gather_debug(ctx, n); if (rc) return rc; }
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(ctx->h_counters, ctx->d_counters.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    ctx->num_photon = n;
+    double dt = now_s() - t0;
+    ctx->stats.num_photon = (uint64_t)n; ctx->stats.num_hit = (uint64_t)ctx->num_hit; ctx->stats.num_ray = ctx->h_counters[0];
+    ctx->stats.launch_seconds = dt;
+    if (launch_seconds) *launch_seconds = dt;
+    ctx->have_event = true;
+    return PHOX_OK;
+}
+
+extern "C" int64_t phox_num_photon(const phox_context* ctx) { return ctx && ctx->have_event ? ctx->num_photon : 0; }
+extern "C" int64_t phox_num_hit(const phox_context* ctx) { return ctx && ctx->have_event ? ctx->num_hit : 0; }
+extern "C" const void* phox_hits_device(const phox_context* ctx) { return ctx && ctx->have_event && ctx->num_hit ? ctx->d_hit.p : nullptr; }
+
+extern "C" int phox_get_hits(phox_context* ctx, void* dst) {
+    if (!ctx) return PHOX_E_ARG;
+    if (!ctx->have_event) return ctx->fail(PHOX_E_STATE, "phox_get_hits: no event");
+    if (ctx->num_hit == 0) return PHOX_OK;
+    if (!dst) return ctx->fail(PHOX_E_ARG, "phox_get_hits: null destination");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(dst, ctx->d_hit.p, (size_t)ctx->num_hit * 64, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PHOX_OK;
+}
+
+extern "C" int64_t phox_get_array(phox_context* ctx, const char* name, void* dst, int64_t dst_bytes) {
+    if (!ctx || !name) return PHOX_E_ARG;
+    if (!ctx->have_event) return ctx->fail(PHOX_E_STATE, "phox_get_array: no event");
+    const void* src = nullptr;
+    int64_t bytes = 0;
+    std::string n(name);
+    if (n == "photon") { src = ctx->h_photon.data(); bytes = (int64_t)ctx->h_photon.size() * 64; }
+    else if (n == "record") { src = ctx->h_record.data(); bytes = (int64_t)ctx->h_record.size() * 64; }
+    else if (n == "seq") { src = ctx->h_seq.data(); bytes = (int64_t)ctx->h_seq.size() * 32; }
+    else if (n == "prd") { src = ctx->h_prd.data(); bytes = (int64_t)ctx->h_prd.size() * 32; }
+    else if (n == "hit") {
+        bytes = ctx->num_hit * 64;
+        if (!dst) return bytes;
+        if (dst_bytes < bytes) return ctx->fail(PHOX_E_ARG, "phox_get_array: destination too small");
+        int rc = phox_get_hits(ctx, dst);
+        return rc ? rc : bytes;
+    } else return ctx->fail(PHOX_E_ARG, "phox_get_array: unknown array name");
+    if (!dst) return bytes;
+    if (dst_bytes < bytes) return ctx->fail(PHOX_E_ARG, "phox_get_array: destination too small");
+    if (bytes) std::memcpy(dst, src, (size_t)bytes);
+    return bytes;
+}
+
+extern "C" int phox_get_stats(const phox_context* ctx, phox_stats* st) {
+    if (!ctx || !st) return PHOX_E_ARG;
+    *st = ctx->stats;
+    return PHOX_OK;
+}
+
+extern "C" void phox_reset(phox_context* ctx) {
+    if (!ctx) return;
+    ctx->have_event = false;
+    ctx->num_photon = 0; ctx->num_hit = 0;
+    ctx->h_photon.clear(); ctx->h_record.clear(); ctx->h_seq.clear(); ctx->h_prd.clear();
+    ctx->h_photon.shrink_to_fit(); ctx->h_record.shrink_to_fit(); ctx->h_seq.shrink_to_fit(); ctx->h_prd.shrink_to_fit();
+}
+
+extern "C" int phox_intersect(phox_context* ctx, const float* ray_o_tmin, const float* ray_d, int64_t nray, void* dst_prd, int32_t accel) {
+    if (!ctx) return PHOX_E_ARG;
+    if (!ctx->have_geometry) return ctx->fail(PHOX_E_STATE, "phox_intersect: geometry not set");
+    if (!ray_o_tmin || !ray_d || !dst_prd || nray < 0) return ctx->fail(PHOX_E_ARG, "phox_intersect: bad arguments");
+    if (nray == 0) return PHOX_OK;
+    CK(cudaSetDevice(ctx->device));
+    float4 *d_o = nullptr, *d_d = nullptr;
+    Prd* d_out = nullptr;
+    CK(cudaMalloc(&d_o, (size_t)nray * 16));
+    CK(cudaMalloc(&d_d, (size_t)nray * 16));
+    CK(cudaMalloc(&d_out, (size_t)nray * 32));
+    CK(cudaMemcpyAsync(d_o, ray_o_tmin, (size_t)nray * 16, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_d, ray_d, (size_t)nray * 16, cudaMemcpyHostToDevice, ctx->stream));
+    Scene sc;
+    sc.geo.node = ctx->d_node.p; sc.geo.plan = ctx->d_plan.p; sc.geo.itra = ctx->d_itra.p;
+    sc.prim = ctx->d_prim.p; sc.nodes = ctx->d_bvh.p; sc.inst = ctx->d_inst.p;
+    sc.ninst = ctx->ninst; sc.tlas_root = ctx->tlas_root; sc.accel = accel;
+    const int T = 128;
+    k_intersect<<<(unsigned)((nray + T - 1) / T), T, 0, ctx->stream>>>(sc, d_o, d_d, (unsigned)nray, ctx->cfg.tmax, d_out);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dst_prd, d_out, (size_t)nray * 32, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_o); cudaFree(d_d); cudaFree(d_out);
+    if (e != cudaSuccess) return ctx->cuda_fail(e, "phox_intersect");
+    return PHOX_OK;
+}
+
+extern "C" int phox_rng_sequence(phox_context* ctx, float* dst, int64_t ni, int64_t nv, uint64_t id0, int32_t event_id) {
+    if (!ctx) return PHOX_E_ARG;
+    if (!dst || ni <= 0 || nv <= 0) return ctx->fail(PHOX_E_ARG, "phox_rng_sequence: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    float* d = nullptr;
+    CK(cudaMalloc(&d, (size_t)ni * nv * 4));
+    const int T = 128;
+    k_rng_sequence<<<(unsigned)((ni + T - 1) / T), T, 0, ctx->stream>>>(d, (unsigned)ni, (unsigned)nv, id0, ctx->cfg.rng_seed,
+                                                                          ctx->cfg.rng_offset + ctx->cfg.skipahead_event_offset * (uint64_t)event_id);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dst, d, (size_t)ni * nv * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return ctx->cuda_fail(e, "phox_rng_sequence");
+    return PHOX_OK;
+}

@@ -1,0 +1,405 @@
+// phox_kernels.cuh : the event kernels.
+//
+//   trace()        nearest CSGPrim along a ray: instance BVH -> per-solid BVH -> intersect_prim.
+//                  Replaces optixTrace + __intersection__is + __closesthit__ch + __miss__ms
+//                  (CSGOptiX/CSGOptiX7.cu:110-216, 655-682, 749-847, 869-940).
+//   k_simulate     one thread per photon: seed lookup, RNG init, generate, bounce loop, photon
+//                  write, per-block hit count.  Replaces the simulate raygen
+//                  (CSGOptiX7.cu:405-503) and the thrust seeding passes
+//                  (qudarap/QEvt.cu:181-237, sysrap/iexpand.h:86-142): the genstep of a photon
+//                  is found by binary search in the exclusive prefix sum of genstep.numphoton.
+//   k_hit_offsets  exclusive scan of the per-block hit counts (one block).
+//   k_hit_compact  stable stream compaction of hit photons, ascending photon index.  Replaces
+//                  thrust count_if + copy_if (sysrap/SU.cu:48-56, 91-92, 157-159).
+#pragma once
+#include "phox_types.h"
+#include "phox_math.cuh"
+#include "phox_philox.cuh"
+#include "phox_csg.cuh"
+#include "phox_bvh.cuh"
+#include "phox_physics.cuh"
+
+namespace phox {
+
+struct Scene {
+    Geo geo;
+    const float4* prim;             // Prim[nprim] viewed as 4 x float4
+    const BvhNode* nodes;           // pool: instance tree first, then one tree per solid
+    const InstanceRec* inst;
+    int ninst;
+    int tlas_root;                  // node index of the instance tree
+    int accel;                      // PHOX_ACCEL_*
+};
+
+struct SimParams {
+    Scene scene;
+    Tables tables;
+    // event
+    const Genstep* genstep;
+    const unsigned long long* gs_prefix;    // [num_genstep+1] exclusive prefix of numphoton within this launch
+    int num_genstep;
+    const Photon* input_photon;
+    unsigned long long input_base;          // absolute photon index of input_photon[0]
+    unsigned long long photon_offset;       // absolute index of slot 0 of this launch
+    unsigned num_photon;                    // slots in this launch
+    int event_index;
+    // outputs (null = not kept)
+    Photon* photon;
+    Seq* seq;
+    Photon* record;
+    Prd* prd;
+    int max_record;
+    unsigned* block_hits;                   // [gridDim.x]
+    unsigned long long* counters;           // [0] = rays traced
+    // config
+    int max_bounce;
+    float tmin, tmin0, tmax, max_time, refine_distance;
+    unsigned eps0_mask, hit_mask, refine;
+    unsigned long long seed, rng_offset, skipahead;
+    int burn;
+};
+
+struct Nearest {
+    float t;
+    float3 n;                       // object-frame normal
+    int prim;                       // global CSGPrim index
+    int inst;
+    unsigned boundary;
+};
+
+PHOX_D void keep_nearest(Nearest& best, const Scene& sc, const float4* root, const float4& is, int prim_idx, int inst_idx, float tmin) {
+    float t = is.w;
+    if (!(t > tmin)) return;                 // OptiX rejects reports outside (tmin, tmax]
+    // ties go to the lower (instance, prim) pair so the answer does not depend on traversal order
+    bool closer = t < best.t ||
+                  (t == best.t && (best.prim < 0 || inst_idx < best.inst || (inst_idx == best.inst && prim_idx < best.prim)));
+    if (closer) {
+        best.t = t;
+        best.n = f3(is.x, is.y, is.z);
+        best.prim = prim_idx;
+        best.inst = inst_idx;
+        best.boundary = __float_as_uint(__ldg(root + 1).z);
+    }
+}
+
+constexpr int kBvhStack = 64;
+constexpr int kTravReturn = (int)0x80000000;     // stack marker: leave the current solid, back to the instance tree
+constexpr int kTravDone = 0x7ffffffe;
+
+// Single-loop traversal of both BVH levels.  `cur` is a node index (>= 0, relative to the current
+// tree root) or a leaf (~item): an instance while in the top tree, a CSGPrim inside a solid.
+// Children are visited near-first, the far one parked on the stack with its entry distance so it
+// can be dropped once a nearer hit is known.  There is exactly one prim-test site in the loop.
+PHOX_D void traverse_bvh(Nearest& best, const Scene& sc, float tmin, const float3& o_w, const float3& d_w) {
+    int stack[kBvhStack];
+    float stack_t[kBvhStack];
+    int sp = 0;
+    float3 o = o_w, d = d_w;
+    float3 idir = f3(1.f / d.x, 1.f / d.y, 1.f / d.z);
+    int root = sc.tlas_root;
+    bool in_solid = false;
+    int inst_idx = 0;
+    int cur = sc.ninst == 1 ? ~0 : 0;
+
+    while (cur != kTravDone) {
+        if (cur == kTravReturn) {
+            in_solid = false; o = o_w; d = d_w;
+            idir = f3(1.f / d.x, 1.f / d.y, 1.f / d.z);
+            root = sc.tlas_root;
+            cur = kTravDone;
+        } else if (cur < 0) {
+            if (!in_solid) {                                  // enter an instance
+                inst_idx = ~cur;
+                const InstanceRec* ir = sc.inst + inst_idx;
+                int4 meta = __ldg(reinterpret_cast<const int4*>(&ir->solid));   // solid, identity, is_identity, bvh_root
+                if (!meta.z) {
+                    float4 r0 = __ldg(&ir->inv[0]), r1 = __ldg(&ir->inv[1]), r2 = __ldg(&ir->inv[2]), r3 = __ldg(&ir->inv[3]);
+                    o = xform(r0, r1, r2, r3, o_w, 1.f);
+                    d = xform(r0, r1, r2, r3, d_w, 0.f);
+                    idir = f3(1.f / d.x, 1.f / d.y, 1.f / d.z);
+                }
+                root = meta.w;
+                in_solid = true;
+                if (sp < kBvhStack) { stack[sp] = kTravReturn; stack_t[sp] = -CUDART_INF_F; sp++; }
+                cur = 0;
+                continue;
+            }
+            {                                                  // a CSGPrim: the one intersect site
+                int prim_idx = ~cur;
+                float4 p0 = __ldg(sc.prim + 4 * prim_idx);
+                const float4* nroot = sc.geo.node + 4 * __float_as_int(p0.y);
+                float4 is = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (intersect_prim(is, nroot, sc.geo, tmin, o, d)) keep_nearest(best, sc, nroot, is, prim_idx, inst_idx, tmin);
+            }
+            cur = kTravDone;
+        } else {
+            const float4* np = reinterpret_cast<const float4*>(sc.nodes + root + cur);
+            float4 a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2);
+            int4 ch = __ldg(reinterpret_cast<const int4*>(np + 3));
+            float t0 = box_entry(a.x, a.y, a.z, a.w, b.x, b.y, o, idir, tmin, best.t);
+            float t1 = ch.y == kBvhNoChild ? CUDART_INF_F : box_entry(b.z, b.w, c.x, c.y, c.z, c.w, o, idir, tmin, best.t);
+            bool h0 = t0 < CUDART_INF_F, h1 = t1 < CUDART_INF_F;
+            if (h0 && h1) {
+                int nearc = ch.x, farc = ch.y; float tfar = t1;
+                if (t1 < t0) { nearc = ch.y; farc = ch.x; tfar = t0; }
+                if (sp < kBvhStack) { stack[sp] = farc; stack_t[sp] = tfar; sp++; }
+                cur = nearc;
+                continue;
+            } else if (h0) { cur = ch.x; continue; }
+            else if (h1) { cur = ch.y; continue; }
+            cur = kTravDone;
+        }
+        // pop the next parked subtree that can still hold a nearer hit
+        while (sp > 0) {
+            sp--;
+            if (stack_t[sp] <= best.t) { cur = stack[sp]; break; }
+        }
+    }
+}
+
+// validation path: every prim of every instance, no boxes involved
+__device__ __noinline__ void traverse_brute(Nearest& best, const Scene& sc, float tmin, const float3& o_w, const float3& d_w) {
+    for (int i = 0; i < sc.ninst; i++) {
+        const InstanceRec* ir = sc.inst + i;
+        int4 meta = __ldg(reinterpret_cast<const int4*>(&ir->solid));
+        float3 o = o_w, d = d_w;
+        if (!meta.z) {
+            float4 r0 = __ldg(&ir->inv[0]), r1 = __ldg(&ir->inv[1]), r2 = __ldg(&ir->inv[2]), r3 = __ldg(&ir->inv[3]);
+            o = xform(r0, r1, r2, r3, o_w, 1.f);
+            d = xform(r0, r1, r2, r3, d_w, 0.f);
+        }
+        int2 pr = __ldg(reinterpret_cast<const int2*>(&ir->prim_offset));
+        for (int k = 0; k < pr.y; k++) {
+            int prim_idx = pr.x + k;
+            float4 p0 = __ldg(sc.prim + 4 * prim_idx);
+            const float4* nroot = sc.geo.node + 4 * __float_as_int(p0.y);
+            float4 is = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (intersect_prim_cold(is, nroot, sc.geo, tmin, o, d)) keep_nearest(best, sc, nroot, is, prim_idx, i, tmin);
+        }
+    }
+}
+
+// nearest intersect in (tmin, tmax]; fills the prd-equivalent.  Returns false on a miss
+// (the reference's miss program sets boundary 0xffff).  Out of line: one compiled body serves
+// every kernel and both trace sites of the bounce loop.
+__device__ __noinline__ bool trace(HitInfo& h, const Scene& sc, const float3& o, const float3& d, float tmin, float tmax) {
+    Nearest best;
+    best.t = tmax; best.prim = -1; best.inst = 0; best.boundary = 0xffffu; best.n = f3(0.f, 0.f, 0.f);
+    if (sc.accel == 0) traverse_bvh(best, sc, tmin, o, d);
+    else traverse_brute(best, sc, tmin, o, d);
+    if (best.prim < 0) {
+        h.normal = f3(0.f, 0.f, 0.f); h.t = 1.f; h.lposcost = 0.f; h.lposfphi = 0.f;
+        h.iindex_identity = 0xffffffffu; h.prim_boundary = 0xffffffffu;
+        return false;
+    }
+    const InstanceRec* ir = sc.inst + best.inst;
+    int4 meta = __ldg(reinterpret_cast<const int4*>(&ir->solid));
+    float3 oo = o, dd = d, n = best.n;
+    if (!meta.z) {
+        float4 r0 = __ldg(&ir->inv[0]), r1 = __ldg(&ir->inv[1]), r2 = __ldg(&ir->inv[2]), r3 = __ldg(&ir->inv[3]);
+        oo = xform(r0, r1, r2, r3, o, 1.f);
+        dd = xform(r0, r1, r2, r3, d, 0.f);
+        n = xform_normal(r0, r1, r2, best.n);       // object -> world uses the inverse-transpose
+    }
+    float3 lpos = oo + best.t * dd;
+    h.normal = n;
+    h.t = best.t;
+    h.lposcost = lpos.z / sqrtf(dot(lpos, lpos));
+    h.lposfphi = (atan2f(lpos.y, lpos.x) + kPi) / (2.0f * kPi);
+    h.iindex_identity = (((unsigned)best.inst & 0xffffu) << 16) | ((unsigned)meta.y & 0xffffu);
+    unsigned gpi = __float_as_uint(__ldg(sc.prim + 4 * best.prim + 3).w);
+    h.prim_boundary = ((gpi & 0xffffu) << 16) | (best.boundary & 0xffffu);
+    return true;
+}
+
+PHOX_D void seq_add(Seq& s, unsigned slot, unsigned flag, unsigned boundary) {      // sseq::add_nibble
+    unsigned iseq = slot / 16u;
+    unsigned shift = 4u * (slot - iseq * 16u);
+    if (iseq < 2u) {
+        s.seqhis[iseq] |= ((unsigned long long)(__ffs(flag) & 0xf)) << shift;
+        s.seqbnd[iseq] |= ((unsigned long long)(boundary & 0xfu)) << shift;
+    }
+}
+
+template <bool DEBUG>
+__global__ void __launch_bounds__(128) k_simulate(const __grid_constant__ SimParams P) {
+    unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    bool live = idx < P.num_photon;
+    bool is_hit = false;
+    unsigned nray = 0;
+
+    if (live) {
+        // seed : which genstep owns slot idx
+        int lo = 0, hi = P.num_genstep;                       // prefix[lo] <= idx < prefix[hi]
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (__ldg(P.gs_prefix + mid) <= (unsigned long long)idx) lo = mid; else hi = mid;
+        }
+        Genstep gs;
+        {
+            const float4* src = reinterpret_cast<const float4*>(P.genstep + lo);
+            float4* dst = reinterpret_cast<float4*>(&gs);
+#pragma unroll
+            for (int k = 0; k < 6; k++) dst[k] = __ldg(src + k);
+        }
+        unsigned long long photon_idx = P.photon_offset + idx;
+
+        Philox rng;
+        rng.init(P.seed, photon_idx, P.rng_offset + P.skipahead * (unsigned long long)P.event_index);
+
+        PhotonState p;
+        generate_photon(p, rng, gs, P.tables, P.input_photon, P.input_base, photon_idx);
+
+        Seq seq;
+        if (DEBUG) {
+            seq.seqhis[0] = seq.seqhis[1] = seq.seqbnd[0] = seq.seqbnd[1] = 0ull;
+            if (P.record && 0 < P.max_record) p.store(P.record + (size_t)P.max_record * idx);
+            if (P.seq) seq_add(seq, 0u, p.flag(), p.boundary());
+        }
+
+        int bounce = 0;
+        while (bounce < P.max_bounce && p.time < P.max_time) {
+            float tmin = (p.obf & P.eps0_mask) ? P.tmin0 : P.tmin;
+            HitInfo h;
+            bool ok = trace(h, P.scene, p.pos, p.mom, tmin, P.tmax);
+            nray++;
+            if (P.refine && ok) {
+                float t_approx = 0.99f * h.t;
+                if (t_approx > P.refine_distance) {
+                    float3 closer = p.pos + t_approx * p.mom;
+                    ok = trace(h, P.scene, closer, p.mom, tmin, P.tmax);
+                    nray++;
+                    h.t += t_approx;
+                }
+            }
+            if (!ok) break;                                   // photon left the world
+            h.normal = normalize(h.normal);
+            if (DEBUG) {
+                if (P.prd && bounce < P.max_record) {
+                    Prd r;
+                    r.nx = h.normal.x; r.ny = h.normal.y; r.nz = h.normal.z; r.t = h.t;
+                    r.lposcost = h.lposcost; r.lposfphi = h.lposfphi;
+                    r.iindex_identity = h.iindex_identity; r.prim_boundary = h.prim_boundary;
+                    P.prd[(size_t)P.max_record * idx + bounce] = r;
+                }
+            }
+            int command = propagate(p, rng, h, P.tables, P.burn != 0);
+            bounce++;
+            if (DEBUG) {
+                if (P.record && bounce < P.max_record) p.store(P.record + (size_t)P.max_record * idx + bounce);
+                if (P.seq) seq_add(seq, (unsigned)bounce, p.flag(), p.boundary());
+            }
+            if (command == FLOW_BREAK) break;
+        }
+        if (DEBUG) { if (P.seq) P.seq[idx] = seq; }
+        if (P.photon) p.store(P.photon + idx);
+        is_hit = (p.flagmask & P.hit_mask) == P.hit_mask;
+    }
+
+    int nhit = __syncthreads_count(is_hit);
+    if (threadIdx.x == 0) P.block_hits[blockIdx.x] = (unsigned)nhit;
+    for (int off = 16; off > 0; off >>= 1) nray += __shfl_down_sync(0xffffffffu, nray, off);
+    if ((threadIdx.x & 31) == 0 && nray) atomicAdd(P.counters, (unsigned long long)nray);
+}
+
+// exclusive scan of block_hits[n] -> block_off[n], total -> total_out[0] (single block, any n)
+__global__ void k_hit_offsets(const unsigned* __restrict__ block_hits, int n, unsigned long long* __restrict__ block_off,
+                              unsigned long long* __restrict__ total_out) {
+    __shared__ unsigned long long s[1024];
+    __shared__ unsigned long long carry;
+    if (threadIdx.x == 0) carry = 0ull;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        int i = base + threadIdx.x;
+        unsigned long long v = i < n ? block_hits[i] : 0ull;
+        s[threadIdx.x] = v;
+        __syncthreads();
+        for (int off = 1; off < 1024; off <<= 1) {
+            unsigned long long t = threadIdx.x >= off ? s[threadIdx.x - off] : 0ull;
+            __syncthreads();
+            s[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (i < n) block_off[i] = carry + s[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += s[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) total_out[0] = carry;
+}
+
+// block b re-reads the flagmasks of its photons and copies the hits, in order, to
+// hit[hit_base + block_off[b] + rank]
+__global__ void __launch_bounds__(128) k_hit_compact(const Photon* __restrict__ photon, unsigned num_photon, unsigned hit_mask,
+                                                      const unsigned long long* __restrict__ block_off, Photon* __restrict__ hit) {
+    __shared__ unsigned warp_count[4];
+    unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    bool is_hit = false;
+    if (idx < num_photon) {
+        unsigned fm = __ldg(&photon[idx].flagmask);
+        is_hit = (fm & hit_mask) == hit_mask;
+    }
+    unsigned ballot = __ballot_sync(0xffffffffu, is_hit);
+    unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if (lane == 0) warp_count[warp] = __popc(ballot);
+    __syncthreads();
+    unsigned before = 0;
+    for (unsigned w = 0; w < warp; w++) before += warp_count[w];
+    if (is_hit) {
+        unsigned rank = before + __popc(ballot & ((1u << lane) - 1u));
+        const float4* src = reinterpret_cast<const float4*>(photon + idx);
+        float4* dst = reinterpret_cast<float4*>(hit + block_off[blockIdx.x] + rank);
+        dst[0] = __ldg(src); dst[1] = __ldg(src + 1); dst[2] = __ldg(src + 2); dst[3] = __ldg(src + 3);
+    }
+}
+
+// numphoton prefix of device-resident gensteps (one block)
+__global__ void k_genstep_prefix(const Genstep* __restrict__ gs, int n, unsigned long long* __restrict__ prefix) {
+    __shared__ unsigned long long s[1024];
+    __shared__ unsigned long long carry;
+    if (threadIdx.x == 0) { carry = 0ull; prefix[0] = 0ull; }
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        int i = base + threadIdx.x;
+        unsigned long long v = i < n ? (unsigned long long)gs[i].u[3] : 0ull;
+        s[threadIdx.x] = v;
+        __syncthreads();
+        for (int off = 1; off < 1024; off <<= 1) {
+            unsigned long long t = threadIdx.x >= off ? s[threadIdx.x - off] : 0ull;
+            __syncthreads();
+            s[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (i < n) prefix[i + 1] = carry + s[threadIdx.x];
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += s[1023];
+        __syncthreads();
+    }
+}
+
+// geometry-only queries (the role of simtrace / CSGScan)
+__global__ void k_intersect(Scene sc, const float4* __restrict__ ray_o_tmin, const float4* __restrict__ ray_d, unsigned n, float tmax,
+                            Prd* __restrict__ out) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 o = ray_o_tmin[i], d = ray_d[i];
+    HitInfo h;
+    trace(h, sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, tmax);
+    Prd r;
+    r.nx = h.normal.x; r.ny = h.normal.y; r.nz = h.normal.z; r.t = h.t;
+    r.lposcost = h.lposcost; r.lposfphi = h.lposfphi;
+    r.iindex_identity = h.iindex_identity; r.prim_boundary = h.prim_boundary;
+    out[i] = r;
+}
+
+// precooked random streams (qudarap/QSim.cu:43-68)
+__global__ void k_rng_sequence(float* __restrict__ out, unsigned ni, unsigned nv, unsigned long long id0,
+                               unsigned long long seed, unsigned long long element_offset) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ni) return;
+    Philox rng;
+    rng.init(seed, id0 + i, element_offset);
+    for (unsigned k = 0; k < nv; k++) out[(size_t)i * nv + k] = rng.uniform();
+}
+
+}  // namespace phox

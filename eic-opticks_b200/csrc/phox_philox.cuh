@@ -1,0 +1,73 @@
+// phox_philox.cuh : counter-based Philox4x32-10 stream, draw-for-draw identical to the curand
+// generator the reference uses:
+//
+//   curand_init(seed, subsequence = absolute photon index, offset, &rng);
+//   skipahead(skipahead_event_offset * event_index, &rng);            qudarap/qrng.h:124-148
+//   u = curand_uniform(&rng)                                          every draw of the physics
+//
+// The algorithm is the published Philox4x32 with 10 rounds (Salmon et al., SC'11) with curand's
+// conventions (CUDA toolkit 12.9 curand_philox4x32_x.h / curand_kernel.h, the third-party
+// dependency named in SURVEY 8c): key = 64-bit seed, counter words (x,y) = 128-bit-block index,
+// (z,w) = subsequence; the four 32-bit outputs of a block are handed out in x,y,z,w order and an
+// element offset n selects block n/4, lane n%4; a uniform is  u32 * 2^-32 + 2^-33  in (0,1].
+//
+// Instead of the 64-byte curandStatePhilox4_32_10 the stream here is 8 registers: the cached
+// block (4), the block counter (2), and the lane; key and subsequence stay in the caller's
+// registers/constants.
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+namespace phox {
+
+struct Philox {
+    uint4    out;        // outputs of block `blk`
+    uint32_t blk_lo, blk_hi;
+    uint32_t sub_lo, sub_hi;
+    uint32_t key_lo, key_hi;
+    uint32_t lane;       // next output of `out` to hand out, 0..3 ; 4 = block exhausted
+
+    static __device__ __forceinline__ uint4 block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+        constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+        for (int r = 0; r < 10; r++) {
+            uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+            uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+            uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+            c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+            k0 += W0; k1 += W1;
+        }
+        return make_uint4(c0, c1, c2, c3);
+    }
+
+    __device__ __forceinline__ void refill() { out = block(blk_lo, blk_hi, sub_lo, sub_hi, key_lo, key_hi); }
+
+    // seed / subsequence / element offset (offset already includes any per-event skipahead)
+    __device__ __forceinline__ void init(uint64_t seed, uint64_t subsequence, uint64_t element_offset) {
+        key_lo = (uint32_t)seed; key_hi = (uint32_t)(seed >> 32);
+        sub_lo = (uint32_t)subsequence; sub_hi = (uint32_t)(subsequence >> 32);
+        uint64_t b = element_offset >> 2;
+        blk_lo = (uint32_t)b; blk_hi = (uint32_t)(b >> 32);
+        lane = (uint32_t)(element_offset & 3u);
+        refill();
+    }
+
+    __device__ __forceinline__ uint32_t next_u32() {
+        if (lane == 4u) {
+            blk_lo += 1u;
+            if (blk_lo == 0u) blk_hi += 1u;     // carry into the subsequence words cannot happen for < 2^66 draws
+            refill();
+            lane = 0u;
+        }
+        uint32_t r = lane == 0u ? out.x : lane == 1u ? out.y : lane == 2u ? out.z : out.w;
+        lane += 1u;
+        return r;
+    }
+
+    // curand_uniform : (0,1]
+    __device__ __forceinline__ float uniform() {
+        return next_u32() * 2.3283064365386963e-10f + (2.3283064365386963e-10f / 2.0f);
+    }
+};
+
+}  // namespace phox

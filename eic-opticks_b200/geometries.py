@@ -1,0 +1,213 @@
+"""Hand-built CSGFoundry + boundary tables for the geometries BASELINE.json's configs name.
+
+These follow the reference's GDML files volume for volume (tests/geom/*.gdml) using the
+translation rules of SURVEY section 9 (boundary = omat/osur/isur/imat, surface lookup order of
+u4/U4Surface.h:422-443, flattening of non-repeated volumes into solid 0, surface payload rule of
+u4/U4SurfaceArray.h:159-240).  They exist so that tests and the bench do not depend on the GDML
+translator; `gdml.py` produces the same arrays from the files themselves.
+
+Each builder returns a dict: foundry (arrays), bnd, optical, icdf (or None), names, and helper
+indices (material lines for gensteps).
+"""
+import numpy as np
+
+from . import foundry as F
+from . import tables as T
+
+EV = 1.0
+
+
+def _finish(fd, bt, icdf=None, extra=None):
+    bnd, optical = bt.arrays()
+    out = dict(foundry=fd.arrays(), bnd=bnd, optical=optical, icdf=icdf, bnd_names=bt.names(), table=bt)
+    if extra:
+        out.update(extra)
+    return out
+
+
+def raindrop():
+    """tests/geom/opticks_raindrop.gdml: Vacuum 240 > Pb 220 > Air 200 > Water 100 (mm boxes).
+    The only detecting surface is the directional border surface drop_pv -> medium_pv
+    (water -> air, EFFICIENCY 1, REFLECTIVITY 0)."""
+    bt = T.BoundaryTable()
+    e2 = ([1.55, 15.5], None)
+    bt.add_material(T.Material("G4_WATER", RINDEX=([1.55, 15.5], [1.333, 1.333]), GROUPVEL=([1.55, 15.5], [224.901, 224.901])))
+    bt.add_material(T.Material("G4_AIR", RINDEX=([1.512, 5.512], [1.1, 1.1]), GROUPVEL=([1.55, 15.5], [224.901, 224.901])))
+    bt.add_material(T.Material("G4_Pb", RINDEX=([1.512, 5.512], [1.0, 1.1]), GROUPVEL=([1.55, 15.5], [224.901, 224.901])))
+    bt.add_material(T.Material("VACUUM", RINDEX=([1.512, 5.512], [1.0, 1.1]), GROUPVEL=([1.55, 15.5], [224.901, 224.901])))
+    bt.add_surface(T.Surface("medium_container_bs", REFLECTIVITY=0.0, EFFICIENCY=1.0))
+    fd = F.Foundry()
+    fd.begin_solid("r0")
+    fd.add_prim(F.box3(240, 240, 240), bt.boundary("VACUUM", "", "", "VACUUM"), name="VACUUM_solid")
+    fd.add_prim(F.box3(220, 220, 220), bt.boundary("VACUUM", "", "", "G4_Pb"), name="G4_Pb_solid")
+    fd.add_prim(F.box3(200, 200, 200), bt.boundary("G4_Pb", "", "", "G4_AIR"), name="G4_AIR_solid")
+    fd.add_prim(F.box3(100, 100, 100), bt.boundary("G4_AIR", "", "medium_container_bs", "G4_WATER"), name="G4_WATER_solid")
+    fd.end_solid()
+    return _finish(fd, bt, extra=dict(water_line=bt.material_line("G4_WATER"), n_water=1.333))
+
+
+def sphere_leak():
+    """tests/geom/sphere_leak.gdml: world sphere r50 (water); Mirror = sphere r30 - sphere r25
+    (n 1.5, sensitive skin EFFICIENCY 1); Glass sphere r15 (water) wrapped in a perfect mirror skin."""
+    bt = T.BoundaryTable()
+    water = dict(RINDEX=([1.55, 15.5], [1.333, 1.333]), ABSLENGTH=([1.55, 15.5], [100000.0, 100000.0]),
+                 RAYLEIGH=([1.55, 15.5], [1000.0, 1000.0]))
+    bt.add_material(T.Material("WaterMaterial", **water))
+    bt.add_material(T.Material("MirrorMaterial", RINDEX=([1.55, 15.5], [1.5, 1.5])))
+    bt.add_surface(T.Surface("MirrorSkinSurface", EFFICIENCY=1.0))
+    bt.add_surface(T.Surface("GlassSkinSurface", REFLECTIVITY=1.0, polished=True))
+    fd = F.Foundry()
+    fd.begin_solid("r0")
+    fd.add_prim(F.sphere(50), bt.boundary("WaterMaterial", "", "", "WaterMaterial"), name="WorldBox")
+    fd.add_prim(F.difference(F.sphere(30), F.sphere(25)),
+                bt.boundary("WaterMaterial", "MirrorSkinSurface", "MirrorSkinSurface", "MirrorMaterial"), name="MirrorSphere")
+    fd.add_prim(F.sphere(15), bt.boundary("WaterMaterial", "GlassSkinSurface", "GlassSkinSurface", "WaterMaterial"), name="GlassSphere")
+    fd.end_solid()
+    return _finish(fd, bt)
+
+
+def sipm8x8():
+    """tests/geom/8x8SiPM_w_CSI_optial_grease.gdml: 8x8 CsI crystals (2x2x8 mm, pitch 2.2) with a
+    0.98 polished skin, grease and window layers, 8x8 SiPM pixels with a detecting skin and the
+    dead strips between them; 194 sibling volumes flattened into solid 0."""
+    bt = T.BoundaryTable()
+    en = [1.0, 4.0]
+    bt.add_material(T.Material("Air", RINDEX=(en, [1.0, 1.0]), ABSLENGTH=(en, [10000.0, 10000.0])))
+    bt.add_material(T.Material("Crystal", RINDEX=(en, [1.82, 1.82]), ABSLENGTH=(en, [400.0, 400.0]), REEMISSIONPROB=(en, [0.0, 0.0])))
+    bt.add_material(T.Material("OpticalGrease", RINDEX=(en, [1.47, 1.47]), ABSLENGTH=(en, [1000.0, 1000.0])))
+    bt.add_material(T.Material("EntranceWindow", RINDEX=(en, [1.55, 1.55]), ABSLENGTH=(en, [1000.0, 1000.0])))
+    bt.add_surface(T.Surface("SiPMActiveSkin", REFLECTIVITY=(en, [0.0, 0.0]), EFFICIENCY=(en, [1.0, 1.0])))
+    bt.add_surface(T.Surface("CrystalSkin", REFLECTIVITY=(en, [0.98, 0.98]), EFFICIENCY=(en, [0.0, 0.0])))
+    bt.add_surface(T.Surface("DeadSkinH", REFLECTIVITY=(en, [0.3, 0.3]), EFFICIENCY=(en, [0.0, 0.0])))
+    bt.add_surface(T.Surface("DeadSkinV", REFLECTIVITY=(en, [0.3, 0.3]), EFFICIENCY=(en, [0.0, 0.0])))
+    b_world = bt.boundary("Air", "", "", "Air")
+    b_grease = bt.boundary("Air", "", "", "OpticalGrease")
+    b_window = bt.boundary("Air", "", "", "EntranceWindow")
+    b_xtal = bt.boundary("Air", "CrystalSkin", "CrystalSkin", "Crystal")
+    b_sipm = bt.boundary("Air", "SiPMActiveSkin", "SiPMActiveSkin", "EntranceWindow")
+    b_deadv = bt.boundary("Air", "DeadSkinV", "DeadSkinV", "EntranceWindow")
+    b_deadh = bt.boundary("Air", "DeadSkinH", "DeadSkinH", "EntranceWindow")
+    fd = F.Foundry()
+    fd.begin_solid("r0")
+    fd.add_prim(F.box3(100, 100, 100), b_world, name="WorldBox")
+    fd.add_prim(F.box3(17.4, 17.4, 0.1), b_grease, F.translate(0, 0, 8.05), name="GreaseLayer")
+    fd.add_prim(F.box3(17.4, 17.4, 0.1), b_window, F.translate(0, 0, 8.15), name="WindowLayer")
+    centers = []
+    for i in range(8):
+        for j in range(8):
+            c = (-8.7 + i * 2.2 + 1.0 - 1.0, -8.7 + j * 2.2, 4.0)
+            fd.add_prim(F.box3(2.0, 2.0, 8.0), b_xtal, F.translate(-8.7 + i * 2.2, -8.7 + j * 2.2, 4.0), name="CrystalPixel")
+            centers.append(c)
+    for i in range(8):
+        for j in range(8):
+            fd.add_prim(F.box3(2.0, 2.0, 0.2), b_sipm, F.translate(-8.7 + i * 2.2, -8.7 + j * 2.2, 8.3), name="SiPMActive")
+    for i in range(8):
+        for j in range(7):
+            fd.add_prim(F.box3(0.2, 2.0, 0.2), b_deadv, F.translate(-8.7 + i * 2.2 + 1.1, -8.7 + j * 2.2, 8.3), name="SiPMDeadV")
+    for i in range(7):
+        fd.add_prim(F.box3(17.4, 0.2, 0.2), b_deadh, F.translate(0, -8.7 + i * 2.2 + 1.1, 8.3), name="SiPMDeadH")
+    fd.end_solid()
+    # scintillation spectrum SCINT_SPECTRUM: 1.5 eV 0, 2.896 eV 1, 4.0 eV 0
+    icdf = T.make_icdf(np.linspace(1.5, 4.0, 2001), np.interp(np.linspace(1.5, 4.0, 2001), [1.5, 2.896, 4.0], [0.0, 1.0, 0.0]))
+    return _finish(fd, bt, icdf, extra=dict(crystal_centers=np.array(centers, dtype=np.float32),
+                                           crystal_line=bt.material_line("Crystal"), n_crystal=1.82,
+                                           scintillation_time=21.5))
+
+
+def pmt_wall(nx=100, ny=100, pitch=250.0):
+    """Synthetic instanced PMT wall (BASELINE config 4): solid 0 = water world box, solid 1 = one
+    PMT (glass bulb = sphere union neck cylinder, inner vacuum sphere behind a photocathode
+    surface), instanced nx*ny times on a grid with sensor identifiers 0..n-1."""
+    bt = T.BoundaryTable()
+    en = [1.55, 6.2]
+    bt.add_material(T.Material("Water", RINDEX=(en, [1.333, 1.333]), ABSLENGTH=(en, [30000.0, 30000.0]), RAYLEIGH=(en, [50000.0, 50000.0])))
+    bt.add_material(T.Material("Pyrex", RINDEX=(en, [1.47, 1.47]), ABSLENGTH=(en, [1000.0, 1000.0])))
+    bt.add_material(T.Material("Vacuum", RINDEX=(en, [1.0, 1.0])))
+    bt.add_surface(T.Surface("Photocathode", EFFICIENCY=(en, [0.25, 0.25])))
+    b_world = bt.boundary("Water", "", "", "Water")
+    b_glass = bt.boundary("Water", "", "", "Pyrex")
+    b_vac = bt.boundary("Pyrex", "Photocathode", "Photocathode", "Vacuum")
+    half_x, half_y = nx * pitch / 2 + 500.0, ny * pitch / 2 + 500.0
+    fd = F.Foundry()
+    fd.begin_solid("r0")
+    fd.add_prim(F.box3(2 * half_x, 2 * half_y, 4000.0), b_world, name="WorldBox")
+    fd.end_solid()
+    fd.begin_solid("r1")
+    bulb = F.union(F.sphere(100.0), F.cylinder(40.0, -170.0, -80.0))
+    fd.add_prim(bulb, b_glass, name="PMT_glass")
+    fd.add_prim(F.sphere(95.0), b_vac, name="PMT_vacuum")
+    fd.end_solid()
+    fd.add_instance(np.eye(4), 0, -1, -1)
+    k = 0
+    for i in range(nx):
+        for j in range(ny):
+            fd.add_instance(F.translate((i + 0.5) * pitch - nx * pitch / 2, (j + 0.5) * pitch - ny * pitch / 2, 0.0), 1, k, k)
+            k += 1
+    return _finish(fd, bt, extra=dict(half=(half_x, half_y), pitch=pitch, n_pmt=nx * ny))
+
+
+def boolean_zoo():
+    """CSG boolean-heavy solids (BASELINE config 5): difference / intersection / union trees of
+    depth 1-3, zsphere with both caps, cone, tubs with the 1 % inner nudge (u4/U4Solid.h:813-821),
+    polycone-like unions cut by a phi wedge, a convex polyhedron, hyperboloid and list nodes, all
+    glass in scattering / absorbing water inside an absorbing rock box."""
+    bt = T.BoundaryTable()
+    en = [1.55, 6.2]
+    bt.add_material(T.Material("Rock"))
+    bt.add_material(T.Material("Water", RINDEX=(en, [1.333, 1.35]), ABSLENGTH=(en, [2000.0, 1500.0]), RAYLEIGH=(en, [800.0, 400.0])))
+    bt.add_material(T.Material("Glass", RINDEX=(en, [1.48, 1.52]), ABSLENGTH=(en, [500.0, 300.0])))
+    bt.add_surface(T.implicit_surface("Implicit_RINDEX_NoRINDEX_water_rock"))
+    bt.add_surface(T.Surface("DiffuseSkin", REFLECTIVITY=(en, [0.8, 0.8]), polished=False))
+    bt.add_surface(T.Surface("SensorSkin", EFFICIENCY=(en, [0.5, 0.5])))
+    b_world = bt.boundary("Rock", "", "", "Rock")
+    b_water = bt.boundary("Rock", "Implicit_RINDEX_NoRINDEX_water_rock", "Implicit_RINDEX_NoRINDEX_water_rock", "Water")
+    b_glass = bt.boundary("Water", "", "", "Glass")
+    b_diff = bt.boundary("Water", "DiffuseSkin", "DiffuseSkin", "Glass")
+    b_sens = bt.boundary("Water", "SensorSkin", "SensorSkin", "Glass")
+    fd = F.Foundry()
+    fd.begin_solid("r0")
+    fd.add_prim(F.box3(2200, 2200, 2200), b_world, name="Rock")
+    fd.add_prim(F.box3(2000, 2000, 2000), b_water, name="Water")
+    shapes = []
+    # depth-1 trees
+    shapes.append(("box_minus_sphere", F.difference(F.box3(200, 200, 200), F.sphere(120)), b_glass))
+    shapes.append(("sphere_and_box", F.intersection(F.sphere(130), F.box3(200, 200, 200)), b_glass))
+    shapes.append(("cyl_union_cone", F.union(F.cylinder(60, -100, 0), F.cone(60, 0, 10, 120)), b_diff))
+    # tubs: outer cylinder minus inner cylinder lengthened by 1 % of hz each end
+    hz = 100.0
+    shapes.append(("tubs", F.difference(F.cylinder(100, -hz, hz), F.cylinder(70, -hz * 1.01, hz * 1.01)), b_glass))
+    shapes.append(("zsphere", F.zsphere(110, -60, 80), b_sens))
+    shapes.append(("cone", F.cone(100, -80, 30, 80), b_glass))
+    # depth-2 / depth-3 trees
+    shapes.append(("box_minus_2", F.difference(F.difference(F.box3(220, 220, 220), F.sphere(100).placed(F.translate(80, 0, 0))),
+                                              F.cylinder(40, -150, 150).placed(F.translate(-60, 0, 0))), b_glass))
+    shapes.append(("depth3", F.intersection(F.union(F.sphere(100), F.box3(120, 120, 240)),
+                                            F.difference(F.cylinder(110, -130, 130), F.union(F.sphere(50), F.cone(40, 40, 5, 130)))), b_glass))
+    # polycone-like union of cylinder + cone + cylinder cut by a phi wedge
+    poly = F.union(F.union(F.cylinder(50, -120, -40), F.cone(50, -40, 90, 40)), F.cylinder(90, 40, 120))
+    shapes.append(("polycone_phicut", F.intersection(poly, F.phicut(20.0, 250.0)), b_glass))
+    shapes.append(("zsphere_rot", F.zsphere(100, -100 * 0.999, 40).placed(F.rotate_x(35.0)), b_glass))
+    shapes.append(("hyperboloid", F.hyperboloid(50, 80, -100, 100), b_glass))
+    # convex polyhedron: a truncated pyramid (trapezoid)
+    pl = []
+    for sx, sy in ((1, 0), (-1, 0), (0, 1), (0, -1)):
+        n = np.array([sx, sy, 0.3]); n = n / np.linalg.norm(n)
+        pl.append([n[0], n[1], n[2], 90.0 * np.linalg.norm([sx, sy]) / np.linalg.norm([sx, sy, 0.3])])
+    pl.append([0, 0, 1, 100.0]); pl.append([0, 0, -1, 100.0])
+    shapes.append(("trapezoid", F.convexpolyhedron(pl, [-130, -130, -100, 130, 130, 100]), b_glass))
+    # list nodes
+    shapes.append(("discontiguous", F.ListNode(F.CSG_DISCONTIGUOUS, [F.sphere(40).placed(F.translate(-70, 0, 0)), F.box3(60, 60, 60).placed(F.translate(70, 0, 0)),
+                                                                   F.cylinder(30, -40, 40).placed(F.translate(0, 80, 0))]), b_glass))
+    shapes.append(("contiguous", F.ListNode(F.CSG_CONTIGUOUS, [F.sphere(60).placed(F.translate(-40, 0, 0)), F.sphere(60).placed(F.translate(40, 0, 0)),
+                                                             F.box3(100, 50, 50)]), b_glass))
+    shapes.append(("overlap", F.ListNode(F.CSG_OVERLAP, [F.sphere(90), F.box3(140, 140, 140), F.cylinder(80, -100, 100)]), b_glass))
+    grid = 4
+    centers = []
+    for k, (name, shape, b) in enumerate(shapes):
+        ix, iy = k % grid, k // grid
+        c = (-600.0 + ix * 400.0, -600.0 + iy * 400.0, 0.0)
+        centers.append(c)
+        frame = F.rotate_z(10.0 * k) @ F.translate(*c)
+        fd.add_prim(shape, b, frame, mesh_idx=k + 2, name=name)
+    fd.end_solid()
+    return _finish(fd, bt, extra=dict(shape_centers=np.array(centers, dtype=np.float32), shape_names=[s[0] for s in shapes]))

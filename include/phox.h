@@ -1,0 +1,177 @@
+/* phox.h : C ABI of the B200-native optical-photon propagation engine (libphox.so).
+ *
+ * This is the drop-in boundary for the reference's simulate path.  Every entry point takes
+ * plain pointers and sizes; the arrays are the reference's own array layouts so a binding on the
+ * reference side passes its buffers through unchanged (see INTEGRATION.md for the SSimulator
+ * adaptor and the ctypes stub).  All functions return 0 on success or a negative PHOX_E_* code;
+ * phox_last_error() gives the message.  Nothing aborts or raises signals across this ABI
+ * (the reference asserts / raises SIGINT instead: qudarap/QSim.cc:446, CSG/CUDA_CHECK.h).
+ *
+ * A context owns one GPU.  A context is not thread-safe; separate contexts are independent, which
+ * is how the 8 GPUs of a box are driven (one process or thread per context).
+ */
+#ifndef PHOX_H
+#define PHOX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct phox_context phox_context;
+
+enum {
+    PHOX_OK = 0,
+    PHOX_E_ARG = -1,      /* bad argument / arrays inconsistent */
+    PHOX_E_STATE = -2,    /* call order wrong: geometry/tables missing, no event */
+    PHOX_E_CUDA = -3,     /* CUDA runtime error, message has the detail */
+    PHOX_E_NOMEM = -4,    /* event does not fit the configured max_slot / device memory */
+    PHOX_E_NODEVICE = -5  /* no usable CUDA device: there is NO CPU fallback */
+};
+
+/* Event modes follow SEventConfig (sysrap/SEventConfig.cc:1528-1642). */
+enum {
+    PHOX_MODE_MINIMAL = 0,    /* gather hits only                                   */
+    PHOX_MODE_HITPHOTON = 1,  /* hits + photon array                                */
+    PHOX_MODE_HITPHOTONSEQ = 2, /* hits + photon + seq                              */
+    PHOX_MODE_DEBUGLITE = 3,  /* photon, record[max_record], seq, hit               */
+    PHOX_MODE_DEBUGHEAVY = 4  /* DebugLite + prd[max_record]                        */
+};
+
+/* Random-number consumption pattern of the physics (SURVEY 8a "RNG draws per bounce").
+ * The reference's as-built device code is always the DEBUG_TAG variant
+ * (CSGOptiX/CMakeLists.txt:54-56) which consumes extra "burn" uniforms to stay aligned with
+ * Geant4 (qudarap/qsim.h:730-733, 1088-1098, 1188-1201, 1687-1692). */
+enum {
+    PHOX_RNG_PRODUCTION = 0,  /* 2 / 1 / 1 / 1 draws: to_boundary / at_boundary / at_surface / detect */
+    PHOX_RNG_DEBUG_TAG = 1    /* 4 / 2(+4 on reflect) / 2 / 1 : matches the reference build */
+};
+
+/* How rays find their nearest CSGPrim. */
+enum {
+    PHOX_ACCEL_BVH = 0,       /* two-level BVH built on the GPU (instances, then prims per solid) */
+    PHOX_ACCEL_BRUTE = 1      /* loop over every instance and prim: validation of the BVH only   */
+};
+
+/* Defaults are the reference's: sysrap/SEventConfig.cc:37-115, CSGOptiX/CSGOptiX.cc:651-668,
+ * qudarap/QRng.cc:52-54. phox_default_config() fills them in. */
+typedef struct phox_config {
+    int32_t  max_bounce;            /* OPTICKS_MAX_BOUNCE, 31                                   */
+    int32_t  event_mode;            /* PHOX_MODE_*, Minimal                                     */
+    int32_t  max_record;            /* record/prd slots per photon in debug modes, <= 32        */
+    int32_t  rng_mode;              /* PHOX_RNG_*, DEBUG_TAG                                    */
+    int32_t  accel;                 /* PHOX_ACCEL_*                                             */
+    uint32_t hit_mask;              /* OPTICKS_HIT_MASK, SD = 0x40                              */
+    uint32_t epsilon0_mask;         /* OPTICKS_PROPAGATE_EPSILON0_MASK: TO|CK|SI|SC|RE = 0x37   */
+    uint32_t propagate_refine;      /* OPTICKS_PROPAGATE_REFINE, 0                              */
+    float    propagate_epsilon;     /* tmin after boundary flags, 0.05 mm                       */
+    float    propagate_epsilon0;    /* tmin after the epsilon0_mask flags, 0.05 mm              */
+    float    refine_distance;       /* OPTICKS_PROPAGATE_REFINE_DISTANCE, 5000 mm               */
+    float    tmax;                  /* ray tmax, 1e6 mm                                         */
+    float    max_time;              /* OPTICKS_MAX_TIME, 1e27 ns                                */
+    uint32_t pad0;
+    uint64_t rng_seed;              /* curand_init seed, 0                                      */
+    uint64_t rng_offset;            /* curand_init offset (QRng__SEED_OFFSET), 0                */
+    uint64_t skipahead_event_offset;/* OPTICKS_EVENT_SKIPAHEAD, 100000 draws per event index    */
+    int64_t  max_slot;              /* photons per launch; 0 = 0.87*VRAM/(64*1.75) heuristic
+                                       (sysrap/SEventConfig.cc:1897-1903)                       */
+} phox_config;
+
+void phox_default_config(phox_config* cfg);
+
+/* Lifecycle.  Replaces CSGOptiX::Create / ~CSGOptiX (CSGOptiX/CSGOptiX.cc:367-392). */
+phox_context* phox_create(int device);
+void          phox_destroy(phox_context* ctx);
+const char*   phox_last_error(const phox_context* ctx);   /* ctx may be NULL: creation errors */
+const char*   phox_desc(const phox_context* ctx);         /* SSimulator::desc                 */
+
+/* Geometry: the CSGFoundry arrays (CSG/CSGFoundry.h:253-263; upload CSG/CSGFoundry.cc:3377-3405).
+ *   solid : CSGSolid[nsolid] 48 B     prim : CSGPrim[nprim] 64 B     node : CSGNode[nnode] 64 B
+ *   plan  : float4[nplan]             itra : qat4[nitra] inverse node transforms
+ *   inst  : qat4[ninst] instance transforms, 4th column ints = (ins_idx, gas_idx,
+ *           sensor_identifier+1, sensor_index) (sysrap/sqat4.h:345-407)
+ * Builds the two-level BVH on the device (replaces SBT::createGAS/createIAS,
+ * CSGOptiX/SBT.cc:277-370). */
+int phox_set_geometry(phox_context* ctx,
+                      const void* solid, int64_t nsolid,
+                      const void* prim,  int64_t nprim,
+                      const void* node,  int64_t nnode,
+                      const void* plan,  int64_t nplan,
+                      const void* itra,  int64_t nitra,
+                      const void* inst,  int64_t ninst);
+
+/* Physics tables: the SSim arrays that QSim::UploadComponents consumes (qudarap/QSim.cc:134-180).
+ *   bnd     : float32 [nbnd,4,2,nwl,4]  boundary texture payload (qudarap/QBnd.cc:130-194)
+ *   domain  : wavelength of sample 0 and the step in nm (60, 1 for the 761-sample fine domain)
+ *   optical : int32 [4*nbnd,4]          (sysrap/sstandard.h:311-441)
+ *   icdf    : float32 [icdf_ny,icdf_nx] scintillation inverse-CDF rows (3 x 4096, hd_factor 20;
+ *             qudarap/QScint.cc:84-120) or NULL when no scintillator                      */
+int phox_set_tables(phox_context* ctx,
+                    const float* bnd, int64_t nbnd, int64_t nwl,
+                    float domain_low, float domain_step,
+                    const int32_t* optical,
+                    const float* icdf, int64_t icdf_ny, int64_t icdf_nx, int32_t hd_factor);
+
+int phox_set_config(phox_context* ctx, const phox_config* cfg);
+int phox_get_config(const phox_context* ctx, phox_config* cfg);
+
+/* One event: gensteps in (quad6[ngenstep], host memory), hits out.  Replaces
+ * SSimulator::simulate(eventID) / NP* CSGOptiX::simulate(const NP* gs, int eventID)
+ * (sysrap/SSimulator.h:30, CSGOptiX/CSGOptiX.cc:798-826, qudarap/QSim.cc:428-617).
+ *   input_photon : sphoton[ninput] for an OpticksGenstep_INPUT_PHOTON genstep, else NULL
+ *   photon_offset: absolute index of this call's first photon (RNG subsequence and sphoton.index
+ *                  use absolute indices: CSGOptiX/CSGOptiX7.cu:415-419), so that a rank handling
+ *                  a slice of a bigger event gives results identical to the whole-event run
+ * Events bigger than max_slot run as several launches (sysrap/SGenstep.h:249-323).
+ * On return the launch seconds are in *launch_seconds (may be NULL). */
+int phox_simulate(phox_context* ctx,
+                  const void* genstep, int64_t ngenstep,
+                  const void* input_photon, int64_t ninput,
+                  int32_t event_id, uint64_t photon_offset,
+                  double* launch_seconds);
+
+/* Same event, but gensteps / input photons are already resident in device memory and hits stay
+ * on the device (phox_hits_device).  This is the HBM-resident path that bench.py times as
+ * `value`; phox_simulate is the host-buffer path it times as `e2e`. */
+int phox_simulate_device(phox_context* ctx,
+                         const void* d_genstep, int64_t ngenstep,
+                         const void* d_input_photon, int64_t ninput,
+                         int32_t event_id, uint64_t photon_offset,
+                         double* launch_seconds);
+
+/* Results of the last event; buffers are valid until phox_reset (SEvt::getNumHit / getHit,
+ * sysrap/SEvt.cc:4924-4991).  Hits are in ascending absolute photon index. */
+int64_t phox_num_photon(const phox_context* ctx);
+int64_t phox_num_hit(const phox_context* ctx);
+int     phox_get_hits(phox_context* ctx, void* dst_sphoton);      /* host dst, 64 B * num_hit */
+const void* phox_hits_device(const phox_context* ctx);             /* device pointer          */
+
+/* Named arrays of the last event, when the event mode keeps them:
+ * "photon" (64 B/photon), "record" (64 B * max_record), "seq" (32 B), "prd" (32 B * max_record),
+ * "hit".  Returns the byte size when dst is NULL. */
+int64_t phox_get_array(phox_context* ctx, const char* name, void* dst, int64_t dst_bytes);
+
+/* Counters of the last event: total bounces (= intersect queries), launches, kernels launched. */
+typedef struct phox_stats {
+    uint64_t num_photon, num_hit, num_ray, num_launch, num_kernel;
+    double   launch_seconds, upload_seconds, gather_seconds;
+} phox_stats;
+int phox_get_stats(const phox_context* ctx, phox_stats* st);
+
+void phox_reset(phox_context* ctx);   /* SSimulator::reset(eventID) */
+
+/* Geometry queries without physics (the simtrace / CSGScan role, CSGOptiX/CSGOptiX7.cu:536-577,
+ * CSG/CSGScan.cu:11): nray rays (origin xyz + tmin, direction xyz + unused) -> quad2 prd each. */
+int phox_intersect(phox_context* ctx, const float* ray_o_tmin, const float* ray_d, int64_t nray,
+                   void* dst_prd, int32_t accel);
+
+/* Precooked random streams (qudarap/QSim.cu:43-68): first nv curand_uniform floats of
+ * subsequences [id0, id0+ni). dst is host float32[ni*nv]. */
+int phox_rng_sequence(phox_context* ctx, float* dst, int64_t ni, int64_t nv, uint64_t id0,
+                      int32_t event_id);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

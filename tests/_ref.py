@@ -1,0 +1,79 @@
+"""ctypes access to the checkers under oracle/ (tests only).
+
+    RefGPU  : oracle/_ref/libphoxref_{debugtag,production}.so - the REFERENCE's device headers compiled
+              unmodified behind a brute-force traversal harness (oracle/ref_gpu_harness.cu)
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE = os.path.join(ROOT, "oracle")
+
+
+class RefConfig(C.Structure):
+    _fields_ = [("max_bounce", C.c_int), ("max_record", C.c_int), ("event_index", C.c_int), ("pad", C.c_int),
+                ("tmin", C.c_float), ("tmin0", C.c_float), ("tmax", C.c_float), ("max_time", C.c_float),
+                ("eps0mask", C.c_uint), ("pad1", C.c_uint),
+                ("seed", C.c_uint64), ("offset", C.c_uint64), ("skipahead", C.c_uint64), ("photon_offset", C.c_uint64)]
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class RefGPU:
+    def __init__(self, variant="debugtag"):
+        path = os.path.join(ORACLE, "_ref", "libphoxref_%s.so" % variant)
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = C.CDLL(path)
+        self.lib.phoxref_last_error.restype = C.c_char_p
+        self.lib.phoxref_simulate.restype = C.c_int
+        self.lib.phoxref_intersect.restype = C.c_int
+        self.production = bool(self.lib.phoxref_is_production())
+
+    @staticmethod
+    def _geo(fd):
+        a = {k: np.ascontiguousarray(fd[k], dtype=(np.int32 if k == "solid" else np.float32)) for k in ("solid", "prim", "node", "plan", "itra", "inst")}
+        args = []
+        for k in ("solid", "prim", "node", "plan", "itra", "inst"):
+            args += [_p(a[k]) if len(a[k]) else None, C.c_int(len(a[k]))]
+        return a, args
+
+    def simulate(self, geom, gensteps, input_photons=None, event_id=0, photon_offset=0, max_bounce=31, max_record=32,
+                 tmin=0.05, tmin0=0.05, tmax=1e6, max_time=1e27, eps0mask=0x37, seed=0, offset=0, skipahead=100000, hd_factor=20):
+        fd = geom["foundry"]
+        keep, gargs = self._geo(fd)
+        bnd = np.ascontiguousarray(geom["bnd"], dtype=np.float32)
+        optical = np.ascontiguousarray(geom["optical"], dtype=np.int32)
+        icdf = geom.get("icdf")
+        icdf = None if icdf is None else np.ascontiguousarray(icdf, dtype=np.float32)
+        gs = np.ascontiguousarray(gensteps, dtype=np.float32).reshape(-1, 6, 4)
+        n = int(gs.view(np.uint32)[:, 0, 3].sum())
+        ip = None if input_photons is None else np.ascontiguousarray(input_photons, dtype=np.float32)
+        cfg = RefConfig(max_bounce, max_record, event_id, 0, tmin, tmin0, tmax, max_time, eps0mask, 0, seed, offset, skipahead, photon_offset)
+        photon = np.zeros((n, 4, 4), dtype=np.float32)
+        dbg = not self.production
+        record = np.zeros((n, max_record, 4, 4), dtype=np.float32) if dbg else None
+        seq = np.zeros((n, 2, 2), dtype=np.uint64) if dbg else None
+        prd = np.zeros((n, max_record, 2, 4), dtype=np.float32) if dbg else None
+        nray = C.c_uint64(0)
+        rc = self.lib.phoxref_simulate(*gargs, _p(bnd), C.c_int(bnd.shape[0]), C.c_int(bnd.shape[3]), C.c_float(60.0), C.c_float(1.0), _p(optical),
+                                       _p(icdf), C.c_int(0 if icdf is None else icdf.shape[1]), C.c_int(hd_factor),
+                                       _p(gs), C.c_int(len(gs)), _p(ip), C.c_int(0 if ip is None else len(ip)), C.byref(cfg),
+                                       _p(photon), _p(record), _p(seq), _p(prd), C.byref(nray))
+        if rc != 0:
+            raise RuntimeError("phoxref_simulate: " + self.lib.phoxref_last_error().decode())
+        return dict(photon=photon, record=record, seq=seq, prd=prd, nray=nray.value)
+
+    def intersect(self, geom, origin, direction, tmin=0.0, tmax=1e6):
+        keep, gargs = self._geo(geom["foundry"])
+        o = np.zeros((len(origin), 4), dtype=np.float32); o[:, :3] = origin; o[:, 3] = tmin
+        d = np.zeros((len(origin), 4), dtype=np.float32); d[:, :3] = direction
+        out = np.zeros((len(o), 2, 4), dtype=np.float32)
+        rc = self.lib.phoxref_intersect(*gargs, _p(o), _p(d), C.c_int(len(o)), C.c_float(tmax), _p(out))
+        if rc != 0:
+            raise RuntimeError("phoxref_intersect: " + self.lib.phoxref_last_error().decode())
+        return out
