@@ -1,0 +1,278 @@
+#!/usr/bin/env python
+"""bench.py : photons propagated / s on N B200s (BASELINE.json metric), one JSON line on rank 0.
+
+    python bench.py --gpus 1 --steps K --warmup W            # this engine (libphox.so)
+    python bench.py --impl reference ...                     # the CPU arm (oracle port, host threads)
+    torchrun --nproc-per-node N bench.py --gpus N ...        # one rank per GPU, weak scaling
+
+A "step" is one event: the hot path (genstep -> photons -> bounce loop -> hits) over one batch of
+synthetic gensteps.  Default workload = the configuration the north_star target is quoted on, the
+8x8 CsI+SiPM scintillation geometry (BASELINE config 3) with 12.5 M photons per GPU
+(100 M / 8 GPUs); --workload selects the other configs.
+
+    value   photons/s, whole job, gensteps already resident in HBM, hits left on the device
+            (phox_simulate_device), timed with CUDA events on the launch stream, max over ranks
+    e2e     same metric through the public host-buffer API (Simulator.simulate_np): gensteps in
+            pinned host memory -> H2D -> simulate -> hits D2H, every step
+    roofline  HBM roofline of the dominant kernel (k_simulate); algorithmic bytes per photon are
+            SURVEY 8(d)'s reference-equivalent figure 132 + 128 f_hit; duration = CUDA events
+            recorded around the kernel inside the library, live in the timed region
+    cpu_baseline  the CPU oracle (a port, NOT Geant4 and NOT the OptiX build - neither installs
+            here) on a bounded sample of the same workload, all host threads
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def oracle_throughput(w, sample_photons, nthreads=0):
+    """time the CPU oracle on the first gensteps of the workload holding ~sample_photons photons"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _ref import Oracle
+    gs = w["gensteps"]
+    num = gs.view(np.uint32)[:, 0, 3].astype(np.int64)
+    ip = w["input_photons"]
+    if ip is not None:
+        n = min(sample_photons, len(ip))
+        g = gs[:1].copy(); g.view(np.uint32)[0, 0, 3] = n
+        sub, ipn = g, ip[:n]
+    else:
+        k = int(np.searchsorted(np.cumsum(num), sample_photons)) + 1
+        sub, ipn = gs[:k], None
+        n = int(num[:k].sum())
+    orc = Oracle()
+    threads = orc.num_threads() if nthreads <= 0 else nthreads
+    t0 = time.perf_counter()
+    r = orc.simulate(w["geom"], sub, ipn, max_bounce=w["config"].get("max_bounce", 31), use_boxes=True, nthreads=threads, arrays=False)
+    dt = time.perf_counter() - t0
+    return dict(value=n / dt, seconds=dt, photons=n, cores=threads, rays=r["nray"], hits=r["nhit"])
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="phox", choices=["phox", "reference"])
+    ap.add_argument("--workload", default="sipm8x8_scint")
+    ap.add_argument("--photons", type=int, default=12_500_000, help="photons per GPU per step")
+    ap.add_argument("--cpu-sample", type=int, default=2_000_000, help="photons of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    warm = max(args.warmup, 3) if args.impl == "phox" else max(args.warmup, 0)
+
+    from eic_opticks_b200 import workloads
+
+    # ---------------- reference arm: CPU implementation of the path on the host cores ----------------
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        w = workloads.WORKLOADS[args.workload](num_photon=min(args.photons, args.cpu_sample * 2))
+        for _ in range(min(warm, 1)):
+            oracle_throughput(w, args.cpu_sample // 4)
+        vals = [oracle_throughput(w, args.cpu_sample) for _ in range(max(args.steps, 1))]
+        tot_ph = sum(v["photons"] for v in vals); tot_s = sum(v["seconds"] for v in vals)
+        value = tot_ph / tot_s
+        sample = "%d photons (first gensteps of the %s workload) per step, brute-force prim loop with prim-box pre-test" % (vals[0]["photons"], args.workload)
+        print(json.dumps({
+            "impl": "reference", "metric": "photons propagated/sec", "value": value, "unit": "photons/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / len(vals), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": args.workload, "photons_per_step": vals[0]["photons"], "max_bounce": w["config"].get("max_bounce", 31),
+                                                            "note": "CPU oracle port of the reference path (Geant4 and the OptiX build cannot be installed here)"},
+            "cpu_baseline": {"value": value, "unit": "photons/s", "cores": vals[0]["cores"], "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "photons/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}))
+        return 0
+
+    # ---------------- this engine ------------------------------------------------------------------
+    import torch
+    import torch.distributed as dist
+    import eic_opticks_b200 as ph
+    from eic_opticks_b200 import parallel
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the engine has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # weak scaling: the global event has world * photons; rank r takes its contiguous genstep share
+    w = workloads.WORKLOADS[args.workload](num_photon=args.photons * world)
+    g = w["geom"]
+    gs_r, ip_r, off_r, cnt_r = parallel.shard_event(w["gensteps"], rank, world, w["input_photons"])
+    sim = ph.Simulator.Create(g["foundry"], g["bnd"], g["optical"], g["icdf"], device=local_rank, event_mode=ph.MODE_MINIMAL, **w["config"])
+    stream = torch.cuda.current_stream(dev)
+    sim.set_stream(stream.cuda_stream)
+
+    d_gs = torch.from_numpy(gs_r).to(dev)
+    d_ip = torch.from_numpy(ip_r).to(dev) if ip_r is not None else None
+    h_gs = torch.from_numpy(gs_r).pin_memory()
+    h_ip = torch.from_numpy(ip_r).pin_memory() if ip_r is not None else None
+    h_hits = torch.empty((max(cnt_r, 1), 4, 4), dtype=torch.float32).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)     # 256 MB > 126 MB L2
+
+    def step_device(event_id):
+        sim.simulate_device(d_gs.data_ptr(), len(gs_r), d_ip.data_ptr() if d_ip is not None else 0, 0 if ip_r is None else len(ip_r), event_id, off_r)
+        if world > 1:
+            nh = sim.num_hit()
+            hits = torch.empty((nh, 4, 4), dtype=torch.float32, device=dev)
+            if nh:
+                sim.get_hits_device(hits.data_ptr())
+            parallel.gather_hits(hits)
+
+    def step_e2e(event_id):
+        gs_np = h_gs.numpy(); ip_np = h_ip.numpy() if h_ip is not None else None
+        sim.simulate_np_into(gs_np, event_id, ip_np, off_r, h_hits.numpy())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps, sampler=None):
+        st_sum = dict(num_kernel=0, simulate_kernel_seconds=0.0, compact_kernel_seconds=0.0, num_ray=0, num_hit=0, num_launch=0)
+        barrier()
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ms = 0.0
+        for k in range(steps):
+            flush.fill_(float(k))                      # evict L2 between timed iterations (not timed)
+            torch.cuda.synchronize(dev)
+            e0.record(stream)
+            fn(1 + k)
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            ms += e0.elapsed_time(e1)
+            st = sim.stats()
+            for key in st_sum:
+                st_sum[key] += st[key]
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), st_sum, clocks
+
+    for k in range(warm):
+        step_device(0)
+    for k in range(2):
+        step_e2e(0)
+    ms_dev, st_dev, clocks = timed(step_device, args.steps, ClockSampler(local_rank))
+    ms_e2e, st_e2e, _ = timed(step_e2e, args.steps)
+
+    tot = torch.tensor([float(cnt_r)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    photons_per_step = float(tot.item())
+    value = photons_per_step * args.steps / (ms_dev * 1e-3)
+    e2e = photons_per_step * args.steps / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        peak, peak_kind = load_peaks()
+        f_hit = st_dev["num_hit"] / max(1, cnt_r * args.steps)
+        bytes_per_photon = 132.0 + 128.0 * f_hit if ip_r is None else 196.0 + 128.0 * f_hit
+        kern_s = st_dev["simulate_kernel_seconds"] / max(1, st_dev["num_launch"])
+        achieved = cnt_r * bytes_per_photon / kern_s / 1e9
+        out = {
+            "metric": "photons propagated/sec", "value": value, "unit": "photons/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "photons_per_gpu_per_step": cnt_r, "gensteps_per_gpu": int(len(gs_r)), "max_bounce": sim.cfg.max_bounce,
+                       "event_mode": "Minimal", "rng_mode": "DEBUG_TAG", "accel": "two-level BVH", "l2": "256 MB flush between timed steps",
+                       "sharding": "gensteps partitioned over ranks, absolute photon offsets, hits all-gathered (NCCL) each step" if world > 1 else "single GPU"},
+            "rays_per_s": st_dev["num_ray"] * world / (ms_dev * 1e-3), "bounces_per_photon": st_dev["num_ray"] / max(1, cnt_r * args.steps),
+            "hit_fraction": f_hit,
+            "e2e": {"value": e2e, "unit": "photons/s", "h2d_bytes_per_step": int(gs_r.nbytes + (ip_r.nbytes if ip_r is not None else 0)),
+                    "d2h_bytes_per_step": int(64 * st_e2e["num_hit"] / max(1, args.steps)), "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(st_dev["num_kernel"] + st_e2e["num_kernel"]),
+            "roofline": {"bound": "hbm", "kernel": "k_simulate", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_kind, "traffic": None, "kernel_ms": kern_s * 1e3, "algorithmic_bytes_per_photon": bytes_per_photon,
+                         "kernel_share_of_step": st_dev["simulate_kernel_seconds"] / (ms_dev * 1e-3),
+                         "note": "the bounce loop is latency/issue bound, not HBM bound (tables and geometry are cache resident); see profiles/"},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline:
+            wc = workloads.WORKLOADS[args.workload](num_photon=min(args.photons, args.cpu_sample * 2))
+            cb = oracle_throughput(wc, args.cpu_sample)
+            out["cpu_baseline"] = {"value": cb["value"], "unit": "photons/s", "cores": cb["cores"], "kind": "port",
+                                   "sample": "%d photons of the same workload, CPU oracle (not Geant4), %.1f s" % (cb["photons"], cb["seconds"])}
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    sim.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

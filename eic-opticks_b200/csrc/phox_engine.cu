@@ -56,6 +56,8 @@ struct DevBuf {
 struct phox_context {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string err;
     std::string description;
     phox_config cfg;
@@ -152,7 +154,9 @@ extern "C" phox_context* phox_create(int device) {
     ctx->device = device;
     phox_default_config(&ctx->cfg);
     std::memset(&ctx->stats, 0, sizeof(ctx->stats));
-    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    ctx->stream = ctx->own_stream;
+    for (int k = 0; k < 4 && e == cudaSuccess; k++) e = cudaEventCreate(&ctx->ev[k]);
     if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_counters, 4 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = ctx->d_counters.reserve(4);
     if (e != cudaSuccess) {
@@ -193,7 +197,8 @@ extern "C" void phox_destroy(phox_context* ctx) {
     ctx->d_block_hits.release(); ctx->d_block_off.release(); ctx->d_counters.release();
     bvh_scratch_free(ctx->bvh_scratch);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    for (int k = 0; k < 4; k++) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
 
@@ -288,7 +293,16 @@ extern "C" int phox_set_geometry(phox_context* ctx, const void* solid_, int64_t 
 
     // boxes: per-prim boxes straight from CSGPrim, per-solid union, per-instance world boxes
     std::vector<float> boxes((size_t)(nprim + ninst) * 6);
-    for (int64_t p = 0; p < nprim; p++) for (int k = 0; k < 6; k++) boxes[6 * p + k] = prim[p].f[8 + k];
+    // Prim boxes are padded by a few ulps of their coordinates: a prim computes its hit distance in
+    // its own frame, the box test works in the solid frame, and at coincident faces (crystal on
+    // grease, window on SiPM ...) the two roundings must not let the box cull a prim whose own t
+    // ties with or just undercuts the current nearest hit.
+    for (int64_t p = 0; p < nprim; p++) {
+        float m = 1.f;
+        for (int k = 0; k < 6; k++) m = std::max(m, std::fabs(prim[p].f[8 + k]));
+        float pad = 2e-6f * m;
+        for (int k = 0; k < 3; k++) { boxes[6 * p + k] = prim[p].f[8 + k] - pad; boxes[6 * p + 3 + k] = prim[p].f[11 + k] + pad; }
+    }
     std::vector<float> solid_box((size_t)nsolid * 6);
     for (int64_t s = 0; s < nsolid; s++) {
         float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -408,6 +422,14 @@ extern "C" int phox_set_tables(phox_context* ctx, const float* bnd, int64_t nbnd
     return PHOX_OK;
 }
 
+extern "C" int phox_set_stream(phox_context* ctx, void* cuda_stream) {
+    if (!ctx) return PHOX_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return PHOX_OK;
+}
+
 extern "C" int phox_set_config(phox_context* ctx, const phox_config* cfg) {
     if (!ctx || !cfg) return PHOX_E_ARG;
     if (cfg->max_bounce < 0) return ctx->fail(PHOX_E_ARG, "phox_set_config: max_bounce < 0");
@@ -496,9 +518,11 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
     P.seed = c.rng_seed; P.rng_offset = c.rng_offset; P.skipahead = c.skipahead_event_offset;
     P.burn = c.rng_mode == PHOX_RNG_DEBUG_TAG ? 1 : 0;
 
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     if (dbg) k_simulate<true><<<nblock, T, 0, ctx->stream>>>(P);
     else k_simulate<false><<<nblock, T, 0, ctx->stream>>>(P);
     CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     k_hit_offsets<<<1, 1024, 0, ctx->stream>>>(ctx->d_block_hits.p, nblock, ctx->d_block_off.p, ctx->d_counters.p + 1);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
@@ -511,6 +535,13 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
         CK(cudaGetLastError());
         ctx->stats.num_kernel += 1;
     }
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev[2]));
+    float ms_sim = 0.f, ms_rest = 0.f;
+    CK(cudaEventElapsedTime(&ms_sim, ctx->ev[0], ctx->ev[1]));
+    CK(cudaEventElapsedTime(&ms_rest, ctx->ev[1], ctx->ev[2]));
+    ctx->stats.simulate_kernel_seconds += ms_sim * 1e-3;
+    ctx->stats.compact_kernel_seconds += ms_rest * 1e-3;
     ctx->num_hit += nhit;
     ctx->stats.num_launch += 1;
     return PHOX_OK;
@@ -668,6 +699,16 @@ extern "C" int phox_get_hits(phox_context* ctx, void* dst) {
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(dst, ctx->d_hit.p, (size_t)ctx->num_hit * 64, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return PHOX_OK;
+}
+
+extern "C" int phox_get_hits_device(phox_context* ctx, void* d_dst) {
+    if (!ctx) return PHOX_E_ARG;
+    if (!ctx->have_event) return ctx->fail(PHOX_E_STATE, "phox_get_hits_device: no event");
+    if (ctx->num_hit == 0) return PHOX_OK;
+    if (!d_dst) return ctx->fail(PHOX_E_ARG, "phox_get_hits_device: null destination");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(d_dst, ctx->d_hit.p, (size_t)ctx->num_hit * 64, cudaMemcpyDeviceToDevice, ctx->stream));
     return PHOX_OK;
 }
 

@@ -43,6 +43,7 @@ class Stats(C.Structure):
         ("num_photon", C.c_uint64), ("num_hit", C.c_uint64), ("num_ray", C.c_uint64),
         ("num_launch", C.c_uint64), ("num_kernel", C.c_uint64),
         ("launch_seconds", C.c_double), ("upload_seconds", C.c_double), ("gather_seconds", C.c_double),
+        ("simulate_kernel_seconds", C.c_double), ("compact_kernel_seconds", C.c_double),
     ]
 
 
@@ -56,6 +57,7 @@ SYMBOLS = {
     "phox_set_geometry": (C.c_int, [C.c_void_p] + [C.c_void_p, C.c_int64] * 6),
     "phox_set_tables": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_float, C.c_float,
                                   C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32]),
+    "phox_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "phox_set_config": (C.c_int, [C.c_void_p, C.POINTER(Config)]),
     "phox_get_config": (C.c_int, [C.c_void_p, C.POINTER(Config)]),
     "phox_simulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
@@ -66,6 +68,7 @@ SYMBOLS = {
     "phox_num_hit": (C.c_int64, [C.c_void_p]),
     "phox_get_hits": (C.c_int, [C.c_void_p, C.c_void_p]),
     "phox_hits_device": (C.c_void_p, [C.c_void_p]),
+    "phox_get_hits_device": (C.c_int, [C.c_void_p, C.c_void_p]),
     "phox_get_array": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
     "phox_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "phox_reset": (None, [C.c_void_p]),

@@ -120,6 +120,10 @@ class Simulator:
                                              _ptr(icdf) if icdf is not None else None, 3 if icdf is not None else 0,
                                              icdf.shape[1] if icdf is not None else 0, hd_factor))
 
+    def set_stream(self, cuda_stream_ptr):
+        """run on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); 0 restores the own stream"""
+        self._check(self.lib.phox_set_stream(self.ctx, C.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None))
+
     def set_config(self, **kw):
         for k, v in kw.items():
             if not hasattr(self.cfg, k):
@@ -152,6 +156,23 @@ class Simulator:
                                            len(ip) if ip is not None else 0, event_id, photon_offset, C.byref(dt)))
         self.last_launch_seconds = dt.value
         return self.get_hits()
+
+    def simulate_np_into(self, gensteps, event_id, input_photons, photon_offset, out):
+        """simulate_np writing the hits into a caller buffer (e.g. pinned memory); returns the hit count"""
+        dt = C.c_double(0.0)
+        ip = input_photons
+        self._check(self.lib.phox_simulate(self.ctx, _ptr(gensteps), len(gensteps), _ptr(ip) if ip is not None else None,
+                                           len(ip) if ip is not None else 0, event_id, photon_offset, C.byref(dt)))
+        self.last_launch_seconds = dt.value
+        n = self.num_hit()
+        assert n <= len(out)
+        if n:
+            self._check(self.lib.phox_get_hits(self.ctx, _ptr(out)))
+        return n
+
+    def get_hits_device(self, d_dst_ptr):
+        """copy the hit records into device memory owned by the caller (async on the context's stream)"""
+        self._check(self.lib.phox_get_hits_device(self.ctx, C.c_void_p(d_dst_ptr)))
 
     def simulate_device(self, d_genstep_ptr, ngs, d_input_ptr=0, ninput=0, event_id=0, photon_offset=0):
         """device-resident variant: pointers are raw CUDA addresses (e.g. torch.Tensor.data_ptr())"""

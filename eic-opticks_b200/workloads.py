@@ -1,0 +1,110 @@
+"""Synthetic workloads for the BASELINE.json configs: geometry + tables + gensteps.
+
+Gensteps normally come from Geant4 (absent here), so each workload fabricates them with the field
+semantics of the reference collectors (u4/U4.cc:82-143, 196-252) from a fixed numpy seed.
+Every function returns a dict: geom, gensteps (n,6,4) float32, input_photons or None, config
+overrides (e.g. max_bounce), name, and the expected total photon count.
+"""
+import numpy as np
+
+from . import geometries as GEO
+from . import gensteps as G
+
+SEED = 20261017
+
+
+def _poisson_split(rng, total, n):
+    """n positive counts summing exactly to total, Poisson-like spread"""
+    mean = total / n
+    c = rng.poisson(mean, n).astype(np.int64)
+    c = np.maximum(c, 1)
+    diff = total - int(c.sum())
+    # spread the remainder deterministically
+    step = 1 if diff > 0 else -1
+    k = 0
+    while diff != 0:
+        if c[k % n] + step >= 1:
+            c[k % n] += step
+            diff -= step
+        k += 1
+    return c
+
+
+def sipm8x8_scint(num_photon=12_500_000, photons_per_genstep=1000, cerenkov_fraction=0.1, seed=SEED):
+    """BASELINE config 3: 8x8 CsI + SiPM, scintillation (+ Cerenkov) gensteps inside random crystals,
+    OPTICKS_MAX_BOUNCE=32 as in tests/test_GPUPhotonSource_8x8SiPM.sh:5."""
+    geom = GEO.sipm8x8()
+    rng = np.random.default_rng(seed)
+    ngs = max(1, num_photon // photons_per_genstep)
+    counts = _poisson_split(rng, num_photon, ngs)
+    cc = geom["crystal_centers"]
+    pos = cc[rng.integers(0, len(cc), ngs)] + rng.uniform(-0.95, 0.95, (ngs, 3)) * np.array([1.0, 1.0, 3.95])
+    dirs = rng.normal(size=(ngs, 3))
+    dirs /= np.linalg.norm(dirs, axis=1)[:, None]
+    step = rng.uniform(0.02, 0.05, ngs)               # short steps keep the whole step inside the crystal
+    is_ck = rng.uniform(size=ngs) < cerenkov_fraction
+    gs = G.scint_gensteps(pos, dirs, 1.0, counts, geom["crystal_line"], geom["scintillation_time"])
+    gs[:, 2, :3] = dirs * step[:, None]
+    gs[:, 2, 3] = step
+    n = geom["n_crystal"]
+    ck = G.cerenkov_gensteps(pos, dirs, 1.0, counts, geom["crystal_line"], 1.0, 300.0, 700.0, n,
+                             pre_velocity=299.0, post_velocity=298.5, mean_photons=(30.0, 29.0))
+    ck[:, 2, :3] = dirs * step[:, None]
+    ck[:, 2, 3] = step
+    gs[is_ck] = ck[is_ck]
+    return dict(name="sipm8x8_scint", geom=geom, gensteps=np.ascontiguousarray(gs), input_photons=None,
+                config=dict(max_bounce=32), num_photon=int(counts.sum()))
+
+
+def raindrop_cerenkov(num_photon=10_000_000, photons_per_genstep=1000, seed=SEED):
+    """BASELINE config 2: muon-like track (dir (0,0.2,0.8)) through the water box, Cerenkov gensteps
+    along it, ~1000 photons each."""
+    geom = GEO.raindrop()
+    rng = np.random.default_rng(seed)
+    ngs = max(1, num_photon // photons_per_genstep)
+    counts = _poisson_split(rng, num_photon, ngs)
+    d = np.array([0.0, 0.2, 0.8])
+    d /= np.linalg.norm(d)
+    s = np.linspace(-48.0, 47.0, ngs)
+    pos = s[:, None] * d[None, :] + rng.normal(0, 0.05, (ngs, 3))
+    n = geom["n_water"]
+    gs = G.cerenkov_gensteps(pos, d, 1.0, counts, geom["water_line"], 1.0, 80.0, 800.0, n, pre_velocity=299.79, post_velocity=299.78,
+                             mean_photons=(2.0, 1.9))
+    gs[:, 1, 3] = (s + 48.0) / 299.79
+    return dict(name="raindrop_cerenkov", geom=geom, gensteps=np.ascontiguousarray(gs), input_photons=None, config=dict(), num_photon=int(counts.sum()))
+
+
+def sphere_leak_torch(num_photon=1_000_000):
+    """BASELINE config 1: config/sphere_leak.json torch (disc r 0.1 at the origin, mom (0,0.3,1),
+    420 nm) scaled to 1e6 photons, generated on the host and fed as input photons like
+    GPUPhotonSource does (src/GPUPhotonSourceMinimal.h:57-88)."""
+    geom = GEO.sphere_leak()
+    t = dict(pos=[0.0, 0.0, 0.0], time=0.0, mom=G._normalize_f32([0.0, 0.3, 1.0]), pol=[1.0, 0.0, 0.0], wavelength=420.0, radius=0.1,
+             numphoton=num_photon, type="disc")
+    ph = G.torch_photons(t, num_photon, seed=0)
+    return dict(name="sphere_leak_torch", geom=geom, gensteps=G.input_photon_genstep(num_photon), input_photons=ph, config=dict(), num_photon=num_photon)
+
+
+def pmt_wall_torch(num_photon=10_000_000, nx=100, ny=100):
+    """BASELINE config 4 (scaled per launch): instanced PMT wall, photons from a wide disc above it,
+    supplied as an input-photon array like GPUPhotonFileSource (src/GPUPhotonFileSource.h:51-87)."""
+    geom = GEO.pmt_wall(nx, ny)
+    hx, hy = geom["half"]
+    t = dict(pos=[0.0, 0.0, 1500.0], time=0.0, mom=[0.0, 0.0, -1.0], pol=[1.0, 0.0, 0.0], wavelength=420.0, radius=float(min(hx, hy) - 600.0),
+             numphoton=num_photon, type="disc")
+    ph = G.torch_photons(t, num_photon, seed=0)
+    pu = ph.view(np.uint32)
+    pu[:, 3, :] = 0                                   # file-source photons carry zero flags
+    return dict(name="pmt_wall_torch", geom=geom, gensteps=G.input_photon_genstep(num_photon), input_photons=ph, config=dict(), num_photon=num_photon)
+
+
+def boolean_zoo_torch(num_photon=1_000_000):
+    """BASELINE config 5: boolean-heavy solids lit from an inward-facing sphere source (torch genstep)."""
+    geom = GEO.boolean_zoo()
+    t = dict(pos=[0.0, 0.0, 0.0], time=0.0, mom=[0.0, 0.0, 1.0], pol=[1.0, 0.0, 0.0], wavelength=440.0, radius=-950.0, numphoton=num_photon,
+             type="sphere", zenith=[0.0, 1.0], azimuth=[0.0, 1.0])
+    return dict(name="boolean_zoo_torch", geom=geom, gensteps=G.torch_genstep(t, num_photon), input_photons=None, config=dict(), num_photon=num_photon)
+
+
+WORKLOADS = dict(sipm8x8_scint=sipm8x8_scint, raindrop_cerenkov=raindrop_cerenkov, sphere_leak_torch=sphere_leak_torch,
+                 pmt_wall_torch=pmt_wall_torch, boolean_zoo_torch=boolean_zoo_torch)

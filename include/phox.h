@@ -113,6 +113,11 @@ int phox_set_tables(phox_context* ctx,
                     const int32_t* optical,
                     const float* icdf, int64_t icdf_ny, int64_t icdf_nx, int32_t hd_factor);
 
+/* Run all work of this context on the caller's CUDA stream (cudaStream_t as void*; NULL restores the
+ * context's own stream).  Lets a host framework order and time the engine with its own events -
+ * the reference always uses the default stream (CSGOptiX/CSGOptiX.cc:1170-1176). */
+int phox_set_stream(phox_context* ctx, void* cuda_stream);
+
 int phox_set_config(phox_context* ctx, const phox_config* cfg);
 int phox_get_config(const phox_context* ctx, phox_config* cfg);
 
@@ -146,6 +151,9 @@ int64_t phox_num_photon(const phox_context* ctx);
 int64_t phox_num_hit(const phox_context* ctx);
 int     phox_get_hits(phox_context* ctx, void* dst_sphoton);      /* host dst, 64 B * num_hit */
 const void* phox_hits_device(const phox_context* ctx);             /* device pointer          */
+int     phox_get_hits_device(phox_context* ctx, void* d_dst);      /* device dst (e.g. the send buffer
+                                                                      of the NCCL hit gather), async on
+                                                                      the context's stream            */
 
 /* Named arrays of the last event, when the event mode keeps them:
  * "photon" (64 B/photon), "record" (64 B * max_record), "seq" (32 B), "prd" (32 B * max_record),
@@ -156,6 +164,8 @@ int64_t phox_get_array(phox_context* ctx, const char* name, void* dst, int64_t d
 typedef struct phox_stats {
     uint64_t num_photon, num_hit, num_ray, num_launch, num_kernel;
     double   launch_seconds, upload_seconds, gather_seconds;
+    double   simulate_kernel_seconds;   /* device time of the simulate kernel(s), CUDA events on the launch stream */
+    double   compact_kernel_seconds;    /* device time of hit offset scan + compaction */
 } phox_stats;
 int phox_get_stats(const phox_context* ctx, phox_stats* st);
 
