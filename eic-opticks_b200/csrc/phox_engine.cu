@@ -73,6 +73,7 @@ struct phox_context {
     int nprim = 0, nnode = 0, nplan = 0, nitra = 0, ninst = 0, nsolid = 0;
     int tlas_root = 0;
     int build_kernels = 0;
+    int sim_grid[2] = {0, 0};               // persistent grid size of k_simulate<false/true>
 
     // tables
     bool have_tables = false;
@@ -168,6 +169,13 @@ extern "C" phox_context* phox_create(int device) {
     cudaGetDeviceProperties(&prop, device);
     size_t free_b = 0;
     cudaMemGetInfo(&free_b, &ctx->vram_total);
+    for (int dbg = 0; dbg < 2; dbg++) {
+        int per_sm = 0;
+        e = dbg ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_simulate<true>, kSimThreads, 0)
+                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_simulate<false>, kSimThreads, 0);
+        if (e != cudaSuccess || per_sm < 1) per_sm = 1;
+        ctx->sim_grid[dbg] = per_sm * prop.multiProcessorCount;
+    }
     char buf[256];
     std::snprintf(buf, sizeof(buf), "phox: B200-native simulate engine on device %d (%s, sm_%d%d, %d SMs, %.1f GB)", device, prop.name,
                   prop.major, prop.minor, prop.multiProcessorCount, ctx->vram_total / 1e9);
@@ -482,8 +490,8 @@ static bool mode_keeps_prd(int m) { return m == PHOX_MODE_DEBUGHEAVY; }
 // one launch over slots [0,n) ; gensteps + prefix already on the device
 static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned long long* d_prefix, int ngs, const Photon* d_input,
                       unsigned long long input_base, unsigned long long photon_offset, int64_t n, int event_id) {
-    const int T = 128;
-    int nblock = (int)((n + T - 1) / T);
+    const int T = kHitTile;
+    int nblock = (int)((n + T - 1) / T);                        // hit-compaction tiles
     const phox_config& c = ctx->cfg;
     int mode = c.event_mode;
     bool dbg = mode_keeps_seq(mode) || mode_keeps_record(mode) || mode_keeps_prd(mode);
@@ -510,7 +518,7 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
     P.record = mode_keeps_record(mode) ? ctx->d_record.p : nullptr;
     P.prd = mode_keeps_prd(mode) ? ctx->d_prd.p : nullptr;
     P.max_record = c.max_record;
-    P.block_hits = ctx->d_block_hits.p;
+    P.work_counter = reinterpret_cast<unsigned*>(ctx->d_counters.p + 3);
     P.counters = ctx->d_counters.p;
     P.max_bounce = c.max_bounce;
     P.tmin = c.propagate_epsilon; P.tmin0 = c.propagate_epsilon0; P.tmax = c.tmax; P.max_time = c.max_time;
@@ -518,17 +526,23 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
     P.seed = c.rng_seed; P.rng_offset = c.rng_offset; P.skipahead = c.skipahead_event_offset;
     P.burn = c.rng_mode == PHOX_RNG_DEBUG_TAG ? 1 : 0;
 
+    CK(cudaMemsetAsync(ctx->d_counters.p + 3, 0, sizeof(unsigned long long), ctx->stream));
+    // persistent grid: every SM gets as many resident blocks as the kernel's registers allow
+    int sim_blocks = ctx->sim_grid[dbg ? 1 : 0];
+    sim_blocks = (int)std::min<int64_t>(sim_blocks, (n + kSimThreads - 1) / kSimThreads);
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-    if (dbg) k_simulate<true><<<nblock, T, 0, ctx->stream>>>(P);
-    else k_simulate<false><<<nblock, T, 0, ctx->stream>>>(P);
+    if (dbg) k_simulate<true><<<sim_blocks, kSimThreads, 0, ctx->stream>>>(P);
+    else k_simulate<false><<<sim_blocks, kSimThreads, 0, ctx->stream>>>(P);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    k_hit_count<<<nblock, T, 0, ctx->stream>>>(ctx->d_photon.p, (unsigned)n, c.hit_mask, ctx->d_block_hits.p);
+    CK(cudaGetLastError());
     k_hit_offsets<<<1, 1024, 0, ctx->stream>>>(ctx->d_block_hits.p, nblock, ctx->d_block_off.p, ctx->d_counters.p + 1);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     int64_t nhit = (int64_t)ctx->h_counters[1];
-    ctx->stats.num_kernel += 2;
+    ctx->stats.num_kernel += 3;
     if (nhit > 0) {
         CK(ctx->d_hit.reserve((size_t)(ctx->num_hit + nhit), true, ctx->stream));
         k_hit_compact<<<nblock, T, 0, ctx->stream>>>(ctx->d_photon.p, (unsigned)n, c.hit_mask, ctx->d_block_off.p, ctx->d_hit.p + ctx->num_hit);

@@ -16,6 +16,9 @@
 #include "phox_math.cuh"
 #include "phox_philox.cuh"
 #include "phox_csg.cuh"
+#ifndef PHOX_SIM_MIN_BLOCKS
+#define PHOX_SIM_MIN_BLOCKS 4
+#endif
 #include "phox_bvh.cuh"
 #include "phox_physics.cuh"
 
@@ -49,7 +52,7 @@ struct SimParams {
     Photon* record;
     Prd* prd;
     int max_record;
-    unsigned* block_hits;                   // [gridDim.x]
+    unsigned* work_counter;                 // next unclaimed photon slot of this launch
     unsigned long long* counters;           // [0] = rays traced
     // config
     int max_bounce;
@@ -64,10 +67,9 @@ struct Nearest {
     float3 n;                       // object-frame normal
     int prim;                       // global CSGPrim index
     int inst;
-    unsigned boundary;
 };
 
-PHOX_D void keep_nearest(Nearest& best, const Scene& sc, const float4* root, const float4& is, int prim_idx, int inst_idx, float tmin) {
+PHOX_D void keep_nearest(Nearest& best, const float4& is, int prim_idx, int inst_idx, float tmin) {
     float t = is.w;
     if (!(t > tmin)) return;                 // OptiX rejects reports outside (tmin, tmax]
     // ties go to the lower (instance, prim) pair so the answer does not depend on traversal order
@@ -78,18 +80,19 @@ PHOX_D void keep_nearest(Nearest& best, const Scene& sc, const float4* root, con
         best.n = f3(is.x, is.y, is.z);
         best.prim = prim_idx;
         best.inst = inst_idx;
-        best.boundary = __float_as_uint(__ldg(root + 1).z);
     }
 }
 
 constexpr int kBvhStack = 64;
 constexpr int kTravReturn = (int)0x80000000;     // stack marker: leave the current solid, back to the instance tree
-constexpr int kTravDone = 0x7ffffffe;
+constexpr int kTravDone = (int)0x80000001;
 
-// Single-loop traversal of both BVH levels.  `cur` is a node index (>= 0, relative to the current
-// tree root) or a leaf (~item): an instance while in the top tree, a CSGPrim inside a solid.
-// Children are visited near-first, the far one parked on the stack with its entry distance so it
-// can be dropped once a nearer hit is known.  There is exactly one prim-test site in the loop.
+// Traversal of both BVH levels in "while-while" form (Aila & Laine): every lane first walks internal
+// nodes until it holds a leaf, then the lanes that hold one run the CSG prim test together - so the
+// expensive, divergent part (intersect_prim) executes with as many lanes as possible.  `cur` is a node
+// index (>= 0, relative to the current tree root), a leaf (~item: an instance in the top tree, a
+// CSGPrim inside a solid) or one of the two markers.  Children are visited near-first; the far one is
+// parked on the stack with its entry distance so it is dropped once a nearer hit is known.
 PHOX_D void traverse_bvh(Nearest& best, const Scene& sc, float tmin, const float3& o_w, const float3& d_w) {
     int stack[kBvhStack];
     float stack_t[kBvhStack];
@@ -101,38 +104,16 @@ PHOX_D void traverse_bvh(Nearest& best, const Scene& sc, float tmin, const float
     int inst_idx = 0;
     int cur = sc.ninst == 1 ? ~0 : 0;
 
-    while (cur != kTravDone) {
-        if (cur == kTravReturn) {
-            in_solid = false; o = o_w; d = d_w;
-            idir = f3(1.f / d.x, 1.f / d.y, 1.f / d.z);
-            root = sc.tlas_root;
-            cur = kTravDone;
-        } else if (cur < 0) {
-            if (!in_solid) {                                  // enter an instance
-                inst_idx = ~cur;
-                const InstanceRec* ir = sc.inst + inst_idx;
-                int4 meta = __ldg(reinterpret_cast<const int4*>(&ir->solid));   // solid, identity, is_identity, bvh_root
-                if (!meta.z) {
-                    float4 r0 = __ldg(&ir->inv[0]), r1 = __ldg(&ir->inv[1]), r2 = __ldg(&ir->inv[2]), r3 = __ldg(&ir->inv[3]);
-                    o = xform(r0, r1, r2, r3, o_w, 1.f);
-                    d = xform(r0, r1, r2, r3, d_w, 0.f);
-                    idir = f3(1.f / d.x, 1.f / d.y, 1.f / d.z);
-                }
-                root = meta.w;
-                in_solid = true;
-                if (sp < kBvhStack) { stack[sp] = kTravReturn; stack_t[sp] = -CUDART_INF_F; sp++; }
-                cur = 0;
-                continue;
-            }
-            {                                                  // a CSGPrim: the one intersect site
-                int prim_idx = ~cur;
-                float4 p0 = __ldg(sc.prim + 4 * prim_idx);
-                const float4* nroot = sc.geo.node + 4 * __float_as_int(p0.y);
-                float4 is = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (intersect_prim(is, nroot, sc.geo, tmin, o, d)) keep_nearest(best, sc, nroot, is, prim_idx, inst_idx, tmin);
-            }
-            cur = kTravDone;
-        } else {
+    auto pop = [&]() -> int {
+        while (sp > 0) {
+            sp--;
+            if (stack_t[sp] <= best.t) return stack[sp];
+        }
+        return kTravDone;
+    };
+
+    while (true) {
+        while (cur >= 0) {                                     // internal nodes
             const float4* np = reinterpret_cast<const float4*>(sc.nodes + root + cur);
             float4 a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2);
             int4 ch = __ldg(reinterpret_cast<const int4*>(np + 3));
@@ -144,16 +125,45 @@ PHOX_D void traverse_bvh(Nearest& best, const Scene& sc, float tmin, const float
                 if (t1 < t0) { nearc = ch.y; farc = ch.x; tfar = t0; }
                 if (sp < kBvhStack) { stack[sp] = farc; stack_t[sp] = tfar; sp++; }
                 cur = nearc;
-                continue;
-            } else if (h0) { cur = ch.x; continue; }
-            else if (h1) { cur = ch.y; continue; }
-            cur = kTravDone;
+            } else if (h0) cur = ch.x;
+            else if (h1) cur = ch.y;
+            else cur = pop();
         }
-        // pop the next parked subtree that can still hold a nearer hit
-        while (sp > 0) {
-            sp--;
-            if (stack_t[sp] <= best.t) { cur = stack[sp]; break; }
+        if (cur == kTravDone) break;
+        if (cur == kTravReturn) {                              // back to the instance tree
+            if (in_solid && !(o.x == o_w.x && o.y == o_w.y && o.z == o_w.z && d.x == d_w.x && d.y == d_w.y && d.z == d_w.z)) {
+                o = o_w; d = d_w;
+                idir = f3(1.f / d.x, 1.f / d.y, 1.f / d.z);
+            }
+            in_solid = false;
+            root = sc.tlas_root;
+            cur = pop();
+            continue;
         }
+        if (!in_solid) {                                       // leaf of the instance tree: enter the solid
+            inst_idx = ~cur;
+            const InstanceRec* ir = sc.inst + inst_idx;
+            int4 meta = __ldg(reinterpret_cast<const int4*>(&ir->solid));   // solid, identity, is_identity, bvh_root
+            if (!meta.z) {
+                float4 r0 = __ldg(&ir->inv[0]), r1 = __ldg(&ir->inv[1]), r2 = __ldg(&ir->inv[2]), r3 = __ldg(&ir->inv[3]);
+                o = xform(r0, r1, r2, r3, o_w, 1.f);
+                d = xform(r0, r1, r2, r3, d_w, 0.f);
+                idir = f3(1.f / d.x, 1.f / d.y, 1.f / d.z);
+            }
+            root = meta.w;
+            in_solid = true;
+            if (sc.ninst > 1 && sp < kBvhStack) { stack[sp] = kTravReturn; stack_t[sp] = -CUDART_INF_F; sp++; }
+            cur = 0;
+            continue;
+        }
+        {                                                      // a CSGPrim: the one intersect site
+            int prim_idx = ~cur;
+            float4 p0 = __ldg(sc.prim + 4 * prim_idx);
+            const float4* nroot = sc.geo.node + 4 * __float_as_int(p0.y);
+            float4 is = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (intersect_prim(is, nroot, sc.geo, tmin, o, d)) keep_nearest(best, is, prim_idx, inst_idx, tmin);
+        }
+        cur = pop();
     }
 }
 
@@ -174,7 +184,7 @@ __device__ __noinline__ void traverse_brute(Nearest& best, const Scene& sc, floa
             float4 p0 = __ldg(sc.prim + 4 * prim_idx);
             const float4* nroot = sc.geo.node + 4 * __float_as_int(p0.y);
             float4 is = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (intersect_prim_cold(is, nroot, sc.geo, tmin, o, d)) keep_nearest(best, sc, nroot, is, prim_idx, i, tmin);
+            if (intersect_prim_cold(is, nroot, sc.geo, tmin, o, d)) keep_nearest(best, is, prim_idx, i, tmin);
         }
     }
 }
@@ -182,9 +192,9 @@ __device__ __noinline__ void traverse_brute(Nearest& best, const Scene& sc, floa
 // nearest intersect in (tmin, tmax]; fills the prd-equivalent.  Returns false on a miss
 // (the reference's miss program sets boundary 0xffff).  Out of line: one compiled body serves
 // every kernel and both trace sites of the bounce loop.
-__device__ __noinline__ bool trace(HitInfo& h, const Scene& sc, const float3& o, const float3& d, float tmin, float tmax) {
+__device__ __noinline__ bool trace(HitInfo& h, const Scene& sc, const float3& o, const float3& d, float tmin, float tmax, bool want_fphi) {
     Nearest best;
-    best.t = tmax; best.prim = -1; best.inst = 0; best.boundary = 0xffffu; best.n = f3(0.f, 0.f, 0.f);
+    best.t = tmax; best.prim = -1; best.inst = 0; best.n = f3(0.f, 0.f, 0.f);
     if (sc.accel == 0) traverse_bvh(best, sc, tmin, o, d);
     else traverse_brute(best, sc, tmin, o, d);
     if (best.prim < 0) {
@@ -205,10 +215,12 @@ __device__ __noinline__ bool trace(HitInfo& h, const Scene& sc, const float3& o,
     h.normal = n;
     h.t = best.t;
     h.lposcost = lpos.z / sqrtf(dot(lpos, lpos));
-    h.lposfphi = (atan2f(lpos.y, lpos.x) + kPi) / (2.0f * kPi);
+    h.lposfphi = want_fphi ? (atan2f(lpos.y, lpos.x) + kPi) / (2.0f * kPi) : 0.f;     // only the prd debug array reads it
     h.iindex_identity = (((unsigned)best.inst & 0xffffu) << 16) | ((unsigned)meta.y & 0xffffu);
+    float4 p0 = __ldg(sc.prim + 4 * best.prim);
+    unsigned boundary = __float_as_uint(__ldg(sc.geo.node + 4 * __float_as_int(p0.y) + 1).z);
     unsigned gpi = __float_as_uint(__ldg(sc.prim + 4 * best.prim + 3).w);
-    h.prim_boundary = ((gpi & 0xffffu) << 16) | (best.boundary & 0xffffu);
+    h.prim_boundary = ((gpi & 0xffffu) << 16) | (boundary & 0xffffu);
     return true;
 }
 
@@ -221,85 +233,125 @@ PHOX_D void seq_add(Seq& s, unsigned slot, unsigned flag, unsigned boundary) {  
     }
 }
 
+// Persistent bounce-loop kernel.  The grid is sized to the machine (SMs x resident blocks), not to
+// the event: each warp pulls photon slots from a global counter and REFILLS lanes whose photon has
+// finished, so lanes do not idle while the longest history of the warp runs out (bounce counts are
+// long-tailed: 1 .. max_bounce).  A photon's result depends only on its absolute index (RNG
+// subsequence), never on which lane ran it, so this reordering cannot change any output.
+constexpr int kSimThreads = 128;
+constexpr int kRefillMin = 8;        // refill when at least this many lanes of the warp are idle
+
 template <bool DEBUG>
-__global__ void __launch_bounds__(128) k_simulate(const __grid_constant__ SimParams P) {
-    unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
-    bool live = idx < P.num_photon;
-    bool is_hit = false;
-    unsigned nray = 0;
+__global__ void __launch_bounds__(kSimThreads, PHOX_SIM_MIN_BLOCKS) k_simulate(const __grid_constant__ SimParams P) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    bool active = false, exhausted = false;
+    unsigned idx = 0, nray = 0;
+    int bounce = 0;
+    PhotonState p;
+    Philox rng;
+    Seq seq;
 
-    if (live) {
-        // seed : which genstep owns slot idx
-        int lo = 0, hi = P.num_genstep;                       // prefix[lo] <= idx < prefix[hi]
-        while (hi - lo > 1) {
-            int mid = (lo + hi) >> 1;
-            if (__ldg(P.gs_prefix + mid) <= (unsigned long long)idx) lo = mid; else hi = mid;
-        }
-        Genstep gs;
-        {
-            const float4* src = reinterpret_cast<const float4*>(P.genstep + lo);
-            float4* dst = reinterpret_cast<float4*>(&gs);
+    while (true) {
+        unsigned need = __ballot_sync(0xffffffffu, !active);
+        if (!exhausted && (__popc(need) >= kRefillMin)) {
+            unsigned base = 0;
+            int leader = __ffs(need) - 1;
+            if ((int)lane == leader) base = atomicAdd(P.work_counter, (unsigned)__popc(need));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (base + (unsigned)__popc(need) >= P.num_photon) exhausted = true;
+            unsigned mine = base + (unsigned)__popc(need & lt_mask);
+            if (!active && mine < P.num_photon) {
+                idx = mine;
+                // seed : which genstep owns slot idx (binary search in the numphoton prefix sum)
+                int lo = 0, hi = P.num_genstep;
+                while (hi - lo > 1) {
+                    int mid = (lo + hi) >> 1;
+                    if (__ldg(P.gs_prefix + mid) <= (unsigned long long)idx) lo = mid; else hi = mid;
+                }
+                Genstep gs;
+                {
+                    const float4* src = reinterpret_cast<const float4*>(P.genstep + lo);
+                    float4* dst = reinterpret_cast<float4*>(&gs);
 #pragma unroll
-            for (int k = 0; k < 6; k++) dst[k] = __ldg(src + k);
-        }
-        unsigned long long photon_idx = P.photon_offset + idx;
-
-        Philox rng;
-        rng.init(P.seed, photon_idx, P.rng_offset + P.skipahead * (unsigned long long)P.event_index);
-
-        PhotonState p;
-        generate_photon(p, rng, gs, P.tables, P.input_photon, P.input_base, photon_idx);
-
-        Seq seq;
-        if (DEBUG) {
-            seq.seqhis[0] = seq.seqhis[1] = seq.seqbnd[0] = seq.seqbnd[1] = 0ull;
-            if (P.record && 0 < P.max_record) p.store(P.record + (size_t)P.max_record * idx);
-            if (P.seq) seq_add(seq, 0u, p.flag(), p.boundary());
-        }
-
-        int bounce = 0;
-        while (bounce < P.max_bounce && p.time < P.max_time) {
-            float tmin = (p.obf & P.eps0_mask) ? P.tmin0 : P.tmin;
-            HitInfo h;
-            bool ok = trace(h, P.scene, p.pos, p.mom, tmin, P.tmax);
-            nray++;
-            if (P.refine && ok) {
-                float t_approx = 0.99f * h.t;
-                if (t_approx > P.refine_distance) {
-                    float3 closer = p.pos + t_approx * p.mom;
-                    ok = trace(h, P.scene, closer, p.mom, tmin, P.tmax);
-                    nray++;
-                    h.t += t_approx;
+                    for (int k = 0; k < 6; k++) dst[k] = __ldg(src + k);
+                }
+                unsigned long long photon_idx = P.photon_offset + idx;
+                rng.init(P.seed, photon_idx, P.rng_offset + P.skipahead * (unsigned long long)P.event_index);
+                generate_photon(p, rng, gs, P.tables, P.input_photon, P.input_base, photon_idx);
+                bounce = 0;
+                active = true;
+                if (DEBUG) {
+                    seq.seqhis[0] = seq.seqhis[1] = seq.seqbnd[0] = seq.seqbnd[1] = 0ull;
+                    if (P.record && 0 < P.max_record) p.store(P.record + (size_t)P.max_record * idx);
+                    if (P.seq) seq_add(seq, 0u, p.flag(), p.boundary());
                 }
             }
-            if (!ok) break;                                   // photon left the world
-            h.normal = normalize(h.normal);
-            if (DEBUG) {
-                if (P.prd && bounce < P.max_record) {
-                    Prd r;
-                    r.nx = h.normal.x; r.ny = h.normal.y; r.nz = h.normal.z; r.t = h.t;
-                    r.lposcost = h.lposcost; r.lposfphi = h.lposfphi;
-                    r.iindex_identity = h.iindex_identity; r.prim_boundary = h.prim_boundary;
-                    P.prd[(size_t)P.max_record * idx + bounce] = r;
+        }
+        if (!__any_sync(0xffffffffu, active)) {
+            if (exhausted) break;
+            continue;
+        }
+        if (active) {
+            bool finished = !(bounce < P.max_bounce && p.time < P.max_time);
+            if (!finished) {
+                float tmin = (p.obf & P.eps0_mask) ? P.tmin0 : P.tmin;
+                HitInfo h;
+                bool ok = trace(h, P.scene, p.pos, p.mom, tmin, P.tmax, DEBUG && P.prd != nullptr);
+                nray++;
+                if (P.refine && ok) {
+                    float t_approx = 0.99f * h.t;
+                    if (t_approx > P.refine_distance) {
+                        float3 closer = p.pos + t_approx * p.mom;
+                        ok = trace(h, P.scene, closer, p.mom, tmin, P.tmax, DEBUG && P.prd != nullptr);
+                        nray++;
+                        h.t += t_approx;
+                    }
+                }
+                if (!ok) finished = true;                       // photon left the world
+                else {
+                    h.normal = normalize(h.normal);
+                    if (DEBUG) {
+                        if (P.prd && bounce < P.max_record) {
+                            Prd r;
+                            r.nx = h.normal.x; r.ny = h.normal.y; r.nz = h.normal.z; r.t = h.t;
+                            r.lposcost = h.lposcost; r.lposfphi = h.lposfphi;
+                            r.iindex_identity = h.iindex_identity; r.prim_boundary = h.prim_boundary;
+                            P.prd[(size_t)P.max_record * idx + bounce] = r;
+                        }
+                    }
+                    int command = propagate(p, rng, h, P.tables, P.burn != 0);
+                    bounce++;
+                    if (DEBUG) {
+                        if (P.record && bounce < P.max_record) p.store(P.record + (size_t)P.max_record * idx + bounce);
+                        if (P.seq) seq_add(seq, (unsigned)bounce, p.flag(), p.boundary());
+                    }
+                    if (command == FLOW_BREAK || !(bounce < P.max_bounce && p.time < P.max_time)) finished = true;
                 }
             }
-            int command = propagate(p, rng, h, P.tables, P.burn != 0);
-            bounce++;
-            if (DEBUG) {
-                if (P.record && bounce < P.max_record) p.store(P.record + (size_t)P.max_record * idx + bounce);
-                if (P.seq) seq_add(seq, (unsigned)bounce, p.flag(), p.boundary());
+            if (finished) {
+                if (DEBUG) { if (P.seq) P.seq[idx] = seq; }
+                if (P.photon) p.store(P.photon + idx);
+                active = false;
             }
-            if (command == FLOW_BREAK) break;
         }
-        if (DEBUG) { if (P.seq) P.seq[idx] = seq; }
-        if (P.photon) p.store(P.photon + idx);
-        is_hit = (p.flagmask & P.hit_mask) == P.hit_mask;
     }
-
-    int nhit = __syncthreads_count(is_hit);
-    if (threadIdx.x == 0) P.block_hits[blockIdx.x] = (unsigned)nhit;
     for (int off = 16; off > 0; off >>= 1) nray += __shfl_down_sync(0xffffffffu, nray, off);
-    if ((threadIdx.x & 31) == 0 && nray) atomicAdd(P.counters, (unsigned long long)nray);
+    if (lane == 0 && nray) atomicAdd(P.counters, (unsigned long long)nray);
+}
+
+// hits per tile of kHitTile photons (reads only the flagmask word of each photon)
+constexpr int kHitTile = 128;
+__global__ void __launch_bounds__(kHitTile) k_hit_count(const Photon* __restrict__ photon, unsigned num_photon, unsigned hit_mask,
+                                                       unsigned* __restrict__ block_hits) {
+    unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    bool is_hit = false;
+    if (idx < num_photon) {
+        unsigned fm = __ldg(&photon[idx].flagmask);
+        is_hit = (fm & hit_mask) == hit_mask;
+    }
+    int n = __syncthreads_count(is_hit);
+    if (threadIdx.x == 0) block_hits[blockIdx.x] = (unsigned)n;
 }
 
 // exclusive scan of block_hits[n] -> block_off[n], total -> total_out[0] (single block, any n)
@@ -330,7 +382,7 @@ __global__ void k_hit_offsets(const unsigned* __restrict__ block_hits, int n, un
 
 // block b re-reads the flagmasks of its photons and copies the hits, in order, to
 // hit[hit_base + block_off[b] + rank]
-__global__ void __launch_bounds__(128) k_hit_compact(const Photon* __restrict__ photon, unsigned num_photon, unsigned hit_mask,
+__global__ void __launch_bounds__(kHitTile) k_hit_compact(const Photon* __restrict__ photon, unsigned num_photon, unsigned hit_mask,
                                                       const unsigned long long* __restrict__ block_off, Photon* __restrict__ hit) {
     __shared__ unsigned warp_count[4];
     unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -384,7 +436,7 @@ __global__ void k_intersect(Scene sc, const float4* __restrict__ ray_o_tmin, con
     if (i >= n) return;
     float4 o = ray_o_tmin[i], d = ray_d[i];
     HitInfo h;
-    trace(h, sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, tmax);
+    trace(h, sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, tmax, true);
     Prd r;
     r.nx = h.normal.x; r.ny = h.normal.y; r.nz = h.normal.z; r.t = h.t;
     r.lposcost = h.lposcost; r.lposfphi = h.lposfphi;
