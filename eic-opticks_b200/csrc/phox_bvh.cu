@@ -1,13 +1,11 @@
-// phox_bvh.cu : GPU construction of one binary LBVH (see phox_bvh.cuh for the role it plays).
+// phox_bvh.cu : GPU construction of one binary BVH (see phox_bvh.cuh for the role it plays).
 //
 // Pipeline, all on the device:
 //   1. k_bounds     : block-reduce the union of the item boxes
 //   2. k_morton     : 30-bit Morton code of each box centre, key = code<<32 | item (unique keys)
 //   3. k_bitonic*   : sort the 64-bit keys (padded to a power of two)
-//   4. k_hierarchy  : Karras 2012 "Maximizing parallelism in the construction of BVHs": each
-//                     internal node finds its key range and split from common-prefix lengths
-//   5. k_refit      : leaves walk up; the second arrival at a node merges the child boxes
-//   6. k_emit       : write the 64 B two-child-box nodes
+//   4. k_ploc       : PLOC agglomerative clustering over the Morton order (surface-area driven), which
+//                     writes the 64 B two-child-box nodes directly; the last merge is node 0, the root
 // Geometry is small (hundreds of prims, ~1e4 instances) so build time is irrelevant next to the
 // per-event work; what matters is that nothing geometry-sized is built on the host.
 #include "phox_bvh.cuh"
@@ -77,91 +75,97 @@ __global__ void k_bitonic_step(unsigned long long* __restrict__ keys, int npad, 
     }
 }
 
-__device__ __forceinline__ int prefix_len(const unsigned long long* keys, int n, int i, int j) {
-    if (j < 0 || j >= n) return -1;
-    return __clzll(keys[i] ^ keys[j]);       // keys are unique, so never 64
+__device__ __forceinline__ float merged_area(const float* a, const float* b) {
+    float dx = fmaxf(a[3], b[3]) - fminf(a[0], b[0]);
+    float dy = fmaxf(a[4], b[4]) - fminf(a[1], b[1]);
+    float dz = fmaxf(a[5], b[5]) - fminf(a[2], b[2]);
+    return dx * dy + dy * dz + dz * dx;
 }
 
-// internal node i in [0, n-1) ; children encoded: >=0 internal, <0 ~leaf_position
-__global__ void k_hierarchy(const unsigned long long* __restrict__ keys, int n, int* __restrict__ left, int* __restrict__ right,
-                            int* __restrict__ parent_internal, int* __restrict__ parent_leaf) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n - 1) return;
-    int d = (prefix_len(keys, n, i, i + 1) - prefix_len(keys, n, i, i - 1)) >= 0 ? 1 : -1;
-    int dmin = prefix_len(keys, n, i, i - d);
-    int lmax = 2;
-    while (prefix_len(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
-    int l = 0;
-    for (int t = lmax / 2; t >= 1; t /= 2) {
-        if (prefix_len(keys, n, i, i + (l + t) * d) > dmin) l += t;
+// PLOC - parallel locally-ordered clustering (Meister & Bittner 2018): bottom-up agglomeration of the
+// Morton-ordered clusters.  Every round each cluster looks `radius` neighbours to either side for the
+// partner giving the smallest merged surface area; mutual choices merge into a new node.  Large boxes
+// (a world volume, slabs spanning the whole detector) only merge late, i.e. end up near the root,
+// which is what keeps rays that start deep inside small volumes from visiting them at every level.
+// One block builds one tree: geometry is small (<= ~1e4 items) and built once.
+constexpr int kPlocRadius = 16;
+__global__ void __launch_bounds__(1024) k_ploc(const float* __restrict__ boxes, const unsigned long long* __restrict__ keys, int n, int base_item,
+                                               float* __restrict__ cbox0, float* __restrict__ cbox1, int* __restrict__ cid0, int* __restrict__ cid1,
+                                               int* __restrict__ nn, int* __restrict__ keep, BvhNode* __restrict__ out) {
+    __shared__ int s_scan[1024];
+    __shared__ int s_count, s_next_node;
+    const int T = blockDim.x, tid = threadIdx.x;
+    float* cb = cbox0; float* cb2 = cbox1; int* id = cid0; int* id2 = cid1;
+    for (int i = tid; i < n; i += T) {
+        int item = (int)(keys[i] & 0xffffffffull);
+        for (int k = 0; k < 6; k++) cb[6 * i + k] = boxes[6 * item + k];
+        id[i] = ~(base_item + item);
     }
-    int j = i + l * d;
-    int dnode = prefix_len(keys, n, i, j);
-    int s = 0;
-    for (int t = (l + 1) / 2;; t = (t + 1) / 2) {
-        if (prefix_len(keys, n, i, i + (s + t) * d) > dnode) s += t;
-        if (t == 1) break;
-    }
-    int gamma = i + s * d + min(d, 0);
-    int lo = min(i, j), hi = max(i, j);
-    int lc = (lo == gamma) ? ~gamma : gamma;
-    int rc = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
-    left[i] = lc; right[i] = rc;
-    if (lc >= 0) parent_internal[lc] = i; else parent_leaf[~lc] = i;
-    if (rc >= 0) parent_internal[rc] = i; else parent_leaf[~rc] = i;
-    if (i == 0) parent_internal[0] = -1;
-}
-
-__global__ void k_refit(const float* __restrict__ boxes, const unsigned long long* __restrict__ keys, int n,
-                        const int* __restrict__ left, const int* __restrict__ right,
-                        const int* __restrict__ parent_internal, const int* __restrict__ parent_leaf,
-                        float* __restrict__ node_box, int* __restrict__ visit) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int node = parent_leaf[i];
-    while (node >= 0) {
-        if (atomicAdd(&visit[node], 1) == 0) return;      // first child to arrive stops; the second carries on
-        __threadfence();
-        float bx[6];
-        for (int side = 0; side < 2; side++) {
-            int c = side == 0 ? left[node] : right[node];
-            const float* src = c >= 0 ? node_box + 6 * c : boxes + 6 * (int)(keys[~c] & 0xffffffffull);
-            for (int k = 0; k < 3; k++) {
-                float lo = __ldcg(src + k), hi = __ldcg(src + 3 + k);
-                bx[k] = side == 0 ? lo : fminf(bx[k], lo);
-                bx[3 + k] = side == 0 ? hi : fmaxf(bx[3 + k], hi);
+    if (tid == 0) { s_count = n; s_next_node = n - 2; }          // nodes are handed out downwards: the last merge is node 0 = root
+    __syncthreads();
+    int count = n;
+    while (count > 1) {
+        for (int i = tid; i < count; i += T) {                   // nearest neighbour in the window
+            float best = CUDART_INF_F; int bj = -1;
+            int j0 = max(0, i - kPlocRadius), j1 = min(count - 1, i + kPlocRadius);
+            for (int j = j0; j <= j1; j++) {
+                if (j == i) continue;
+                float a = merged_area(cb + 6 * i, cb + 6 * j);
+                if (a < best) { best = a; bj = j; }
+            }
+            nn[i] = bj;
+        }
+        __syncthreads();
+        for (int i = tid; i < count; i += T) {                   // mutual pairs merge (the lower index owns the new node)
+            int j = nn[i];
+            bool mutual = nn[j] == i;
+            if (mutual && i < j) {
+                int node = atomicSub(&s_next_node, 1);
+                BvhNode nd;
+                const float* A = cb + 6 * i; const float* B = cb + 6 * j;
+                nd.a = make_float4(A[0], A[1], A[2], A[3]);
+                nd.b = make_float4(A[4], A[5], B[0], B[1]);
+                nd.c = make_float4(B[2], B[3], B[4], B[5]);
+                nd.d = make_int4(id[i], id[j], 0, 0);
+                out[node] = nd;
+                for (int k = 0; k < 3; k++) { cb2[6 * i + k] = fminf(A[k], B[k]); cb2[6 * i + 3 + k] = fmaxf(A[3 + k], B[3 + k]); }
+                id2[i] = node;
+                keep[i] = 1;
+            } else if (mutual) {
+                keep[i] = 0;
+            } else {
+                for (int k = 0; k < 6; k++) cb2[6 * i + k] = cb[6 * i + k];
+                id2[i] = id[i];
+                keep[i] = 1;
             }
         }
-        for (int k = 0; k < 6; k++) node_box[6 * node + k] = bx[k];
-        __threadfence();
-        node = parent_internal[node];
-    }
-}
-
-__global__ void k_emit(const float* __restrict__ boxes, const unsigned long long* __restrict__ keys, int n, int base_item,
-                       const int* __restrict__ left, const int* __restrict__ right, const float* __restrict__ node_box,
-                       BvhNode* __restrict__ out) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n - 1) return;
-    float bx[2][6];
-    int ch[2];
-    for (int side = 0; side < 2; side++) {
-        int c = side == 0 ? left[i] : right[i];
-        const float* src;
-        if (c >= 0) { src = node_box + 6 * c; ch[side] = c; }
-        else {
-            int item = (int)(keys[~c] & 0xffffffffull);
-            src = boxes + 6 * item;
-            ch[side] = ~(base_item + item);
+        __syncthreads();
+        // order-preserving compaction of the kept clusters
+        int chunk = (count + T - 1) / T;
+        int lo = min(count, tid * chunk), hi = min(count, lo + chunk);
+        int local = 0;
+        for (int i = lo; i < hi; i++) local += keep[i];
+        s_scan[tid] = local;
+        __syncthreads();
+        for (int off = 1; off < T; off <<= 1) {
+            int v = tid >= off ? s_scan[tid - off] : 0;
+            __syncthreads();
+            s_scan[tid] += v;
+            __syncthreads();
         }
-        for (int k = 0; k < 6; k++) bx[side][k] = src[k];
+        int pos = s_scan[tid] - local;
+        for (int i = lo; i < hi; i++) {
+            if (keep[i]) {
+                for (int k = 0; k < 6; k++) cb[6 * pos + k] = cb2[6 * i + k];
+                id[pos] = id2[i];
+                pos++;
+            }
+        }
+        if (tid == T - 1) s_count = s_scan[T - 1];
+        __syncthreads();
+        count = s_count;
+        __syncthreads();
     }
-    BvhNode nd;
-    nd.a = make_float4(bx[0][0], bx[0][1], bx[0][2], bx[0][3]);
-    nd.b = make_float4(bx[0][4], bx[0][5], bx[1][0], bx[1][1]);
-    nd.c = make_float4(bx[1][2], bx[1][3], bx[1][4], bx[1][5]);
-    nd.d = make_int4(ch[0], ch[1], 0, 0);
-    out[i] = nd;
 }
 
 __global__ void k_single(const float* __restrict__ boxes, int base_item, BvhNode* __restrict__ out) {
@@ -195,12 +199,12 @@ cudaError_t bvh_build(const float* d_boxes, int n, int base_item, BvhNode* d_out
     size_t off = 0;
     size_t o_keys = off;    off = align_up(off + sizeof(unsigned long long) * npad, 256);
     size_t o_bounds = off;  off = align_up(off + sizeof(float) * 8, 256);
-    size_t o_left = off;    off = align_up(off + sizeof(int) * n, 256);
-    size_t o_right = off;   off = align_up(off + sizeof(int) * n, 256);
-    size_t o_pint = off;    off = align_up(off + sizeof(int) * n, 256);
-    size_t o_pleaf = off;   off = align_up(off + sizeof(int) * n, 256);
-    size_t o_visit = off;   off = align_up(off + sizeof(int) * n, 256);
-    size_t o_nbox = off;    off = align_up(off + sizeof(float) * 6 * n, 256);
+    size_t o_cb0 = off;     off = align_up(off + sizeof(float) * 6 * n, 256);
+    size_t o_cb1 = off;     off = align_up(off + sizeof(float) * 6 * n, 256);
+    size_t o_id0 = off;     off = align_up(off + sizeof(int) * n, 256);
+    size_t o_id1 = off;     off = align_up(off + sizeof(int) * n, 256);
+    size_t o_nn = off;      off = align_up(off + sizeof(int) * n, 256);
+    size_t o_keep = off;    off = align_up(off + sizeof(int) * n, 256);
     if (scratch.bytes < off) {
         bvh_scratch_free(scratch);
         cudaError_t e = cudaMalloc(&scratch.buf, off);
@@ -210,12 +214,6 @@ cudaError_t bvh_build(const float* d_boxes, int n, int base_item, BvhNode* d_out
     char* base = (char*)scratch.buf;
     auto* keys = (unsigned long long*)(base + o_keys);
     auto* bounds = (float*)(base + o_bounds);
-    int* left = (int*)(base + o_left);
-    int* right = (int*)(base + o_right);
-    int* pint = (int*)(base + o_pint);
-    int* pleaf = (int*)(base + o_pleaf);
-    int* visit = (int*)(base + o_visit);
-    float* nbox = (float*)(base + o_nbox);
 
     const int T = 256;
     int kc = 0;
@@ -223,10 +221,8 @@ cudaError_t bvh_build(const float* d_boxes, int n, int base_item, BvhNode* d_out
     k_morton<<<(npad + T - 1) / T, T, 0, stream>>>(d_boxes, n, npad, bounds, keys); kc++;
     for (int k = 2; k <= npad; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) { k_bitonic_step<<<(npad + T - 1) / T, T, 0, stream>>>(keys, npad, j, k); kc++; }
-    cudaMemsetAsync(visit, 0, sizeof(int) * n, stream);
-    k_hierarchy<<<(n + T - 1) / T, T, 0, stream>>>(keys, n, left, right, pint, pleaf); kc++;
-    k_refit<<<(n + T - 1) / T, T, 0, stream>>>(d_boxes, keys, n, left, right, pint, pleaf, nbox, visit); kc++;
-    k_emit<<<(n + T - 1) / T, T, 0, stream>>>(d_boxes, keys, n, base_item, left, right, nbox, d_out); kc++;
+    k_ploc<<<1, 1024, 0, stream>>>(d_boxes, keys, n, base_item, (float*)(base + o_cb0), (float*)(base + o_cb1), (int*)(base + o_id0),
+                                   (int*)(base + o_id1), (int*)(base + o_nn), (int*)(base + o_keep), d_out); kc++;
     if (kernel_count) *kernel_count += kc;
     return cudaGetLastError();
 }

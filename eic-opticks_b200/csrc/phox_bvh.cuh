@@ -3,8 +3,8 @@
 //
 // Level 1 ("instance BVH") is built over the world-space boxes of the instances (inst qat4 x
 // solid box); level 2 is one BVH per CSGSolid over the CSGPrim boxes (CSGPrim.h q2,q3: the same
-// boxes the reference hands to optixAccelBuild as custom-primitive AABBs).  Both are binary LBVHs
-// built on the GPU (Morton codes -> sort -> Karras hierarchy -> bottom-up refit) and then laid out
+// boxes the reference hands to optixAccelBuild as custom-primitive AABBs).  Both are binary BVHs
+// built on the GPU (Morton codes -> sort -> PLOC surface-area clustering) and then laid out
 // as 64-byte nodes that hold BOTH children's boxes, so one 64 B fetch decides two subtrees.
 #pragma once
 #include <cuda_runtime.h>
@@ -50,13 +50,14 @@ void bvh_scratch_free(BvhScratch& scratch);
 // slab test against a box given as lo/hi ; returns entry distance, or +inf when missed.
 // idir may hold +-inf for axis-parallel rays; fminf/fmaxf drop the NaN of 0*inf.
 __device__ __forceinline__ float box_entry(float lox, float loy, float loz, float hix, float hiy, float hiz,
-                                           const float3& o, const float3& idir, float tmin, float tbest) {
+                                           const float3& o, const float3& idir, float tmin, float tbest, float& texit) {
     float tx0 = (lox - o.x) * idir.x, tx1 = (hix - o.x) * idir.x;
     float ty0 = (loy - o.y) * idir.y, ty1 = (hiy - o.y) * idir.y;
     float tz0 = (loz - o.z) * idir.z, tz1 = (hiz - o.z) * idir.z;
     float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), tmin));
     float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), tbest));
     tf *= 1.0000004f;        // conservative: never cull a box whose prim would report a hit at its face
+    texit = tf;
     return tn <= tf ? tn : CUDART_INF_F;
 }
 #endif

@@ -117,12 +117,15 @@ PHOX_D void traverse_bvh(Nearest& best, const Scene& sc, float tmin, const float
             const float4* np = reinterpret_cast<const float4*>(sc.nodes + root + cur);
             float4 a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2);
             int4 ch = __ldg(reinterpret_cast<const int4*>(np + 3));
-            float t0 = box_entry(a.x, a.y, a.z, a.w, b.x, b.y, o, idir, tmin, best.t);
-            float t1 = ch.y == kBvhNoChild ? CUDART_INF_F : box_entry(b.z, b.w, c.x, c.y, c.z, c.w, o, idir, tmin, best.t);
+            float e0, e1 = 0.f;
+            float t0 = box_entry(a.x, a.y, a.z, a.w, b.x, b.y, o, idir, tmin, best.t, e0);
+            float t1 = ch.y == kBvhNoChild ? CUDART_INF_F : box_entry(b.z, b.w, c.x, c.y, c.z, c.w, o, idir, tmin, best.t, e1);
             bool h0 = t0 < CUDART_INF_F, h1 = t1 < CUDART_INF_F;
             if (h0 && h1) {
                 int nearc = ch.x, farc = ch.y; float tfar = t1;
-                if (t1 < t0) { nearc = ch.y; farc = ch.x; tfar = t0; }
+                // nearer entry first; when the ray starts inside both boxes (equal entries) the box it
+                // leaves sooner is the likelier home of the nearest surface
+                if (t1 < t0 || (t1 == t0 && e1 < e0)) { nearc = ch.y; farc = ch.x; tfar = t0; }
                 if (sp < kBvhStack) { stack[sp] = farc; stack_t[sp] = tfar; sp++; }
                 cur = nearc;
             } else if (h0) cur = ch.x;

@@ -10,7 +10,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libphox.so")
+LIB_PATH = os.environ.get("PHOX_LIB") or os.path.join(CSRC, "libphox.so")   # PHOX_LIB: tuning builds only
 
 PHOX_OK = 0
 MODE_MINIMAL, MODE_HITPHOTON, MODE_HITPHOTONSEQ, MODE_DEBUGLITE, MODE_DEBUGHEAVY = range(5)
