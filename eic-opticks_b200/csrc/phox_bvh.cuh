@@ -47,8 +47,12 @@ cudaError_t bvh_build(const float* d_boxes, int n, int base_item, BvhNode* d_out
 void bvh_scratch_free(BvhScratch& scratch);
 
 #if defined(__CUDACC__)
-// slab test against a box given as lo/hi ; returns entry distance, or +inf when missed.
-// idir may hold +-inf for axis-parallel rays; fminf/fmaxf drop the NaN of 0*inf.
+// slab test against a box given as lo/hi ; returns entry distance, or +inf when missed, and the exit
+// distance in texit.  (lo - o) * idir is kept in this exact-difference form on purpose: the cheaper
+// fma(lo, idir, -o*idir) loses ~|o|/|lo-o| ulps to cancellation and would cull boxes far from the
+// origin wrongly.  idir may hold +-inf for axis-parallel rays; fminf/fmaxf drop the NaN of 0*inf.
+// The test only culls: prim boxes are padded at build time and tf is widened, so it is conservative
+// against the prims' own arithmetic.
 __device__ __forceinline__ float box_entry(float lox, float loy, float loz, float hix, float hiy, float hiz,
                                            const float3& o, const float3& idir, float tmin, float tbest, float& texit) {
     float tx0 = (lox - o.x) * idir.x, tx1 = (hix - o.x) * idir.x;

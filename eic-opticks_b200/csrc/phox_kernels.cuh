@@ -17,7 +17,7 @@
 #include "phox_philox.cuh"
 #include "phox_csg.cuh"
 #ifndef PHOX_SIM_MIN_BLOCKS
-#define PHOX_SIM_MIN_BLOCKS 4
+#define PHOX_SIM_MIN_BLOCKS 12     // 40 registers, 48 warps/SM: the loop is latency bound, occupancy beats spill-free code (profiles/)
 #endif
 #include "phox_bvh.cuh"
 #include "phox_physics.cuh"

@@ -11,9 +11,9 @@
 // (z,w) = subsequence; the four 32-bit outputs of a block are handed out in x,y,z,w order and an
 // element offset n selects block n/4, lane n%4; a uniform is  u32 * 2^-32 + 2^-33  in (0,1].
 //
-// Instead of the 64-byte curandStatePhilox4_32_10 the stream here is 8 registers: the cached
-// block (4), the block counter (2), and the lane; key and subsequence stay in the caller's
-// registers/constants.
+// Instead of the 64-byte curandStatePhilox4_32_10 the stream caches TWO consecutive blocks (8
+// outputs) plus the block counter and a position, so that the refill (10 Philox rounds) can be done
+// at points where the warp is converged (align()) instead of inside divergent physics branches.
 #pragma once
 #include <stdint.h>
 #include <cuda_runtime.h>
@@ -21,11 +21,11 @@
 namespace phox {
 
 struct Philox {
-    uint4    out;        // outputs of block `blk`
+    uint4    a, b;       // outputs of blocks `blk` and `blk + 1`
     uint32_t blk_lo, blk_hi;
     uint32_t sub_lo, sub_hi;
     uint32_t key_lo, key_hi;
-    uint32_t lane;       // next output of `out` to hand out, 0..3 ; 4 = block exhausted
+    uint32_t pos;        // next draw, 0..7 into (a,b); 8 = both blocks used up
 
     static __device__ __forceinline__ uint4 block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
         constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
@@ -40,27 +40,40 @@ struct Philox {
         return make_uint4(c0, c1, c2, c3);
     }
 
-    __device__ __forceinline__ void refill() { out = block(blk_lo, blk_hi, sub_lo, sub_hi, key_lo, key_hi); }
+    // a <- b, b <- the block after it
+    __device__ __forceinline__ void advance() {
+        blk_lo += 1u;
+        if (blk_lo == 0u) blk_hi += 1u;         // carry into the subsequence words cannot happen for < 2^66 draws
+        uint32_t nlo = blk_lo + 1u, nhi = blk_hi + (nlo == 0u ? 1u : 0u);
+        a = b;
+        b = block(nlo, nhi, sub_lo, sub_hi, key_lo, key_hi);
+    }
 
     // seed / subsequence / element offset (offset already includes any per-event skipahead)
     __device__ __forceinline__ void init(uint64_t seed, uint64_t subsequence, uint64_t element_offset) {
         key_lo = (uint32_t)seed; key_hi = (uint32_t)(seed >> 32);
         sub_lo = (uint32_t)subsequence; sub_hi = (uint32_t)(subsequence >> 32);
-        uint64_t b = element_offset >> 2;
-        blk_lo = (uint32_t)b; blk_hi = (uint32_t)(b >> 32);
-        lane = (uint32_t)(element_offset & 3u);
-        refill();
+        uint64_t blk = element_offset >> 2;
+        blk_lo = (uint32_t)blk; blk_hi = (uint32_t)(blk >> 32);
+        pos = (uint32_t)(element_offset & 3u);
+        a = block(blk_lo, blk_hi, sub_lo, sub_hi, key_lo, key_hi);
+        uint32_t nlo = blk_lo + 1u, nhi = blk_hi + (nlo == 0u ? 1u : 0u);
+        b = block(nlo, nhi, sub_lo, sub_hi, key_lo, key_hi);
+    }
+
+    // Call where the warp is converged (top of a bounce, before the surface/boundary draws): afterwards
+    // at least 5 draws are cached, so the 4 + 2 draws of a typical bounce never refill inside divergent
+    // code.  Has no effect on the sequence of numbers handed out.
+    __device__ __forceinline__ void align() {
+        if (pos >= 4u) { advance(); pos -= 4u; }
     }
 
     __device__ __forceinline__ uint32_t next_u32() {
-        if (lane == 4u) {
-            blk_lo += 1u;
-            if (blk_lo == 0u) blk_hi += 1u;     // carry into the subsequence words cannot happen for < 2^66 draws
-            refill();
-            lane = 0u;
-        }
-        uint32_t r = lane == 0u ? out.x : lane == 1u ? out.y : lane == 2u ? out.z : out.w;
-        lane += 1u;
+        if (pos == 8u) { advance(); pos = 4u; }
+        uint32_t p = pos;
+        uint32_t r = p < 4u ? (p == 0u ? a.x : p == 1u ? a.y : p == 2u ? a.z : a.w)
+                            : (p == 4u ? b.x : p == 5u ? b.y : p == 6u ? b.z : b.w);
+        pos = p + 1u;
         return r;
     }
 

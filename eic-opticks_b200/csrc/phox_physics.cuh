@@ -402,6 +402,7 @@ PHOX_D int propagate(PhotonState& p, Philox& rng, const HitInfo& h, const Tables
     {
         const float absorption_length = material1.y, scattering_length = material1.z, reemission_prob = material1.w;
         const float distance_to_boundary = h.t;
+        rng.align();
         if (burn) { rng.uniform(); rng.uniform(); }
         float u_scattering = rng.uniform();
         float u_absorption = rng.uniform();
@@ -444,6 +445,7 @@ PHOX_D int propagate(PhotonState& p, Philox& rng, const HitInfo& h, const Tables
     }
 
     if (command == FLOW_BOUNDARY) {
+        rng.align();
         const unsigned ems = __ldg(tb.optical + su_line).y;
         bool at_surface = false;
         if (ems == EMS_NoSurface) {
