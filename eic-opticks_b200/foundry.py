@@ -360,3 +360,29 @@ def load_foundry(folder):
     m = os.path.join(folder, "meshname.txt")
     out["meshname"] = open(m).read().split("\n")[:-1] if os.path.exists(m) else []
     return out
+
+
+def save_geometry(geom, folder):
+    """Persist foundry + tables the way a reference geometry directory is laid out:
+    <folder>/CSGFoundry/*.npy and <folder>/CSGFoundry/SSim/stree/standard/{bnd,optical,icdf}.npy"""
+    fd = os.path.join(folder, "CSGFoundry")
+    save_foundry(geom["foundry"], fd)
+    ss = os.path.join(fd, "SSim", "stree", "standard")
+    os.makedirs(ss, exist_ok=True)
+    np.save(os.path.join(ss, "bnd.npy"), np.ascontiguousarray(geom["bnd"], dtype=np.float32))
+    np.save(os.path.join(ss, "optical.npy"), np.ascontiguousarray(geom["optical"], dtype=np.int32))
+    if geom.get("icdf") is not None:
+        np.save(os.path.join(ss, "icdf.npy"), np.ascontiguousarray(geom["icdf"], dtype=np.float32))
+    with open(os.path.join(ss, "bnd_names.txt"), "w") as f:
+        f.write("\n".join(geom.get("bnd_names", [])) + "\n")
+
+
+def load_geometry(folder):
+    fd = os.path.join(folder, "CSGFoundry")
+    ss = os.path.join(fd, "SSim", "stree", "standard")
+    out = dict(foundry=load_foundry(fd), bnd=np.load(os.path.join(ss, "bnd.npy")), optical=np.load(os.path.join(ss, "optical.npy")))
+    p = os.path.join(ss, "icdf.npy")
+    out["icdf"] = np.load(p) if os.path.exists(p) else None
+    n = os.path.join(ss, "bnd_names.txt")
+    out["bnd_names"] = open(n).read().split("\n")[:-1] if os.path.exists(n) else []
+    return out

@@ -147,3 +147,17 @@ def test_partition_gensteps_and_shard_event():
     got = [parallel.shard_event(G.input_photon_genstep(10), r, 3, ip) for r in range(3)]
     assert [g_[2] for g_ in got] == [0, 3, 6] and sum(g_[3] for g_ in got) == 10
     assert all(g_[0].view(np.uint32)[0, 0, 3] == g_[3] for g_ in got)
+
+
+def test_cxx_adaptor_compiles_standalone_and_geometry_dir_roundtrip(tmp_path):
+    import subprocess
+    src = tmp_path / "t.cpp"
+    src.write_text('#include "PhoxSimulator.h"\n#include "phox_npy.h"\nint main(){ SSimulator* s = nullptr; (void)s; return 0; }\n')
+    r = subprocess.run(["/usr/bin/g++", "-std=c++17", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    g = ph.geometries.sipm8x8()
+    F.save_geometry(g, str(tmp_path / "geom"))
+    back = F.load_geometry(str(tmp_path / "geom"))
+    assert (back["bnd"] == g["bnd"]).all() and (back["optical"] == g["optical"]).all() and (back["icdf"] == g["icdf"]).all()
+    assert back["bnd_names"] == g["bnd_names"]
+    assert os.path.exists(os.path.join(ROOT, "eic-opticks_b200", "apps", "PhoxPhotonFileSource"))

@@ -241,3 +241,25 @@ def test_bad_arguments_give_error_codes_not_crashes():
     with pytest.raises(ph.PhoxError):
         sim.set_config(max_record=99)
     sim.close()
+
+
+def test_cxx_file_source_driver_known_answer(tmp_path):
+    """the C++ host driver (apps/PhoxPhotonFileSource.cpp on include/PhoxSimulator.h) reproduces the
+    GPUPhotonFileSource contract: 10 file photons -> 'Opticks: NumHits:  10', hit text file with the
+    wavelengths preserved (tests/test_GPUPhotonFileSource.sh:23-118)."""
+    import subprocess
+    from eic_opticks_b200 import foundry as F
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "eic-opticks_b200", "apps", "PhoxPhotonFileSource")
+    assert os.path.exists(exe), "run __graft_entry__.build()"
+    F.save_geometry(ph.geometries.raindrop(), str(tmp_path / "geom"))
+    out = tmp_path / "opticks_hits_output.txt"
+    r = subprocess.run([exe, "-g", str(tmp_path / "geom"), "-p", os.path.join(root, "tests", "golden", "photons_file_source.txt"), "-o", str(out)],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert "Loaded 10 photons" in r.stdout and "Opticks: NumHits:  10" in r.stdout
+    lines = open(out).read().strip().split("\n")
+    assert len(lines) == 10
+    assert sorted(float(l.split()[1]) for l in lines) == [420.0] * 3 + [450.0] * 2 + [500.0] * 5
+    r2 = subprocess.run([exe, "-g", str(tmp_path / "geom")], capture_output=True, text=True, timeout=60)      # missing -p must fail
+    assert r2.returncode != 0
