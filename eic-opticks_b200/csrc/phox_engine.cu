@@ -781,8 +781,15 @@ extern "C" int phox_intersect(phox_context* ctx, const float* ray_o_tmin, const 
     sc.prim = ctx->d_prim.p; sc.nodes = ctx->d_bvh.p; sc.inst = ctx->d_inst.p;
     sc.ninst = ctx->ninst; sc.tlas_root = ctx->tlas_root; sc.accel = accel;
     const int T = 128;
+    cudaEventRecord(ctx->ev[0], ctx->stream);
     k_intersect<<<(unsigned)((nray + T - 1) / T), T, 0, ctx->stream>>>(sc, d_o, d_d, (unsigned)nray, ctx->cfg.tmax, d_out);
+    cudaEventRecord(ctx->ev[1], ctx->stream);
     cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && cudaEventSynchronize(ctx->ev[1]) == cudaSuccess) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+        ctx->stats.simulate_kernel_seconds = ms * 1e-3;          // device time of the query kernel
+    }
     if (e == cudaSuccess) e = cudaMemcpyAsync(dst_prd, d_out, (size_t)nray * 32, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(d_o); cudaFree(d_d); cudaFree(d_out);
