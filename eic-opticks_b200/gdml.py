@@ -1,0 +1,362 @@
+"""GDML -> CSGFoundry arrays + bnd/optical/icdf tables, without Geant4.
+
+Restates the translation the reference performs with Geant4 in the loop:
+
+    GDML read (G4GDMLParser: units, <define> constants/variables/expressions/matrices, <loop>)
+    -> G4 solids -> sn CSG trees            u4/U4Solid.h:494-1112   (box, orb/sphere(+rmin), tubs(+rmin, 1 % inner nudge
+                                                                      :813-821), cons(+rmin), trd, booleans with displaced
+                                                                      right-hand side u4/U4Transform.h:106-116)
+    -> structural tree + boundaries         u4/U4Tree.h:752-900, u4/U4TreeBorder.h:124-250 (omat/osur/isur/imat, implicit
+                                                                      RINDEX->NoRINDEX absorbers), u4/U4Surface.h:422-443
+    -> CSGFoundry                           CSG/CSGImport.cc:151-603 (one CSGPrim per volume, preorder, all in solid 0 -
+                                                                      sysrap/stree.h factorises only subtrees repeated
+                                                                      >= 500 times, which none of the shipped files have)
+    -> bnd / optical                        sysrap/sstandard.h:311-530, u4/U4Material.cc:632-718, u4/U4SurfaceArray.h:159-240
+    -> scintillation ICDF                   u4/U4Scint.h:406-470
+
+Geant4 itself is the third-party piece that is absent here; where its behaviour matters it is restated
+from its published algorithms: G4PhysicsVector::Value (linear interpolation, clamped),
+G4MaterialPropertiesTable::CalculateGROUPVEL, G4GDMLRead rotation convention (rotateX, rotateY, rotateZ,
+placement with the inverse), G4Scintillation's trapezoid integral of the emission spectrum.
+
+Not covered (asserts, like the reference does for phi segments u4/U4Solid.h:555-561): phi/theta segments,
+polycone, trap, ellipsoid, assemblies, replicas, NIST materials by name, instancing (FREQ_CUT 500).
+"""
+import math
+import re
+import xml.etree.ElementTree as ET
+
+import numpy as np
+
+from . import foundry as F
+from . import tables as T
+
+# Geant4 system of units (CLHEP/Units/SystemOfUnits.h): mm, ns, MeV, rad are 1
+UNITS = dict(mm=1.0, cm=10.0, m=1000.0, um=1e-3, nm=1e-6, km=1e6, rad=1.0, mrad=1e-3, deg=math.pi / 180.0, degree=math.pi / 180.0,
+             ns=1.0, s=1e9, ms=1e6, us=1e3, ps=1e-3, eV=1e-6, keV=1e-3, MeV=1.0, GeV=1e3, TeV=1e6, pi=math.pi, twopi=2 * math.pi,
+             halfpi=math.pi / 2, g=1.0, kg=1e3, mole=1.0, cm3=1000.0, m3=1e9, kelvin=1.0, K=1.0, perCent=0.01)
+MATH = {k: getattr(math, k) for k in ("sin", "cos", "tan", "asin", "acos", "atan", "atan2", "sqrt", "exp", "log", "log10", "pow", "floor", "ceil", "fabs")}
+MATH["abs"] = abs
+MATH["min"] = min
+MATH["max"] = max
+
+FINISH = dict(polished=0, polishedfrontpainted=1, polishedbackpainted=2, ground=3, groundfrontpainted=4, groundbackpainted=5)
+
+
+def strip_ptr(name):
+    """names exported by Geant4 carry 0x... pointer suffixes; the reference strips them (sstr::StripTail)"""
+    return re.sub(r"0x[0-9a-fA-F]+$", "", name or "")
+
+
+class Evaluator:
+    def __init__(self):
+        self.ns = dict(UNITS)
+        self.ns.update(MATH)
+
+    def __call__(self, expr, default=0.0):
+        if expr is None:
+            return default
+        if isinstance(expr, (int, float)):
+            return float(expr)
+        e = expr.strip()
+        if not e:
+            return default
+        e = e.replace("^", "**")
+        e = re.sub(r"\[([^\]]+)\]", r"_\1", e)           # name[i] style indexing -> name_i
+        return float(eval(e, {"__builtins__": {}}, self.ns))
+
+    def set(self, name, value):
+        self.ns[name] = value
+
+
+def rotation_matrix(rx, ry, rz):
+    """G4GDMLRead::GetRotationMatrix: rot.rotateX(x); rot.rotateY(y); rot.rotateZ(z)  (active rotations applied in
+    that order, column-vector convention) -> rot = Rz Ry Rx"""
+    cx, sx, cy, sy, cz, sz = math.cos(rx), math.sin(rx), math.cos(ry), math.sin(ry), math.cos(rz), math.sin(rz)
+    Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+    Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+    Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+    return Rz @ Ry @ Rx
+
+
+def placement_matrix(pos, rot):
+    """object transform of a placement / displaced solid as a row-vector 4x4 (u4/U4Transform.h:66-73):
+    GDML rotations are FRAME rotations, the object rotation is the inverse; p_world = p_local * M"""
+    R_obj = rotation_matrix(*rot).T                     # inverse of a rotation = transpose
+    m = np.eye(4)
+    m[:3, :3] = R_obj.T                                 # row-vector convention holds the transpose of the column-vector matrix
+    m[3, :3] = pos
+    return m
+
+
+calculate_groupvel = T.groupvel_from_rindex
+
+
+class GDML:
+    def __init__(self, path):
+        self.ev = Evaluator()
+        self.root = ET.parse(path).getroot()
+        self.matrices, self.positions, self.rotations = {}, {}, {}
+        self.materials, self.opticalsurfaces, self.solids, self.volumes = {}, {}, {}, {}
+        self.material_order, self.skins, self.borders = [], [], []
+        self._read_define(self.root.find("define"))
+        self._read_materials(self.root.find("materials"))
+        self._read_solids(self.root.find("solids"))
+        self._read_structure(self.root.find("structure"))
+        self.world = self.root.find("setup").find("world").get("ref")
+
+    # ---- define --------------------------------------------------------------------------------
+    def _lunit(self, el, default="mm"):
+        return UNITS[el.get("lunit", el.get("unit", default))]
+
+    def _vec(self, el, kind):
+        u = UNITS[el.get("unit", "mm" if kind == "position" else "rad")]
+        return tuple(self.ev(el.get(a), 0.0) * u for a in ("x", "y", "z"))
+
+    def _read_define(self, d):
+        if d is None:
+            return
+        for el in d:
+            if el.tag in ("constant", "variable", "quantity"):
+                v = self.ev(el.get("value"))
+                if el.tag == "quantity" and el.get("unit"):
+                    v *= UNITS[el.get("unit")]
+                self.ev.set(el.get("name"), v)
+            elif el.tag == "matrix":
+                coldim = int(self.ev(el.get("coldim")))
+                vals = [self.ev(t) for t in (el.get("values") or el.get("value") or "").split()]
+                self.matrices[el.get("name")] = np.array(vals, dtype=np.float64).reshape(-1, coldim)
+            elif el.tag == "position":
+                self.positions[el.get("name")] = self._vec(el, "position")
+            elif el.tag == "rotation":
+                self.rotations[el.get("name")] = self._vec(el, "rotation")
+
+    def _property(self, el):
+        """-> scalar (CONST properties) or (energy_eV ascending, values)"""
+        ref = el.get("ref")
+        if ref is None:
+            return self.ev(el.get("value"))
+        m = self.matrices[ref]
+        if m.shape[1] == 1:
+            return float(m[0, 0])
+        e = m[:, 0] / UNITS["eV"]
+        order = np.argsort(e, kind="stable")
+        return e[order], m[order, 1]
+
+    # ---- materials ---------------------------------------------------------------------------------
+    def _read_materials(self, ms):
+        for el in ms.findall("material"):
+            props = {p.get("name"): self._property(p) for p in el.findall("property")}
+            name = el.get("name")
+            self.materials[name] = props
+            self.material_order.append(name)
+
+    # ---- solids --------------------------------------------------------------------------------------
+    def _read_solids(self, ss):
+        for el in ss:
+            name = el.get("name")
+            if el.tag == "opticalsurface":
+                fin = el.get("finish", "0")
+                finish = FINISH[fin] if fin in FINISH else int(self.ev(fin))
+                self.opticalsurfaces[name] = dict(finish=finish, value=self.ev(el.get("value", "1")),
+                                                  props={p.get("name"): self._property(p) for p in el.findall("property")})
+            else:
+                self.solids[name] = el
+
+    def solid_tree(self, name):
+        """GDML solid -> foundry Leaf/Op tree in the solid's own frame (U4Solid::Convert)"""
+        el = self.solids[name]
+        lu = self._lunit(el)
+        au = UNITS[el.get("aunit", "rad")]
+        g = lambda a, d=0.0: self.ev(el.get(a), d)
+        tag = el.tag
+        if tag == "box":
+            return F.box3(g("x") * lu, g("y") * lu, g("z") * lu)
+        if tag in ("sphere", "orb"):
+            rmax = (g("rmax") if tag == "sphere" else g("r")) * lu
+            rmin = g("rmin") * lu if tag == "sphere" else 0.0
+            dphi, dtheta = g("deltaphi", 2 * math.pi / au) * au, g("deltatheta", math.pi / au) * au
+            assert dphi >= 2 * math.pi - 1e-9 and dtheta >= math.pi - 1e-9 and g("startphi") == 0 and g("starttheta") == 0, \
+                "sphere phi/theta segments are not translated (u4/U4Solid.h:555-561 asserts too)"
+            outer = F.sphere(rmax)
+            return outer if rmin <= 0 else F.difference(outer, F.sphere(rmin))
+        if tag == "tube":
+            rmax, rmin, hz = g("rmax") * lu, g("rmin") * lu, g("z") * lu / 2.0
+            assert g("deltaphi", 2 * math.pi / au) * au >= 2 * math.pi - 1e-9, "tube phi segments are not translated"
+            outer = F.cylinder(rmax, -hz, hz)
+            if rmin <= 0:
+                return outer
+            nudge = hz * 0.01                                # u4/U4Solid.h:813-821 : inner lengthened by 1 % of hz each end
+            return F.difference(outer, F.cylinder(rmin, -(hz + nudge), hz + nudge))
+        if tag == "cone":
+            hz = g("z") * lu / 2.0
+            assert g("deltaphi", 2 * math.pi / au) * au >= 2 * math.pi - 1e-9, "cone phi segments are not translated"
+            outer = F.cone(g("rmax1") * lu, -hz, g("rmax2") * lu, hz)
+            if g("rmin1") <= 0 and g("rmin2") <= 0:
+                return outer
+            nudge = hz * 0.01
+            r1, r2 = g("rmin1") * lu, g("rmin2") * lu
+            slope = (r2 - r1) / (2 * hz)
+            return F.difference(outer, F.cone(max(r1 - slope * nudge, 0.0), -(hz + nudge), max(r2 + slope * nudge, 0.0), hz + nudge))
+        if tag == "trd":
+            x1, x2, y1, y2, hz = g("x1") * lu / 2, g("x2") * lu / 2, g("y1") * lu / 2, g("y2") * lu / 2, g("z") * lu / 2
+            pl = []
+            for sgn in (1, -1):
+                n = np.array([sgn * 2 * hz, 0.0, x1 - x2]); n /= np.linalg.norm(n)
+                pl.append([n[0], n[1], n[2], n[0] * sgn * x1 + n[2] * (-hz)])
+                n = np.array([0.0, sgn * 2 * hz, y1 - y2]); n /= np.linalg.norm(n)
+                pl.append([n[0], n[1], n[2], n[1] * sgn * y1 + n[2] * (-hz)])
+            pl.append([0, 0, 1, hz]); pl.append([0, 0, -1, hz])
+            xm, ym = max(x1, x2), max(y1, y2)
+            return F.convexpolyhedron(pl, [-xm, -ym, -hz, xm, ym, hz])
+        if tag in ("subtraction", "union", "intersection"):
+            a = self.solid_tree(el.find("first").get("ref"))
+            b = self.solid_tree(el.find("second").get("ref"))
+            pos = self._inline_or_ref(el, "position")
+            rot = self._inline_or_ref(el, "rotation")
+            m = placement_matrix(pos, rot)
+            b = _place_tree(b, m)
+            return {"subtraction": F.difference, "union": F.union, "intersection": F.intersection}[tag](a, b)
+        raise NotImplementedError("GDML solid <%s> (%s) is not translated" % (tag, name))
+
+    def _inline_or_ref(self, el, kind):
+        e = el.find(kind)
+        if e is not None:
+            return self._vec(e, kind)
+        r = el.find(kind + "ref")
+        if r is not None:
+            return (self.positions if kind == "position" else self.rotations)[r.get("ref")]
+        return (0.0, 0.0, 0.0)
+
+    # ---- structure -------------------------------------------------------------------------------------
+    def _expand(self, parent):
+        """children of a volume with <loop> elements unrolled (G4GDMLRead::LoopRead)"""
+        for el in parent:
+            if el.tag == "loop":
+                var = el.get("for")
+                lo, hi, st = int(self.ev(el.get("from"))), int(self.ev(el.get("to"))), int(self.ev(el.get("step", "1")))
+                for v in range(lo, hi + 1, st):
+                    self.ev.set(var, float(v))
+                    for sub in self._expand(el):
+                        yield sub
+            else:
+                yield el
+
+    def _read_structure(self, st):
+        for el in st:
+            if el.tag == "volume":
+                phys = []
+                for ch in self._expand(el):
+                    if ch.tag != "physvol":
+                        continue
+                    name = ch.get("name", "")
+                    name = re.sub(r"\{(\w+)\}", lambda m: str(int(self.ev.ns[m.group(1)])), name)
+                    phys.append(dict(name=name, volume=ch.find("volumeref").get("ref"), pos=self._inline_or_ref(ch, "position"),
+                                     rot=self._inline_or_ref(ch, "rotation"), copynumber=int(ch.get("copynumber", "0"))))
+                aux = {a.get("auxtype"): a.get("auxvalue") for a in el.findall("auxiliary")}
+                self.volumes[el.get("name")] = dict(material=el.find("materialref").get("ref"), solid=el.find("solidref").get("ref"), phys=phys, aux=aux)
+            elif el.tag == "skinsurface":
+                self.skins.append(dict(name=el.get("name"), surface=el.get("surfaceproperty"), volume=el.find("volumeref").get("ref")))
+            elif el.tag == "bordersurface":
+                pv = [p.get("ref") for p in el.findall("physvolref")]
+                self.borders.append(dict(name=el.get("name"), surface=el.get("surfaceproperty"), pv1=pv[0], pv2=pv[1]))
+
+
+def _place_tree(t, m):
+    if isinstance(t, F.Leaf):
+        return t.placed(m)
+    if isinstance(t, F.ListNode):
+        return F.ListNode(t.typecode, [s.placed(m) for s in t.subs])
+    return F.Op(t.typecode, _place_tree(t.left, m), _place_tree(t.right, m))
+
+
+def translate(path):
+    """GDML file -> dict(foundry, bnd, optical, icdf, bnd_names, ...) in the layout of geometries.py builders"""
+    g = GDML(path)
+    bt = T.BoundaryTable()
+
+    # materials in file order (G4Material table order)
+    has_rindex = {}
+    scint = None
+    for name in g.material_order:
+        p = g.materials[name]
+        rindex = p.get("RINDEX")
+        gv = p.get("GROUPVEL")
+        if gv is None and rindex is not None and not np.isscalar(rindex):
+            gv = calculate_groupvel(*rindex)
+        bt.add_material(T.Material(strip_ptr(name), RINDEX=rindex, ABSLENGTH=p.get("ABSLENGTH"), RAYLEIGH=p.get("RAYLEIGH"),
+                                   REEMISSIONPROB=p.get("REEMISSIONPROB"), GROUPVEL=gv))
+        has_rindex[name] = rindex is not None
+        if scint is None and all(k in p for k in ("FASTCOMPONENT", "SLOWCOMPONENT", "REEMISSIONPROB")):
+            scint = (name, p["FASTCOMPONENT"], p.get("FASTTIMECONSTANT", p.get("SCINTILLATIONTIMECONSTANT1")))
+
+    # logical surfaces: border surfaces first, then skin surfaces (U4Surface::Collect)
+    def add_surface(lname, osname):
+        os_ = g.opticalsurfaces[osname]
+        pr = os_["props"]
+        bt.add_surface(T.Surface(strip_ptr(lname), REFLECTIVITY=pr.get("REFLECTIVITY"), EFFICIENCY=pr.get("EFFICIENCY"),
+                                 polished=os_["finish"] in (0, 1, 2), optical_surface_name=strip_ptr(osname), finish=os_["finish"], value=os_["value"]))
+    for b in g.borders:
+        add_surface(b["name"], b["surface"])
+    for s in g.skins:
+        add_surface(s["name"], s["surface"])
+    border_lookup = {(b["pv1"], b["pv2"]): strip_ptr(b["name"]) for b in g.borders}
+    skin_lookup = {s["volume"]: strip_ptr(s["name"]) for s in g.skins}
+
+    def find_surface(pre, post):
+        """U4Surface::Find (u4/U4Surface.h:422-443); pre/post = (pv name, lv name, mother lv name)"""
+        if pre is None or post is None:
+            return ""
+        s = border_lookup.get((pre[0], post[0]))
+        if s:
+            return s
+        entered_daughter = post[2] == pre[1]
+        order = (post[1], pre[1]) if entered_daughter else (pre[1], post[1])
+        for lv in order:
+            if lv in skin_lookup:
+                return skin_lookup[lv]
+        return ""
+
+    fd = F.Foundry()
+    fd.begin_solid("r0")
+    info = dict(prim_names=[], sensitive_prims=[])
+    implicit_added = set()
+
+    def visit(pv_name, lv_name, mother, frame):
+        """preorder walk (U4Tree::initNodes_r): mother = (pv name, lv name, its mother lv name) or None"""
+        vol = g.volumes[lv_name]
+        imat = vol["material"]
+        omat = g.volumes[mother[1]]["material"] if mother else imat
+        me = (pv_name, lv_name, mother[1] if mother else None)
+        osur = find_surface(mother, me) if mother else ""
+        isur = find_surface(me, mother) if (mother and has_rindex[imat]) else ""
+        i_r, o_r = has_rindex[imat], has_rindex[omat]
+        if not osur and o_r and not i_r and mother:            # implicit_osur (U4TreeBorder.h:110, 222-250)
+            osur = "Implicit_RINDEX_NoRINDEX_%s_%s" % (strip_ptr(mother[0]), strip_ptr(pv_name))
+        if not isur and i_r and not o_r and mother:            # implicit_isur
+            isur = "Implicit_RINDEX_NoRINDEX_%s_%s" % (strip_ptr(pv_name), strip_ptr(mother[0]))
+        for s in (osur, isur):
+            if s.startswith("Implicit_") and s not in implicit_added:
+                bt.add_surface(T.implicit_surface(s))
+                implicit_added.add(s)
+        boundary = bt.boundary(strip_ptr(omat), osur, isur, strip_ptr(imat))
+        fd.add_prim(g.solid_tree(vol["solid"]), boundary, frame, name=strip_ptr(vol["solid"]))
+        info["prim_names"].append(strip_ptr(pv_name))
+        if "SensDet" in vol["aux"]:
+            info["sensitive_prims"].append(len(info["prim_names"]) - 1)
+        for ph in vol["phys"]:
+            visit(ph["name"], ph["volume"], me, placement_matrix(ph["pos"], ph["rot"]) @ frame)
+
+    visit(g.world + "_PV", g.world, None, np.eye(4))
+    fd.end_solid()
+
+    icdf = None
+    extra = dict(gdml=g, prim_names=info["prim_names"], sensitive_prims=info["sensitive_prims"], table=bt)
+    if scint is not None:
+        name, spectrum, tau = scint
+        icdf = T.make_icdf(spectrum[0], spectrum[1])
+        extra.update(scintillator=strip_ptr(name), scintillation_time=tau)
+    bnd, optical = bt.arrays()
+    out = dict(foundry=fd.arrays(), bnd=bnd, optical=optical, icdf=icdf, bnd_names=bt.names())
+    out.update(extra)
+    return out

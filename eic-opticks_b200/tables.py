@@ -47,32 +47,31 @@ def sample(prop, default):
 
 
 def groupvel_from_rindex(energy_ev, rindex):
-    """G4MaterialPropertiesTable::CalculateGROUPVEL (Geant4 11, the dependency the reference gets
-    GROUPVEL from when a material gives only RINDEX): vg = c / (n + dn/dlogE), evaluated on bin
-    edges/centres as Geant4 does, result defined on the same energies."""
-    e = np.asarray(energy_ev, dtype=np.float64)
-    n = np.asarray(rindex, dtype=np.float64)
-    if len(e) < 2:
-        return e, np.full_like(e, C_LIGHT / n[0])
-    vg = np.zeros_like(e)
-    # first point
-    n0, n1, e0, e1 = n[0], n[1], e[0], e[1]
-    v = C_LIGHT / (n0 + (n1 - n0) / np.log(e1 / e0))
-    if v < 0 or v > C_LIGHT / n0:
-        v = C_LIGHT / n0
-    vg[0] = v
-    for i in range(2, len(e)):
-        # value at the centre of bin (i-2, i-1) ... Geant4 stores at 0.5*(E0+E1)
-        pass
-    # Geant4 places intermediate values at bin-centre energies; for the flat RINDEX tables of the
-    # shipped geometries all of them equal c/n, so the simpler node-wise formula is used here.
-    for i in range(1, len(e)):
-        n0, n1, e0, e1 = n[i - 1], n[i], e[i - 1], e[i]
-        v = C_LIGHT / (n1 + (n1 - n0) / np.log(e1 / e0))
-        if v < 0 or v > C_LIGHT / n1:
-            v = C_LIGHT / n1
-        vg[i] = v
-    return e, vg
+    """G4MaterialPropertiesTable::CalculateGROUPVEL (Geant4 11, the dependency the reference gets GROUPVEL from
+    when a material gives only RINDEX): vg = c / (n + dn/dlogE); first and last points at the end energies,
+    intermediate ones at bin mid-points; anything but 'normal dispersion' clamps to c/n."""
+    import math
+    c = C_LIGHT
+    E, n = list(np.asarray(energy_ev, dtype=np.float64)), list(np.asarray(rindex, dtype=np.float64))
+    if len(E) < 2:
+        return np.array(E), np.array([c / n[0]])
+    oe, ov = [], []
+    E0, n0, E1, n1 = E[0], n[0], E[1], n[1]
+    vg = c / (n0 + (n1 - n0) / math.log(E1 / E0))
+    if vg < 0 or vg > c / n0:
+        vg = c / n0
+    oe.append(E0); ov.append(vg)
+    for i in range(2, len(E)):
+        vg = c / (0.5 * (n0 + n1) + (n1 - n0) / math.log(E1 / E0))
+        if vg < 0 or vg > c / (0.5 * (n0 + n1)):
+            vg = c / (0.5 * (n0 + n1))
+        oe.append(0.5 * (E0 + E1)); ov.append(vg)
+        E0, n0, E1, n1 = E1, n1, E[i], n[i]
+    vg = c / (n1 + (n1 - n0) / math.log(E1 / E0))
+    if vg < 0 or vg > c / n1:
+        vg = c / n1
+    oe.append(E1); ov.append(vg)
+    return np.array(oe), np.array(ov)
 
 
 class Material:
@@ -200,20 +199,19 @@ class BoundaryTable:
 
 
 def make_icdf(energy_ev, spectrum, nx=4096, hd_factor=20):
-    """Scintillation inverse CDF texture (3, nx): wavelength as a function of the cumulative
-    probability.  Follows U4Scint (u4/U4Scint.h:406-470): the emission spectrum (vs energy) is
-    integrated to a CDF, which is inverted on nx points for the full range and, for the two
-    high-definition layers, on the lowest and highest 1/hd_factor of the probability range."""
+    """Scintillation inverse-CDF texture (3, nx), U4Scint::CreateGeant4InterpolatedInverseCDF
+    (u4/U4Scint.h:406-470): the emission spectrum (vs ascending energy) is integrated with the trapezoid
+    rule (G4Scintillation::BuildThePhysicsTable), and energy = integral.GetEnergy(u * max) is sampled at
+    u = j/nx for the full range (row 0), j/(hd*nx) (row 1) and 1 - 1/hd + j/(hd*nx) (row 2); stored as
+    wavelength = hc/energy, so wavelength DEscends with u."""
     e = np.asarray(energy_ev, dtype=np.float64)
     s = np.asarray(spectrum, dtype=np.float64)
-    # trapezoidal cumulative integral over energy, normalised
     cdf = np.concatenate([[0.0], np.cumsum(0.5 * (s[1:] + s[:-1]) * np.diff(e))])
-    cdf /= cdf[-1]
-    out = np.zeros((3, nx), dtype=np.float64)
+    mx = cdf[-1]
+    j = np.arange(nx, dtype=np.float64)
     edge = 1.0 / hd_factor if hd_factor else 0.0
-    for row, (lo, hi) in enumerate(((0.0, 1.0), (0.0, edge), (1.0 - edge, 1.0))):
-        u = lo + (hi - lo) * (np.arange(nx) / float(nx))
-        # the reference samples 1-u so that wavelength ascends with u
-        en = np.interp(1.0 - u, cdf, e)
-        out[row] = HC_EVNM / en
+    out = np.zeros((3, nx), dtype=np.float64)
+    us = (j / nx, j / (hd_factor * nx) if hd_factor else j / nx, 1.0 - edge + (j / (hd_factor * nx) if hd_factor else 0.0))
+    for row, u in enumerate(us):
+        out[row] = HC_EVNM / np.interp(u * mx, cdf, e)
     return out.astype(np.float32)

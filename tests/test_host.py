@@ -123,7 +123,8 @@ def test_boundary_table_conventions():
     k = names.index("Air/SiPMActiveSkin/SiPMActiveSkin/EntranceWindow")
     assert np.allclose(bnd[k, 2, 0, 0], [1.0, 0.0, 0.0, 0.0])                                      # sensor: detect = efficiency
     assert g["crystal_line"] == 4 * i + 3
-    assert g["icdf"].shape == (3, 4096) and (np.diff(g["icdf"][0]) >= -1e-3).all()
+    assert g["icdf"].shape == (3, 4096) and (np.diff(g["icdf"][0]) <= 1e-3).all()      # energy ascends with u, wavelength descends
+    assert abs(g["icdf"][0, 0] - 1239.84198 / 1.5) < 0.01 and g["icdf"][2, -1] < 311.0
 
 
 def test_partition_gensteps_and_shard_event():
