@@ -211,3 +211,28 @@ def boolean_zoo():
         fd.add_prim(shape, b, frame, mesh_idx=k + 2, name=name)
     fd.end_solid()
     return _finish(fd, bt, extra=dict(shape_centers=np.array(centers, dtype=np.float32), shape_names=[s[0] for s in shapes]))
+
+
+def scintillator_tank():
+    """Parity stress geometry (not a reference file): a sphere of liquid scintillator with strongly wavelength-dependent
+    RINDEX / ABSLENGTH / RAYLEIGH / REEMISSIONPROB inside an acrylic shell inside water, enclosed by a detecting skin.
+    Exercises bulk re-emission (ICDF lookups), Rayleigh scattering and texture interpolation at fractional wavelengths."""
+    bt = T.BoundaryTable()
+    en = [1.55, 2.07, 2.48, 3.10, 4.13, 6.2]
+    bt.add_material(T.Material("LS", RINDEX=(en, [1.47, 1.48, 1.49, 1.51, 1.55, 1.60]), ABSLENGTH=(en, [8000.0, 6000.0, 3000.0, 600.0, 60.0, 5.0]),
+                               RAYLEIGH=(en, [9000.0, 4000.0, 2000.0, 800.0, 300.0, 100.0]), REEMISSIONPROB=(en, [0.0, 0.1, 0.4, 0.8, 0.8, 0.6])))
+    bt.add_material(T.Material("Acrylic", RINDEX=(en, [1.48, 1.49, 1.50, 1.51, 1.53, 1.56]), ABSLENGTH=(en, [4000.0, 4000.0, 3000.0, 1000.0, 100.0, 10.0])))
+    bt.add_material(T.Material("Water", RINDEX=(en, [1.33, 1.333, 1.337, 1.343, 1.36, 1.40]), ABSLENGTH=(en, [20000.0, 30000.0, 25000.0, 9000.0, 900.0, 90.0]),
+                               RAYLEIGH=(en, [100000.0, 60000.0, 30000.0, 12000.0, 4000.0, 1000.0])))
+    bt.add_surface(T.Surface("PMTSkin", EFFICIENCY=(en, [0.02, 0.1, 0.25, 0.3, 0.15, 0.02])))
+    fd = F.Foundry()
+    fd.begin_solid("r0")
+    fd.add_prim(F.sphere(2200.0), bt.boundary("Water", "", "", "Water"), name="World")
+    fd.add_prim(F.difference(F.sphere(2000.0), F.sphere(1990.0)), bt.boundary("Water", "PMTSkin", "PMTSkin", "Water"), name="PMTShell")
+    fd.add_prim(F.sphere(1020.0), bt.boundary("Water", "", "", "Acrylic"), name="Acrylic")
+    fd.add_prim(F.sphere(1000.0), bt.boundary("Acrylic", "", "", "LS"), name="LS")
+    fd.end_solid()
+    # emission spectrum peaked at ~2.9 eV (430 nm)
+    e = np.linspace(2.0, 4.0, 41)
+    icdf = T.make_icdf(e, np.exp(-0.5 * ((e - 2.9) / 0.25) ** 2))
+    return _finish(fd, bt, icdf, extra=dict(ls_line=bt.material_line("LS"), scintillation_time=4.5))

@@ -108,3 +108,26 @@ def boolean_zoo_torch(num_photon=1_000_000):
 
 WORKLOADS = dict(sipm8x8_scint=sipm8x8_scint, raindrop_cerenkov=raindrop_cerenkov, sphere_leak_torch=sphere_leak_torch,
                  pmt_wall_torch=pmt_wall_torch, boolean_zoo_torch=boolean_zoo_torch)
+
+
+def scintillator_tank(num_photon=1_000_000, photons_per_genstep=500, seed=SEED):
+    """parity stress workload: scintillation + Cerenkov gensteps inside the LS sphere of geometries.scintillator_tank"""
+    geom = GEO.scintillator_tank()
+    rng = np.random.default_rng(seed)
+    ngs = max(1, num_photon // photons_per_genstep)
+    counts = _poisson_split(rng, num_photon, ngs)
+    r = 900.0 * rng.uniform(size=ngs) ** (1 / 3.0)
+    u = rng.normal(size=(ngs, 3)); u /= np.linalg.norm(u, axis=1)[:, None]
+    pos = u * r[:, None]
+    dirs = rng.normal(size=(ngs, 3)); dirs /= np.linalg.norm(dirs, axis=1)[:, None]
+    gs = G.scint_gensteps(pos, dirs, 1.0, counts, geom["ls_line"], geom["scintillation_time"], mean_velocity=200.0)
+    gs[:, 2, :3] = dirs * 2.0
+    gs[:, 2, 3] = 2.0
+    ck = G.cerenkov_gensteps(pos, dirs, 2.0, counts, geom["ls_line"], 1.05, 200.0, 700.0, 1.60, pre_velocity=290.0, post_velocity=288.0,
+                             mean_photons=(40.0, 38.0))
+    is_ck = rng.uniform(size=ngs) < 0.3
+    gs[is_ck] = ck[is_ck]
+    return dict(name="scintillator_tank", geom=geom, gensteps=np.ascontiguousarray(gs), input_photons=None, config=dict(), num_photon=int(counts.sum()))
+
+
+WORKLOADS["scintillator_tank"] = scintillator_tank

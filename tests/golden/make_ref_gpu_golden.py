@@ -15,7 +15,8 @@ CASES = [("sipm8x8_scint", dict(num_photon=3000, photons_per_genstep=50)),
          ("raindrop_cerenkov", dict(num_photon=2000, photons_per_genstep=100)),
          ("sphere_leak_torch", dict(num_photon=1500)),
          ("pmt_wall_torch", dict(num_photon=3000)),
-         ("boolean_zoo_torch", dict(num_photon=4000))]
+         ("boolean_zoo_torch", dict(num_photon=4000)),
+         ("scintillator_tank", dict(num_photon=4000, photons_per_genstep=100))]
 
 if __name__ == "__main__":
     out_dir = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden")
@@ -23,7 +24,7 @@ if __name__ == "__main__":
     for variant in ("debugtag", "production"):
         ref = RefGPU(variant)
         for name, kw in CASES:
-            if variant == "production" and name not in ("sipm8x8_scint", "boolean_zoo_torch"):
+            if variant == "production" and name not in ("sipm8x8_scint", "boolean_zoo_torch", "scintillator_tank"):
                 continue
             w = workloads.WORKLOADS[name](**kw)
             r = ref.simulate(w["geom"], w["gensteps"], w["input_photons"], max_bounce=w["config"].get("max_bounce", 31))

@@ -24,7 +24,8 @@ CASES = [("sipm8x8_scint", dict(num_photon=30000, photons_per_genstep=100)),
          ("raindrop_cerenkov", dict(num_photon=20000, photons_per_genstep=100)),
          ("sphere_leak_torch", dict(num_photon=10000)),
          ("pmt_wall_torch", dict(num_photon=30000, nx=20, ny=20)),
-         ("boolean_zoo_torch", dict(num_photon=40000))]
+         ("boolean_zoo_torch", dict(num_photon=40000)),
+         ("scintillator_tank", dict(num_photon=30000, photons_per_genstep=100))]      # re-emission, Rayleigh, dispersive tables
 
 
 def make_sim(w, **cfg):
