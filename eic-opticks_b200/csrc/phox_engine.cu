@@ -797,6 +797,28 @@ extern "C" int phox_intersect(phox_context* ctx, const float* ray_o_tmin, const 
     return PHOX_OK;
 }
 
+extern "C" int phox_boundary_lookup(phox_context* ctx, const float* nm, const uint32_t* line, const uint32_t* k, int64_t n, float* dst) {
+    if (!ctx) return PHOX_E_ARG;
+    if (!ctx->have_tables) return ctx->fail(PHOX_E_STATE, "phox_boundary_lookup: tables not set");
+    if (!nm || !line || !k || !dst || n <= 0) return ctx->fail(PHOX_E_ARG, "phox_boundary_lookup: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    float* d_nm = nullptr; unsigned *d_line = nullptr, *d_k = nullptr; float4* d_out = nullptr;
+    CK(cudaMalloc(&d_nm, n * 4)); CK(cudaMalloc(&d_line, n * 4)); CK(cudaMalloc(&d_k, n * 4)); CK(cudaMalloc(&d_out, n * 16));
+    CK(cudaMemcpyAsync(d_nm, nm, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_line, line, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_k, k, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    Tables tb;
+    tb.bnd_tex = ctx->bnd_tex; tb.icdf_tex = ctx->icdf_tex; tb.optical = ctx->d_optical.p;
+    tb.nx = ctx->nx; tb.ny = ctx->ny; tb.nm0 = ctx->nm0; tb.nms = ctx->nms; tb.hd_factor = ctx->hd_factor;
+    k_boundary_lookup<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(tb, d_nm, d_line, d_k, (unsigned)n, d_out);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dst, d_out, n * 16, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_nm); cudaFree(d_line); cudaFree(d_k); cudaFree(d_out);
+    if (e != cudaSuccess) return ctx->cuda_fail(e, "phox_boundary_lookup");
+    return PHOX_OK;
+}
+
 extern "C" int phox_rng_sequence(phox_context* ctx, float* dst, int64_t ni, int64_t nv, uint64_t id0, int32_t event_id) {
     if (!ctx) return PHOX_E_ARG;
     if (!dst || ni <= 0 || nv <= 0) return ctx->fail(PHOX_E_ARG, "phox_rng_sequence: bad arguments");

@@ -447,6 +447,13 @@ __global__ void k_intersect(Scene sc, const float4* __restrict__ ray_o_tmin, con
     out[i] = r;
 }
 
+// boundary texture readback (QSim.cu boundary_lookup_line role)
+__global__ void k_boundary_lookup(Tables tb, const float* __restrict__ nm, const unsigned* __restrict__ line, const unsigned* __restrict__ k,
+                                  unsigned n, float4* __restrict__ out) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = bnd_lookup(tb, nm[i], line[i], k[i]);
+}
+
 // precooked random streams (qudarap/QSim.cu:43-68)
 __global__ void k_rng_sequence(float* __restrict__ out, unsigned ni, unsigned nv, unsigned long long id0,
                                unsigned long long seed, unsigned long long element_offset) {

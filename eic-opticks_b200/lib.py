@@ -73,6 +73,7 @@ SYMBOLS = {
     "phox_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "phox_reset": (None, [C.c_void_p]),
     "phox_intersect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]),
+    "phox_boundary_lookup": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "phox_rng_sequence": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_int32]),
 }
 

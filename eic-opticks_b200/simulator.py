@@ -239,6 +239,15 @@ class Simulator:
         self._check(self.lib.phox_intersect(self.ctx, _ptr(o), _ptr(d), len(o), _ptr(out), accel))
         return out
 
+    def boundary_lookup(self, nm, line, k):
+        """hardware-texture readback of the boundary table: (n,) wavelengths, lines, payload groups -> (n,4)"""
+        nm = np.ascontiguousarray(nm, dtype=np.float32)
+        line = np.ascontiguousarray(line, dtype=np.uint32)
+        k = np.ascontiguousarray(k, dtype=np.uint32)
+        out = np.empty((len(nm), 4), dtype=np.float32)
+        self._check(self.lib.phox_boundary_lookup(self.ctx, _ptr(nm), _ptr(line), _ptr(k), len(nm), _ptr(out)))
+        return out
+
     def rng_sequence(self, ni, nv, id0=0, event_id=0):
         out = np.empty((ni, nv), dtype=np.float32)
         self._check(self.lib.phox_rng_sequence(self.ctx, _ptr(out), ni, nv, id0, event_id))

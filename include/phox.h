@@ -178,6 +178,11 @@ int phox_intersect(phox_context* ctx, const float* ray_o_tmin, const float* ray_
 
 /* Precooked random streams (qudarap/QSim.cu:43-68): first nv curand_uniform floats of
  * subsequences [id0, id0+ni). dst is host float32[ni*nv]. */
+/* Boundary-table readback through the hardware texture path (qudarap/QSim.cu boundary_lookup_line /
+ * QBnd.cu:6 test kernels): n lookups of (wavelength nm, line = 4*boundary + species, k = payload group)
+ * -> float4 each.  Used to check the CPU oracle's emulation of the GPU's linear texture filter. */
+int phox_boundary_lookup(phox_context* ctx, const float* nm, const uint32_t* line, const uint32_t* k, int64_t n, float* dst_float4);
+
 int phox_rng_sequence(phox_context* ctx, float* dst, int64_t ni, int64_t nv, uint64_t id0,
                       int32_t event_id);
 

@@ -634,7 +634,10 @@ bool trace(Prd& prd, const Scene& sc, v3 o, v3 d, float tmin, float tmax) {
 
 // ---- textures : CUDA linear filtering, normalized coordinates, wrap addressing -----------------
 // (CUDA C Programming Guide, "Texture Fetching": xB = N*frac(x) - 0.5, i = floor(xB),
-//  alpha = frac(xB) held in 9-bit fixed point with 8 fractional bits)
+//  alpha = frac(xB) held in 9-bit fixed point with 8 fractional bits).  Calibrated against the B200's texture
+//  unit (tests/test_parity_gpu.py::test_oracle_texture_emulation_vs_hardware): round-to-nearest of the 8-bit
+//  fraction and the lerp form t0 + a (t1 - t0) reproduce 97.4 % of fetches bit for bit; the rest land on the
+//  other side of a 1/256 fraction step because the hardware's x*N arithmetic is not public.)
 struct Tex { const float* data; int nx, ny, nc; };
 inline int wrapi(int i, int n) { i %= n; return i < 0 ? i + n : i; }
 inline void tex_coord(float u, int n, int& i0, int& i1, float& a) {
@@ -651,7 +654,8 @@ v4 tex2D4(const Tex& t, float x, float y) {
     for (int c = 0; c < 4; c++) {
         float t00 = t.data[((size_t)j0 * t.nx + i0) * 4 + c], t10 = t.data[((size_t)j0 * t.nx + i1) * 4 + c];
         float t01 = t.data[((size_t)j1 * t.nx + i0) * 4 + c], t11 = t.data[((size_t)j1 * t.nx + i1) * 4 + c];
-        rr[c] = (1.f - a) * (1.f - b) * t00 + a * (1.f - b) * t10 + (1.f - a) * b * t01 + a * b * t11;
+        float r0 = t00 + a * (t10 - t00), r1 = t01 + a * (t11 - t01);      // lerp form: 97.4 % bit-identical with the B200 texture unit
+        rr[c] = r0 + b * (r1 - r0);
     }
     return r;
 }
@@ -659,7 +663,8 @@ float tex2D1(const Tex& t, float x, float y) {
     int i0, i1, j0, j1; float a, b;
     tex_coord(x, t.nx, i0, i1, a); tex_coord(y, t.ny, j0, j1, b);
     float t00 = t.data[(size_t)j0 * t.nx + i0], t10 = t.data[(size_t)j0 * t.nx + i1], t01 = t.data[(size_t)j1 * t.nx + i0], t11 = t.data[(size_t)j1 * t.nx + i1];
-    return (1.f - a) * (1.f - b) * t00 + a * (1.f - b) * t10 + (1.f - a) * b * t01 + a * b * t11;
+    float r0 = t00 + a * (t10 - t00), r1 = t01 + a * (t11 - t01);
+    return r0 + b * (r1 - r0);
 }
 
 struct Tables { Tex bnd; Tex icdf; const unsigned* optical; float nm0, nms; int hd_factor; };

@@ -92,7 +92,10 @@ def test_photon_by_photon_vs_cpu_oracle(name, kw):
     sim = make_sim(w, event_mode=ph.MODE_HITPHOTONSEQ)
     hits = sim.simulate_np(w["gensteps"], 0, w["input_photons"])
     p, seq = sim.get_array("photon"), sim.get_array("seq")
-    check_against(name + "/oracle", p, seq, orc["photon"], orc["seq"], min_same=0.995)
+    # dispersive tables: the oracle's emulation of the texture filter matches the hardware bit for bit on 97.4 % of
+    # fetches (see test_oracle_texture_emulation_vs_hardware); the others move lengths by up to 1/256 of a table step
+    fq = 0.98 if name == "scintillator_tank" else 0.9995
+    check_against(name + "/oracle", p, seq, orc["photon"], orc["seq"], min_same=0.99 if name == "scintillator_tank" else 0.995, float_q=fq)
     assert abs(len(hits) - orc["nhit"]) <= max(5, 0.005 * len(p))
     sim.close()
 
@@ -264,3 +267,27 @@ def test_cxx_file_source_driver_known_answer(tmp_path):
     assert sorted(float(l.split()[1]) for l in lines) == [420.0] * 3 + [450.0] * 2 + [500.0] * 5
     r2 = subprocess.run([exe, "-g", str(tmp_path / "geom")], capture_output=True, text=True, timeout=60)      # missing -p must fail
     assert r2.returncode != 0
+
+
+def test_oracle_texture_emulation_vs_hardware():
+    """the CPU oracle's restatement of CUDA linear texture filtering (8-bit fraction, lerp form) against the
+    B200 texture unit on a dispersive boundary table at random fractional wavelengths"""
+    g = ph.geometries.scintillator_tank()
+    sim = ph.Simulator.Create(g["foundry"], g["bnd"], g["optical"], g["icdf"])
+    rng = np.random.default_rng(0)
+    n = 100000
+    nm = rng.uniform(60, 820, n).astype(np.float32)
+    nm[:1000] = np.round(nm[:1000])
+    line = rng.integers(0, 4 * len(g["bnd_names"]), n).astype(np.uint32)
+    k = rng.integers(0, 2, n).astype(np.uint32)
+    hw = sim.boundary_lookup(nm, line, k)
+    tex = np.ascontiguousarray(g["bnd"].reshape(-1, 761, 4), dtype=np.float32)
+    x = ((nm - np.float32(60.0)) / np.float32(1.0) + np.float32(0.5)) / np.float32(761)
+    y = ((2 * line + k).astype(np.float32) + np.float32(0.5)) / np.float32(tex.shape[0])
+    emu = Oracle().tex2d4(tex.reshape(tex.shape[0], -1), np.stack([x, y], axis=1))
+    same = (emu.view(np.uint32) == hw.view(np.uint32)).all(axis=1)
+    rel = np.abs(emu - hw) / np.maximum(np.abs(hw), 1e-6)
+    assert same.mean() > 0.95, same.mean()
+    assert np.quantile(rel, 0.999) < 1e-4 and rel.max() < 0.03
+    assert same[:1000].all()                        # integer wavelengths hit table samples exactly
+    sim.close()
