@@ -284,7 +284,7 @@ def test_oracle_texture_emulation_vs_hardware():
     tex = np.ascontiguousarray(g["bnd"].reshape(-1, 761, 4), dtype=np.float32)
     x = ((nm - np.float32(60.0)) / np.float32(1.0) + np.float32(0.5)) / np.float32(761)
     y = ((2 * line + k).astype(np.float32) + np.float32(0.5)) / np.float32(tex.shape[0])
-    emu = Oracle().tex2d4(tex.reshape(tex.shape[0], -1), np.stack([x, y], axis=1))
+    emu = Oracle().tex2d4(tex, np.stack([x, y], axis=1))               # tex is (ny, nx, 4)
     same = (emu.view(np.uint32) == hw.view(np.uint32)).all(axis=1)
     rel = np.abs(emu - hw) / np.maximum(np.abs(hw), 1e-6)
     assert same.mean() > 0.95, same.mean()
