@@ -77,7 +77,7 @@ class ClockSampler:
                 self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
             except Exception:
                 pass
-            self.stop_flag.wait(0.02)
+            self.stop_flag.wait(0.1)
 
     def start(self):
         if self.nv is None:

@@ -17,7 +17,10 @@
 #include "phox_philox.cuh"
 #include "phox_csg.cuh"
 #ifndef PHOX_SIM_MIN_BLOCKS
-#define PHOX_SIM_MIN_BLOCKS 12     // 40 registers, 48 warps/SM: the loop is latency bound, occupancy beats spill-free code (profiles/)
+#define PHOX_SIM_MIN_BLOCKS 8      // 64 registers, 32 warps/SM: the loop is latency bound, occupancy beats spill-free code (profiles/)
+#endif
+#ifndef PHOX_HOT_LEAF
+#define PHOX_HOT_LEAF 0            // 0: one out-of-line copy of the CSG leaf code serves every site (instruction-fetch bound kernel)
 #endif
 #include "phox_bvh.cuh"
 #include "phox_physics.cuh"
@@ -164,7 +167,11 @@ PHOX_D void traverse_bvh(Nearest& best, const Scene& sc, float tmin, const float
             float4 p0 = __ldg(sc.prim + 4 * prim_idx);
             const float4* nroot = sc.geo.node + 4 * __float_as_int(p0.y);
             float4 is = make_float4(0.f, 0.f, 0.f, 0.f);
+#if PHOX_HOT_LEAF
             if (intersect_prim(is, nroot, sc.geo, tmin, o, d)) keep_nearest(best, is, prim_idx, inst_idx, tmin);
+#else
+            if (intersect_prim_cold(is, nroot, sc.geo, tmin, o, d)) keep_nearest(best, is, prim_idx, inst_idx, tmin);
+#endif
         }
         cur = pop();
     }

@@ -27,7 +27,9 @@ struct Philox {
     uint32_t key_lo, key_hi;
     uint32_t pos;        // next draw, 0..7 into (a,b); 8 = both blocks used up
 
-    static __device__ __forceinline__ uint4 block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+    // Out of line on purpose: uniform() is expanded at ~30 draw sites and each would otherwise carry its own
+    // copy of the 10 rounds; the simulate kernel is instruction-fetch bound (profiles/), so code size matters.
+    static __device__ __noinline__ uint4 block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
         constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
         for (int r = 0; r < 10; r++) {

@@ -314,7 +314,8 @@ PHOX_D void generate_carrier(PhotonState& p, const Genstep& gs, unsigned long lo
 }
 
 // qsim::generate_photon : input photons are indexed by the absolute photon id like the reference
-PHOX_D void generate_photon(PhotonState& p, Philox& rng, const Genstep& gs, const Tables& tb,
+// out of line: runs once per photon, must not sit in the instruction stream of the bounce loop
+__device__ __noinline__ void generate_photon(PhotonState& p, Philox& rng, const Genstep& gs, const Tables& tb,
                             const Photon* input_photon, unsigned long long input_base, unsigned long long photon_id) {
     switch (gs.gencode()) {
         case GS_CARRIER: generate_carrier(p, gs, photon_id); break;
