@@ -222,7 +222,7 @@ __device__ __noinline__ bool trace(HitInfo& h, const Scene& sc, const float3& o,
         n = xform_normal(r0, r1, r2, best.n);       // object -> world uses the inverse-transpose
     }
     float3 lpos = oo + best.t * dd;
-    h.normal = n;
+    h.normal = normalize(n);        // the raygen normalises every normal (CSGOptiX7.cu:470-471); done here so that one compiled body serves all kernels
     h.t = best.t;
     h.lposcost = lpos.z / sqrtf(dot(lpos, lpos));
     h.lposfphi = want_fphi ? (atan2f(lpos.y, lpos.x) + kPi) / (2.0f * kPi) : 0.f;     // only the prd debug array reads it
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(kSimThreads, PHOX_SIM_MIN_BLOCKS) k_simulate(c
                 }
                 if (!ok) finished = true;                       // photon left the world
                 else {
-                    h.normal = normalize(h.normal);
+                    // (the normal was normalised at the end of trace(), CSGOptiX7.cu:470-471)
                     if (DEBUG) {
                         if (P.prd && bounce < P.max_record) {
                             Prd r;

@@ -382,7 +382,8 @@ PHOX_D void rayleigh_scatter(PhotonState& p, Philox& rng) {
 
 // One bounce: the photon has a ray hit `h` (normal normalised, world frame).  Returns the flow
 // command; on BREAK the photon is finished.  `burn` selects the DEBUG_TAG consumption pattern.
-PHOX_D int propagate(PhotonState& p, Philox& rng, const HitInfo& h, const Tables& tb, bool burn) {
+// out of line: ONE compiled body for every kernel instantiation, so event modes cannot differ by FMA contraction
+__device__ __noinline__ int propagate(PhotonState& p, Philox& rng, const HitInfo& h, const Tables& tb, bool burn) {
     const unsigned boundary = h.boundary();
     const float3 normal = h.normal;
     float cosTheta = dot(p.mom, normal);

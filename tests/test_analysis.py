@@ -1,0 +1,41 @@
+"""history tables / chi2 / event directories on CPU-oracle events."""
+import numpy as np
+
+from eic_opticks_b200 import analysis as A, workloads
+from _ref import Oracle
+
+
+def test_seqhis_labels_and_table():
+    seq = np.zeros((5, 2, 2), dtype=np.uint64)
+    seq[:3, 0, 0] = 0x7c3          # TO BT SD
+    seq[3:, 0, 0] = 0x83           # TO SA
+    t = A.seqhis_table(seq)
+    assert t[0][:2] == ("TO BT SD", 3) and t[1][:2] == ("TO SA", 2)
+    s17 = (0x3 | sum(0xA << (4 * k) for k in range(1, 16)), 0xA)    # 17 steps spill into the second word
+    assert A.seqhis_label(s17).split() == ["TO"] + ["SR"] * 16
+
+
+def test_chi2_consistent_between_rng_modes_and_inconsistent_when_physics_changes(tmp_path):
+    orc = Oracle()
+    w = workloads.scintillator_tank(num_photon=40000, photons_per_genstep=200)
+    a = orc.simulate(w["geom"], w["gensteps"], debug_tag=True)
+    b = orc.simulate(w["geom"], w["gensteps"], debug_tag=False)          # different random streams, same physics
+    chi2, ndf, rows = A.chi2_histories(a["seq"], b["seq"])
+    assert ndf > 10 and chi2 / ndf < 2.0, (chi2, ndf)
+    # change the physics (truncate histories at 2 bounces): the table must disagree
+    c = orc.simulate(w["geom"], w["gensteps"], debug_tag=True, max_bounce=2)
+    chi2c, ndfc, _ = A.chi2_histories(a["seq"], c["seq"])
+    assert chi2c / ndfc > 10.0
+    # the same event compared with itself
+    assert A.chi2_histories(a["seq"], a["seq"])[0] == 0.0
+    d = A.save_event(str(tmp_path), 0, dict(photon=a["photon"], seq=a["seq"], record=a["record"], genstep=w["gensteps"]), meta=dict(rng="DEBUG_TAG"))
+    back = A.load_event(str(tmp_path), 0)
+    assert (back["seq"] == a["seq"]).all() and back["photon"].shape == (40000, 4, 4) and back["domain"].shape == (2, 4, 4)
+    assert d.endswith("A000")
+
+
+def test_rng_sequence_file_naming(tmp_path):
+    u = Oracle().rng_sequence(100, 256, 0)
+    p = A.save_rng_sequence(str(tmp_path), u)
+    assert p.endswith("rng_sequence_f_ni100_nj16_nk16_tranche100/rng_sequence_f_ni100_nj16_nk16_ioffset000000.npy")
+    assert np.load(p).shape == (100, 16, 16)
