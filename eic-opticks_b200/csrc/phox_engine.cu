@@ -91,6 +91,9 @@ struct phox_context {
     DevBuf<Seq> d_seq;
     DevBuf<Prd> d_prd;
     DevBuf<unsigned> d_block_hits;
+    DevBuf<unsigned> d_active[2], d_ndraw, d_wave_count;        // wavefront form: live-photon lists, draw counts, list lengths
+    DevBuf<Prd> d_wave_hits;
+    int wave_grid[3][2] = {{0, 0}, {0, 0}, {0, 0}};             // persistent grid sizes of generate/trace/propagate, <false/true>
     DevBuf<unsigned long long> d_block_off;
     DevBuf<unsigned long long> d_counters;     // [0] rays, [1] hit total of the launch
     unsigned long long* h_counters = nullptr;  // pinned mirror
@@ -115,6 +118,11 @@ struct phox_context {
         cudaError_t _e = (call);                                   \
         if (_e != cudaSuccess) return ctx->cuda_fail(_e, #call);   \
     } while (0)
+
+// what PHOX_KERNEL_AUTO resolves to (the faster form on the north-star workload, see DESIGN.md / profiles/)
+#ifndef PHOX_KERNEL_AUTO_CHOICE
+#define PHOX_KERNEL_AUTO_CHOICE PHOX_KERNEL_WAVEFRONT
+#endif
 
 extern "C" void phox_default_config(phox_config* c) {
     if (!c) return;
@@ -175,7 +183,19 @@ extern "C" phox_context* phox_create(int device) {
                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_simulate<false>, kSimThreads, 0);
         if (e != cudaSuccess || per_sm < 1) per_sm = 1;
         ctx->sim_grid[dbg] = per_sm * prop.multiProcessorCount;
+        int w[3] = {0, 0, 0};
+        if (dbg) {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[0], k_wf_generate<true>, kWaveThreads, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[1], k_wf_trace<true>, kWaveThreads, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[2], k_wf_propagate<true>, kWaveThreads, 0);
+        } else {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[0], k_wf_generate<false>, kWaveThreads, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[1], k_wf_trace<false>, kWaveThreads, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[2], k_wf_propagate<false>, kWaveThreads, 0);
+        }
+        for (int k = 0; k < 3; k++) ctx->wave_grid[k][dbg] = std::max(w[k], 1) * prop.multiProcessorCount;
     }
+    cudaGetLastError();
     char buf[256];
     std::snprintf(buf, sizeof(buf), "phox: B200-native simulate engine on device %d (%s, sm_%d%d, %d SMs, %.1f GB)", device, prop.name,
                   prop.major, prop.minor, prop.multiProcessorCount, ctx->vram_total / 1e9);
@@ -203,6 +223,7 @@ extern "C" void phox_destroy(phox_context* ctx) {
     ctx->d_genstep.release(); ctx->d_prefix.release(); ctx->d_input.release(); ctx->d_photon.release();
     ctx->d_record.release(); ctx->d_hit.release(); ctx->d_seq.release(); ctx->d_prd.release();
     ctx->d_block_hits.release(); ctx->d_block_off.release(); ctx->d_counters.release();
+    ctx->d_active[0].release(); ctx->d_active[1].release(); ctx->d_ndraw.release(); ctx->d_wave_count.release(); ctx->d_wave_hits.release();
     bvh_scratch_free(ctx->bvh_scratch);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     for (int k = 0; k < 4; k++) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
@@ -444,6 +465,7 @@ extern "C" int phox_set_config(phox_context* ctx, const phox_config* cfg) {
     if (cfg->max_record < 0 || cfg->max_record > 32) return ctx->fail(PHOX_E_ARG, "phox_set_config: max_record must be 0..32 (sseq::SLOTS)");
     if (cfg->event_mode < PHOX_MODE_MINIMAL || cfg->event_mode > PHOX_MODE_DEBUGHEAVY) return ctx->fail(PHOX_E_ARG, "phox_set_config: unknown event_mode");
     if (cfg->max_slot < 0) return ctx->fail(PHOX_E_ARG, "phox_set_config: max_slot < 0");
+    if (cfg->kernel_mode > PHOX_KERNEL_WAVEFRONT) return ctx->fail(PHOX_E_ARG, "phox_set_config: unknown kernel_mode");
     ctx->cfg = *cfg;
     return PHOX_OK;
 }
@@ -502,6 +524,9 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
     if (mode_keeps_seq(mode)) CK(ctx->d_seq.reserve((size_t)n));
     if (mode_keeps_record(mode)) CK(ctx->d_record.reserve((size_t)n * c.max_record));
     if (mode_keeps_prd(mode)) CK(ctx->d_prd.reserve((size_t)n * c.max_record));
+    // record / prd slots past the end of a history read as zero (debug modes only, so not on the production path)
+    if (mode_keeps_record(mode) && c.max_record) CK(cudaMemsetAsync(ctx->d_record.p, 0, (size_t)n * c.max_record * sizeof(Photon), ctx->stream));
+    if (mode_keeps_prd(mode) && c.max_record) CK(cudaMemsetAsync(ctx->d_prd.p, 0, (size_t)n * c.max_record * sizeof(Prd), ctx->stream));
 
     SimParams P;
     std::memset(&P, 0, sizeof(P));
@@ -526,15 +551,50 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
     P.seed = c.rng_seed; P.rng_offset = c.rng_offset; P.skipahead = c.skipahead_event_offset;
     P.burn = c.rng_mode == PHOX_RNG_DEBUG_TAG ? 1 : 0;
 
-    CK(cudaMemsetAsync(ctx->d_counters.p + 3, 0, sizeof(unsigned long long), ctx->stream));
-    // persistent grid: every SM gets as many resident blocks as the kernel's registers allow
-    int sim_blocks = ctx->sim_grid[dbg ? 1 : 0];
-    sim_blocks = (int)std::min<int64_t>(sim_blocks, (n + kSimThreads - 1) / kSimThreads);
-    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-    if (dbg) k_simulate<true><<<sim_blocks, kSimThreads, 0, ctx->stream>>>(P);
-    else k_simulate<false><<<sim_blocks, kSimThreads, 0, ctx->stream>>>(P);
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    const bool wavefront = (c.kernel_mode == PHOX_KERNEL_AUTO ? PHOX_KERNEL_AUTO_CHOICE : c.kernel_mode) == PHOX_KERNEL_WAVEFRONT;
+    if (!wavefront) {
+        CK(cudaMemsetAsync(ctx->d_counters.p + 3, 0, sizeof(unsigned long long), ctx->stream));
+        // persistent grid: every SM gets as many resident blocks as the kernel's registers allow
+        int sim_blocks = ctx->sim_grid[dbg ? 1 : 0];
+        sim_blocks = (int)std::min<int64_t>(sim_blocks, (n + kSimThreads - 1) / kSimThreads);
+        CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+        if (dbg) k_simulate<true><<<sim_blocks, kSimThreads, 0, ctx->stream>>>(P);
+        else k_simulate<false><<<sim_blocks, kSimThreads, 0, ctx->stream>>>(P);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+        ctx->stats.num_kernel += 1;
+    } else {
+        // wavefront: generate, then per bounce a trace kernel and a physics kernel over the live list;
+        // list lengths stay on the device, so there is no host synchronisation inside the loop
+        CK(ctx->d_active[0].reserve((size_t)n)); CK(ctx->d_active[1].reserve((size_t)n));
+        CK(ctx->d_ndraw.reserve((size_t)n)); CK(ctx->d_wave_hits.reserve((size_t)n));
+        CK(ctx->d_wave_count.reserve((size_t)c.max_bounce + 2));
+        CK(cudaMemsetAsync(ctx->d_wave_count.p, 0, ((size_t)c.max_bounce + 2) * sizeof(unsigned), ctx->stream));
+        ctx->h_counters[3] = (unsigned long long)n;              // pinned staging for the first list length (low word)
+        CK(cudaMemcpyAsync(ctx->d_wave_count.p, &ctx->h_counters[3], sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+        WaveParams W;
+        std::memset(&W, 0, sizeof(W));
+        W.sim = P;
+        W.ndraw = ctx->d_ndraw.p; W.hits = ctx->d_wave_hits.p;
+        const int d = dbg ? 1 : 0;
+        int64_t need = (n + kWaveThreads - 1) / kWaveThreads;
+        auto grid = [&](int k) { return (unsigned)std::max<int64_t>(1, std::min<int64_t>(ctx->wave_grid[k][d], need)); };
+        CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+        W.active_out = ctx->d_active[0].p;
+        if (dbg) k_wf_generate<true><<<grid(0), kWaveThreads, 0, ctx->stream>>>(W);
+        else k_wf_generate<false><<<grid(0), kWaveThreads, 0, ctx->stream>>>(W);
+        CK(cudaGetLastError());
+        for (int b = 0; b < c.max_bounce; b++) {
+            W.active_in = ctx->d_active[b & 1].p; W.active_out = ctx->d_active[(b + 1) & 1].p;
+            W.count_in = ctx->d_wave_count.p + b; W.count_out = ctx->d_wave_count.p + b + 1;
+            W.bounce = b;
+            if (dbg) { k_wf_trace<true><<<grid(1), kWaveThreads, 0, ctx->stream>>>(W); k_wf_propagate<true><<<grid(2), kWaveThreads, 0, ctx->stream>>>(W); }
+            else { k_wf_trace<false><<<grid(1), kWaveThreads, 0, ctx->stream>>>(W); k_wf_propagate<false><<<grid(2), kWaveThreads, 0, ctx->stream>>>(W); }
+        }
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+        ctx->stats.num_kernel += 1 + 2 * (uint64_t)c.max_bounce;
+    }
     k_hit_count<<<nblock, T, 0, ctx->stream>>>(ctx->d_photon.p, (unsigned)n, c.hit_mask, ctx->d_block_hits.p);
     CK(cudaGetLastError());
     k_hit_offsets<<<1, 1024, 0, ctx->stream>>>(ctx->d_block_hits.p, nblock, ctx->d_block_off.p, ctx->d_counters.p + 1);

@@ -350,6 +350,157 @@ __global__ void __launch_bounds__(kSimThreads, PHOX_SIM_MIN_BLOCKS) k_simulate(c
     if (lane == 0 && nray) atomicAdd(P.counters, (unsigned long long)nray);
 }
 
+// ---- wavefront form of the same loop ----------------------------------------------------------------
+// One bounce = two small kernels over the list of photons still alive: k_wf_trace (ray -> hit record)
+// and k_wf_propagate (hit record -> physics, survivors appended to the next list).  Photon state lives in
+// the output photon array itself (64 B per slot, final as soon as the photon stops), the random stream
+// as a 4-byte draw count (Philox is counter based), the hit as a 32 B quad2 indexed by list position.
+// Compared with the persistent kernel each phase has a small instruction footprint and few live
+// registers, every lane works on a live photon, and because survivors are appended block by block in
+// list order, the photons of one genstep - which mostly sit in the same volume - stay together in a
+// warp bounce after bounce (coherent traversal).  trace() and propagate() are the same out-of-line
+// bodies the persistent kernel calls, so both forms give bit-identical results.
+struct WaveParams {
+    SimParams sim;
+    unsigned* active_in;            // photon slots alive at this bounce
+    unsigned* active_out;           // survivors (next bounce)
+    const unsigned* count_in;       // device-side length of active_in
+    unsigned* count_out;            // device-side length of active_out (zeroed beforehand)
+    unsigned* ndraw;                // per slot: uniforms consumed so far
+    Seq* seq_state;                 // per slot history being built (debug modes)
+    Prd* hits;                      // per list position: hit of this bounce
+    int bounce;                     // bounces done so far by every photon of active_in
+};
+
+#ifndef PHOX_WF_TRACE_MIN_BLOCKS
+#define PHOX_WF_TRACE_MIN_BLOCKS 4      // resident 256-thread blocks per SM the trace kernel is compiled for (register cap 65536/(256*N))
+#endif
+constexpr int kWaveThreads = 256;
+constexpr unsigned kWaveNoHit = 0xffffffffu;    // prim_boundary of a list entry whose photon is final (miss or time over)
+
+template <bool DEBUG>
+__global__ void __launch_bounds__(kWaveThreads) k_wf_generate(const __grid_constant__ WaveParams W) {
+    const SimParams& P = W.sim;
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < P.num_photon; idx += gridDim.x * blockDim.x) {
+        int lo = 0, hi = P.num_genstep;
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (__ldg(P.gs_prefix + mid) <= (unsigned long long)idx) lo = mid; else hi = mid;
+        }
+        Genstep gs;
+        {
+            const float4* src = reinterpret_cast<const float4*>(P.genstep + lo);
+            float4* dst = reinterpret_cast<float4*>(&gs);
+#pragma unroll
+            for (int k = 0; k < 6; k++) dst[k] = __ldg(src + k);
+        }
+        unsigned long long photon_idx = P.photon_offset + idx;
+        unsigned long long base = P.rng_offset + P.skipahead * (unsigned long long)P.event_index;
+        Philox rng;
+        rng.init(P.seed, photon_idx, base);
+        PhotonState p;
+        generate_photon(p, rng, gs, P.tables, P.input_photon, P.input_base, photon_idx);
+        p.store(P.photon + idx);
+        W.ndraw[idx] = rng.consumed(base);
+        W.active_out[idx] = idx;
+        if (DEBUG) {
+            Seq seq;
+            seq.seqhis[0] = seq.seqhis[1] = seq.seqbnd[0] = seq.seqbnd[1] = 0ull;
+            if (P.record && 0 < P.max_record) p.store(P.record + (size_t)P.max_record * idx);
+            if (P.seq) { seq_add(seq, 0u, p.flag(), p.boundary()); P.seq[idx] = seq; }
+        }
+    }
+}
+
+template <bool DEBUG>
+__global__ void __launch_bounds__(kWaveThreads, PHOX_WF_TRACE_MIN_BLOCKS) k_wf_trace(const __grid_constant__ WaveParams W) {
+    const SimParams& P = W.sim;
+    const unsigned count = *W.count_in;
+    unsigned nray = 0;
+    for (unsigned a = blockIdx.x * blockDim.x + threadIdx.x; a < count; a += gridDim.x * blockDim.x) {
+        unsigned idx = W.active_in[a];
+        const float4* ph = reinterpret_cast<const float4*>(P.photon + idx);
+        float4 q0 = ph[0], q1 = ph[1];
+        unsigned obf = __float_as_uint(ph[3].x);
+        Prd r;
+        r.nx = r.ny = r.nz = 0.f; r.t = -1.f; r.lposcost = r.lposfphi = 0.f; r.iindex_identity = 0xffffffffu; r.prim_boundary = kWaveNoHit;
+        if (q0.w < P.max_time) {                                // else the while-condition of the raygen loop fails: photon is final
+            float tmin = (obf & P.eps0_mask) ? P.tmin0 : P.tmin;
+            float3 o = f3(q0.x, q0.y, q0.z), d = f3(q1.x, q1.y, q1.z);
+            HitInfo h;
+            bool ok = trace(h, P.scene, o, d, tmin, P.tmax, DEBUG && P.prd != nullptr);
+            nray++;
+            if (P.refine && ok) {
+                float t_approx = 0.99f * h.t;
+                if (t_approx > P.refine_distance) {
+                    float3 closer = o + t_approx * d;
+                    ok = trace(h, P.scene, closer, d, tmin, P.tmax, DEBUG && P.prd != nullptr);
+                    nray++;
+                    h.t += t_approx;
+                }
+            }
+            if (ok) {
+                r.nx = h.normal.x; r.ny = h.normal.y; r.nz = h.normal.z; r.t = h.t;
+                r.lposcost = h.lposcost; r.lposfphi = h.lposfphi;
+                r.iindex_identity = h.iindex_identity; r.prim_boundary = h.prim_boundary;
+                if (DEBUG) { if (P.prd && W.bounce < P.max_record) P.prd[(size_t)P.max_record * idx + W.bounce] = r; }
+            }
+        }
+        W.hits[a] = r;
+    }
+    for (int off = 16; off > 0; off >>= 1) nray += __shfl_down_sync(0xffffffffu, nray, off);
+    if ((threadIdx.x & 31u) == 0 && nray) atomicAdd(P.counters, (unsigned long long)nray);
+}
+
+template <bool DEBUG>
+__global__ void __launch_bounds__(kWaveThreads) k_wf_propagate(const __grid_constant__ WaveParams W) {
+    __shared__ unsigned s_warp[kWaveThreads / 32];
+    __shared__ unsigned s_base;
+    const SimParams& P = W.sim;
+    const unsigned count = *W.count_in;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (unsigned base_a = blockIdx.x * blockDim.x; base_a < count; base_a += gridDim.x * blockDim.x) {
+        unsigned a = base_a + threadIdx.x;
+        bool survive = false;
+        unsigned idx = 0;
+        if (a < count) {
+            idx = W.active_in[a];
+            Prd r = W.hits[a];
+            if (r.prim_boundary != kWaveNoHit) {            // a miss (or time over) leaves the photon as it is: final
+                PhotonState p;
+                p.load_rw(P.photon + idx);
+                unsigned long long base = P.rng_offset + P.skipahead * (unsigned long long)P.event_index;
+                Philox rng;
+                rng.init(P.seed, P.photon_offset + idx, base + W.ndraw[idx]);
+                HitInfo h;
+                h.normal = f3(r.nx, r.ny, r.nz); h.t = r.t; h.lposcost = r.lposcost; h.lposfphi = r.lposfphi;
+                h.iindex_identity = r.iindex_identity; h.prim_boundary = r.prim_boundary;
+                int command = propagate(p, rng, h, P.tables, P.burn != 0);
+                int bounce = W.bounce + 1;
+                p.store(P.photon + idx);
+                W.ndraw[idx] = rng.consumed(base);
+                if (DEBUG) {
+                    if (P.record && bounce < P.max_record) p.store(P.record + (size_t)P.max_record * idx + bounce);
+                    if (P.seq) { Seq seq = P.seq[idx]; seq_add(seq, (unsigned)bounce, p.flag(), p.boundary()); P.seq[idx] = seq; }
+                }
+                survive = !(command == FLOW_BREAK) && bounce < P.max_bounce && p.time < P.max_time;
+            }
+        }
+        // append the survivors of this chunk to the next list, in order within the chunk
+        unsigned ballot = __ballot_sync(0xffffffffu, survive);
+        if (lane == 0) s_warp[warp] = __popc(ballot);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned tot = 0;
+            for (int w = 0; w < kWaveThreads / 32; w++) { unsigned c = s_warp[w]; s_warp[w] = tot; tot += c; }
+            s_base = tot ? atomicAdd(W.count_out, tot) : 0u;
+        }
+        __syncthreads();
+        if (survive) W.active_out[s_base + s_warp[warp] + __popc(ballot & ((1u << lane) - 1u))] = idx;
+        __syncthreads();
+    }
+}
+
 // hits per tile of kHitTile photons (reads only the flagmask word of each photon)
 constexpr int kHitTile = 128;
 __global__ void __launch_bounds__(kHitTile) k_hit_count(const Photon* __restrict__ photon, unsigned num_photon, unsigned hit_mask,

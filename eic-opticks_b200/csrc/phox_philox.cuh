@@ -79,6 +79,13 @@ struct Philox {
         return r;
     }
 
+    // uniforms handed out so far, counted from element offset `base` (lets a stream be parked as 4 bytes
+    // and re-created with init(seed, subsequence, base + consumed))
+    __device__ __forceinline__ uint32_t consumed(uint64_t base) const {
+        uint64_t blk = ((uint64_t)blk_hi << 32) | blk_lo;
+        return (uint32_t)(blk * 4ull + pos - base);
+    }
+
     // curand_uniform : (0,1]
     __device__ __forceinline__ float uniform() {
         return next_u32() * 2.3283064365386963e-10f + (2.3283064365386963e-10f / 2.0f);

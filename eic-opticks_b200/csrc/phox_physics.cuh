@@ -62,6 +62,14 @@ struct PhotonState {                // sphoton in registers
         pol = f3(c.x, c.y, c.z); wavelength = c.w;
         obf = __float_as_uint(d.x); identity = __float_as_uint(d.y); index = __float_as_uint(d.z); flagmask = __float_as_uint(d.w);
     }
+    PHOX_D void load_rw(const Photon* src) {                 // for slots the same kernel also writes (no read-only path)
+        const float4* s = reinterpret_cast<const float4*>(src);
+        float4 a = s[0], b = s[1], c = s[2], d = s[3];
+        pos = f3(a.x, a.y, a.z); time = a.w;
+        mom = f3(b.x, b.y, b.z); hitcount_iindex = __float_as_uint(b.w);
+        pol = f3(c.x, c.y, c.z); wavelength = c.w;
+        obf = __float_as_uint(d.x); identity = __float_as_uint(d.y); index = __float_as_uint(d.z); flagmask = __float_as_uint(d.w);
+    }
     PHOX_D void store(Photon* dst) const {
         float4* o = reinterpret_cast<float4*>(dst);
         o[0] = make_float4(pos.x, pos.y, pos.z, time);

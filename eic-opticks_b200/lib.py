@@ -16,6 +16,7 @@ PHOX_OK = 0
 MODE_MINIMAL, MODE_HITPHOTON, MODE_HITPHOTONSEQ, MODE_DEBUGLITE, MODE_DEBUGHEAVY = range(5)
 RNG_PRODUCTION, RNG_DEBUG_TAG = 0, 1
 ACCEL_BVH, ACCEL_BRUTE = 0, 1
+KERNEL_AUTO, KERNEL_PERSISTENT, KERNEL_WAVEFRONT = 0, 1, 2
 
 
 class PhoxError(RuntimeError):
@@ -32,7 +33,7 @@ class Config(C.Structure):
         ("hit_mask", C.c_uint32), ("epsilon0_mask", C.c_uint32), ("propagate_refine", C.c_uint32),
         ("propagate_epsilon", C.c_float), ("propagate_epsilon0", C.c_float),
         ("refine_distance", C.c_float), ("tmax", C.c_float), ("max_time", C.c_float),
-        ("pad0", C.c_uint32),
+        ("kernel_mode", C.c_uint32),
         ("rng_seed", C.c_uint64), ("rng_offset", C.c_uint64), ("skipahead_event_offset", C.c_uint64),
         ("max_slot", C.c_int64),
     ]

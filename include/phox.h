@@ -48,6 +48,14 @@ enum {
     PHOX_RNG_DEBUG_TAG = 1    /* 4 / 2(+4 on reflect) / 2 / 1 : matches the reference build */
 };
 
+/* How the bounce loop is scheduled on the GPU.  Both forms call the same trace and propagate code and
+ * give bit-identical results. */
+enum {
+    PHOX_KERNEL_AUTO = 0,       /* the faster form for the build (currently wavefront)                        */
+    PHOX_KERNEL_PERSISTENT = 1, /* one fused kernel, persistent warps that refill idle lanes                  */
+    PHOX_KERNEL_WAVEFRONT = 2   /* per bounce: trace kernel + physics kernel over the list of live photons    */
+};
+
 /* How rays find their nearest CSGPrim. */
 enum {
     PHOX_ACCEL_BVH = 0,       /* two-level BVH built on the GPU (instances, then prims per solid) */
@@ -70,7 +78,7 @@ typedef struct phox_config {
     float    refine_distance;       /* OPTICKS_PROPAGATE_REFINE_DISTANCE, 5000 mm               */
     float    tmax;                  /* ray tmax, 1e6 mm                                         */
     float    max_time;              /* OPTICKS_MAX_TIME, 1e27 ns                                */
-    uint32_t pad0;
+    uint32_t kernel_mode;           /* PHOX_KERNEL_*: how the bounce loop is scheduled (results are identical) */
     uint64_t rng_seed;              /* curand_init seed, 0                                      */
     uint64_t rng_offset;            /* curand_init offset (QRng__SEED_OFFSET), 0                */
     uint64_t skipahead_event_offset;/* OPTICKS_EVENT_SKIPAHEAD, 100000 draws per event index    */

@@ -162,6 +162,44 @@ def test_multi_launch_slicing_equals_single_launch():
     sim.close()
 
 
+@pytest.mark.parametrize("name,kw", CASES)
+def test_wavefront_form_is_bit_identical_to_persistent_form(name, kw):
+    """The two forms of the bounce loop (include/phox.h PHOX_KERNEL_*) call the same compiled trace/propagate
+    bodies and re-create each photon's Philox stream from its draw count, so every output byte must agree."""
+    w = workloads.WORKLOADS[name](**kw)
+    out = {}
+    for mode in (ph.KERNEL_PERSISTENT, ph.KERNEL_WAVEFRONT):
+        for em, extra in ((ph.MODE_MINIMAL, {}), (ph.MODE_DEBUGHEAVY, dict(max_record=12))):
+            sim = make_sim(w, event_mode=em, kernel_mode=mode, **extra)
+            h = sim.simulate_np(w["gensteps"], 2, w["input_photons"]).copy()
+            arrs = {"hit": h}
+            if em != ph.MODE_MINIMAL:
+                for k in ("photon", "seq", "record", "prd"):
+                    arrs[k] = sim.get_array(k).copy()
+            arrs["num_ray"] = np.array([sim.stats()["num_ray"]])
+            out[(mode, em)] = arrs
+            sim.close()
+    for em in (ph.MODE_MINIMAL, ph.MODE_DEBUGHEAVY):
+        a, b = out[(ph.KERNEL_PERSISTENT, em)], out[(ph.KERNEL_WAVEFRONT, em)]
+        assert a.keys() == b.keys()
+        for k in a:
+            assert a[k].shape == b[k].shape, (name, k, a[k].shape, b[k].shape)
+            assert a[k].tobytes() == b[k].tobytes(), (name, em, k)
+    assert len(out[(ph.KERNEL_WAVEFRONT, ph.MODE_MINIMAL)]["hit"]) > 0
+
+
+def test_wavefront_form_with_launch_slicing_and_time_cut():
+    w = workloads.sipm8x8_scint(num_photon=50000, photons_per_genstep=100)
+    res = []
+    for mode in (ph.KERNEL_PERSISTENT, ph.KERNEL_WAVEFRONT):
+        sim = make_sim(w, event_mode=ph.MODE_HITPHOTONSEQ, kernel_mode=mode, max_slot=7000, max_time=3.0, max_bounce=9)
+        h = sim.simulate_np(w["gensteps"], 1).copy()
+        res.append((h, sim.get_array("photon").copy(), sim.get_array("seq").copy()))
+        sim.close()
+    for a, b in zip(*res):
+        assert a.shape == b.shape and a.tobytes() == b.tobytes()
+
+
 @pytest.mark.parametrize("name,kw", [CASES[0], CASES[3]])
 def test_rank_sharding_concatenates_to_single_gpu_result(name, kw):
     w = workloads.WORKLOADS[name](**dict(kw, num_photon=24000))
