@@ -14,9 +14,12 @@ synthetic gensteps.  Default workload = the configuration the north_star target 
             (phox_simulate_device), timed with CUDA events on the launch stream, max over ranks
     e2e     same metric through the public host-buffer API (Simulator.simulate_np): gensteps in
             pinned host memory -> H2D -> simulate -> hits D2H, every step
-    roofline  HBM roofline of the dominant kernel (k_simulate); algorithmic bytes per photon are
-            SURVEY 8(d)'s reference-equivalent figure 132 + 128 f_hit; duration = CUDA events
-            recorded around the kernel inside the library, live in the timed region
+    roofline  HBM roofline of the dominant kernel (k_wf_trace, ~2/3 of the bounce loop): 72 algorithmic
+            bytes per live ray x rays per launch / average launch duration, from CUDA events the
+            library records between the kernels on the launch stream (a separate pass of <= 3 steps
+            with phox_set_profiling on, right after the timed region).  The path-level figure of
+            SURVEY 8(d), 132 + 128 f_hit bytes per photon over the whole bounce loop, is reported
+            beside it (path_*)
     cpu_baseline  the CPU oracle (a port, NOT Geant4 and NOT the OptiX build - neither installs
             here) on a bounded sample of the same workload, all host threads
 """
@@ -61,11 +64,17 @@ class ClockSampler:
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            # first use of each query can block the driver for a long time on a fresh box: pay that here, outside the timed region
+            pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            (pynvml.nvmlDeviceGetCurrentClocksEventReasons if hasattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons")
+             else pynvml.nvmlDeviceGetCurrentClocksThrottleReasons)(self.h)
+            pynvml.nvmlDeviceGetPowerUsage(self.h)
         except Exception:
             self.nv = None
 
     def _loop(self):
         nv = self.nv
+        self.stop_flag.wait(0.03)
         while not self.stop_flag.is_set():
             try:
                 self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
@@ -230,11 +239,12 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), st_sum, clocks
 
+    sampler = ClockSampler(local_rank)
     for k in range(warm):
         step_device(0)
     for k in range(2):
         step_e2e(0)
-    ms_dev, st_dev, clocks = timed(step_device, args.steps, ClockSampler(local_rank))
+    ms_dev, st_dev, clocks = timed(step_device, args.steps, sampler)
     ms_e2e, st_e2e, _ = timed(step_e2e, args.steps)
 
     tot = torch.tensor([float(cnt_r)], dtype=torch.float64, device=dev)
@@ -244,27 +254,57 @@ def main():
     value = photons_per_step * args.steps / (ms_dev * 1e-3)
     e2e = photons_per_step * args.steps / (ms_e2e * 1e-3)
 
+    # per-kernel pass (not part of `value`): CUDA events between the kernels of the bounce loop, on the launch stream
+    sim.set_profiling(True)
+    prof = dict(trace_kernel_seconds=0.0, propagate_kernel_seconds=0.0, num_trace_launch=0, num_ray=0, simulate_kernel_seconds=0.0)
+    for k in range(min(args.steps, 3)):
+        flush.fill_(float(k)); torch.cuda.synchronize(dev)
+        step_device(100 + k)
+        torch.cuda.synchronize(dev)
+        st = sim.stats()
+        for key in prof:
+            prof[key] += st[key]
+    sim.set_profiling(False)
+
     if rank == 0:
         peak, peak_kind = load_peaks()
         f_hit = st_dev["num_hit"] / max(1, cnt_r * args.steps)
         bytes_per_photon = 132.0 + 128.0 * f_hit if ip_r is None else 196.0 + 128.0 * f_hit
-        kern_s = st_dev["simulate_kernel_seconds"] / max(1, st_dev["num_launch"])
-        achieved = cnt_r * bytes_per_photon / kern_s / 1e9
+        loop_s = st_dev["simulate_kernel_seconds"] / max(1, st_dev["num_launch"])
+        wave = prof["num_trace_launch"] > 0
+        if wave:
+            # dominant kernel = k_wf_trace.  Algorithmic bytes per live ray: 4 (list entry) + 36 (pos, time, mom, flag word)
+            # read + 32 (quad2 hit record) written = 72 B; one launch processes the photons still alive at that bounce.
+            ray_bytes = 72.0
+            kern_s = prof["trace_kernel_seconds"] / prof["num_trace_launch"]
+            rays_per_launch = prof["num_ray"] / prof["num_trace_launch"]
+            achieved = rays_per_launch * ray_bytes / kern_s / 1e9
+            kernel_name = "k_wf_trace"
+            share = prof["trace_kernel_seconds"] / max(1e-12, prof["simulate_kernel_seconds"])
+        else:
+            kern_s, achieved, kernel_name, share = loop_s, cnt_r * bytes_per_photon / loop_s / 1e9, "k_simulate", st_dev["simulate_kernel_seconds"] / (ms_dev * 1e-3)
+            rays_per_launch, ray_bytes = st_dev["num_ray"] / max(1, st_dev["num_launch"]), None
         out = {
             "metric": "photons propagated/sec", "value": value, "unit": "photons/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "photons_per_gpu_per_step": cnt_r, "gensteps_per_gpu": int(len(gs_r)), "max_bounce": sim.cfg.max_bounce,
-                       "event_mode": "Minimal", "rng_mode": "DEBUG_TAG", "accel": "two-level BVH", "kernel_mode": args.kernel_mode, "l2": "256 MB flush between timed steps",
+                       "event_mode": "Minimal", "rng_mode": "DEBUG_TAG", "accel": "two-level BVH", "kernel_mode": args.kernel_mode,
+                       "l2": "256 MB flush between timed steps",
                        "sharding": "gensteps partitioned over ranks, absolute photon offsets, hits all-gathered (NCCL) each step" if world > 1 else "single GPU"},
             "rays_per_s": st_dev["num_ray"] * world / (ms_dev * 1e-3), "bounces_per_photon": st_dev["num_ray"] / max(1, cnt_r * args.steps),
             "hit_fraction": f_hit,
             "e2e": {"value": e2e, "unit": "photons/s", "h2d_bytes_per_step": int(gs_r.nbytes + (ip_r.nbytes if ip_r is not None else 0)),
                     "d2h_bytes_per_step": int(64 * st_e2e["num_hit"] / max(1, args.steps)), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(st_dev["num_kernel"] + st_e2e["num_kernel"]),
-            "roofline": {"bound": "hbm", "kernel": "k_simulate", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_kind, "traffic": None, "kernel_ms": kern_s * 1e3, "algorithmic_bytes_per_photon": bytes_per_photon,
-                         "kernel_share_of_step": st_dev["simulate_kernel_seconds"] / (ms_dev * 1e-3),
-                         "note": "the bounce loop is latency/issue bound, not HBM bound (tables and geometry are cache resident); see profiles/"},
+            "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_kind, "traffic": None, "kernel_ms": kern_s * 1e3,
+                         "algorithmic_bytes_per_ray": ray_bytes, "rays_per_launch": rays_per_launch,
+                         "kernel_share_of_bounce_loop": share,
+                         "bounce_loop_ms": loop_s * 1e3, "bounce_loop_share_of_step": st_dev["simulate_kernel_seconds"] / (ms_dev * 1e-3),
+                         "path_algorithmic_bytes_per_photon": bytes_per_photon, "path_achieved_gbs": cnt_r * bytes_per_photon / loop_s / 1e9,
+                         "propagate_kernel_ms": (prof["propagate_kernel_seconds"] / prof["num_trace_launch"] * 1e3) if wave else None,
+                         "note": "the bounce loop is latency/issue bound, not HBM bound (geometry and tables are cache resident); "
+                                 "ncu traffic and stall breakdown in profiles/"},
             "clocks": clocks,
         }
         if not args.no_cpu_baseline:

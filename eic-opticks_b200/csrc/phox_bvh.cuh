@@ -64,6 +64,21 @@ __device__ __forceinline__ float box_entry(float lox, float loy, float loz, floa
     texit = tf;
     return tn <= tf ? tn : CUDART_INF_F;
 }
+
+// For a box that IS the prim (box3 leaf without rotation) whose padded copy is (lo, hi): when the ray origin lies
+// inside the box shrunk by `slack` on every entering side, the prim's own answer is its exit face, which cannot be
+// nearer than the exit of the shrunk box.  Returns that bound (scaled down by a few ulps), else `entry`.
+// Axis-parallel rays give inf - inf = NaN on the parallel axes, which fminf/fmaxf drop.
+__device__ __forceinline__ float box_exit_bound(float lox, float loy, float loz, float hix, float hiy, float hiz,
+                                                const float3& o, const float3& idir, float slack, float entry) {
+    float sx = slack * fabsf(idir.x), sy = slack * fabsf(idir.y), sz = slack * fabsf(idir.z);
+    float tx0 = (lox - o.x) * idir.x, tx1 = (hix - o.x) * idir.x;
+    float ty0 = (loy - o.y) * idir.y, ty1 = (hiy - o.y) * idir.y;
+    float tz0 = (loz - o.z) * idir.z, tz1 = (hiz - o.z) * idir.z;
+    float near_max = fmaxf(fmaxf(fminf(tx0, tx1) + sx, fminf(ty0, ty1) + sy), fminf(tz0, tz1) + sz);
+    float far_min = fminf(fminf(fmaxf(tx0, tx1) - sx, fmaxf(ty0, ty1) - sy), fmaxf(tz0, tz1) - sz);
+    return near_max < 0.f ? fmaxf(entry, far_min * 0.999999f) : entry;
+}
 #endif
 
 }  // namespace phox

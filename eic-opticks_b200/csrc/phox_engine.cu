@@ -58,6 +58,8 @@ struct phox_context {
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool profiling = false;                 // phox_set_profiling: events between the kernels of the wavefront form
+    std::vector<cudaEvent_t> prof_ev;
     std::string err;
     std::string description;
     phox_config cfg;
@@ -95,6 +97,7 @@ struct phox_context {
     DevBuf<Prd> d_wave_hits;
     int wave_grid[3][2] = {{0, 0}, {0, 0}, {0, 0}};             // persistent grid sizes of generate/trace/propagate, <false/true>
     DevBuf<unsigned long long> d_block_off;
+    DevBuf<float> d_slack;                     // per CSGPrim: exit-bound slack of prims that are exactly a box (0 = not such a prim)
     DevBuf<unsigned long long> d_counters;     // [0] rays, [1] hit total of the launch
     unsigned long long* h_counters = nullptr;  // pinned mirror
     std::vector<Photon> h_photon;              // concatenated per-launch arrays in debug modes
@@ -179,19 +182,19 @@ extern "C" phox_context* phox_create(int device) {
     cudaMemGetInfo(&free_b, &ctx->vram_total);
     for (int dbg = 0; dbg < 2; dbg++) {
         int per_sm = 0;
-        e = dbg ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_simulate<true>, kSimThreads, 0)
-                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_simulate<false>, kSimThreads, 0);
+        e = dbg ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_simulate<true>, kSimThreads, kSimThreads * kTraceSmemPerThread)
+                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_simulate<false>, kSimThreads, kSimThreads * kTraceSmemPerThread);
         if (e != cudaSuccess || per_sm < 1) per_sm = 1;
         ctx->sim_grid[dbg] = per_sm * prop.multiProcessorCount;
         int w[3] = {0, 0, 0};
         if (dbg) {
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[0], k_wf_generate<true>, kWaveThreads, 0);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[1], k_wf_trace<true>, kWaveThreads, 0);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[2], k_wf_propagate<true>, kWaveThreads, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[1], k_wf_trace<true>, kWaveThreads, kWaveThreads * kTraceSmemPerThread);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[2], k_wf_propagate<true>, kPropThreads, 0);
         } else {
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[0], k_wf_generate<false>, kWaveThreads, 0);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[1], k_wf_trace<false>, kWaveThreads, 0);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[2], k_wf_propagate<false>, kWaveThreads, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[1], k_wf_trace<false>, kWaveThreads, kWaveThreads * kTraceSmemPerThread);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[2], k_wf_propagate<false>, kPropThreads, 0);
         }
         for (int k = 0; k < 3; k++) ctx->wave_grid[k][dbg] = std::max(w[k], 1) * prop.multiProcessorCount;
     }
@@ -223,10 +226,12 @@ extern "C" void phox_destroy(phox_context* ctx) {
     ctx->d_genstep.release(); ctx->d_prefix.release(); ctx->d_input.release(); ctx->d_photon.release();
     ctx->d_record.release(); ctx->d_hit.release(); ctx->d_seq.release(); ctx->d_prd.release();
     ctx->d_block_hits.release(); ctx->d_block_off.release(); ctx->d_counters.release();
+    ctx->d_slack.release();
     ctx->d_active[0].release(); ctx->d_active[1].release(); ctx->d_ndraw.release(); ctx->d_wave_count.release(); ctx->d_wave_hits.release();
     bvh_scratch_free(ctx->bvh_scratch);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     for (int k = 0; k < 4; k++) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
+    for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -332,6 +337,39 @@ extern "C" int phox_set_geometry(phox_context* ctx, const void* solid_, int64_t 
         float pad = 2e-6f * m;
         for (int k = 0; k < 3; k++) { boxes[6 * p + k] = prim[p].f[8 + k] - pad; boxes[6 * p + 3 + k] = prim[p].f[11 + k] + pad; }
     }
+    // Prims that ARE their box (a single un-complemented box3 leaf, no rotation): from inside such a prim the hit
+    // is the exit face, so the traversal may drop it once a nearer hit is known (phox_kernels.cuh, exit bound).
+    // slack = distance by which the padded box must be shrunk to lie inside the true box with a pad to spare.
+    std::vector<float> slack((size_t)nprim, 0.f);
+    const Node* hnode = (const Node*)node_;
+    const Qat4* hitra = (const Qat4*)itra_;
+    for (int64_t p = 0; p < nprim; p++) {
+        if (prim[p].num_node() != 1) continue;
+        int no = prim[p].node_offset();
+        if (no < 0 || no >= nnode) continue;
+        const Node& nd = hnode[no];
+        if (nd.typecode() != CSG_BOX3 || nd.complement()) continue;
+        float c[3] = {0.f, 0.f, 0.f};
+        unsigned ti = nd.transform_idx();
+        if (ti > 0) {
+            if ((int64_t)ti > nitra) continue;
+            const Qat4& q = hitra[ti - 1];                 // inverse transform, row-vector convention: translation in row 3
+            bool pure = q.f[0] == 1.f && q.f[5] == 1.f && q.f[10] == 1.f && q.f[1] == 0.f && q.f[2] == 0.f && q.f[4] == 0.f &&
+                        q.f[6] == 0.f && q.f[8] == 0.f && q.f[9] == 0.f;
+            if (!pure) continue;
+            for (int k = 0; k < 3; k++) c[k] = -q.f[12 + k];
+        }
+        float m = 1.f, worst = 0.f;
+        bool inside = true;
+        for (int k = 0; k < 3; k++) {
+            float tlo = c[k] - 0.5f * nd.f[k], thi = c[k] + 0.5f * nd.f[k];
+            float plo = boxes[6 * p + k], phi = boxes[6 * p + 3 + k];
+            if (!(plo <= tlo && thi <= phi)) inside = false;
+            worst = std::max(worst, std::max(tlo - plo, phi - thi));
+            m = std::max(m, std::max(std::fabs(plo), std::fabs(phi)));
+        }
+        if (inside && nd.f[0] > 0.f && nd.f[1] > 0.f && nd.f[2] > 0.f) slack[p] = worst + 4e-6f * m;
+    }
     std::vector<float> solid_box((size_t)nsolid * 6);
     for (int64_t s = 0; s < nsolid; s++) {
         float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -391,6 +429,8 @@ extern "C" int phox_set_geometry(phox_context* ctx, const void* solid_, int64_t 
     CK(ctx->d_bvh.reserve((size_t)pool));
     CK(cudaMemcpyAsync(ctx->d_inst.p, recs.data(), recs.size() * sizeof(InstanceRec), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_boxes.p, boxes.data(), boxes.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx->d_slack.reserve(std::max<size_t>(1, (size_t)nprim)));
+    CK(cudaMemcpyAsync(ctx->d_slack.p, slack.data(), (size_t)nprim * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
 
     ctx->build_kernels = 0;
@@ -399,6 +439,12 @@ extern "C" int phox_set_geometry(phox_context* ctx, const void* solid_, int64_t 
         if (solid[s].num_prim == 0) continue;
         CK(bvh_build(ctx->d_boxes.p + 6 * (size_t)solid[s].prim_offset, solid[s].num_prim, solid[s].prim_offset, ctx->d_bvh.p + solid_root[s],
                      ctx->bvh_scratch, ctx->stream, &ctx->build_kernels));
+#if PHOX_EXACT_BOX
+        k_mark_exact_boxes<<<(std::max(solid[s].num_prim - 1, 1) + 127) / 128, 128, 0, ctx->stream>>>(
+            ctx->d_bvh.p + solid_root[s], std::max(solid[s].num_prim - 1, 1), ctx->d_slack.p);
+        CK(cudaGetLastError());
+        ctx->build_kernels += 1;
+#endif
         CK(cudaStreamSynchronize(ctx->stream));     // scratch is reused by the next build
     }
     CK(cudaStreamSynchronize(ctx->stream));
@@ -467,6 +513,12 @@ extern "C" int phox_set_config(phox_context* ctx, const phox_config* cfg) {
     if (cfg->max_slot < 0) return ctx->fail(PHOX_E_ARG, "phox_set_config: max_slot < 0");
     if (cfg->kernel_mode > PHOX_KERNEL_WAVEFRONT) return ctx->fail(PHOX_E_ARG, "phox_set_config: unknown kernel_mode");
     ctx->cfg = *cfg;
+    return PHOX_OK;
+}
+
+extern "C" int phox_set_profiling(phox_context* ctx, int on) {
+    if (!ctx) return PHOX_E_ARG;
+    ctx->profiling = on != 0;
     return PHOX_OK;
 }
 
@@ -558,8 +610,8 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
         int sim_blocks = ctx->sim_grid[dbg ? 1 : 0];
         sim_blocks = (int)std::min<int64_t>(sim_blocks, (n + kSimThreads - 1) / kSimThreads);
         CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-        if (dbg) k_simulate<true><<<sim_blocks, kSimThreads, 0, ctx->stream>>>(P);
-        else k_simulate<false><<<sim_blocks, kSimThreads, 0, ctx->stream>>>(P);
+        if (dbg) k_simulate<true><<<sim_blocks, kSimThreads, kSimThreads * kTraceSmemPerThread, ctx->stream>>>(P);
+        else k_simulate<false><<<sim_blocks, kSimThreads, kSimThreads * kTraceSmemPerThread, ctx->stream>>>(P);
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->ev[1], ctx->stream));
         ctx->stats.num_kernel += 1;
@@ -577,19 +629,32 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
         W.sim = P;
         W.ndraw = ctx->d_ndraw.p; W.hits = ctx->d_wave_hits.p;
         const int d = dbg ? 1 : 0;
-        int64_t need = (n + kWaveThreads - 1) / kWaveThreads;
-        auto grid = [&](int k) { return (unsigned)std::max<int64_t>(1, std::min<int64_t>(ctx->wave_grid[k][d], need)); };
+        auto grid = [&](int k, int threads = kWaveThreads) {
+            return (unsigned)std::max<int64_t>(1, std::min<int64_t>(ctx->wave_grid[k][d], (n + threads - 1) / threads));
+        };
         CK(cudaEventRecord(ctx->ev[0], ctx->stream));
         W.active_out = ctx->d_active[0].p;
         if (dbg) k_wf_generate<true><<<grid(0), kWaveThreads, 0, ctx->stream>>>(W);
         else k_wf_generate<false><<<grid(0), kWaveThreads, 0, ctx->stream>>>(W);
         CK(cudaGetLastError());
+        const bool prof = ctx->profiling;
+        if (prof) while (ctx->prof_ev.size() < 2 * (size_t)c.max_bounce + 1) { cudaEvent_t e; CK(cudaEventCreate(&e)); ctx->prof_ev.push_back(e); }
         for (int b = 0; b < c.max_bounce; b++) {
             W.active_in = ctx->d_active[b & 1].p; W.active_out = ctx->d_active[(b + 1) & 1].p;
             W.count_in = ctx->d_wave_count.p + b; W.count_out = ctx->d_wave_count.p + b + 1;
             W.bounce = b;
-            if (dbg) { k_wf_trace<true><<<grid(1), kWaveThreads, 0, ctx->stream>>>(W); k_wf_propagate<true><<<grid(2), kWaveThreads, 0, ctx->stream>>>(W); }
-            else { k_wf_trace<false><<<grid(1), kWaveThreads, 0, ctx->stream>>>(W); k_wf_propagate<false><<<grid(2), kWaveThreads, 0, ctx->stream>>>(W); }
+            if (prof) {        // same launches, with an event before each kernel
+                CK(cudaEventRecord(ctx->prof_ev[2 * b], ctx->stream));
+                if (dbg) k_wf_trace<true><<<grid(1), kWaveThreads, kWaveThreads * kTraceSmemPerThread, ctx->stream>>>(W);
+                else k_wf_trace<false><<<grid(1), kWaveThreads, kWaveThreads * kTraceSmemPerThread, ctx->stream>>>(W);
+                CK(cudaEventRecord(ctx->prof_ev[2 * b + 1], ctx->stream));
+                if (dbg) k_wf_propagate<true><<<grid(2, kPropThreads), kPropThreads, 0, ctx->stream>>>(W);
+                else k_wf_propagate<false><<<grid(2, kPropThreads), kPropThreads, 0, ctx->stream>>>(W);
+                if (b == c.max_bounce - 1) CK(cudaEventRecord(ctx->prof_ev[2 * b + 2], ctx->stream));
+                continue;
+            }
+            if (dbg) { k_wf_trace<true><<<grid(1), kWaveThreads, kWaveThreads * kTraceSmemPerThread, ctx->stream>>>(W); k_wf_propagate<true><<<grid(2, kPropThreads), kPropThreads, 0, ctx->stream>>>(W); }
+            else { k_wf_trace<false><<<grid(1), kWaveThreads, kWaveThreads * kTraceSmemPerThread, ctx->stream>>>(W); k_wf_propagate<false><<<grid(2, kPropThreads), kPropThreads, 0, ctx->stream>>>(W); }
         }
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->ev[1], ctx->stream));
@@ -616,6 +681,19 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
     CK(cudaEventElapsedTime(&ms_rest, ctx->ev[1], ctx->ev[2]));
     ctx->stats.simulate_kernel_seconds += ms_sim * 1e-3;
     ctx->stats.compact_kernel_seconds += ms_rest * 1e-3;
+    if (wavefront && ctx->profiling && c.max_bounce > 0) {
+        std::vector<unsigned> live((size_t)c.max_bounce + 2);
+        CK(cudaMemcpy(live.data(), ctx->d_wave_count.p, live.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
+        for (int b = 0; b < c.max_bounce; b++) {
+            if (live[b] == 0) break;                // later kernels found an empty list
+            float ms_t = 0.f, ms_p = 0.f;
+            CK(cudaEventElapsedTime(&ms_t, ctx->prof_ev[2 * b], ctx->prof_ev[2 * b + 1]));
+            CK(cudaEventElapsedTime(&ms_p, ctx->prof_ev[2 * b + 1], ctx->prof_ev[2 * b + 2]));
+            ctx->stats.trace_kernel_seconds += ms_t * 1e-3;
+            ctx->stats.propagate_kernel_seconds += ms_p * 1e-3;
+            ctx->stats.num_trace_launch += 1;
+        }
+    }
     ctx->num_hit += nhit;
     ctx->stats.num_launch += 1;
     return PHOX_OK;
@@ -842,7 +920,7 @@ extern "C" int phox_intersect(phox_context* ctx, const float* ray_o_tmin, const 
     sc.ninst = ctx->ninst; sc.tlas_root = ctx->tlas_root; sc.accel = accel;
     const int T = 128;
     cudaEventRecord(ctx->ev[0], ctx->stream);
-    k_intersect<<<(unsigned)((nray + T - 1) / T), T, 0, ctx->stream>>>(sc, d_o, d_d, (unsigned)nray, ctx->cfg.tmax, d_out);
+    k_intersect<<<(unsigned)((nray + T - 1) / T), T, T * kTraceSmemPerThread, ctx->stream>>>(sc, d_o, d_d, (unsigned)nray, ctx->cfg.tmax, d_out);
     cudaEventRecord(ctx->ev[1], ctx->stream);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess && cudaEventSynchronize(ctx->ev[1]) == cudaSuccess) {

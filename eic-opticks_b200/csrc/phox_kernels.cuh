@@ -22,6 +22,18 @@
 #ifndef PHOX_HOT_LEAF
 #define PHOX_HOT_LEAF 0            // 0: one out-of-line copy of the CSG leaf code serves every site (instruction-fetch bound kernel)
 #endif
+#ifndef PHOX_WF_PREFETCH
+#define PHOX_WF_PREFETCH 0
+#endif
+#ifndef PHOX_WF_WARP_APPEND
+#define PHOX_WF_WARP_APPEND 0
+#endif
+#ifndef PHOX_EXACT_BOX
+#define PHOX_EXACT_BOX 1           // exit-distance bound for prims that are exactly their box (see traverse_bvh)
+#endif
+#ifndef PHOX_SMEM_STACK
+#define PHOX_SMEM_STACK 0          // traversal-stack entries per thread kept in shared memory (0: whole stack in local memory)
+#endif
 #include "phox_bvh.cuh"
 #include "phox_physics.cuh"
 
@@ -87,6 +99,7 @@ PHOX_D void keep_nearest(Nearest& best, const float4& is, int prim_idx, int inst
 }
 
 constexpr int kBvhStack = 64;
+constexpr int kTraceSmemPerThread = PHOX_SMEM_STACK * (int)sizeof(int2);    // dynamic shared memory every kernel that calls trace() is launched with, per thread
 constexpr int kTravReturn = (int)0x80000000;     // stack marker: leave the current solid, back to the instance tree
 constexpr int kTravDone = (int)0x80000001;
 
@@ -97,16 +110,36 @@ constexpr int kTravDone = (int)0x80000001;
 // CSGPrim inside a solid) or one of the two markers.  Children are visited near-first; the far one is
 // parked on the stack with its entry distance so it is dropped once a nearer hit is known.
 PHOX_D void traverse_bvh(Nearest& best, const Scene& sc, float tmin, const float3& o_w, const float3& d_w) {
+#if PHOX_SMEM_STACK > 0
+    // the first PHOX_SMEM_STACK entries of the per-thread stack live in shared memory (interleaved by thread:
+    // conflict free), deeper ones - rare - in local memory.  Local-memory stores are written through to L2,
+    // so a local stack alone made ~80 % of the trace kernel's L2 traffic (profiles/).
+    extern __shared__ int2 s_trav[];                        // [PHOX_SMEM_STACK][blockDim.x] of (item, entry distance)
+    int2* sstack = s_trav + threadIdx.x;
+    const unsigned sstride = blockDim.x;
+    int2 lstack[kBvhStack - PHOX_SMEM_STACK];
+    int sp = 0;
+    auto push = [&](int item, float t) {
+        if (sp < PHOX_SMEM_STACK) sstack[sp * sstride] = make_int2(item, __float_as_int(t));
+        else if (sp < kBvhStack) lstack[sp - PHOX_SMEM_STACK] = make_int2(item, __float_as_int(t));
+        else return;
+        sp++;
+    };
+    auto pop = [&]() -> int {
+        while (sp > 0) {
+            sp--;
+            int2 e = sp < PHOX_SMEM_STACK ? sstack[sp * sstride] : lstack[sp - PHOX_SMEM_STACK];
+            if (__int_as_float(e.y) <= best.t) return e.x;
+        }
+        return kTravDone;
+    };
+#else
     int stack[kBvhStack];
     float stack_t[kBvhStack];
     int sp = 0;
-    float3 o = o_w, d = d_w;
-    float3 idir = f3(1.f / d.x, 1.f / d.y, 1.f / d.z);
-    int root = sc.tlas_root;
-    bool in_solid = false;
-    int inst_idx = 0;
-    int cur = sc.ninst == 1 ? ~0 : 0;
-
+    auto push = [&](int item, float t) {
+        if (sp < kBvhStack) { stack[sp] = item; stack_t[sp] = t; sp++; }
+    };
     auto pop = [&]() -> int {
         while (sp > 0) {
             sp--;
@@ -114,6 +147,13 @@ PHOX_D void traverse_bvh(Nearest& best, const Scene& sc, float tmin, const float
         }
         return kTravDone;
     };
+#endif
+    float3 o = o_w, d = d_w;
+    float3 idir = f3(1.f / d.x, 1.f / d.y, 1.f / d.z);
+    int root = sc.tlas_root;
+    bool in_solid = false;
+    int inst_idx = 0;
+    int cur = sc.ninst == 1 ? ~0 : 0;
 
     while (true) {
         while (cur >= 0) {                                     // internal nodes
@@ -124,12 +164,25 @@ PHOX_D void traverse_bvh(Nearest& best, const Scene& sc, float tmin, const float
             float t0 = box_entry(a.x, a.y, a.z, a.w, b.x, b.y, o, idir, tmin, best.t, e0);
             float t1 = ch.y == kBvhNoChild ? CUDART_INF_F : box_entry(b.z, b.w, c.x, c.y, c.z, c.w, o, idir, tmin, best.t, e1);
             bool h0 = t0 < CUDART_INF_F, h1 = t1 < CUDART_INF_F;
+#if PHOX_EXACT_BOX
+            // c0/c1: no hit of the child can be nearer than this.  Normally the entry distance; for a prim that
+            // is exactly its box and holds the ray origin, (a lower bound of) the exit distance - which lets the
+            // enclosing volumes (the world box of every Geant4 geometry first of all) go untested once the
+            // photon's own volume has answered.
+            float c0 = t0, c1 = t1;
+            if (ch.z | ch.w) {
+                if (ch.z != 0 && h0) { c0 = box_exit_bound(a.x, a.y, a.z, a.w, b.x, b.y, o, idir, __int_as_float(ch.z), t0); h0 = c0 <= best.t; }
+                if (ch.w != 0 && h1) { c1 = box_exit_bound(b.z, b.w, c.x, c.y, c.z, c.w, o, idir, __int_as_float(ch.w), t1); h1 = c1 <= best.t; }
+            }
+#else
+            const float c0 = t0, c1 = t1;
+#endif
             if (h0 && h1) {
-                int nearc = ch.x, farc = ch.y; float tfar = t1;
+                int nearc = ch.x, farc = ch.y; float tfar = c1;
                 // nearer entry first; when the ray starts inside both boxes (equal entries) the box it
                 // leaves sooner is the likelier home of the nearest surface
-                if (t1 < t0 || (t1 == t0 && e1 < e0)) { nearc = ch.y; farc = ch.x; tfar = t0; }
-                if (sp < kBvhStack) { stack[sp] = farc; stack_t[sp] = tfar; sp++; }
+                if (t1 < t0 || (t1 == t0 && e1 < e0)) { nearc = ch.y; farc = ch.x; tfar = c0; }
+                push(farc, tfar);
                 cur = nearc;
             } else if (h0) cur = ch.x;
             else if (h1) cur = ch.y;
@@ -158,7 +211,7 @@ PHOX_D void traverse_bvh(Nearest& best, const Scene& sc, float tmin, const float
             }
             root = meta.w;
             in_solid = true;
-            if (sc.ninst > 1 && sp < kBvhStack) { stack[sp] = kTravReturn; stack_t[sp] = -CUDART_INF_F; sp++; }
+            if (sc.ninst > 1) push(kTravReturn, -CUDART_INF_F);
             cur = 0;
             continue;
         }
@@ -376,6 +429,11 @@ struct WaveParams {
 #define PHOX_WF_TRACE_MIN_BLOCKS 4      // resident 256-thread blocks per SM the trace kernel is compiled for (register cap 65536/(256*N))
 #endif
 constexpr int kWaveThreads = 256;
+#ifndef PHOX_WF_PROP_THREADS
+#define PHOX_WF_PROP_THREADS 256        // block of the physics kernel = run length of the ordered survivor append
+#endif
+constexpr int kPropThreads = PHOX_WF_PROP_THREADS;
+PHOX_D void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 constexpr unsigned kWaveNoHit = 0xffffffffu;    // prim_boundary of a list entry whose photon is final (miss or time over)
 
 template <bool DEBUG>
@@ -417,13 +475,20 @@ __global__ void __launch_bounds__(kWaveThreads, PHOX_WF_TRACE_MIN_BLOCKS) k_wf_t
     const SimParams& P = W.sim;
     const unsigned count = *W.count_in;
     unsigned nray = 0;
-    for (unsigned a = blockIdx.x * blockDim.x + threadIdx.x; a < count; a += gridDim.x * blockDim.x) {
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned a = blockIdx.x * blockDim.x + threadIdx.x; a < count; a += stride) {
         unsigned idx = W.active_in[a];
+#if PHOX_WF_PREFETCH
+        unsigned idx_next = a + stride < count ? W.active_in[a + stride] : idx;     // issued together with this iteration's loads
+#endif
         const float4* ph = reinterpret_cast<const float4*>(P.photon + idx);
         float4 q0 = ph[0], q1 = ph[1];
         unsigned obf = __float_as_uint(ph[3].x);
         Prd r;
         r.nx = r.ny = r.nz = 0.f; r.t = -1.f; r.lposcost = r.lposfphi = 0.f; r.iindex_identity = 0xffffffffu; r.prim_boundary = kWaveNoHit;
+#if PHOX_WF_PREFETCH
+        prefetch_l2(P.photon + idx_next);                       // the next photon of this thread comes from DRAM while this one is traced
+#endif
         if (q0.w < P.max_time) {                                // else the while-condition of the raygen loop fails: photon is final
             float tmin = (obf & P.eps0_mask) ? P.tmin0 : P.tmin;
             float3 o = f3(q0.x, q0.y, q0.z), d = f3(q1.x, q1.y, q1.z);
@@ -453,9 +518,11 @@ __global__ void __launch_bounds__(kWaveThreads, PHOX_WF_TRACE_MIN_BLOCKS) k_wf_t
 }
 
 template <bool DEBUG>
-__global__ void __launch_bounds__(kWaveThreads) k_wf_propagate(const __grid_constant__ WaveParams W) {
-    __shared__ unsigned s_warp[kWaveThreads / 32];
+__global__ void __launch_bounds__(kPropThreads) k_wf_propagate(const __grid_constant__ WaveParams W) {
+#if !PHOX_WF_WARP_APPEND
+    __shared__ unsigned s_warp[kPropThreads / 32];
     __shared__ unsigned s_base;
+#endif
     const SimParams& P = W.sim;
     const unsigned count = *W.count_in;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -486,19 +553,38 @@ __global__ void __launch_bounds__(kWaveThreads) k_wf_propagate(const __grid_cons
                 survive = !(command == FLOW_BREAK) && bounce < P.max_bounce && p.time < P.max_time;
             }
         }
-        // append the survivors of this chunk to the next list, in order within the chunk
         unsigned ballot = __ballot_sync(0xffffffffu, survive);
+#if PHOX_WF_WARP_APPEND
+        // append the survivors of this warp to the next list with one atomic per warp: slots of a warp stay
+        // adjacent and in order, which is all the coherence of the next bounce needs
+        unsigned wbase = 0;
+        if (lane == 0 && ballot) wbase = atomicAdd(W.count_out, (unsigned)__popc(ballot));
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        if (survive) W.active_out[wbase + __popc(ballot & ((1u << lane) - 1u))] = idx;
+#else
+        // append the survivors of this chunk to the next list, in order within the chunk
         if (lane == 0) s_warp[warp] = __popc(ballot);
         __syncthreads();
         if (threadIdx.x == 0) {
             unsigned tot = 0;
-            for (int w = 0; w < kWaveThreads / 32; w++) { unsigned c = s_warp[w]; s_warp[w] = tot; tot += c; }
+            for (int w = 0; w < kPropThreads / 32; w++) { unsigned c = s_warp[w]; s_warp[w] = tot; tot += c; }
             s_base = tot ? atomicAdd(W.count_out, tot) : 0u;
         }
         __syncthreads();
         if (survive) W.active_out[s_base + s_warp[warp] + __popc(ballot & ((1u << lane) - 1u))] = idx;
         __syncthreads();
+#endif
     }
+}
+
+// after a solid's BVH is built: leaf children whose CSGPrim is exactly its box get that prim's slack in d.z / d.w
+__global__ void k_mark_exact_boxes(BvhNode* nodes, int nnode, const float* __restrict__ slack) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnode) return;
+    int4 d = nodes[i].d;
+    d.z = (d.x < 0) ? __float_as_int(slack[~d.x]) : 0;
+    d.w = (d.y < 0 && d.y != kBvhNoChild) ? __float_as_int(slack[~d.y]) : 0;
+    nodes[i].d = d;
 }
 
 // hits per tile of kHitTile photons (reads only the flagmask word of each photon)

@@ -45,6 +45,7 @@ class Stats(C.Structure):
         ("num_launch", C.c_uint64), ("num_kernel", C.c_uint64),
         ("launch_seconds", C.c_double), ("upload_seconds", C.c_double), ("gather_seconds", C.c_double),
         ("simulate_kernel_seconds", C.c_double), ("compact_kernel_seconds", C.c_double),
+        ("trace_kernel_seconds", C.c_double), ("propagate_kernel_seconds", C.c_double), ("num_trace_launch", C.c_uint64),
     ]
 
 
@@ -72,6 +73,7 @@ SYMBOLS = {
     "phox_get_hits_device": (C.c_int, [C.c_void_p, C.c_void_p]),
     "phox_get_array": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
     "phox_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
+    "phox_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "phox_reset": (None, [C.c_void_p]),
     "phox_intersect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]),
     "phox_boundary_lookup": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),

@@ -223,6 +223,10 @@ class Simulator:
             self._check(self.lib.phox_get_array(self.ctx, name.encode(), _ptr(out), out.nbytes))
         return out
 
+    def set_profiling(self, on=True):
+        """per-kernel CUDA-event timing of the bounce loop (stats trace_/propagate_kernel_seconds)"""
+        self._check(self.lib.phox_set_profiling(self.ctx, 1 if on else 0))
+
     def stats(self):
         st = L.Stats()
         self._check(self.lib.phox_get_stats(self.ctx, C.byref(st)))

@@ -174,8 +174,17 @@ typedef struct phox_stats {
     double   launch_seconds, upload_seconds, gather_seconds;
     double   simulate_kernel_seconds;   /* device time of the simulate kernel(s), CUDA events on the launch stream */
     double   compact_kernel_seconds;    /* device time of hit offset scan + compaction */
+    /* filled only while phox_set_profiling(ctx, 1) is in effect (wavefront form): per-kernel device times */
+    double   trace_kernel_seconds;      /* sum over the trace kernels of the event */
+    double   propagate_kernel_seconds;  /* sum over the physics kernels of the event */
+    uint64_t num_trace_launch;          /* trace kernels that had live photons */
 } phox_stats;
 int phox_get_stats(const phox_context* ctx, phox_stats* st);
+
+/* Per-kernel timing of the bounce loop (CUDA events between the kernels of the wavefront form).  Off by
+ * default: the extra event records are kept out of production launches.  Used by bench.py for the roofline
+ * of the dominant kernel. */
+int phox_set_profiling(phox_context* ctx, int on);
 
 void phox_reset(phox_context* ctx);   /* SSimulator::reset(eventID) */
 
