@@ -136,6 +136,7 @@ def main():
     ap.add_argument("--photons", type=int, default=12_500_000, help="photons per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=2_000_000, help="photons of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--max-slot", type=int, default=0, help="photons per launch (0 = library default); an event is sliced at genstep granularity")
     ap.add_argument("--kernel-mode", default="auto", choices=["auto", "persistent", "wavefront"], help="form of the bounce loop (include/phox.h PHOX_KERNEL_*)")
     args = ap.parse_args()
 
@@ -186,6 +187,8 @@ def main():
     gs_r, ip_r, off_r, cnt_r = parallel.shard_event(w["gensteps"], rank, world, w["input_photons"])
     kmode = {"auto": 0, "persistent": 1, "wavefront": 2}[args.kernel_mode]
     sim = ph.Simulator.Create(g["foundry"], g["bnd"], g["optical"], g["icdf"], device=local_rank, event_mode=ph.MODE_MINIMAL, kernel_mode=kmode, **w["config"])
+    if args.max_slot > 0:
+        sim.set_config(max_slot=args.max_slot)
     stream = torch.cuda.current_stream(dev)
     sim.set_stream(stream.cuda_stream)
 
@@ -288,7 +291,7 @@ def main():
             "metric": "photons propagated/sec", "value": value, "unit": "photons/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "photons_per_gpu_per_step": cnt_r, "gensteps_per_gpu": int(len(gs_r)), "max_bounce": sim.cfg.max_bounce,
-                       "event_mode": "Minimal", "rng_mode": "DEBUG_TAG", "accel": "two-level BVH", "kernel_mode": args.kernel_mode,
+                       "event_mode": "Minimal", "rng_mode": "DEBUG_TAG", "accel": "two-level BVH", "kernel_mode": args.kernel_mode, "max_slot": args.max_slot,
                        "l2": "256 MB flush between timed steps",
                        "sharding": "gensteps partitioned over ranks, absolute photon offsets, hits all-gathered (NCCL) each step" if world > 1 else "single GPU"},
             "rays_per_s": st_dev["num_ray"] * world / (ms_dev * 1e-3), "bounces_per_photon": st_dev["num_ray"] / max(1, cnt_r * args.steps),

@@ -182,18 +182,18 @@ extern "C" phox_context* phox_create(int device) {
     cudaMemGetInfo(&free_b, &ctx->vram_total);
     for (int dbg = 0; dbg < 2; dbg++) {
         int per_sm = 0;
-        e = dbg ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_simulate<true>, kSimThreads, kSimThreads * kTraceSmemPerThread)
-                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_simulate<false>, kSimThreads, kSimThreads * kTraceSmemPerThread);
+        e = dbg ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_simulate<true>, kSimThreads, 0)
+                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_simulate<false>, kSimThreads, 0);
         if (e != cudaSuccess || per_sm < 1) per_sm = 1;
         ctx->sim_grid[dbg] = per_sm * prop.multiProcessorCount;
         int w[3] = {0, 0, 0};
         if (dbg) {
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[0], k_wf_generate<true>, kWaveThreads, 0);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[1], k_wf_trace<true>, kWaveThreads, kWaveThreads * kTraceSmemPerThread);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[1], k_wf_trace<true>, kWaveThreads, 0);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[2], k_wf_propagate<true>, kPropThreads, 0);
         } else {
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[0], k_wf_generate<false>, kWaveThreads, 0);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[1], k_wf_trace<false>, kWaveThreads, kWaveThreads * kTraceSmemPerThread);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[1], k_wf_trace<false>, kWaveThreads, 0);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[2], k_wf_propagate<false>, kPropThreads, 0);
         }
         for (int k = 0; k < 3; k++) ctx->wave_grid[k][dbg] = std::max(w[k], 1) * prop.multiProcessorCount;
@@ -610,8 +610,8 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
         int sim_blocks = ctx->sim_grid[dbg ? 1 : 0];
         sim_blocks = (int)std::min<int64_t>(sim_blocks, (n + kSimThreads - 1) / kSimThreads);
         CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-        if (dbg) k_simulate<true><<<sim_blocks, kSimThreads, kSimThreads * kTraceSmemPerThread, ctx->stream>>>(P);
-        else k_simulate<false><<<sim_blocks, kSimThreads, kSimThreads * kTraceSmemPerThread, ctx->stream>>>(P);
+        if (dbg) k_simulate<true><<<sim_blocks, kSimThreads, 0, ctx->stream>>>(P);
+        else k_simulate<false><<<sim_blocks, kSimThreads, 0, ctx->stream>>>(P);
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->ev[1], ctx->stream));
         ctx->stats.num_kernel += 1;
@@ -645,16 +645,16 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
             W.bounce = b;
             if (prof) {        // same launches, with an event before each kernel
                 CK(cudaEventRecord(ctx->prof_ev[2 * b], ctx->stream));
-                if (dbg) k_wf_trace<true><<<grid(1), kWaveThreads, kWaveThreads * kTraceSmemPerThread, ctx->stream>>>(W);
-                else k_wf_trace<false><<<grid(1), kWaveThreads, kWaveThreads * kTraceSmemPerThread, ctx->stream>>>(W);
+                if (dbg) k_wf_trace<true><<<grid(1), kWaveThreads, 0, ctx->stream>>>(W);
+                else k_wf_trace<false><<<grid(1), kWaveThreads, 0, ctx->stream>>>(W);
                 CK(cudaEventRecord(ctx->prof_ev[2 * b + 1], ctx->stream));
                 if (dbg) k_wf_propagate<true><<<grid(2, kPropThreads), kPropThreads, 0, ctx->stream>>>(W);
                 else k_wf_propagate<false><<<grid(2, kPropThreads), kPropThreads, 0, ctx->stream>>>(W);
                 if (b == c.max_bounce - 1) CK(cudaEventRecord(ctx->prof_ev[2 * b + 2], ctx->stream));
                 continue;
             }
-            if (dbg) { k_wf_trace<true><<<grid(1), kWaveThreads, kWaveThreads * kTraceSmemPerThread, ctx->stream>>>(W); k_wf_propagate<true><<<grid(2, kPropThreads), kPropThreads, 0, ctx->stream>>>(W); }
-            else { k_wf_trace<false><<<grid(1), kWaveThreads, kWaveThreads * kTraceSmemPerThread, ctx->stream>>>(W); k_wf_propagate<false><<<grid(2, kPropThreads), kPropThreads, 0, ctx->stream>>>(W); }
+            if (dbg) { k_wf_trace<true><<<grid(1), kWaveThreads, 0, ctx->stream>>>(W); k_wf_propagate<true><<<grid(2, kPropThreads), kPropThreads, 0, ctx->stream>>>(W); }
+            else { k_wf_trace<false><<<grid(1), kWaveThreads, 0, ctx->stream>>>(W); k_wf_propagate<false><<<grid(2, kPropThreads), kPropThreads, 0, ctx->stream>>>(W); }
         }
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->ev[1], ctx->stream));
@@ -920,7 +920,7 @@ extern "C" int phox_intersect(phox_context* ctx, const float* ray_o_tmin, const 
     sc.ninst = ctx->ninst; sc.tlas_root = ctx->tlas_root; sc.accel = accel;
     const int T = 128;
     cudaEventRecord(ctx->ev[0], ctx->stream);
-    k_intersect<<<(unsigned)((nray + T - 1) / T), T, T * kTraceSmemPerThread, ctx->stream>>>(sc, d_o, d_d, (unsigned)nray, ctx->cfg.tmax, d_out);
+    k_intersect<<<(unsigned)((nray + T - 1) / T), T, 0, ctx->stream>>>(sc, d_o, d_d, (unsigned)nray, ctx->cfg.tmax, d_out);
     cudaEventRecord(ctx->ev[1], ctx->stream);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess && cudaEventSynchronize(ctx->ev[1]) == cudaSuccess) {

@@ -22,17 +22,8 @@
 #ifndef PHOX_HOT_LEAF
 #define PHOX_HOT_LEAF 0            // 0: one out-of-line copy of the CSG leaf code serves every site (instruction-fetch bound kernel)
 #endif
-#ifndef PHOX_WF_PREFETCH
-#define PHOX_WF_PREFETCH 0
-#endif
-#ifndef PHOX_WF_WARP_APPEND
-#define PHOX_WF_WARP_APPEND 0
-#endif
 #ifndef PHOX_EXACT_BOX
 #define PHOX_EXACT_BOX 1           // exit-distance bound for prims that are exactly their box (see traverse_bvh)
-#endif
-#ifndef PHOX_SMEM_STACK
-#define PHOX_SMEM_STACK 0          // traversal-stack entries per thread kept in shared memory (0: whole stack in local memory)
 #endif
 #include "phox_bvh.cuh"
 #include "phox_physics.cuh"
@@ -99,7 +90,6 @@ PHOX_D void keep_nearest(Nearest& best, const float4& is, int prim_idx, int inst
 }
 
 constexpr int kBvhStack = 64;
-constexpr int kTraceSmemPerThread = PHOX_SMEM_STACK * (int)sizeof(int2);    // dynamic shared memory every kernel that calls trace() is launched with, per thread
 constexpr int kTravReturn = (int)0x80000000;     // stack marker: leave the current solid, back to the instance tree
 constexpr int kTravDone = (int)0x80000001;
 
@@ -110,30 +100,6 @@ constexpr int kTravDone = (int)0x80000001;
 // CSGPrim inside a solid) or one of the two markers.  Children are visited near-first; the far one is
 // parked on the stack with its entry distance so it is dropped once a nearer hit is known.
 PHOX_D void traverse_bvh(Nearest& best, const Scene& sc, float tmin, const float3& o_w, const float3& d_w) {
-#if PHOX_SMEM_STACK > 0
-    // the first PHOX_SMEM_STACK entries of the per-thread stack live in shared memory (interleaved by thread:
-    // conflict free), deeper ones - rare - in local memory.  Local-memory stores are written through to L2,
-    // so a local stack alone made ~80 % of the trace kernel's L2 traffic (profiles/).
-    extern __shared__ int2 s_trav[];                        // [PHOX_SMEM_STACK][blockDim.x] of (item, entry distance)
-    int2* sstack = s_trav + threadIdx.x;
-    const unsigned sstride = blockDim.x;
-    int2 lstack[kBvhStack - PHOX_SMEM_STACK];
-    int sp = 0;
-    auto push = [&](int item, float t) {
-        if (sp < PHOX_SMEM_STACK) sstack[sp * sstride] = make_int2(item, __float_as_int(t));
-        else if (sp < kBvhStack) lstack[sp - PHOX_SMEM_STACK] = make_int2(item, __float_as_int(t));
-        else return;
-        sp++;
-    };
-    auto pop = [&]() -> int {
-        while (sp > 0) {
-            sp--;
-            int2 e = sp < PHOX_SMEM_STACK ? sstack[sp * sstride] : lstack[sp - PHOX_SMEM_STACK];
-            if (__int_as_float(e.y) <= best.t) return e.x;
-        }
-        return kTravDone;
-    };
-#else
     int stack[kBvhStack];
     float stack_t[kBvhStack];
     int sp = 0;
@@ -147,7 +113,6 @@ PHOX_D void traverse_bvh(Nearest& best, const Scene& sc, float tmin, const float
         }
         return kTravDone;
     };
-#endif
     float3 o = o_w, d = d_w;
     float3 idir = f3(1.f / d.x, 1.f / d.y, 1.f / d.z);
     int root = sc.tlas_root;
@@ -252,14 +217,11 @@ __device__ __noinline__ void traverse_brute(Nearest& best, const Scene& sc, floa
     }
 }
 
-// nearest intersect in (tmin, tmax]; fills the prd-equivalent.  Returns false on a miss
-// (the reference's miss program sets boundary 0xffff).  Out of line: one compiled body serves
-// every kernel and both trace sites of the bounce loop.
-__device__ __noinline__ bool trace(HitInfo& h, const Scene& sc, const float3& o, const float3& d, float tmin, float tmax, bool want_fphi) {
-    Nearest best;
-    best.t = tmax; best.prim = -1; best.inst = 0; best.n = f3(0.f, 0.f, 0.f);
-    if (sc.accel == 0) traverse_bvh(best, sc, tmin, o, d);
-    else traverse_brute(best, sc, tmin, o, d);
+// Turns the winner of a traversal into the prd-equivalent (the closest-hit program's job, CSGOptiX7.cu:749-847, and
+// the IS program's local-position terms, :919-934).  Out of line: every float that reaches the physics is computed by
+// ONE compiled body (this function and intersect_prim_cold), whatever kernel ran the traversal around it - that is
+// what keeps the persistent and the wavefront form, and the debug and production kernels, bit-identical.
+__device__ __noinline__ bool hit_finish(HitInfo& h, const Scene& sc, const Nearest& best, const float3& o, const float3& d, bool want_fphi) {
     if (best.prim < 0) {
         h.normal = f3(0.f, 0.f, 0.f); h.t = 1.f; h.lposcost = 0.f; h.lposfphi = 0.f;
         h.iindex_identity = 0xffffffffu; h.prim_boundary = 0xffffffffu;
@@ -275,7 +237,7 @@ __device__ __noinline__ bool trace(HitInfo& h, const Scene& sc, const float3& o,
         n = xform_normal(r0, r1, r2, best.n);       // object -> world uses the inverse-transpose
     }
     float3 lpos = oo + best.t * dd;
-    h.normal = normalize(n);        // the raygen normalises every normal (CSGOptiX7.cu:470-471); done here so that one compiled body serves all kernels
+    h.normal = normalize(n);        // the raygen normalises every normal (CSGOptiX7.cu:470-471)
     h.t = best.t;
     h.lposcost = lpos.z / sqrtf(dot(lpos, lpos));
     h.lposfphi = want_fphi ? (atan2f(lpos.y, lpos.x) + kPi) / (2.0f * kPi) : 0.f;     // only the prd debug array reads it
@@ -285,6 +247,23 @@ __device__ __noinline__ bool trace(HitInfo& h, const Scene& sc, const float3& o,
     unsigned gpi = __float_as_uint(__ldg(sc.prim + 4 * best.prim + 3).w);
     h.prim_boundary = ((gpi & 0xffffu) << 16) | (boundary & 0xffffu);
     return true;
+}
+
+// nearest intersect in (tmin, tmax]; fills the prd-equivalent.  Returns false on a miss (the reference's miss
+// program sets boundary 0xffff).  Inline form: the traversal is compiled into the calling kernel, where the scene
+// pointers are kernel parameters (constant bank) instead of loads through a reference.  The boxes only cull; hit
+// distances and normals come from the out-of-line prim evaluators and hit_finish.
+PHOX_D bool trace_inline(HitInfo& h, const Scene& sc, const float3& o, const float3& d, float tmin, float tmax, bool want_fphi) {
+    Nearest best;
+    best.t = tmax; best.prim = -1; best.inst = 0; best.n = f3(0.f, 0.f, 0.f);
+    if (sc.accel == 0) traverse_bvh(best, sc, tmin, o, d);
+    else traverse_brute(best, sc, tmin, o, d);
+    return hit_finish(h, sc, best, o, d, want_fphi);
+}
+
+// out-of-line form for kernels with several trace sites (persistent kernel, geometry queries)
+__device__ __noinline__ bool trace(HitInfo& h, const Scene& sc, const float3& o, const float3& d, float tmin, float tmax, bool want_fphi) {
+    return trace_inline(h, sc, o, d, tmin, tmax, want_fphi);
 }
 
 PHOX_D void seq_add(Seq& s, unsigned slot, unsigned flag, unsigned boundary) {      // sseq::add_nibble
@@ -433,7 +412,6 @@ constexpr int kWaveThreads = 256;
 #define PHOX_WF_PROP_THREADS 256        // block of the physics kernel = run length of the ordered survivor append
 #endif
 constexpr int kPropThreads = PHOX_WF_PROP_THREADS;
-PHOX_D void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 constexpr unsigned kWaveNoHit = 0xffffffffu;    // prim_boundary of a list entry whose photon is final (miss or time over)
 
 template <bool DEBUG>
@@ -478,31 +456,26 @@ __global__ void __launch_bounds__(kWaveThreads, PHOX_WF_TRACE_MIN_BLOCKS) k_wf_t
     const unsigned stride = gridDim.x * blockDim.x;
     for (unsigned a = blockIdx.x * blockDim.x + threadIdx.x; a < count; a += stride) {
         unsigned idx = W.active_in[a];
-#if PHOX_WF_PREFETCH
-        unsigned idx_next = a + stride < count ? W.active_in[a + stride] : idx;     // issued together with this iteration's loads
-#endif
         const float4* ph = reinterpret_cast<const float4*>(P.photon + idx);
         float4 q0 = ph[0], q1 = ph[1];
         unsigned obf = __float_as_uint(ph[3].x);
         Prd r;
         r.nx = r.ny = r.nz = 0.f; r.t = -1.f; r.lposcost = r.lposfphi = 0.f; r.iindex_identity = 0xffffffffu; r.prim_boundary = kWaveNoHit;
-#if PHOX_WF_PREFETCH
-        prefetch_l2(P.photon + idx_next);                       // the next photon of this thread comes from DRAM while this one is traced
-#endif
         if (q0.w < P.max_time) {                                // else the while-condition of the raygen loop fails: photon is final
             float tmin = (obf & P.eps0_mask) ? P.tmin0 : P.tmin;
             float3 o = f3(q0.x, q0.y, q0.z), d = f3(q1.x, q1.y, q1.z);
             HitInfo h;
-            bool ok = trace(h, P.scene, o, d, tmin, P.tmax, DEBUG && P.prd != nullptr);
-            nray++;
-            if (P.refine && ok) {
-                float t_approx = 0.99f * h.t;
-                if (t_approx > P.refine_distance) {
-                    float3 closer = o + t_approx * d;
-                    ok = trace(h, P.scene, closer, d, tmin, P.tmax, DEBUG && P.prd != nullptr);
-                    nray++;
-                    h.t += t_approx;
-                }
+            bool ok;
+            float3 from = o;
+            float t_add = 0.f;
+            for (int pass = 0;; pass++) {                       // one inlined trace site; pass 1 = PropagateRefine re-trace from 0.99 t
+                ok = trace_inline(h, P.scene, from, d, tmin, P.tmax, DEBUG && P.prd != nullptr);
+                nray++;
+                if (pass == 1) { h.t += t_add; break; }
+                if (!(P.refine && ok)) break;
+                t_add = 0.99f * h.t;
+                if (!(t_add > P.refine_distance)) break;
+                from = o + t_add * d;
             }
             if (ok) {
                 r.nx = h.normal.x; r.ny = h.normal.y; r.nz = h.normal.z; r.t = h.t;
@@ -519,10 +492,8 @@ __global__ void __launch_bounds__(kWaveThreads, PHOX_WF_TRACE_MIN_BLOCKS) k_wf_t
 
 template <bool DEBUG>
 __global__ void __launch_bounds__(kPropThreads) k_wf_propagate(const __grid_constant__ WaveParams W) {
-#if !PHOX_WF_WARP_APPEND
     __shared__ unsigned s_warp[kPropThreads / 32];
     __shared__ unsigned s_base;
-#endif
     const SimParams& P = W.sim;
     const unsigned count = *W.count_in;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -554,14 +525,6 @@ __global__ void __launch_bounds__(kPropThreads) k_wf_propagate(const __grid_cons
             }
         }
         unsigned ballot = __ballot_sync(0xffffffffu, survive);
-#if PHOX_WF_WARP_APPEND
-        // append the survivors of this warp to the next list with one atomic per warp: slots of a warp stay
-        // adjacent and in order, which is all the coherence of the next bounce needs
-        unsigned wbase = 0;
-        if (lane == 0 && ballot) wbase = atomicAdd(W.count_out, (unsigned)__popc(ballot));
-        wbase = __shfl_sync(0xffffffffu, wbase, 0);
-        if (survive) W.active_out[wbase + __popc(ballot & ((1u << lane) - 1u))] = idx;
-#else
         // append the survivors of this chunk to the next list, in order within the chunk
         if (lane == 0) s_warp[warp] = __popc(ballot);
         __syncthreads();
@@ -573,7 +536,6 @@ __global__ void __launch_bounds__(kPropThreads) k_wf_propagate(const __grid_cons
         __syncthreads();
         if (survive) W.active_out[s_base + s_warp[warp] + __popc(ballot & ((1u << lane) - 1u))] = idx;
         __syncthreads();
-#endif
     }
 }
 
