@@ -56,6 +56,7 @@ class ClockSampler:
         self.index = index
         self.sm, self.reasons, self.power = [], set(), []
         self.stop_flag = threading.Event()
+        self.recording = threading.Event()
         self.thread = None
         self.smax = None
         try:
@@ -74,25 +75,33 @@ class ClockSampler:
 
     def _loop(self):
         nv = self.nv
-        self.stop_flag.wait(0.03)
         while not self.stop_flag.is_set():
             try:
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
                     else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in self.REASONS.items():
-                    if r & bit:
-                        self.reasons.add(name)
-                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                if self.recording.is_set():
+                    self.sm.append(sm)
+                    self.power.append(pw)
+                    for bit, name in self.REASONS.items():
+                        if r & bit:
+                            self.reasons.add(name)
             except Exception:
                 pass
             self.stop_flag.wait(0.1)
 
     def start(self):
+        """start the sampling thread (before the warm-up: the first NVML calls made from a new thread block the
+        driver for 50-150 ms, measured, which must not fall into the timed region); samples are kept only between
+        begin() and stop()"""
         if self.nv is None:
             return
         self.thread = threading.Thread(target=self._loop, daemon=True)
         self.thread.start()
+
+    def begin(self):
+        self.recording.set()
 
     def stop(self):
         if self.nv is None or self.thread is None:
@@ -136,6 +145,7 @@ def main():
     ap.add_argument("--photons", type=int, default=12_500_000, help="photons per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=2_000_000, help="photons of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="diagnosis: do not sample NVML clocks during the timed region")
     ap.add_argument("--max-slot", type=int, default=0, help="photons per launch (0 = library default); an event is sliced at genstep granularity")
     ap.add_argument("--kernel-mode", default="auto", choices=["auto", "persistent", "wavefront"], help="form of the bounce loop (include/phox.h PHOX_KERNEL_*)")
     args = ap.parse_args()
@@ -221,9 +231,10 @@ def main():
         st_sum = dict(num_kernel=0, simulate_kernel_seconds=0.0, compact_kernel_seconds=0.0, num_ray=0, num_hit=0, num_launch=0)
         barrier()
         if sampler:
-            sampler.start()
+            sampler.begin()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ms = 0.0
+        per_step = []
         for k in range(steps):
             flush.fill_(float(k))                      # evict L2 between timed iterations (not timed)
             torch.cuda.synchronize(dev)
@@ -231,7 +242,8 @@ def main():
             fn(1 + k)
             e1.record(stream)
             torch.cuda.synchronize(dev)
-            ms += e0.elapsed_time(e1)
+            per_step.append(e0.elapsed_time(e1))
+            ms += per_step[-1]
             st = sim.stats()
             for key in st_sum:
                 st_sum[key] += st[key]
@@ -240,14 +252,17 @@ def main():
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        st_sum["step_ms"] = [round(v, 3) for v in per_step]
         return float(t.item()), st_sum, clocks
 
     sampler = ClockSampler(local_rank)
+    if not args.no_clocks:
+        sampler.start()
     for k in range(warm):
         step_device(0)
     for k in range(2):
         step_e2e(0)
-    ms_dev, st_dev, clocks = timed(step_device, args.steps, sampler)
+    ms_dev, st_dev, clocks = timed(step_device, args.steps, None if args.no_clocks else sampler)
     ms_e2e, st_e2e, _ = timed(step_e2e, args.steps)
 
     tot = torch.tensor([float(cnt_r)], dtype=torch.float64, device=dev)
@@ -295,7 +310,7 @@ def main():
                        "l2": "256 MB flush between timed steps",
                        "sharding": "gensteps partitioned over ranks, absolute photon offsets, hits all-gathered (NCCL) each step" if world > 1 else "single GPU"},
             "rays_per_s": st_dev["num_ray"] * world / (ms_dev * 1e-3), "bounces_per_photon": st_dev["num_ray"] / max(1, cnt_r * args.steps),
-            "hit_fraction": f_hit,
+            "hit_fraction": f_hit, "step_ms": st_dev["step_ms"], "e2e_step_ms": st_e2e["step_ms"],
             "e2e": {"value": e2e, "unit": "photons/s", "h2d_bytes_per_step": int(gs_r.nbytes + (ip_r.nbytes if ip_r is not None else 0)),
                     "d2h_bytes_per_step": int(64 * st_e2e["num_hit"] / max(1, args.steps)), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(st_dev["num_kernel"] + st_e2e["num_kernel"]),

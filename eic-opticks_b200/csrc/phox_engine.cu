@@ -935,6 +935,59 @@ extern "C" int phox_intersect(phox_context* ctx, const float* ray_o_tmin, const 
     return PHOX_OK;
 }
 
+extern "C" int64_t phox_simtrace(phox_context* ctx, const void* genstep, int64_t num_genstep, const void* input_simtrace, int64_t num_input,
+                                 void* dst_simtrace, int64_t capacity) {
+    if (!ctx) return PHOX_E_ARG;
+    if (!ctx->have_geometry) return ctx->fail(PHOX_E_STATE, "phox_simtrace: geometry not set");
+    if (!genstep || num_genstep <= 0 || num_input < 0 || capacity < 0) return ctx->fail(PHOX_E_ARG, "phox_simtrace: bad arguments");
+    const Genstep* gs = (const Genstep*)genstep;
+    std::vector<unsigned long long> prefix((size_t)num_genstep + 1, 0ull);
+    int64_t need_input = 0;
+    for (int64_t i = 0; i < num_genstep; i++) {
+        int code = gs[i].gencode();
+        if (code != GS_FRAME && code != GS_INPUT_PHOTON_SIMTRACE) return ctx->fail(PHOX_E_ARG, "phox_simtrace: genstep is neither FRAME nor INPUT_PHOTON_SIMTRACE");
+        prefix[i + 1] = prefix[i] + gs[i].numphoton();
+        if (code == GS_INPUT_PHOTON_SIMTRACE) need_input = (int64_t)prefix[i + 1];      // slots index the input array directly (qsim.h:2455)
+    }
+    int64_t n = (int64_t)prefix[num_genstep];
+    if (n > 0x7fffffffll) return ctx->fail(PHOX_E_ARG, "phox_simtrace: more than 2^31 rays in one call");
+    if (need_input > 0 && (!input_simtrace || num_input < need_input)) return ctx->fail(PHOX_E_ARG, "phox_simtrace: input simtrace array shorter than the gensteps ask for");
+    if (!dst_simtrace) return n;                                 // size query
+    if (capacity < n) return ctx->fail(PHOX_E_ARG, "phox_simtrace: destination too small");
+    if (n == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    Genstep* d_gs = nullptr; unsigned long long* d_prefix = nullptr; float4 *d_in = nullptr, *d_out = nullptr;
+    cudaError_t e = cudaMalloc(&d_gs, (size_t)num_genstep * sizeof(Genstep));
+    if (e == cudaSuccess) e = cudaMalloc(&d_prefix, prefix.size() * 8);
+    if (e == cudaSuccess && need_input > 0) e = cudaMalloc(&d_in, (size_t)need_input * 64);
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, (size_t)n * 64);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_gs, gs, (size_t)num_genstep * sizeof(Genstep), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_prefix, prefix.data(), prefix.size() * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && need_input > 0) e = cudaMemcpyAsync(d_in, input_simtrace, (size_t)need_input * 64, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        const phox_config& c = ctx->cfg;
+        SimtraceParams S;
+        std::memset(&S, 0, sizeof(S));
+        S.scene.geo.node = ctx->d_node.p; S.scene.geo.plan = ctx->d_plan.p; S.scene.geo.itra = ctx->d_itra.p;
+        S.scene.prim = ctx->d_prim.p; S.scene.nodes = ctx->d_bvh.p; S.scene.inst = ctx->d_inst.p;
+        S.scene.ninst = ctx->ninst; S.scene.tlas_root = ctx->tlas_root; S.scene.accel = c.accel;
+        S.genstep = d_gs; S.gs_prefix = d_prefix; S.num_genstep = (int)num_genstep;
+        S.input = d_in; S.input_base = 0; S.photon_offset = 0; S.num = (unsigned)n;
+        S.tmin = c.propagate_epsilon; S.tmax = c.tmax; S.refine_distance = c.refine_distance; S.refine = c.propagate_refine;
+        S.seed = c.rng_seed; S.rng_offset = c.rng_offset;
+        S.out = d_out;
+        const int T = 128;
+        k_simtrace<<<(unsigned)((n + T - 1) / T), T, 0, ctx->stream>>>(S);
+        e = cudaGetLastError();
+        ctx->stats.num_kernel += 1;
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dst_simtrace, d_out, (size_t)n * 64, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_gs); cudaFree(d_prefix); cudaFree(d_in); cudaFree(d_out);
+    if (e != cudaSuccess) return ctx->cuda_fail(e, "phox_simtrace");
+    return n;
+}
+
 extern "C" int phox_boundary_lookup(phox_context* ctx, const float* nm, const uint32_t* line, const uint32_t* k, int64_t n, float* dst) {
     if (!ctx) return PHOX_E_ARG;
     if (!ctx->have_tables) return ctx->fail(PHOX_E_STATE, "phox_boundary_lookup: tables not set");

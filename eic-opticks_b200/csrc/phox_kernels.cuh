@@ -221,7 +221,9 @@ __device__ __noinline__ void traverse_brute(Nearest& best, const Scene& sc, floa
 // the IS program's local-position terms, :919-934).  Out of line: every float that reaches the physics is computed by
 // ONE compiled body (this function and intersect_prim_cold), whatever kernel ran the traversal around it - that is
 // what keeps the persistent and the wavefront form, and the debug and production kernels, bit-identical.
-__device__ __noinline__ bool hit_finish(HitInfo& h, const Scene& sc, const Nearest& best, const float3& o, const float3& d, bool want_fphi) {
+constexpr unsigned kHitFphi = 1u;          // fill lposfphi (only the prd debug array and simtrace read it)
+constexpr unsigned kHitRawNormal = 2u;     // leave the normal as the closest-hit program delivers it (simtrace); the simulate raygen normalises
+__device__ __noinline__ bool hit_finish(HitInfo& h, const Scene& sc, const Nearest& best, const float3& o, const float3& d, unsigned flags) {
     if (best.prim < 0) {
         h.normal = f3(0.f, 0.f, 0.f); h.t = 1.f; h.lposcost = 0.f; h.lposfphi = 0.f;
         h.iindex_identity = 0xffffffffu; h.prim_boundary = 0xffffffffu;
@@ -237,10 +239,10 @@ __device__ __noinline__ bool hit_finish(HitInfo& h, const Scene& sc, const Neare
         n = xform_normal(r0, r1, r2, best.n);       // object -> world uses the inverse-transpose
     }
     float3 lpos = oo + best.t * dd;
-    h.normal = normalize(n);        // the raygen normalises every normal (CSGOptiX7.cu:470-471)
+    h.normal = (flags & kHitRawNormal) ? n : normalize(n);        // the simulate raygen normalises every normal (CSGOptiX7.cu:470-471)
     h.t = best.t;
     h.lposcost = lpos.z / sqrtf(dot(lpos, lpos));
-    h.lposfphi = want_fphi ? (atan2f(lpos.y, lpos.x) + kPi) / (2.0f * kPi) : 0.f;     // only the prd debug array reads it
+    h.lposfphi = (flags & kHitFphi) ? (atan2f(lpos.y, lpos.x) + kPi) / (2.0f * kPi) : 0.f;
     h.iindex_identity = (((unsigned)best.inst & 0xffffu) << 16) | ((unsigned)meta.y & 0xffffu);
     float4 p0 = __ldg(sc.prim + 4 * best.prim);
     unsigned boundary = __float_as_uint(__ldg(sc.geo.node + 4 * __float_as_int(p0.y) + 1).z);
@@ -253,17 +255,17 @@ __device__ __noinline__ bool hit_finish(HitInfo& h, const Scene& sc, const Neare
 // program sets boundary 0xffff).  Inline form: the traversal is compiled into the calling kernel, where the scene
 // pointers are kernel parameters (constant bank) instead of loads through a reference.  The boxes only cull; hit
 // distances and normals come from the out-of-line prim evaluators and hit_finish.
-PHOX_D bool trace_inline(HitInfo& h, const Scene& sc, const float3& o, const float3& d, float tmin, float tmax, bool want_fphi) {
+PHOX_D bool trace_inline(HitInfo& h, const Scene& sc, const float3& o, const float3& d, float tmin, float tmax, unsigned flags) {
     Nearest best;
     best.t = tmax; best.prim = -1; best.inst = 0; best.n = f3(0.f, 0.f, 0.f);
     if (sc.accel == 0) traverse_bvh(best, sc, tmin, o, d);
     else traverse_brute(best, sc, tmin, o, d);
-    return hit_finish(h, sc, best, o, d, want_fphi);
+    return hit_finish(h, sc, best, o, d, flags);
 }
 
 // out-of-line form for kernels with several trace sites (persistent kernel, geometry queries)
-__device__ __noinline__ bool trace(HitInfo& h, const Scene& sc, const float3& o, const float3& d, float tmin, float tmax, bool want_fphi) {
-    return trace_inline(h, sc, o, d, tmin, tmax, want_fphi);
+__device__ __noinline__ bool trace(HitInfo& h, const Scene& sc, const float3& o, const float3& d, float tmin, float tmax, unsigned flags) {
+    return trace_inline(h, sc, o, d, tmin, tmax, flags);
 }
 
 PHOX_D void seq_add(Seq& s, unsigned slot, unsigned flag, unsigned boundary) {      // sseq::add_nibble
@@ -339,13 +341,13 @@ __global__ void __launch_bounds__(kSimThreads, PHOX_SIM_MIN_BLOCKS) k_simulate(c
             if (!finished) {
                 float tmin = (p.obf & P.eps0_mask) ? P.tmin0 : P.tmin;
                 HitInfo h;
-                bool ok = trace(h, P.scene, p.pos, p.mom, tmin, P.tmax, DEBUG && P.prd != nullptr);
+                bool ok = trace(h, P.scene, p.pos, p.mom, tmin, P.tmax, (DEBUG && P.prd != nullptr) ? kHitFphi : 0u);
                 nray++;
                 if (P.refine && ok) {
                     float t_approx = 0.99f * h.t;
                     if (t_approx > P.refine_distance) {
                         float3 closer = p.pos + t_approx * p.mom;
-                        ok = trace(h, P.scene, closer, p.mom, tmin, P.tmax, DEBUG && P.prd != nullptr);
+                        ok = trace(h, P.scene, closer, p.mom, tmin, P.tmax, (DEBUG && P.prd != nullptr) ? kHitFphi : 0u);
                         nray++;
                         h.t += t_approx;
                     }
@@ -469,7 +471,7 @@ __global__ void __launch_bounds__(kWaveThreads, PHOX_WF_TRACE_MIN_BLOCKS) k_wf_t
             float3 from = o;
             float t_add = 0.f;
             for (int pass = 0;; pass++) {                       // one inlined trace site; pass 1 = PropagateRefine re-trace from 0.99 t
-                ok = trace_inline(h, P.scene, from, d, tmin, P.tmax, DEBUG && P.prd != nullptr);
+                ok = trace_inline(h, P.scene, from, d, tmin, P.tmax, (DEBUG && P.prd != nullptr) ? kHitFphi : 0u);
                 nray++;
                 if (pass == 1) { h.t += t_add; break; }
                 if (!(P.refine && ok)) break;
@@ -645,12 +647,87 @@ __global__ void k_intersect(Scene sc, const float4* __restrict__ ray_o_tmin, con
     if (i >= n) return;
     float4 o = ray_o_tmin[i], d = ray_d[i];
     HitInfo h;
-    trace(h, sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, tmax, true);
+    trace(h, sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, tmax, kHitFphi);
     Prd r;
     r.nx = h.normal.x; r.ny = h.normal.y; r.nz = h.normal.z; r.t = h.t;
     r.lposcost = h.lposcost; r.lposfphi = h.lposfphi;
     r.iindex_identity = h.iindex_identity; r.prim_boundary = h.prim_boundary;
     out[i] = r;
+}
+
+// simtrace (CSGOptiX7.cu:536-577): one ray per slot from FRAME gensteps (qsim.h:2459-2511: local position gs.q1,
+// direction from 2 uniforms in the plane named by gridaxes, both through the genstep's own transform gs.q2..q5) or
+// from caller-supplied rays (INPUT_PHOTON_SIMTRACE, qsim.h:2455), one trace, record in sevent::add_simtrace layout
+// (sevent.h:670-697): q0 normal+t, q1 intersect position+tmin, q2 origin+prim/boundary, q3 direction+iindex/identity.
+struct SimtraceParams {
+    Scene scene;
+    const Genstep* genstep;
+    const unsigned long long* gs_prefix;
+    int num_genstep;
+    const float4* input;                 // quad4 per slot (q0 position, q1 direction) for INPUT_PHOTON_SIMTRACE gensteps
+    unsigned long long input_base;
+    unsigned long long photon_offset;
+    unsigned num;
+    float tmin, tmax, refine_distance;
+    unsigned refine;
+    unsigned long long seed, rng_offset;
+    float4* out;                         // quad4 per slot
+};
+enum : int { GS_FRAME = 17, GS_INPUT_PHOTON_SIMTRACE = 20 };        // OpticksGenstep.h:38,41
+enum : int { AX_XYZ = 0, AX_YZ = 1, AX_XZ = 2, AX_XY = 3 };          // sxyz.h:3
+
+__global__ void k_simtrace(const __grid_constant__ SimtraceParams S) {
+    unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= S.num) return;
+    int lo = 0, hi = S.num_genstep;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (__ldg(S.gs_prefix + mid) <= (unsigned long long)idx) lo = mid; else hi = mid;
+    }
+    const Genstep& gs = S.genstep[lo];
+    unsigned long long photon_idx = S.photon_offset + idx;
+    float3 pos = f3(0.f, 0.f, 0.f), mom = f3(0.f, 0.f, 1.f);
+    if (gs.gencode() == GS_INPUT_PHOTON_SIMTRACE) {
+        float4 a = __ldg(S.input + 4 * (photon_idx - S.input_base)), b = __ldg(S.input + 4 * (photon_idx - S.input_base) + 1);
+        pos = f3(a.x, a.y, a.z); mom = f3(b.x, b.y, b.z);
+    } else if (gs.gencode() == GS_FRAME) {
+        Philox rng;
+        rng.init(S.seed, photon_idx, S.rng_offset);                  // sim->rng->init(rng, 0, photon_idx): event index 0
+        float u0 = rng.uniform();
+        float sinPhi, cosPhi;
+        sincosf(2.f * kPi * u0, &sinPhi, &cosPhi);
+        float u1 = rng.uniform();
+        float cosTheta = 2.f * u1 - 1.f;
+        float sinTheta = sqrtf(1.f - cosTheta * cosTheta);
+        float3 l = f3(gs.f[4], gs.f[5], gs.f[6]), m;
+        switch (gs.i[1]) {
+            case AX_YZ: m = f3(0.f, cosPhi, sinPhi); break;
+            case AX_XZ: m = f3(cosPhi, 0.f, sinPhi); break;
+            case AX_XY: m = f3(cosPhi, sinPhi, 0.f); break;
+            default:    m = f3(sinTheta * cosPhi, sinTheta * sinPhi, cosTheta); break;
+        }
+        const float* q = gs.f + 8;                                   // rows q2..q5 of the genstep = qat4, row-vector convention
+        pos = f3(q[0] * l.x + q[4] * l.y + q[8] * l.z + q[12] * 1.f, q[1] * l.x + q[5] * l.y + q[9] * l.z + q[13] * 1.f,
+                 q[2] * l.x + q[6] * l.y + q[10] * l.z + q[14] * 1.f);
+        mom = f3(q[0] * m.x + q[4] * m.y + q[8] * m.z + q[12] * 0.f, q[1] * m.x + q[5] * m.y + q[9] * m.z + q[13] * 0.f,
+                 q[2] * m.x + q[6] * m.y + q[10] * m.z + q[14] * 0.f);
+    }
+    HitInfo h;
+    bool ok = trace(h, S.scene, pos, mom, S.tmin, S.tmax, kHitFphi | kHitRawNormal);
+    if (S.refine && ok) {
+        float t_approx = 0.99f * h.t;
+        if (t_approx > S.refine_distance) {
+            float3 closer = pos + t_approx * mom;
+            ok = trace(h, S.scene, closer, mom, S.tmin, S.tmax, kHitFphi | kHitRawNormal);
+            h.t += t_approx;
+        }
+    }
+    if (!ok) { h.normal = f3(0.6f, 0.6f, 0.6f); h.t = 1.f; }          // miss program: background colour in q0.xyz, t = 1 (CSGOptiX7.cu:655-682, SBT.cc:181-193)
+    float4* o = S.out + 4 * (size_t)idx;
+    o[0] = make_float4(h.normal.x, h.normal.y, h.normal.z, h.t);
+    o[1] = make_float4(pos.x + h.t * mom.x, pos.y + h.t * mom.y, pos.z + h.t * mom.z, S.tmin);
+    o[2] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(h.prim_boundary));
+    o[3] = make_float4(mom.x, mom.y, mom.z, __uint_as_float(h.iindex_identity));
 }
 
 // boundary texture readback (QSim.cu boundary_lookup_line role)

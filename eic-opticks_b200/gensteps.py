@@ -224,6 +224,86 @@ def scint_gensteps(pos, direction, step_length, numphoton, matline, scintillatio
     return gs
 
 
+# ---- simtrace gensteps (sysrap/SFrameGenstep.cc, SGenstep.h) -----------------------------------------------------------
+GS_FRAME, GS_INPUT_PHOTON_SIMTRACE = 17, 20        # OpticksGenstep.h:38,41
+AX_XYZ, AX_YZ, AX_XZ, AX_XY = 0, 1, 2, 3           # sxyz.h:3
+
+
+def grid_axes(nx, ny, nz):
+    """SGenstep::GridAxes (SGenstep.h:137-153): which plane a planar grid lies in, XYZ for anything else"""
+    if nx == 0 and ny > 0 and nz > 0:
+        return AX_YZ
+    if nx > 0 and ny == 0 and nz > 0:
+        return AX_XZ
+    if nx > 0 and ny > 0 and nz == 0:
+        return AX_XY
+    return AX_XYZ
+
+
+def standardize_cegs(cegs):
+    """SFrameGenstep::StandardizeCEGS: nx:ny:nz:n or nx:ny:nz:dx:dy:dz:n -> ix0:ix1:iy0:iy1:iz0:iz1:n:high"""
+    c = [int(v) for v in cegs]
+    if len(c) == 4:
+        nx, ny, nz, n = c
+        return [-nx, nx, -ny, ny, -nz, nz, n, 1]
+    if len(c) == 7:
+        nx, ny, nz, dx, dy, dz, n = c
+        return [-nx + dx, nx + dx, -ny + dy, ny + dy, -nz + dz, nz + dz, n, 1]
+    if len(c) == 8:
+        return c
+    raise ValueError("cegs must have 4, 7 or 8 integers")
+
+
+def frame_gensteps(ce, cegs, gridscale=1.0, geotran=None, ce_offset=((0.0, 0.0, 0.0),), ce_scale=True, radial_range=None):
+    """SFrameGenstep::MakeCenterExtentGenstep (SFrameGenstep.cc:604-735): a grid of FRAME gensteps around a
+    center-extent `ce` = (cx, cy, cz, extent).  Grid point (ix,iy,iz) sits at local offset i*gridscale*extent; each
+    genstep carries the transform  translate(offset) . geotran  (row-vector convention, so the small local shift is
+    applied first) in q2..q5, gridaxes in q0.y, the packed signed-char id (ix,iy,iz,plane) in q0.z and
+    photons_per_genstep in q0.w.  geotran None = translation to ce.xyz (the usual frame of a target volume)."""
+    c = standardize_cegs(cegs)
+    high = c[7]
+    assert 1 <= high <= 8
+    scale = float(gridscale) / float(high)
+    ix0, ix1, iy0, iy1, iz0, iz1 = [v * high for v in c[:6]]
+    per = c[6]
+    axes = grid_axes((ix1 - ix0) // 2, (iy1 - iy0) // 2, (iz1 - iz0) // 2)
+    local_scale = scale * float(ce[3]) if ce_scale else scale
+    if geotran is None:
+        geotran = np.eye(4, dtype=np.float64)
+        geotran[3, :3] = ce[:3]
+    geotran = np.asarray(geotran, dtype=np.float64).reshape(4, 4)
+    rmin, rmax = (radial_range if radial_range is not None else (0.0, np.inf))
+    out = []
+    for ip, off in enumerate(ce_offset):
+        for ix in range(ix0, ix1 + 1):
+            for iy in range(iy0, iy1 + 1):
+                for iz in range(iz0, iz1 + 1):
+                    t = np.array([ix, iy, iz], dtype=np.float64) * local_scale
+                    if radial_range is not None and not (rmin <= np.sqrt((t * t).sum()) <= rmax):
+                        continue
+                    shift = np.eye(4, dtype=np.float64)
+                    shift[3, :3] = t
+                    m = (shift @ geotran).astype(np.float32)
+                    g = np.zeros((6, 4), dtype=np.float32)
+                    gi = g.view(np.int32)
+                    gi[0, 0] = GS_FRAME
+                    gi[0, 1] = axes
+                    g.view(np.uint32)[0, 2] = np.array([ix, iy, iz, ip], dtype=np.int8).view(np.uint32)[0]      # SGenstep::GenstepID
+                    gi[0, 3] = per
+                    g[1] = (off[0], off[1], off[2], 1.0)
+                    g[2:6] = m
+                    out.append(g)
+    return np.stack(out) if out else np.zeros((0, 6, 4), dtype=np.float32)
+
+
+def input_simtrace_genstep(n):
+    """one INPUT_PHOTON_SIMTRACE genstep carrying n caller-supplied rays (qsim.h:2455)"""
+    g = np.zeros((1, 6, 4), dtype=np.float32)
+    g.view(np.int32)[0, 0, 0] = GS_INPUT_PHOTON_SIMTRACE
+    g.view(np.uint32)[0, 0, 3] = n
+    return g
+
+
 def partition_gensteps(gs, nrank):
     """Contiguous genstep ranges balanced by photon count, one per rank, with the absolute photon
     offset of each range - the concurrent form of SGenstep::GetGenstepSlices

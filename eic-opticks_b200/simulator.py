@@ -252,6 +252,20 @@ class Simulator:
         self._check(self.lib.phox_boundary_lookup(self.ctx, _ptr(nm), _ptr(line), _ptr(k), len(nm), _ptr(out)))
         return out
 
+    def simtrace(self, gensteps, input_simtrace=None):
+        """SSimulator::simtrace: FRAME / INPUT_PHOTON_SIMTRACE gensteps -> (n,4,4) simtrace records
+        (sevent::add_simtrace layout, sysrap/sevent.h:670-697)."""
+        gs = np.ascontiguousarray(gensteps, dtype=np.float32).reshape(-1, 6, 4)
+        ip = None if input_simtrace is None else np.ascontiguousarray(input_simtrace, dtype=np.float32).reshape(-1, 4, 4)
+        n = self.lib.phox_simtrace(self.ctx, _ptr(gs), len(gs), _ptr(ip) if ip is not None else None, 0 if ip is None else len(ip), None, 0)
+        if n < 0:
+            self._check(int(n))
+        out = np.empty((n, 4, 4), dtype=np.float32)
+        m = self.lib.phox_simtrace(self.ctx, _ptr(gs), len(gs), _ptr(ip) if ip is not None else None, 0 if ip is None else len(ip), _ptr(out), n)
+        if m < 0:
+            self._check(int(m))
+        return out
+
     def rng_sequence(self, ni, nv, id0=0, event_id=0):
         out = np.empty((ni, nv), dtype=np.float32)
         self._check(self.lib.phox_rng_sequence(self.ctx, _ptr(out), ni, nv, id0, event_id))

@@ -17,6 +17,7 @@
 //   unsigned nhit = cx->getNumHit();  cx->getHit(hit, i);  cx->reset(eventID);
 #pragma once
 #include <cstdint>
+#include <chrono>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -90,10 +91,28 @@ public:
     }
     void reset(int /*eventID*/) override { phox_reset(ctx_); gs_.clear(); ip_.clear(); ngs_ = nip_ = 0; }
     const char* desc() const override { return phox_desc(ctx_); }
-    // simtrace and render are outside the simulate path this library replaces (SURVEY 8f rank 4, 2.4 "OUT")
-    double simtrace_launch() override { return -1.; }
+    // simtrace (CSGOptiX7.cu:536-577): the collected gensteps must be FRAME / INPUT_PHOTON_SIMTRACE ones; the records
+    // (sevent::add_simtrace layout) are kept for getSimtrace().  Returns wall seconds, -1. without gensteps.
+    double simtrace_launch() override {
+        if (ngs_ == 0) return -1.;
+        auto t0 = std::chrono::steady_clock::now();
+        int64_t n = phox_simtrace(ctx_, gs_.data(), ngs_, nip_ ? ip_.data() : nullptr, nip_, nullptr, 0);
+        if (n < 0) check((int)n);
+        simtrace_.resize((size_t)n * 16);
+        n = phox_simtrace(ctx_, gs_.data(), ngs_, nip_ ? ip_.data() : nullptr, nip_, simtrace_.data(), n);
+        if (n < 0) check((int)n);
+        return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+    double simtrace(int eventID) override { event_id_ = eventID; return simtrace_launch(); }
+    void setInputSimtrace(const void* quad4, int64_t n) {                // rays for an INPUT_PHOTON_SIMTRACE genstep (qsim.h:2455)
+        ip_.assign((const char*)quad4, (const char*)quad4 + n * 64); nip_ = n;
+        gs_.assign(96, 0); ngs_ = 1;
+        int32_t code = 20; uint32_t num = (uint32_t)n;
+        std::memcpy(gs_.data(), &code, 4); std::memcpy(gs_.data() + 12, &num, 4);
+    }
+    const std::vector<float>& getSimtrace() const { return simtrace_; }    // (n,4,4) float32
+    // render is outside the path this library replaces (SURVEY 2.4 "OUT")
     double render_launch() override { return -1.; }
-    double simtrace(int) override { return -1.; }
     double render(const char* = nullptr) override { return -1.; }
 
     // hits, as SEvt::GetNumHit / SEvt::getHit hand them to the apps (sysrap/SEvt.cc:4924-4925, 4991)
@@ -111,4 +130,5 @@ private:
     int64_t ngs_ = 0, nip_ = 0;
     int event_id_ = 0;
     std::vector<PhoxPhoton> hits_;
+    std::vector<float> simtrace_;
 };

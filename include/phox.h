@@ -193,6 +193,17 @@ void phox_reset(phox_context* ctx);   /* SSimulator::reset(eventID) */
 int phox_intersect(phox_context* ctx, const float* ray_o_tmin, const float* ray_d, int64_t nray,
                    void* dst_prd, int32_t accel);
 
+/* SSimulator::simtrace (sysrap/SSimulator.h:26; raygen CSGOptiX/CSGOptiX7.cu:536-577): one ray per slot of the
+ * gensteps, which must be FRAME (17: center-extent grid gensteps, sysrap/SFrameGenstep.cc:604-735; the ray starts at
+ * gs.q1 and takes a random direction in the plane gs.q0.y names, both through the transform in gs.q2..q5,
+ * qudarap/qsim.h:2459-2511) or INPUT_PHOTON_SIMTRACE (20: slot i takes position/direction from input_simtrace[i].q0/q1).
+ * One trace each (tmin = propagate_epsilon, PropagateRefine honoured); results in sevent::add_simtrace layout
+ * (sysrap/sevent.h:670-697), quad4 per slot: q0 normal + t, q1 intersect position + tmin, q2 origin + prim<<16|boundary,
+ * q3 direction + iindex<<16|identity; a miss keeps the miss program's q0 = (0.6,0.6,0.6,1) and 0xffffffff in both ints.
+ * Returns the number of records (= sum of numphoton), or a negative PHOX_E_* code.  dst_simtrace NULL = size query. */
+int64_t phox_simtrace(phox_context* ctx, const void* genstep, int64_t num_genstep, const void* input_simtrace, int64_t num_input,
+                      void* dst_simtrace, int64_t capacity);
+
 /* Precooked random streams (qudarap/QSim.cu:43-68): first nv curand_uniform floats of
  * subsequences [id0, id0+ni). dst is host float32[ni*nv]. */
 /* Boundary-table readback through the hardware texture path (qudarap/QSim.cu boundary_lookup_line /

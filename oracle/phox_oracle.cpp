@@ -1136,6 +1136,53 @@ int oracle_intersect(const int* solid, int nsolid, const void* prim, const void*
     return 0;
 }
 
+// simtrace raygen (CSGOptiX/CSGOptiX7.cu:536-577) with qsim::generate_photon_simtrace_frame (qudarap/qsim.h:2459-2511) and
+// sevent::add_simtrace (sysrap/sevent.h:670-697).  gensteps: FRAME (17) or INPUT_PHOTON_SIMTRACE (20); out: quad4 per slot.
+int oracle_simtrace(const int* solid, int nsolid, const void* prim, const void* node, const void* plan, const float* itra, int nitra,
+                    const float* inst, int ninst, const float* genstep, int ngs, const float* input, float tmin, float tmax,
+                    uint64_t seed, uint64_t offset, float* out, int use_boxes) {
+    Scene sc;
+    if (make_scene(sc, solid, nsolid, prim, node, plan, itra, nitra, inst, ninst, use_boxes)) return -1;
+    std::vector<int64_t> prefix(ngs + 1, 0);
+    for (int g = 0; g < ngs; g++) { unsigned n; memcpy(&n, genstep + 24 * g + 3, 4); prefix[g + 1] = prefix[g] + n; }
+    int64_t total = prefix[ngs];
+#pragma omp parallel for schedule(static)
+    for (int64_t idx = 0; idx < total; idx++) {
+        int g = int(std::upper_bound(prefix.begin(), prefix.end(), idx) - prefix.begin()) - 1;
+        const float* gs = genstep + 24 * g;
+        int gencode, gridaxes; memcpy(&gencode, gs, 4); memcpy(&gridaxes, gs + 1, 4);
+        v3 pos = mk(0, 0, 0), mom = mk(0, 0, 1);
+        if (gencode == 20) {
+            pos = mk(input[16 * idx], input[16 * idx + 1], input[16 * idx + 2]);
+            mom = mk(input[16 * idx + 4], input[16 * idx + 5], input[16 * idx + 6]);
+        } else {
+            Rng rng; rng.init(seed, (uint64_t)idx, offset);
+            float u0 = rng.uniform();
+            float sinPhi = sinf(2.f * PI_F * u0), cosPhi = cosf(2.f * PI_F * u0);
+            float u1 = rng.uniform();
+            float cosTheta = 2.f * u1 - 1.f, sinTheta = sqrtf(1.f - cosTheta * cosTheta);
+            v3 l = mk(gs[4], gs[5], gs[6]), m;
+            switch (gridaxes) {                                            // sxyz.h: XYZ 0, YZ 1, XZ 2, XY 3
+                case 1: m = mk(0.f, cosPhi, sinPhi); break;
+                case 2: m = mk(cosPhi, 0.f, sinPhi); break;
+                case 3: m = mk(cosPhi, sinPhi, 0.f); break;
+                default: m = mk(sinTheta * cosPhi, sinTheta * sinPhi, cosTheta); break;
+            }
+            pos = right_multiply(gs + 8, l, 1.f);                          // qat4(gs) = rows q2..q5
+            mom = right_multiply(gs + 8, m, 0.f);
+        }
+        Prd prd;
+        bool ok = trace(prd, sc, pos, mom, tmin, tmax);
+        if (!ok) { prd.normal = mk(0.6f, 0.6f, 0.6f); prd.t = 1.f; }       // __miss__ms: background colour, t = 1
+        float* o = out + 16 * idx;
+        o[0] = prd.normal.x; o[1] = prd.normal.y; o[2] = prd.normal.z; o[3] = prd.t;
+        o[4] = pos.x + prd.t * mom.x; o[5] = pos.y + prd.t * mom.y; o[6] = pos.z + prd.t * mom.z; o[7] = tmin;
+        o[8] = pos.x; o[9] = pos.y; o[10] = pos.z; memcpy(o + 11, &prd.prim_boundary, 4);
+        o[12] = mom.x; o[13] = mom.y; o[14] = mom.z; memcpy(o + 15, &prd.iindex_identity, 4);
+    }
+    return (int)total;
+}
+
 // one prim, one ray: used to compare against the reference CSG headers compiled for the host
 int oracle_intersect_prim(const void* node, int node_offset, const void* plan, const float* itra, int nitra, const float* o, const float* d, float tmin,
                           float* isect_out) {

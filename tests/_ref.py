@@ -131,6 +131,21 @@ class Oracle:
             raise RuntimeError("oracle_simulate failed")
         return dict(photon=photon, record=record, seq=seq, prd=prd, nray=nray.value, nhit=nhit.value)
 
+    def simtrace(self, geom, gensteps, input_simtrace=None, tmin=0.05, tmax=1e6, seed=0, offset=0, use_boxes=True):
+        fd = geom["foundry"]
+        a = {k: np.ascontiguousarray(fd[k], dtype=(np.int32 if k == "solid" else np.float32)) for k in ("solid", "prim", "node", "plan", "itra", "inst")}
+        gs = np.ascontiguousarray(gensteps, dtype=np.float32).reshape(-1, 6, 4)
+        n = int(gs.view(np.uint32)[:, 0, 3].sum())
+        ip = None if input_simtrace is None else np.ascontiguousarray(input_simtrace, dtype=np.float32)
+        out = np.zeros((n, 4, 4), dtype=np.float32)
+        self.lib.oracle_simtrace.restype = C.c_int
+        rc = self.lib.oracle_simtrace(_p(a["solid"]), C.c_int(len(a["solid"])), _p(a["prim"]), _p(a["node"]), _p(a["plan"]) if len(a["plan"]) else None,
+                                      _p(a["itra"]), C.c_int(len(a["itra"])), _p(a["inst"]), C.c_int(len(a["inst"])), _p(gs), C.c_int(len(gs)),
+                                      _p(ip), C.c_float(tmin), C.c_float(tmax), C.c_uint64(seed), C.c_uint64(offset), _p(out), C.c_int(1 if use_boxes else 0))
+        if rc != n:
+            raise RuntimeError("oracle_simtrace failed")
+        return out
+
     def intersect_prim_batch(self, fd, prim_idx, o, d, tmin):
         node = np.ascontiguousarray(fd["node"], dtype=np.float32)
         plan = np.ascontiguousarray(fd["plan"], dtype=np.float32)

@@ -233,6 +233,39 @@ def test_device_resident_path_equals_host_path():
     sim.close()
 
 
+def test_simtrace_matches_oracle_and_intersect():
+    """SSimulator::simtrace (CSGOptiX7.cu:536-577): FRAME gensteps and caller-supplied rays"""
+    for name, ce, cegs in (("sipm8x8_scint", (0.0, 0.0, 4.0, 12.0), [8, 0, 8, 200]), ("pmt_wall_torch", (0.0, 0.0, 0.0, 2000.0), [6, 6, 0, 100]),
+                           ("boolean_zoo_torch", (0.0, 0.0, 0.0, 400.0), [5, 5, 5, 30])):
+        w = workloads.WORKLOADS[name](num_photon=1000)
+        sim = make_sim(w)
+        gs = G.frame_gensteps(ce, cegs, gridscale=0.1)
+        st = sim.simtrace(gs)
+        ref = Oracle().simtrace(w["geom"], gs)
+        assert st.shape == ref.shape and len(st) == int(gs.view(np.uint32)[:, 0, 3].sum())
+        # origins are exact, directions differ by the ulps of sincosf (device) vs sinf/cosf (host)
+        assert (st[:, 2, :3] == ref[:, 2, :3]).all() and np.abs(st[:, 3, :3] - ref[:, 3, :3]).max() < 1e-6
+        su, ru = st.view(np.uint32), ref.view(np.uint32)
+        same = (su[:, 2, 3] == ru[:, 2, 3]) & (su[:, 3, 3] == ru[:, 3, 3])
+        assert same.mean() > 0.995, (name, same.mean())
+        hit = same & (su[:, 2, 3] != 0xffffffff)
+        assert hit.sum() > 0.5 * len(st)
+        assert np.quantile(np.abs(st[hit, 0, 3] - ref[hit, 0, 3]) / np.maximum(1.0, ref[hit, 0, 3]), 0.999) < 1e-4
+        assert np.allclose(st[hit, 1, :3], st[hit, 2, :3] + st[hit, 0, 3][:, None] * st[hit, 3, :3], rtol=0, atol=1e-3 * max(1.0, ce[3] / 100))
+        miss = su[:, 2, 3] == 0xffffffff
+        if miss.any():                                                          # miss program: background colour, t = 1
+            assert (st[miss, 0] == np.array([0.6, 0.6, 0.6, 1.0], dtype=np.float32)).all() and (su[miss, 3, 3] == 0xffffffff).all()
+        # the same rays fed back as INPUT_PHOTON_SIMTRACE: bit-identical records, and t / identities equal to phox_intersect
+        rays = np.zeros_like(st); rays[:, 0, :3] = st[:, 2, :3]; rays[:, 1, :3] = st[:, 3, :3]
+        st2 = sim.simtrace(G.input_simtrace_genstep(len(rays)), rays)
+        assert st2.tobytes() == st.tobytes()
+        prd = sim.intersect(rays[:, 0, :3], rays[:, 1, :3], tmin=0.05)
+        pu = prd.view(np.uint32)
+        h2 = pu[:, 1, 3] != 0xffffffff
+        assert (h2 == ~miss).all() and (pu[h2, 1, 3] == su[h2, 2, 3]).all() and (pu[h2, 1, 2] == su[h2, 3, 3]).all() and (prd[h2, 0, 3] == st[h2, 0, 3]).all()
+        sim.close()
+
+
 def test_event_index_skipahead_and_rng_sequence():
     w = workloads.sipm8x8_scint(num_photon=1000, photons_per_genstep=100)
     sim = make_sim(w)
