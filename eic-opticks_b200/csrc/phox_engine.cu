@@ -12,6 +12,7 @@
 // There is no CPU fallback: without a CUDA device phox_create fails.
 #include "../../include/phox.h"
 #include "phox_kernels.cuh"
+#include "phox_merge.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -97,6 +98,9 @@ struct phox_context {
     DevBuf<Prd> d_wave_hits;
     int wave_grid[3][2] = {{0, 0}, {0, 0}, {0, 0}};             // persistent grid sizes of generate/trace/propagate, <false/true>
     DevBuf<unsigned long long> d_block_off;
+    DevBuf<Photon> d_merged;                   // result of the last phox_merge_hits / phox_merge
+    DevBuf<Photon> d_merge_in;
+    MergeScratch merge_scratch;
     DevBuf<float> d_slack;                     // per CSGPrim: exit-bound slack of prims that are exactly a box (0 = not such a prim)
     DevBuf<unsigned long long> d_counters;     // [0] rays, [1] hit total of the launch
     unsigned long long* h_counters = nullptr;  // pinned mirror
@@ -227,6 +231,7 @@ extern "C" void phox_destroy(phox_context* ctx) {
     ctx->d_record.release(); ctx->d_hit.release(); ctx->d_seq.release(); ctx->d_prd.release();
     ctx->d_block_hits.release(); ctx->d_block_off.release(); ctx->d_counters.release();
     ctx->d_slack.release();
+    ctx->d_merged.release(); ctx->d_merge_in.release(); merge_scratch_free(ctx->merge_scratch);
     ctx->d_active[0].release(); ctx->d_active[1].release(); ctx->d_ndraw.release(); ctx->d_wave_count.release(); ctx->d_wave_hits.release();
     bvh_scratch_free(ctx->bvh_scratch);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
@@ -986,6 +991,47 @@ extern "C" int64_t phox_simtrace(phox_context* ctx, const void* genstep, int64_t
     cudaFree(d_gs); cudaFree(d_prefix); cudaFree(d_in); cudaFree(d_out);
     if (e != cudaSuccess) return ctx->cuda_fail(e, "phox_simtrace");
     return n;
+}
+
+extern "C" int64_t phox_merge_hits(phox_context* ctx, float time_window, void* dst, int64_t capacity) {
+    if (!ctx) return PHOX_E_ARG;
+    if (!ctx->have_event) return ctx->fail(PHOX_E_STATE, "phox_merge_hits: no event");
+    if (!(time_window >= 0.f) || capacity < 0) return ctx->fail(PHOX_E_ARG, "phox_merge_hits: bad arguments");
+    int64_t n = ctx->num_hit, m = 0;
+    if (n == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->d_merged.reserve((size_t)n));
+    int nk = 0;
+    // the hits are already the hit-mask selection (all bits); the any-bit select of the reference's merge is a no-op on them
+    CK(merge_photons(ctx->d_hit.p, n, 0u, time_window, ctx->d_merged.p, &m, ctx->merge_scratch, ctx->stream, &nk));
+    ctx->stats.num_kernel += (uint64_t)nk;
+    if (!dst) return m;
+    if (capacity < m) return ctx->fail(PHOX_E_ARG, "phox_merge_hits: destination too small");
+    if (m > 0) {
+        CK(cudaMemcpyAsync(dst, ctx->d_merged.p, (size_t)m * sizeof(Photon), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return m;
+}
+
+extern "C" int64_t phox_merge(phox_context* ctx, const void* photons, int64_t n, uint32_t select_mask, float time_window, void* dst, int64_t capacity) {
+    if (!ctx) return PHOX_E_ARG;
+    if (n < 0 || (n > 0 && !photons) || !(time_window >= 0.f) || !dst || capacity < 0) return ctx->fail(PHOX_E_ARG, "phox_merge: bad arguments");
+    if (n == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->d_merge_in.reserve((size_t)n));
+    CK(ctx->d_merged.reserve((size_t)n));
+    CK(cudaMemcpyAsync(ctx->d_merge_in.p, photons, (size_t)n * sizeof(Photon), cudaMemcpyHostToDevice, ctx->stream));
+    int64_t m = 0;
+    int nk = 0;
+    CK(merge_photons(ctx->d_merge_in.p, n, select_mask, time_window, ctx->d_merged.p, &m, ctx->merge_scratch, ctx->stream, &nk));
+    ctx->stats.num_kernel += (uint64_t)nk;
+    if (capacity < m) return ctx->fail(PHOX_E_ARG, "phox_merge: destination too small");
+    if (m > 0) {
+        CK(cudaMemcpyAsync(dst, ctx->d_merged.p, (size_t)m * sizeof(Photon), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return m;
 }
 
 extern "C" int phox_boundary_lookup(phox_context* ctx, const float* nm, const uint32_t* line, const uint32_t* k, int64_t n, float* dst) {

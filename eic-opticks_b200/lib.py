@@ -77,6 +77,8 @@ SYMBOLS = {
     "phox_reset": (None, [C.c_void_p]),
     "phox_intersect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]),
     "phox_simtrace": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
+    "phox_merge_hits": (C.c_int64, [C.c_void_p, C.c_float, C.c_void_p, C.c_int64]),
+    "phox_merge": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_float, C.c_void_p, C.c_int64]),
     "phox_boundary_lookup": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "phox_rng_sequence": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_int32]),
 }

@@ -266,6 +266,27 @@ class Simulator:
             self._check(int(m))
         return out
 
+    def merge_hits(self, time_window):
+        """hits of the current event merged per (identity, time bucket) on the device (QEvt::PerLaunchMerge role)"""
+        m = self.lib.phox_merge_hits(self.ctx, time_window, None, 0)
+        if m < 0:
+            self._check(int(m))
+        out = np.empty((m, 4, 4), dtype=np.float32)
+        if m:
+            r = self.lib.phox_merge_hits(self.ctx, time_window, _ptr(out), m)
+            if r < 0:
+                self._check(int(r))
+        return out
+
+    def merge(self, photons, time_window, select_mask=0):
+        """merge any (n,4,4) sphoton array (QEvt::FinalMerge role: concatenated per-launch / per-rank results)"""
+        ph = np.ascontiguousarray(photons, dtype=np.float32).reshape(-1, 4, 4)
+        out = np.empty_like(ph)
+        m = self.lib.phox_merge(self.ctx, _ptr(ph), len(ph), select_mask, time_window, _ptr(out), len(out))
+        if m < 0:
+            self._check(int(m))
+        return out[:m].copy()
+
     def rng_sequence(self, ni, nv, id0=0, event_id=0):
         out = np.empty((ni, nv), dtype=np.float32)
         self._check(self.lib.phox_rng_sequence(self.ctx, _ptr(out), ni, nv, id0, event_id))

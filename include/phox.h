@@ -204,6 +204,17 @@ int phox_intersect(phox_context* ctx, const float* ray_o_tmin, const float* ray_
 int64_t phox_simtrace(phox_context* ctx, const void* genstep, int64_t num_genstep, const void* input_simtrace, int64_t num_input,
                       void* dst_simtrace, int64_t capacity);
 
+/* Hit merging by (sensor identity, time bucket): SPM::merge_partial_select (sysrap/SPM.cu:153-290) with the sphoton
+ * functors (sysrap/sphoton.h:277-304; driven by QEvt::PerLaunchMerge / QEvt::FinalMerge, qudarap/QEvt.cc:1170-1248).
+ * key = (identity << 48) | uint(time / time_window); within a key the earliest photon survives with flagmask = OR and
+ * hitcount = sum of the group; output in ascending key order.  time_window 0 = no merging (the selection as it is).
+ *   phox_merge_hits : the hits of the current event, on the device (dst NULL = count only).
+ *   phox_merge      : any host sphoton array (the FinalMerge of per-launch / per-rank results); select_mask is the
+ *                     reference's any-bit flagmask selection, 0 = take every record.
+ * Both return the number of merged records or a negative PHOX_E_* code. */
+int64_t phox_merge_hits(phox_context* ctx, float time_window, void* dst, int64_t capacity);
+int64_t phox_merge(phox_context* ctx, const void* photons, int64_t n, uint32_t select_mask, float time_window, void* dst, int64_t capacity);
+
 /* Precooked random streams (qudarap/QSim.cu:43-68): first nv curand_uniform floats of
  * subsequences [id0, id0+ni). dst is host float32[ni*nv]. */
 /* Boundary-table readback through the hardware texture path (qudarap/QSim.cu boundary_lookup_line /

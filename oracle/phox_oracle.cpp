@@ -1183,6 +1183,40 @@ int oracle_simtrace(const int* solid, int nsolid, const void* prim, const void* 
     return (int)total;
 }
 
+// hit merging: SPM::merge_partial_select (sysrap/SPM.cu:153-290) with sphoton::select_pred / key_functor / reduce_op
+// (sysrap/sphoton.h:277-304).  stable sort by key, then a left fold of each group.  Returns the merged count.
+int oracle_merge(const float* photons, int n, unsigned mask, float tw, float* out) {
+    struct P { float f[16]; };
+    const P* in = (const P*)photons;
+    auto u = [](const P& p, int k) { unsigned v; memcpy(&v, &p.f[k], 4); return v; };
+    std::vector<int> sel;
+    for (int i = 0; i < n; i++) if (mask == 0u || (u(in[i], 15) & mask) != 0u) sel.push_back(i);
+    P* o = (P*)out;
+    if (tw == 0.f) { for (size_t k = 0; k < sel.size(); k++) o[k] = in[sel[k]]; return (int)sel.size(); }
+    auto key = [&](int i) { unsigned id = u(in[i], 13) & 0x00ffffffu; unsigned bucket = (unsigned)(in[i].f[3] / tw); return ((uint64_t)id << 48) | (uint64_t)bucket; };
+    std::stable_sort(sel.begin(), sel.end(), [&](int a, int b) { return key(a) < key(b); });
+    int m = 0;
+    for (size_t k = 0; k < sel.size();) {
+        uint64_t k0 = key(sel[k]);
+        P r = in[sel[k]];
+        unsigned hc = u(r, 7) >> 16;
+        size_t j = k + 1;
+        for (; j < sel.size() && key(sel[j]) == k0; j++) {
+            const P& q = in[sel[j]];
+            unsigned fm = u(r, 15) | u(q, 15);
+            hc += u(q, 7) >> 16;
+            bool r_first = fminf(r.f[3], q.f[3]) == r.f[3];
+            if (!r_first) r = q;
+            memcpy(&r.f[15], &fm, 4);
+        }
+        unsigned hi = (u(r, 7) & 0x0000ffffu) | ((hc & 0xffffu) << 16);
+        memcpy(&r.f[7], &hi, 4);
+        o[m++] = r;
+        k = j;
+    }
+    return m;
+}
+
 // one prim, one ray: used to compare against the reference CSG headers compiled for the host
 int oracle_intersect_prim(const void* node, int node_offset, const void* plan, const float* itra, int nitra, const float* o, const float* d, float tmin,
                           float* isect_out) {

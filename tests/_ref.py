@@ -146,6 +146,13 @@ class Oracle:
             raise RuntimeError("oracle_simtrace failed")
         return out
 
+    def merge(self, photons, time_window, select_mask=0):
+        ph = np.ascontiguousarray(photons, dtype=np.float32).reshape(-1, 4, 4)
+        out = np.zeros_like(ph)
+        self.lib.oracle_merge.restype = C.c_int
+        m = self.lib.oracle_merge(_p(ph), C.c_int(len(ph)), C.c_uint(select_mask), C.c_float(time_window), _p(out))
+        return out[:m].copy()
+
     def intersect_prim_batch(self, fd, prim_idx, o, d, tmin):
         node = np.ascontiguousarray(fd["node"], dtype=np.float32)
         plan = np.ascontiguousarray(fd["plan"], dtype=np.float32)

@@ -266,6 +266,33 @@ def test_simtrace_matches_oracle_and_intersect():
         sim.close()
 
 
+def test_hit_merging_equals_oracle_bit_for_bit():
+    """SPM::merge_partial_select semantics (sysrap/SPM.cu:153-290, sphoton.h:277-304): integer/byte work, so bit-exact"""
+    w = workloads.pmt_wall_torch(num_photon=300000, nx=20, ny=20)
+    sim = make_sim(w)
+    hits = sim.simulate_np(w["gensteps"], 0, w["input_photons"]).copy()
+    assert len(hits) > 1000
+    orc = Oracle()
+    for tw in (0.5, 5.0, 1000.0):
+        a = sim.merge_hits(tw)
+        b = orc.merge(hits, tw)
+        assert a.shape == b.shape and a.tobytes() == b.tobytes(), tw
+        key = (a.view(np.uint32)[:, 3, 1].astype(np.uint64) << np.uint64(48)) | (a[:, 0, 3] / np.float32(tw)).astype(np.uint32).astype(np.uint64)
+        assert (np.diff(key.astype(np.int64)) > 0).all()                        # one record per key, ascending
+        assert (a.view(np.uint32)[:, 1, 3] >> 16).sum() == len(hits)            # hitcounts add up to the unmerged hits
+    assert sim.merge_hits(0.0).tobytes() == hits.tobytes()                      # window 0 = no merging
+    # FinalMerge of two halves merged separately == merge of the whole (rank / launch concatenation), and any-bit selection
+    tw = 5.0
+    half = len(hits) // 2
+    parts = np.concatenate([sim.merge(hits[:half], tw), sim.merge(hits[half:], tw)])
+    assert sim.merge(parts, tw).view(np.uint32)[:, 3, 1:].tobytes() == sim.merge(hits, tw).view(np.uint32)[:, 3, 1:].tobytes()
+    mixed = hits.copy(); mixed.view(np.uint32)[::3, 3, 3] = 0x8                  # every third record loses the SD bit
+    assert sim.merge(mixed, tw, select_mask=0x40).tobytes() == orc.merge(mixed, tw, select_mask=0x40).tobytes()
+    big = np.tile(hits, (max(1, 300000 // len(hits)), 1, 1))                    # several sort tiles per digit, long groups
+    assert sim.merge(big, 2.0).tobytes() == orc.merge(big, 2.0).tobytes()
+    sim.close()
+
+
 def test_event_index_skipahead_and_rng_sequence():
     w = workloads.sipm8x8_scint(num_photon=1000, photons_per_genstep=100)
     sim = make_sim(w)
