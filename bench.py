@@ -259,9 +259,9 @@ def main():
     if not args.no_clocks:
         sampler.start()
     for k in range(warm):
-        step_device(0)
+        step_device(1 + k)           # same event ids as the timed steps: every buffer reaches its steady-state size here
     for k in range(2):
-        step_e2e(0)
+        step_e2e(1 + k)
     ms_dev, st_dev, clocks = timed(step_device, args.steps, None if args.no_clocks else sampler)
     ms_e2e, st_e2e, _ = timed(step_e2e, args.steps)
 

@@ -37,7 +37,9 @@ struct DevBuf {
     size_t cap = 0;          // elements
     cudaError_t reserve(size_t n, bool keep = false, cudaStream_t st = 0) {
         if (n <= cap) return cudaSuccess;
-        size_t want = keep ? std::max(n, cap + cap / 2) : n;
+        // growing buffers get headroom from the first allocation on: a cudaMalloc + cudaFree pair inside an event costs
+        // ~1 ms alone but was measured at 40-700 ms when another thread of the process is inside the driver (NVML polling)
+        size_t want = keep ? std::max(n + n / 4 + 1024, cap + cap / 2) : n;
         T* q = nullptr;
         cudaError_t e = cudaMalloc(&q, want * sizeof(T));
         if (e != cudaSuccess) return e;

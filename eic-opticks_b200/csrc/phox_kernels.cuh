@@ -22,6 +22,9 @@
 #ifndef PHOX_HOT_LEAF
 #define PHOX_HOT_LEAF 0            // 0: one out-of-line copy of the CSG leaf code serves every site (instruction-fetch bound kernel)
 #endif
+#ifndef PHOX_WF_STREAM
+#define PHOX_WF_STREAM 1           // wavefront kernels read/write the per-photon streams with evict-first hints (ld/st.global.cs)
+#endif
 #ifndef PHOX_EXACT_BOX
 #define PHOX_EXACT_BOX 1           // exit-distance bound for prims that are exactly their box (see traverse_bvh)
 #endif
@@ -414,6 +417,9 @@ constexpr int kWaveThreads = 256;
 #define PHOX_WF_PROP_THREADS 256        // block of the physics kernel = run length of the ordered survivor append
 #endif
 constexpr int kPropThreads = PHOX_WF_PROP_THREADS;
+#ifndef PHOX_WF_PROP_MIN_BLOCKS
+#define PHOX_WF_PROP_MIN_BLOCKS 5       // 48 registers
+#endif
 constexpr unsigned kWaveNoHit = 0xffffffffu;    // prim_boundary of a list entry whose photon is final (miss or time over)
 
 template <bool DEBUG>
@@ -438,9 +444,15 @@ __global__ void __launch_bounds__(kWaveThreads) k_wf_generate(const __grid_const
         rng.init(P.seed, photon_idx, base);
         PhotonState p;
         generate_photon(p, rng, gs, P.tables, P.input_photon, P.input_base, photon_idx);
+#if PHOX_WF_STREAM
+        p.store_cs(P.photon + idx);
+        __stcs(W.ndraw + idx, rng.consumed(base));
+        __stcs(W.active_out + idx, idx);
+#else
         p.store(P.photon + idx);
         W.ndraw[idx] = rng.consumed(base);
         W.active_out[idx] = idx;
+#endif
         if (DEBUG) {
             Seq seq;
             seq.seqhis[0] = seq.seqhis[1] = seq.seqbnd[0] = seq.seqbnd[1] = 0ull;
@@ -457,10 +469,17 @@ __global__ void __launch_bounds__(kWaveThreads, PHOX_WF_TRACE_MIN_BLOCKS) k_wf_t
     unsigned nray = 0;
     const unsigned stride = gridDim.x * blockDim.x;
     for (unsigned a = blockIdx.x * blockDim.x + threadIdx.x; a < count; a += stride) {
+#if PHOX_WF_STREAM
+        unsigned idx = __ldcs(W.active_in + a);
+        const float4* ph = reinterpret_cast<const float4*>(P.photon + idx);
+        float4 q0 = __ldcs(ph), q1 = __ldcs(ph + 1);
+        unsigned obf = __ldcs(reinterpret_cast<const unsigned*>(ph + 3));
+#else
         unsigned idx = W.active_in[a];
         const float4* ph = reinterpret_cast<const float4*>(P.photon + idx);
         float4 q0 = ph[0], q1 = ph[1];
         unsigned obf = __float_as_uint(ph[3].x);
+#endif
         Prd r;
         r.nx = r.ny = r.nz = 0.f; r.t = -1.f; r.lposcost = r.lposfphi = 0.f; r.iindex_identity = 0xffffffffu; r.prim_boundary = kWaveNoHit;
         if (q0.w < P.max_time) {                                // else the while-condition of the raygen loop fails: photon is final
@@ -486,14 +505,22 @@ __global__ void __launch_bounds__(kWaveThreads, PHOX_WF_TRACE_MIN_BLOCKS) k_wf_t
                 if (DEBUG) { if (P.prd && W.bounce < P.max_record) P.prd[(size_t)P.max_record * idx + W.bounce] = r; }
             }
         }
+#if PHOX_WF_STREAM
+        {
+            float4* hp = reinterpret_cast<float4*>(W.hits + a);
+            __stcs(hp, make_float4(r.nx, r.ny, r.nz, r.t));
+            __stcs(hp + 1, make_float4(r.lposcost, r.lposfphi, __uint_as_float(r.iindex_identity), __uint_as_float(r.prim_boundary)));
+        }
+#else
         W.hits[a] = r;
+#endif
     }
     for (int off = 16; off > 0; off >>= 1) nray += __shfl_down_sync(0xffffffffu, nray, off);
     if ((threadIdx.x & 31u) == 0 && nray) atomicAdd(P.counters, (unsigned long long)nray);
 }
 
 template <bool DEBUG>
-__global__ void __launch_bounds__(kPropThreads) k_wf_propagate(const __grid_constant__ WaveParams W) {
+__global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_propagate(const __grid_constant__ WaveParams W) {
     __shared__ unsigned s_warp[kPropThreads / 32];
     __shared__ unsigned s_base;
     const SimParams& P = W.sim;
@@ -504,21 +531,43 @@ __global__ void __launch_bounds__(kPropThreads) k_wf_propagate(const __grid_cons
         bool survive = false;
         unsigned idx = 0;
         if (a < count) {
+#if PHOX_WF_STREAM
+            idx = __ldcs(W.active_in + a);
+            Prd r;
+            {
+                const float4* hp = reinterpret_cast<const float4*>(W.hits + a);
+                float4 h0 = __ldcs(hp), h1 = __ldcs(hp + 1);
+                r.nx = h0.x; r.ny = h0.y; r.nz = h0.z; r.t = h0.w; r.lposcost = h1.x; r.lposfphi = h1.y;
+                r.iindex_identity = __float_as_uint(h1.z); r.prim_boundary = __float_as_uint(h1.w);
+            }
+#else
             idx = W.active_in[a];
             Prd r = W.hits[a];
+#endif
             if (r.prim_boundary != kWaveNoHit) {            // a miss (or time over) leaves the photon as it is: final
                 PhotonState p;
+#if PHOX_WF_STREAM
+                p.load_cs(P.photon + idx);
+                unsigned nd = __ldcs(W.ndraw + idx);
+#else
                 p.load_rw(P.photon + idx);
+                unsigned nd = W.ndraw[idx];
+#endif
                 unsigned long long base = P.rng_offset + P.skipahead * (unsigned long long)P.event_index;
                 Philox rng;
-                rng.init(P.seed, P.photon_offset + idx, base + W.ndraw[idx]);
+                rng.init(P.seed, P.photon_offset + idx, base + nd);
                 HitInfo h;
                 h.normal = f3(r.nx, r.ny, r.nz); h.t = r.t; h.lposcost = r.lposcost; h.lposfphi = r.lposfphi;
                 h.iindex_identity = r.iindex_identity; h.prim_boundary = r.prim_boundary;
                 int command = propagate(p, rng, h, P.tables, P.burn != 0);
                 int bounce = W.bounce + 1;
+#if PHOX_WF_STREAM
+                p.store_cs(P.photon + idx);
+                __stcs(W.ndraw + idx, rng.consumed(base));
+#else
                 p.store(P.photon + idx);
                 W.ndraw[idx] = rng.consumed(base);
+#endif
                 if (DEBUG) {
                     if (P.record && bounce < P.max_record) p.store(P.record + (size_t)P.max_record * idx + bounce);
                     if (P.seq) { Seq seq = P.seq[idx]; seq_add(seq, (unsigned)bounce, p.flag(), p.boundary()); P.seq[idx] = seq; }
@@ -536,7 +585,11 @@ __global__ void __launch_bounds__(kPropThreads) k_wf_propagate(const __grid_cons
             s_base = tot ? atomicAdd(W.count_out, tot) : 0u;
         }
         __syncthreads();
+#if PHOX_WF_STREAM
+        if (survive) __stcs(W.active_out + s_base + s_warp[warp] + __popc(ballot & ((1u << lane) - 1u)), idx);
+#else
         if (survive) W.active_out[s_base + s_warp[warp] + __popc(ballot & ((1u << lane) - 1u))] = idx;
+#endif
         __syncthreads();
     }
 }

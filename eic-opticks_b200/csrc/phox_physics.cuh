@@ -70,6 +70,23 @@ struct PhotonState {                // sphoton in registers
         pol = f3(c.x, c.y, c.z); wavelength = c.w;
         obf = __float_as_uint(d.x); identity = __float_as_uint(d.y); index = __float_as_uint(d.z); flagmask = __float_as_uint(d.w);
     }
+    // streaming variants (ld/st.global.cs): the wavefront kernels touch every record once per bounce; marking the
+    // stream evict-first keeps L1/L2 for what is re-used (BVH nodes, tables, local-memory frames)
+    PHOX_D void load_cs(const Photon* src) {
+        const float4* s = reinterpret_cast<const float4*>(src);
+        float4 a = __ldcs(s), b = __ldcs(s + 1), c = __ldcs(s + 2), d = __ldcs(s + 3);
+        pos = f3(a.x, a.y, a.z); time = a.w;
+        mom = f3(b.x, b.y, b.z); hitcount_iindex = __float_as_uint(b.w);
+        pol = f3(c.x, c.y, c.z); wavelength = c.w;
+        obf = __float_as_uint(d.x); identity = __float_as_uint(d.y); index = __float_as_uint(d.z); flagmask = __float_as_uint(d.w);
+    }
+    PHOX_D void store_cs(Photon* dst) const {
+        float4* o = reinterpret_cast<float4*>(dst);
+        __stcs(o + 0, make_float4(pos.x, pos.y, pos.z, time));
+        __stcs(o + 1, make_float4(mom.x, mom.y, mom.z, __uint_as_float(hitcount_iindex)));
+        __stcs(o + 2, make_float4(pol.x, pol.y, pol.z, wavelength));
+        __stcs(o + 3, make_float4(__uint_as_float(obf), __uint_as_float(identity), __uint_as_float(index), __uint_as_float(flagmask)));
+    }
     PHOX_D void store(Photon* dst) const {
         float4* o = reinterpret_cast<float4*>(dst);
         o[0] = make_float4(pos.x, pos.y, pos.z, time);
