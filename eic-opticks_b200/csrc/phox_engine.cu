@@ -100,6 +100,9 @@ struct phox_context {
     DevBuf<Prd> d_wave_hits;
     int wave_grid[3][2] = {{0, 0}, {0, 0}, {0, 0}};             // persistent grid sizes of generate/trace/propagate, <false/true>
     DevBuf<unsigned long long> d_block_off;
+    DevBuf<unsigned> d_lpos;                   // lite mode: packed local position of each photon's last intersect
+    DevBuf<PhotonLite> d_hitlite;              // lite mode: sphotonlite of every hit, same order as d_hit
+    DevBuf<PhotonLite> d_merged_lite;
     DevBuf<Photon> d_merged;                   // result of the last phox_merge_hits / phox_merge
     DevBuf<Photon> d_merge_in;
     MergeScratch merge_scratch;
@@ -233,6 +236,7 @@ extern "C" void phox_destroy(phox_context* ctx) {
     ctx->d_record.release(); ctx->d_hit.release(); ctx->d_seq.release(); ctx->d_prd.release();
     ctx->d_block_hits.release(); ctx->d_block_off.release(); ctx->d_counters.release();
     ctx->d_slack.release();
+    ctx->d_lpos.release(); ctx->d_hitlite.release(); ctx->d_merged_lite.release();
     ctx->d_merged.release(); ctx->d_merge_in.release(); merge_scratch_free(ctx->merge_scratch);
     ctx->d_active[0].release(); ctx->d_active[1].release(); ctx->d_ndraw.release(); ctx->d_wave_count.release(); ctx->d_wave_hits.release();
     bvh_scratch_free(ctx->bvh_scratch);
@@ -519,6 +523,7 @@ extern "C" int phox_set_config(phox_context* ctx, const phox_config* cfg) {
     if (cfg->event_mode < PHOX_MODE_MINIMAL || cfg->event_mode > PHOX_MODE_DEBUGHEAVY) return ctx->fail(PHOX_E_ARG, "phox_set_config: unknown event_mode");
     if (cfg->max_slot < 0) return ctx->fail(PHOX_E_ARG, "phox_set_config: max_slot < 0");
     if (cfg->kernel_mode > PHOX_KERNEL_WAVEFRONT) return ctx->fail(PHOX_E_ARG, "phox_set_config: unknown kernel_mode");
+    if (cfg->mode_lite > 1) return ctx->fail(PHOX_E_ARG, "phox_set_config: mode_lite must be 0 or 1");
     ctx->cfg = *cfg;
     return PHOX_OK;
 }
@@ -583,6 +588,8 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
     if (mode_keeps_seq(mode)) CK(ctx->d_seq.reserve((size_t)n));
     if (mode_keeps_record(mode)) CK(ctx->d_record.reserve((size_t)n * c.max_record));
     if (mode_keeps_prd(mode)) CK(ctx->d_prd.reserve((size_t)n * c.max_record));
+    const bool lite = c.mode_lite != 0;
+    if (lite) CK(ctx->d_lpos.reserve((size_t)n));
     // record / prd slots past the end of a history read as zero (debug modes only, so not on the production path)
     if (mode_keeps_record(mode) && c.max_record) CK(cudaMemsetAsync(ctx->d_record.p, 0, (size_t)n * c.max_record * sizeof(Photon), ctx->stream));
     if (mode_keeps_prd(mode) && c.max_record) CK(cudaMemsetAsync(ctx->d_prd.p, 0, (size_t)n * c.max_record * sizeof(Prd), ctx->stream));
@@ -601,6 +608,7 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
     P.seq = mode_keeps_seq(mode) ? ctx->d_seq.p : nullptr;
     P.record = mode_keeps_record(mode) ? ctx->d_record.p : nullptr;
     P.prd = mode_keeps_prd(mode) ? ctx->d_prd.p : nullptr;
+    P.lpos = lite ? ctx->d_lpos.p : nullptr;
     P.max_record = c.max_record;
     P.work_counter = reinterpret_cast<unsigned*>(ctx->d_counters.p + 3);
     P.counters = ctx->d_counters.p;
@@ -677,7 +685,9 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
     ctx->stats.num_kernel += 3;
     if (nhit > 0) {
         CK(ctx->d_hit.reserve((size_t)(ctx->num_hit + nhit), true, ctx->stream));
-        k_hit_compact<<<nblock, T, 0, ctx->stream>>>(ctx->d_photon.p, (unsigned)n, c.hit_mask, ctx->d_block_off.p, ctx->d_hit.p + ctx->num_hit);
+        if (lite) CK(ctx->d_hitlite.reserve((size_t)(ctx->num_hit + nhit), true, ctx->stream));
+        k_hit_compact<<<nblock, T, 0, ctx->stream>>>(ctx->d_photon.p, (unsigned)n, c.hit_mask, ctx->d_block_off.p, ctx->d_hit.p + ctx->num_hit,
+                                                     lite ? ctx->d_lpos.p : nullptr, lite ? ctx->d_hitlite.p + ctx->num_hit : nullptr);
         CK(cudaGetLastError());
         ctx->stats.num_kernel += 1;
     }
@@ -1011,6 +1021,39 @@ extern "C" int64_t phox_merge_hits(phox_context* ctx, float time_window, void* d
     if (capacity < m) return ctx->fail(PHOX_E_ARG, "phox_merge_hits: destination too small");
     if (m > 0) {
         CK(cudaMemcpyAsync(dst, ctx->d_merged.p, (size_t)m * sizeof(Photon), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return m;
+}
+
+extern "C" int phox_get_hits_lite(phox_context* ctx, void* dst) {
+    if (!ctx) return PHOX_E_ARG;
+    if (!ctx->have_event) return ctx->fail(PHOX_E_STATE, "phox_get_hits_lite: no event");
+    if (!ctx->cfg.mode_lite) return ctx->fail(PHOX_E_STATE, "phox_get_hits_lite: mode_lite is off");
+    if (ctx->num_hit == 0) return PHOX_OK;
+    if (!dst) return ctx->fail(PHOX_E_ARG, "phox_get_hits_lite: null destination");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(dst, ctx->d_hitlite.p, (size_t)ctx->num_hit * sizeof(PhotonLite), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PHOX_OK;
+}
+
+extern "C" int64_t phox_merge_hits_lite(phox_context* ctx, float time_window, void* dst, int64_t capacity) {
+    if (!ctx) return PHOX_E_ARG;
+    if (!ctx->have_event) return ctx->fail(PHOX_E_STATE, "phox_merge_hits_lite: no event");
+    if (!ctx->cfg.mode_lite) return ctx->fail(PHOX_E_STATE, "phox_merge_hits_lite: mode_lite is off");
+    if (!(time_window >= 0.f) || capacity < 0) return ctx->fail(PHOX_E_ARG, "phox_merge_hits_lite: bad arguments");
+    int64_t n = ctx->num_hit, m = 0;
+    if (n == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->d_merged_lite.reserve((size_t)n));
+    int nk = 0;
+    CK(merge_photons_lite(ctx->d_hitlite.p, n, 0u, time_window, ctx->d_merged_lite.p, &m, ctx->merge_scratch, ctx->stream, &nk));
+    ctx->stats.num_kernel += (uint64_t)nk;
+    if (!dst) return m;
+    if (capacity < m) return ctx->fail(PHOX_E_ARG, "phox_merge_hits_lite: destination too small");
+    if (m > 0) {
+        CK(cudaMemcpyAsync(dst, ctx->d_merged_lite.p, (size_t)m * sizeof(PhotonLite), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
     return m;

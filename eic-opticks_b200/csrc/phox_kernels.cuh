@@ -60,6 +60,7 @@ struct SimParams {
     Seq* seq;
     Photon* record;
     Prd* prd;
+    unsigned* lpos;                         // per slot, lite mode: packed local position of the photon's last intersect (sphotonlite::set_lpos)
     int max_record;
     unsigned* work_counter;                 // next unclaimed photon slot of this launch
     unsigned long long* counters;           // [0] = rays traced
@@ -280,6 +281,14 @@ PHOX_D void seq_add(Seq& s, unsigned slot, unsigned flag, unsigned boundary) {  
     }
 }
 
+// sphotonlite::set_lpos (sysrap/sphotonlite.h:234-245): two u16 fractions; the float -> u16 conversion saturates like
+// the cvt.rzi.u16.f32 nvcc emits for the reference's (uint16_t) cast
+PHOX_D unsigned pack_lpos(float lposcost, float lposfphi) {
+    unsigned a = __float2uint_rz(fminf(fmaxf(lposcost * 65535.f + 0.5f, 0.f), 65535.f));
+    unsigned b = __float2uint_rz(fminf(fmaxf(lposfphi * 65535.f + 0.5f, 0.f), 65535.f));
+    return (a << 16) | b;
+}
+
 // Persistent bounce-loop kernel.  The grid is sized to the machine (SMs x resident blocks), not to
 // the event: each warp pulls photon slots from a global counter and REFILLS lanes whose photon has
 // finished, so lanes do not idle while the longest history of the warp runs out (bounce counts are
@@ -298,6 +307,8 @@ __global__ void __launch_bounds__(kSimThreads, PHOX_SIM_MIN_BLOCKS) k_simulate(c
     PhotonState p;
     Philox rng;
     Seq seq;
+    unsigned last_lpos = 0u;             // lite mode: packed lposcost/lposfphi of the last trace (0 after a miss, like the miss program)
+    const unsigned hit_flags = ((DEBUG && P.prd != nullptr) || P.lpos != nullptr) ? kHitFphi : 0u;
 
     while (true) {
         unsigned need = __ballot_sync(0xffffffffu, !active);
@@ -328,6 +339,7 @@ __global__ void __launch_bounds__(kSimThreads, PHOX_SIM_MIN_BLOCKS) k_simulate(c
                 generate_photon(p, rng, gs, P.tables, P.input_photon, P.input_base, photon_idx);
                 bounce = 0;
                 active = true;
+                last_lpos = 0u;
                 if (DEBUG) {
                     seq.seqhis[0] = seq.seqhis[1] = seq.seqbnd[0] = seq.seqbnd[1] = 0ull;
                     if (P.record && 0 < P.max_record) p.store(P.record + (size_t)P.max_record * idx);
@@ -344,17 +356,18 @@ __global__ void __launch_bounds__(kSimThreads, PHOX_SIM_MIN_BLOCKS) k_simulate(c
             if (!finished) {
                 float tmin = (p.obf & P.eps0_mask) ? P.tmin0 : P.tmin;
                 HitInfo h;
-                bool ok = trace(h, P.scene, p.pos, p.mom, tmin, P.tmax, (DEBUG && P.prd != nullptr) ? kHitFphi : 0u);
+                bool ok = trace(h, P.scene, p.pos, p.mom, tmin, P.tmax, hit_flags);
                 nray++;
                 if (P.refine && ok) {
                     float t_approx = 0.99f * h.t;
                     if (t_approx > P.refine_distance) {
                         float3 closer = p.pos + t_approx * p.mom;
-                        ok = trace(h, P.scene, closer, p.mom, tmin, P.tmax, (DEBUG && P.prd != nullptr) ? kHitFphi : 0u);
+                        ok = trace(h, P.scene, closer, p.mom, tmin, P.tmax, hit_flags);
                         nray++;
                         h.t += t_approx;
                     }
                 }
+                if (P.lpos) last_lpos = ok ? pack_lpos(h.lposcost, h.lposfphi) : 0u;
                 if (!ok) finished = true;                       // photon left the world
                 else {
                     // (the normal was normalised at the end of trace(), CSGOptiX7.cu:470-471)
@@ -379,6 +392,7 @@ __global__ void __launch_bounds__(kSimThreads, PHOX_SIM_MIN_BLOCKS) k_simulate(c
             if (finished) {
                 if (DEBUG) { if (P.seq) P.seq[idx] = seq; }
                 if (P.photon) p.store(P.photon + idx);
+                if (P.lpos) P.lpos[idx] = last_lpos;
                 active = false;
             }
         }
@@ -453,6 +467,7 @@ __global__ void __launch_bounds__(kWaveThreads) k_wf_generate(const __grid_const
         W.ndraw[idx] = rng.consumed(base);
         W.active_out[idx] = idx;
 #endif
+        if (P.lpos) P.lpos[idx] = 0u;
         if (DEBUG) {
             Seq seq;
             seq.seqhis[0] = seq.seqhis[1] = seq.seqbnd[0] = seq.seqbnd[1] = 0ull;
@@ -490,7 +505,7 @@ __global__ void __launch_bounds__(kWaveThreads, PHOX_WF_TRACE_MIN_BLOCKS) k_wf_t
             float3 from = o;
             float t_add = 0.f;
             for (int pass = 0;; pass++) {                       // one inlined trace site; pass 1 = PropagateRefine re-trace from 0.99 t
-                ok = trace_inline(h, P.scene, from, d, tmin, P.tmax, (DEBUG && P.prd != nullptr) ? kHitFphi : 0u);
+                ok = trace_inline(h, P.scene, from, d, tmin, P.tmax, ((DEBUG && P.prd != nullptr) || P.lpos != nullptr) ? kHitFphi : 0u);
                 nray++;
                 if (pass == 1) { h.t += t_add; break; }
                 if (!(P.refine && ok)) break;
@@ -573,6 +588,9 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
                     if (P.seq) { Seq seq = P.seq[idx]; seq_add(seq, (unsigned)bounce, p.flag(), p.boundary()); P.seq[idx] = seq; }
                 }
                 survive = !(command == FLOW_BREAK) && bounce < P.max_bounce && p.time < P.max_time;
+                if (P.lpos && !survive) P.lpos[idx] = pack_lpos(r.lposcost, r.lposfphi);      // the photon's last intersect
+            } else if (P.lpos) {
+                P.lpos[idx] = 0u;                           // the miss program clears the local position
             }
         }
         unsigned ballot = __ballot_sync(0xffffffffu, survive);
@@ -647,7 +665,8 @@ __global__ void k_hit_offsets(const unsigned* __restrict__ block_hits, int n, un
 // block b re-reads the flagmasks of its photons and copies the hits, in order, to
 // hit[hit_base + block_off[b] + rank]
 __global__ void __launch_bounds__(kHitTile) k_hit_compact(const Photon* __restrict__ photon, unsigned num_photon, unsigned hit_mask,
-                                                      const unsigned long long* __restrict__ block_off, Photon* __restrict__ hit) {
+                                                      const unsigned long long* __restrict__ block_off, Photon* __restrict__ hit,
+                                                      const unsigned* __restrict__ lpos, PhotonLite* __restrict__ hitlite) {
     __shared__ unsigned warp_count[4];
     unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     bool is_hit = false;
@@ -665,7 +684,16 @@ __global__ void __launch_bounds__(kHitTile) k_hit_compact(const Photon* __restri
         unsigned rank = before + __popc(ballot & ((1u << lane) - 1u));
         const float4* src = reinterpret_cast<const float4*>(photon + idx);
         float4* dst = reinterpret_cast<float4*>(hit + block_off[blockIdx.x] + rank);
-        dst[0] = __ldg(src); dst[1] = __ldg(src + 1); dst[2] = __ldg(src + 2); dst[3] = __ldg(src + 3);
+        float4 q0 = __ldg(src), q3 = __ldg(src + 3);
+        dst[0] = q0; dst[1] = __ldg(src + 1); dst[2] = __ldg(src + 2); dst[3] = q3;
+        if (hitlite) {                                       // sphotonlite::init + set_lpos (CSGOptiX7.cu:455-463)
+            PhotonLite l;
+            l.hitcount_identity = (1u << 16) | (__float_as_uint(q3.y) & 0xffffu);
+            l.time = q0.w;
+            l.lposcost_lposfphi = lpos[idx];
+            l.flagmask = __float_as_uint(q3.w);
+            hitlite[block_off[blockIdx.x] + rank] = l;
+        }
     }
 }
 

@@ -36,6 +36,19 @@ __global__ void k_merge_keys(const Photon* __restrict__ in, unsigned n, unsigned
     idx[i] = i;
 }
 
+// sphotonlite::key_functor (sysrap/sphotonlite.h): identity = low 16 bits
+__global__ void k_merge_keys_lite(const PhotonLite* __restrict__ in, unsigned n, unsigned mask, float tw, unsigned long long* __restrict__ key,
+                                  unsigned* __restrict__ idx) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PhotonLite p = in[i];
+    bool sel = mask == 0u || (p.flagmask & mask) != 0u;
+    unsigned id = p.hitcount_identity & 0xffffu;
+    unsigned bucket = static_cast<unsigned>(p.time / tw);
+    key[i] = sel ? (((unsigned long long)id << 48) | (unsigned long long)bucket) : kNoKey;
+    idx[i] = i;
+}
+
 // digit histogram of every warp tile: hist[digit * ntile + tile]
 __global__ void __launch_bounds__(32 * kSortWarps) k_radix_hist(const unsigned long long* __restrict__ key, unsigned n, int shift, unsigned ntile,
                                                                 unsigned* __restrict__ hist) {
@@ -146,6 +159,54 @@ __global__ void __launch_bounds__(kHeadTile) k_merge_reduce(const Photon* __rest
     out[o] = r;
 }
 
+// sphotonlite::reduce_op: r = a; time = min; flagmask |= ; hitcount summed, identity of a (and a's local position)
+__global__ void __launch_bounds__(kHeadTile) k_merge_reduce_lite(const PhotonLite* __restrict__ in, const unsigned long long* __restrict__ key,
+                                                                 const unsigned* __restrict__ idx, unsigned n, const unsigned* __restrict__ tile_off,
+                                                                 PhotonLite* __restrict__ out) {
+    __shared__ unsigned wsum[kHeadTile / 32];
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    bool head = i < n && key[i] != kNoKey && (i == 0 || key[i] != key[i - 1]);
+    unsigned b = __ballot_sync(0xffffffffu, head);
+    if (lane == 0) wsum[w] = __popc(b);
+    __syncthreads();
+    unsigned before = 0;
+    for (unsigned k = 0; k < w; k++) before += wsum[k];
+    if (!head) return;
+    unsigned o = tile_off[blockIdx.x] + before + __popc(b & ((1u << lane) - 1u));
+    unsigned long long k0 = key[i];
+    PhotonLite r = in[idx[i]];
+    unsigned hc = r.hitcount_identity >> 16;
+    for (unsigned j = i + 1; j < n && key[j] == k0; j++) {
+        PhotonLite q = in[idx[j]];
+        r.time = fminf(r.time, q.time);
+        r.flagmask |= q.flagmask;
+        hc += q.hitcount_identity >> 16;
+    }
+    r.hitcount_identity = ((hc & 0xffffu) << 16) | (r.hitcount_identity & 0xffffu);
+    out[o] = r;
+}
+
+__global__ void __launch_bounds__(kHeadTile) k_select_count_lite(const PhotonLite* __restrict__ in, unsigned n, unsigned mask, unsigned* __restrict__ tile_cnt) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool sel = i < n && (mask == 0u || (in[i].flagmask & mask) != 0u);
+    int c = __syncthreads_count(sel);
+    if (threadIdx.x == 0) tile_cnt[blockIdx.x] = (unsigned)c;
+}
+__global__ void __launch_bounds__(kHeadTile) k_select_copy_lite(const PhotonLite* __restrict__ in, unsigned n, unsigned mask,
+                                                                const unsigned* __restrict__ tile_off, PhotonLite* __restrict__ out) {
+    __shared__ unsigned wsum[kHeadTile / 32];
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    bool sel = i < n && (mask == 0u || (in[i].flagmask & mask) != 0u);
+    unsigned b = __ballot_sync(0xffffffffu, sel);
+    if (lane == 0) wsum[w] = __popc(b);
+    __syncthreads();
+    unsigned before = 0;
+    for (unsigned k = 0; k < w; k++) before += wsum[k];
+    if (sel) out[tile_off[blockIdx.x] + before + __popc(b & ((1u << lane) - 1u))] = in[i];
+}
+
 // tw == 0: the selection, in input order (tile counts + offsets + ordered copy)
 __global__ void __launch_bounds__(kHeadTile) k_select_count(const Photon* __restrict__ in, unsigned n, unsigned mask, unsigned* __restrict__ tile_cnt) {
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -173,8 +234,10 @@ __global__ void k_total(const unsigned* __restrict__ off, const unsigned* __rest
 
 }  // namespace
 
-cudaError_t merge_photons(const Photon* d_in, int64_t n64, unsigned select_mask, float tw, Photon* d_out, int64_t* n_out, MergeScratch& sc,
-                          cudaStream_t stream, int* kernel_count) {
+static cudaError_t merge_any(bool lite, const void* d_in_, int64_t n64, unsigned select_mask, float tw, void* d_out_, int64_t* n_out, MergeScratch& sc,
+                             cudaStream_t stream, int* kernel_count) {
+    const Photon* d_in = (const Photon*)d_in_; Photon* d_out = (Photon*)d_out_;
+    const PhotonLite* l_in = (const PhotonLite*)d_in_; PhotonLite* l_out = (PhotonLite*)d_out_;
     *n_out = 0;
     if (n64 <= 0) return cudaSuccess;
     if (n64 > 0x7fffffffll) return cudaErrorInvalidValue;
@@ -204,14 +267,17 @@ cudaError_t merge_photons(const Photon* d_in, int64_t n64, unsigned select_mask,
     cudaError_t e;
 
     if (tw == 0.f) {
-        k_select_count<<<nhead, kHeadTile, 0, stream>>>(d_in, n, select_mask, tcnt);
+        if (lite) k_select_count_lite<<<nhead, kHeadTile, 0, stream>>>(l_in, n, select_mask, tcnt);
+        else k_select_count<<<nhead, kHeadTile, 0, stream>>>(d_in, n, select_mask, tcnt);
         cudaMemcpyAsync(toff, tcnt, (size_t)nhead * 4, cudaMemcpyDeviceToDevice, stream);
         k_scan_u32<<<1, 1024, 0, stream>>>(toff, nhead);
         k_total<<<1, 1, 0, stream>>>(toff, tcnt + nhead - 1, nhead, total);
-        k_select_copy<<<nhead, kHeadTile, 0, stream>>>(d_in, n, select_mask, toff, d_out);
+        if (lite) k_select_copy_lite<<<nhead, kHeadTile, 0, stream>>>(l_in, n, select_mask, toff, l_out);
+        else k_select_copy<<<nhead, kHeadTile, 0, stream>>>(d_in, n, select_mask, toff, d_out);
         nk += 4;
     } else {
-        k_merge_keys<<<(n + 255) / 256, 256, 0, stream>>>(d_in, n, select_mask, tw, key0, idx0);
+        if (lite) k_merge_keys_lite<<<(n + 255) / 256, 256, 0, stream>>>(l_in, n, select_mask, tw, key0, idx0);
+        else k_merge_keys<<<(n + 255) / 256, 256, 0, stream>>>(d_in, n, select_mask, tw, key0, idx0);
         nk += 1;
         const unsigned sblocks = (ntile + kSortWarps - 1) / kSortWarps;
         static const int shifts[6] = {0, 8, 16, 24, 48, 56};          // bits 32..47 of a key are always zero (or all ones for unselected entries)
@@ -227,7 +293,8 @@ cudaError_t merge_photons(const Photon* d_in, int64_t n64, unsigned select_mask,
         cudaMemcpyAsync(toff, tcnt, (size_t)nhead * 4, cudaMemcpyDeviceToDevice, stream);
         k_scan_u32<<<1, 1024, 0, stream>>>(toff, nhead);
         k_total<<<1, 1, 0, stream>>>(toff, tcnt + nhead - 1, nhead, total);
-        k_merge_reduce<<<nhead, kHeadTile, 0, stream>>>(d_in, key0, idx0, n, toff, d_out);
+        if (lite) k_merge_reduce_lite<<<nhead, kHeadTile, 0, stream>>>(l_in, key0, idx0, n, toff, l_out);
+        else k_merge_reduce<<<nhead, kHeadTile, 0, stream>>>(d_in, key0, idx0, n, toff, d_out);
         nk += 4;
     }
     e = cudaGetLastError();
@@ -239,6 +306,16 @@ cudaError_t merge_photons(const Photon* d_in, int64_t n64, unsigned select_mask,
     *n_out = (int64_t)h_total;
     if (kernel_count) *kernel_count += nk;
     return cudaSuccess;
+}
+
+cudaError_t merge_photons(const Photon* d_in, int64_t n, unsigned select_mask, float tw, Photon* d_out, int64_t* n_out, MergeScratch& sc,
+                          cudaStream_t stream, int* kernel_count) {
+    return merge_any(false, d_in, n, select_mask, tw, d_out, n_out, sc, stream, kernel_count);
+}
+
+cudaError_t merge_photons_lite(const PhotonLite* d_in, int64_t n, unsigned select_mask, float tw, PhotonLite* d_out, int64_t* n_out, MergeScratch& sc,
+                               cudaStream_t stream, int* kernel_count) {
+    return merge_any(true, d_in, n, select_mask, tw, d_out, n_out, sc, stream, kernel_count);
 }
 
 void merge_scratch_free(MergeScratch& sc) {

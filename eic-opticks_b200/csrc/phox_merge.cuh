@@ -16,6 +16,8 @@ struct MergeScratch {
 // tw > 0: merge per (identity, time / tw) group; tw == 0: selection only, input order.  Synchronises the stream.
 cudaError_t merge_photons(const Photon* d_in, int64_t n, unsigned select_mask, float tw, Photon* d_out, int64_t* n_out, MergeScratch& scratch,
                           cudaStream_t stream, int* kernel_count);
+cudaError_t merge_photons_lite(const PhotonLite* d_in, int64_t n, unsigned select_mask, float tw, PhotonLite* d_out, int64_t* n_out,
+                               MergeScratch& scratch, cudaStream_t stream, int* kernel_count);
 void merge_scratch_free(MergeScratch& scratch);
 
 }  // namespace phox

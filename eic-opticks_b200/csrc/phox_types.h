@@ -74,6 +74,14 @@ struct alignas(16) Photon {           // sphoton
 };
 static_assert(sizeof(Photon) == 64, "Photon must match sphoton");
 
+struct alignas(16) PhotonLite {       // sphotonlite (sysrap/sphotonlite.h)
+    unsigned hitcount_identity;       // hi16 hitcount (starts at 1), lo16 sensor identity
+    float    time;
+    unsigned lposcost_lposfphi;       // hi16 / lo16 : local hit position cos(theta), phi/2pi as u16 fractions
+    unsigned flagmask;
+};
+static_assert(sizeof(PhotonLite) == 16, "PhotonLite must match sphotonlite");
+
 struct alignas(16) Genstep {          // quad6 ; q0.x gencode, q0.z matline, q0.w numphoton
     union { int i[24]; unsigned u[24]; float f[24]; };
     PHOX_HD int gencode() const { return i[0]; }

@@ -36,6 +36,7 @@ class Config(C.Structure):
         ("kernel_mode", C.c_uint32),
         ("rng_seed", C.c_uint64), ("rng_offset", C.c_uint64), ("skipahead_event_offset", C.c_uint64),
         ("max_slot", C.c_int64),
+        ("mode_lite", C.c_uint32), ("reserved0", C.c_uint32),
     ]
 
 
@@ -79,6 +80,8 @@ SYMBOLS = {
     "phox_simtrace": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
     "phox_merge_hits": (C.c_int64, [C.c_void_p, C.c_float, C.c_void_p, C.c_int64]),
     "phox_merge": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_float, C.c_void_p, C.c_int64]),
+    "phox_get_hits_lite": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "phox_merge_hits_lite": (C.c_int64, [C.c_void_p, C.c_float, C.c_void_p, C.c_int64]),
     "phox_boundary_lookup": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "phox_rng_sequence": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_int32]),
 }

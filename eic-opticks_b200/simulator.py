@@ -278,6 +278,25 @@ class Simulator:
                 self._check(int(r))
         return out
 
+    def get_hits_lite(self):
+        """(num_hit, 4) uint32 view of the sphotonlite hits (mode_lite = 1): [hitcount<<16|identity, time bits,
+        lposcost<<16|lposfphi, flagmask]"""
+        n = self.num_hit()
+        out = np.empty((n, 4), dtype=np.uint32)
+        self._check(self.lib.phox_get_hits_lite(self.ctx, _ptr(out) if n else None))
+        return out
+
+    def merge_hits_lite(self, time_window):
+        m = self.lib.phox_merge_hits_lite(self.ctx, time_window, None, 0)
+        if m < 0:
+            self._check(int(m))
+        out = np.empty((m, 4), dtype=np.uint32)
+        if m:
+            r = self.lib.phox_merge_hits_lite(self.ctx, time_window, _ptr(out), m)
+            if r < 0:
+                self._check(int(r))
+        return out
+
     def merge(self, photons, time_window, select_mask=0):
         """merge any (n,4,4) sphoton array (QEvt::FinalMerge role: concatenated per-launch / per-rank results)"""
         ph = np.ascontiguousarray(photons, dtype=np.float32).reshape(-1, 4, 4)

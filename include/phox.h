@@ -84,6 +84,9 @@ typedef struct phox_config {
     uint64_t skipahead_event_offset;/* OPTICKS_EVENT_SKIPAHEAD, 100000 draws per event index    */
     int64_t  max_slot;              /* photons per launch; 0 = 0.87*VRAM/(64*1.75) heuristic
                                        (sysrap/SEventConfig.cc:1897-1903)                       */
+    uint32_t mode_lite;             /* OPTICKS_MODE_LITE: 1 = also keep sphotonlite hits (16 B: identity, time, packed local hit
+                                       position, flagmask; sysrap/sphotonlite.h) -> phox_get_hits_lite / phox_merge_hits_lite */
+    uint32_t reserved0;
 } phox_config;
 
 void phox_default_config(phox_config* cfg);
@@ -214,6 +217,14 @@ int64_t phox_simtrace(phox_context* ctx, const void* genstep, int64_t num_genste
  * Both return the number of merged records or a negative PHOX_E_* code. */
 int64_t phox_merge_hits(phox_context* ctx, float time_window, void* dst, int64_t capacity);
 int64_t phox_merge(phox_context* ctx, const void* photons, int64_t n, uint32_t select_mask, float time_window, void* dst, int64_t capacity);
+
+/* sphotonlite hits (sysrap/sphotonlite.h: {hitcount<<16|identity, time, lposcost<<16|lposfphi as u16 fractions, flagmask},
+ * written by the raygen at CSGOptiX7.cu:455-463 and selected like hits, QEvt::gatherHitLite_).  Needs mode_lite = 1.
+ * phox_get_hits_lite copies num_hit records (16 B each) to host memory; phox_merge_hits_lite merges them per
+ * (identity, time bucket) with the sphotonlite functors (time = min, flagmask = OR, hitcount = sum, identity and local
+ * position of the first of the group in photon order) and returns the merged count (dst NULL = count only). */
+int     phox_get_hits_lite(phox_context* ctx, void* dst);
+int64_t phox_merge_hits_lite(phox_context* ctx, float time_window, void* dst, int64_t capacity);
 
 /* Precooked random streams (qudarap/QSim.cu:43-68): first nv curand_uniform floats of
  * subsequences [id0, id0+ni). dst is host float32[ni*nv]. */

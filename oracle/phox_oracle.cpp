@@ -1062,7 +1062,16 @@ int make_scene(Scene& sc, const int* solid, int nsolid, const void* prim, const 
 
 }  // namespace
 
+// sphotonlite::set_lpos (sysrap/sphotonlite.h:234-245); the u16 conversion saturates like the device's cvt.rzi.u16.f32
+static unsigned pack_lpos(float lposcost, float lposfphi) {
+    auto u16 = [](float v) { float x = v * 65535.f + 0.5f; x = x < 0.f ? 0.f : (x > 65535.f ? 65535.f : x); return (unsigned)x; };
+    return (u16(lposcost) << 16) | u16(lposfphi);
+}
+static unsigned* g_lite_out = nullptr;      // optional sphotonlite[n] output of the next oracle_simulate call
+
 extern "C" {
+
+void oracle_set_lite_out(unsigned* p) { g_lite_out = p; }
 
 // CSGOptiX/CSGOptiX7.cu:405-503 per photon; seeding = QEvt.cu:181-237 (seed[i] = owning genstep)
 int oracle_simulate(const int* solid, int nsolid, const void* prim, int nprim, const void* node, int nnode, const void* plan, int nplan,
@@ -1097,6 +1106,7 @@ int oracle_simulate(const int* solid, int nsolid, const void* prim, int nprim, c
         generate_photon(p, rng, gs[seed[idx]], tb, (const Photon*)input_photon, cfg->photon_offset, photon_idx);
         Seq seq = {{0, 0}, {0, 0}};
         int bounce = 0;
+        unsigned last_lpos = 0u;
         if (rec && 0 < mr) rec[(size_t)mr * idx] = p;                          // sctx::point sysrap/sctx.h:134-140
         if (seqo) seq_add_nibble(seq, 0, p.flag(), p.boundary());
         while (bounce < cfg->max_bounce && p.time < cfg->max_time) {
@@ -1104,6 +1114,7 @@ int oracle_simulate(const int* solid, int nsolid, const void* prim, int nprim, c
             Prd prd;
             bool ok = trace(prd, sc, p.pos, p.mom, tmin, cfg->tmax);
             nray++;
+            last_lpos = ok ? pack_lpos(prd.lposcost, prd.lposfphi) : 0u;
             if (!ok) break;
             prd.normal = normalize(prd.normal);
             if (prdo && bounce < mr) prdo[(size_t)mr * idx + bounce] = prd;    // sctx::trace
@@ -1115,6 +1126,10 @@ int oracle_simulate(const int* solid, int nsolid, const void* prim, int nprim, c
         }
         if (seqo) seqo[idx] = seq;
         if (pout) pout[idx] = p;
+        if (g_lite_out) {                                                      // sphotonlite::init + set_lpos, CSGOptiX7.cu:455-463
+            unsigned* l = g_lite_out + 4 * idx;
+            l[0] = (1u << 16) | (p.identity & 0xffffu); memcpy(l + 1, &p.time, 4); l[2] = last_lpos; l[3] = p.flagmask;
+        }
         if ((p.flagmask & cfg->hit_mask) == cfg->hit_mask) nhit++;
     }
     if (nray_out) *nray_out = nray;
@@ -1212,6 +1227,30 @@ int oracle_merge(const float* photons, int n, unsigned mask, float tw, float* ou
         unsigned hi = (u(r, 7) & 0x0000ffffu) | ((hc & 0xffffu) << 16);
         memcpy(&r.f[7], &hi, 4);
         o[m++] = r;
+        k = j;
+    }
+    return m;
+}
+
+// sphotonlite flavour of the merge (sysrap/sphotonlite.h key_functor / reduce_op): records are 4 x u32
+int oracle_merge_lite(const unsigned* lite, int n, unsigned mask, float tw, unsigned* out) {
+    auto tm = [&](int i) { float t; memcpy(&t, lite + 4 * i + 1, 4); return t; };
+    std::vector<int> sel;
+    for (int i = 0; i < n; i++) if (mask == 0u || (lite[4 * i + 3] & mask) != 0u) sel.push_back(i);
+    if (tw == 0.f) { for (size_t k = 0; k < sel.size(); k++) memcpy(out + 4 * k, lite + 4 * sel[k], 16); return (int)sel.size(); }
+    auto key = [&](int i) { unsigned id = lite[4 * i] & 0xffffu; unsigned bucket = (unsigned)(tm(i) / tw); return ((uint64_t)id << 48) | (uint64_t)bucket; };
+    std::stable_sort(sel.begin(), sel.end(), [&](int a, int b) { return key(a) < key(b); });
+    int m = 0;
+    for (size_t k = 0; k < sel.size();) {
+        uint64_t k0 = key(sel[k]);
+        unsigned r[4]; memcpy(r, lite + 4 * sel[k], 16);
+        float t = tm(sel[k]);
+        unsigned hc = r[0] >> 16;
+        size_t j = k + 1;
+        for (; j < sel.size() && key(sel[j]) == k0; j++) { t = fminf(t, tm(sel[j])); r[3] |= lite[4 * sel[j] + 3]; hc += lite[4 * sel[j]] >> 16; }
+        r[0] = ((hc & 0xffffu) << 16) | (r[0] & 0xffffu);
+        memcpy(r + 1, &t, 4);
+        memcpy(out + 4 * m, r, 16); m++;
         k = j;
     }
     return m;

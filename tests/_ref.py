@@ -103,7 +103,7 @@ class Oracle:
 
     def simulate(self, geom, gensteps, input_photons=None, event_id=0, photon_offset=0, max_bounce=31, max_record=32,
                  tmin=0.05, tmin0=0.05, tmax=1e6, max_time=1e27, eps0mask=0x37, hit_mask=0x40, seed=0, offset=0, skipahead=100000,
-                 hd_factor=20, debug_tag=True, use_boxes=False, nthreads=0, arrays=True):
+                 hd_factor=20, debug_tag=True, use_boxes=False, nthreads=0, arrays=True, lite=False):
         fd = geom["foundry"]
         a = {k: np.ascontiguousarray(fd[k], dtype=(np.int32 if k == "solid" else np.float32)) for k in ("solid", "prim", "node", "plan", "itra", "inst")}
         bnd = np.ascontiguousarray(geom["bnd"], dtype=np.float32)
@@ -120,6 +120,8 @@ class Oracle:
         seq = np.zeros((n, 2, 2), dtype=np.uint64) if arrays else None
         prd = np.zeros((n, max_record, 2, 4), dtype=np.float32) if arrays else None
         nray, nhit = C.c_uint64(0), C.c_uint64(0)
+        lite_arr = np.zeros((n, 4), dtype=np.uint32) if lite else None
+        self.lib.oracle_set_lite_out(_p(lite_arr))
         rc = self.lib.oracle_simulate(_p(a["solid"]), C.c_int(len(a["solid"])), _p(a["prim"]), C.c_int(len(a["prim"])), _p(a["node"]), C.c_int(len(a["node"])),
                                       _p(a["plan"]) if len(a["plan"]) else None, C.c_int(len(a["plan"])), _p(a["itra"]), C.c_int(len(a["itra"])),
                                       _p(a["inst"]), C.c_int(len(a["inst"])),
@@ -127,9 +129,10 @@ class Oracle:
                                       _p(icdf), C.c_int(0 if icdf is None else icdf.shape[1]), C.c_int(hd_factor),
                                       _p(gs), C.c_int(len(gs)), _p(ip), C.c_int(0 if ip is None else len(ip)), C.byref(cfg),
                                       _p(photon), _p(record), _p(seq), _p(prd), C.byref(nray), C.byref(nhit))
+        self.lib.oracle_set_lite_out(None)
         if rc != 0:
             raise RuntimeError("oracle_simulate failed")
-        return dict(photon=photon, record=record, seq=seq, prd=prd, nray=nray.value, nhit=nhit.value)
+        return dict(photon=photon, record=record, seq=seq, prd=prd, nray=nray.value, nhit=nhit.value, lite=lite_arr)
 
     def simtrace(self, geom, gensteps, input_simtrace=None, tmin=0.05, tmax=1e6, seed=0, offset=0, use_boxes=True):
         fd = geom["foundry"]
@@ -145,6 +148,13 @@ class Oracle:
         if rc != n:
             raise RuntimeError("oracle_simtrace failed")
         return out
+
+    def merge_lite(self, lite, time_window, select_mask=0):
+        a = np.ascontiguousarray(lite, dtype=np.uint32).reshape(-1, 4)
+        out = np.zeros_like(a)
+        self.lib.oracle_merge_lite.restype = C.c_int
+        m = self.lib.oracle_merge_lite(_p(a), C.c_int(len(a)), C.c_uint(select_mask), C.c_float(time_window), _p(out))
+        return out[:m].copy()
 
     def merge(self, photons, time_window, select_mask=0):
         ph = np.ascontiguousarray(photons, dtype=np.float32).reshape(-1, 4, 4)

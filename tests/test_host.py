@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_config_struct_matches_header_defaults():
     cfg = ph.lib.default_config()
-    assert C.sizeof(ph.lib.Config) == 88
+    assert C.sizeof(ph.lib.Config) == 96
     assert (cfg.max_bounce, cfg.event_mode, cfg.rng_mode, cfg.accel) == (31, 0, 1, 0)
     assert cfg.hit_mask == 0x40 and cfg.epsilon0_mask == 0x37            # SD ; TO|CK|SI|SC|RE
     assert abs(cfg.propagate_epsilon - 0.05) < 1e-9 and cfg.tmax == 1e6 and cfg.skipahead_event_offset == 100000

@@ -293,6 +293,44 @@ def test_hit_merging_equals_oracle_bit_for_bit():
     sim.close()
 
 
+def test_lite_hits_and_lite_merging():
+    """sphotonlite hits (sysrap/sphotonlite.h; raygen CSGOptiX7.cu:455-463) and their merge; both forms of the loop"""
+    w = workloads.pmt_wall_torch(num_photon=100000, nx=20, ny=20)
+    orc = Oracle()
+    ref = orc.simulate(w["geom"], w["gensteps"], w["input_photons"], max_bounce=w["config"].get("max_bounce", 31), lite=True)
+    res = {}
+    for mode in (ph.KERNEL_PERSISTENT, ph.KERNEL_WAVEFRONT):
+        sim = make_sim(w, event_mode=ph.MODE_HITPHOTON, mode_lite=1, kernel_mode=mode)
+        hits = sim.simulate_np(w["gensteps"], 0, w["input_photons"]).copy()
+        lite = sim.get_hits_lite()
+        assert lite.shape == (len(hits), 4) and len(hits) > 1000
+        hu = hits.view(np.uint32)
+        assert (lite[:, 0] == ((1 << 16) | (hu[:, 3, 1] & 0xffff))).all() and (lite[:, 1] == hu[:, 0, 3]).all() and (lite[:, 3] == hu[:, 3, 3]).all()
+        # packed local positions against the CPU oracle on the photons whose history agrees (float ulps move the u16 by <= 1)
+        p = sim.get_array("photon")
+        idx = hu[:, 3, 2]
+        same = (p.view(np.uint32)[idx, 3, :] == ref["photon"].view(np.uint32)[idx, 3, :]).all(axis=1)
+        a, b = lite[same, 2], ref["lite"][idx[same], 2]
+        assert same.mean() > 0.99
+        assert (np.abs((a >> 16).astype(int) - (b >> 16).astype(int)) <= 1).mean() > 0.999
+        dphi = np.abs((a & 0xffff).astype(int) - (b & 0xffff).astype(int)); dphi = np.minimum(dphi, 65535 - dphi)
+        assert (dphi <= 2).mean() > 0.995
+        assert ((a >> 16) > 0).mean() > 0.5                                    # hits on the front hemisphere of the bulb
+        for tw in (1.0, 50.0):
+            m = sim.merge_hits_lite(tw)
+            assert m.tobytes() == orc.merge_lite(lite, tw).tobytes()
+            assert (m[:, 0] >> 16).sum() == len(hits)
+        assert sim.merge_hits_lite(0.0).tobytes() == lite.tobytes()
+        res[mode] = (hits, lite)
+        sim.close()
+    assert res[ph.KERNEL_PERSISTENT][1].tobytes() == res[ph.KERNEL_WAVEFRONT][1].tobytes()
+    sim = make_sim(w)
+    sim.simulate_np(w["gensteps"], 0, w["input_photons"])
+    with pytest.raises(ph.lib.PhoxError):
+        sim.get_hits_lite()                                                     # mode_lite off: loud, not empty
+    sim.close()
+
+
 def test_event_index_skipahead_and_rng_sequence():
     w = workloads.sipm8x8_scint(num_photon=1000, photons_per_genstep=100)
     sim = make_sim(w)
