@@ -15,8 +15,7 @@
 #include <string>
 #include <vector>
 
-#include "../../include/PhoxSimulator.h"
-#include "../../include/phox_npy.h"
+#include "phox_app_common.h"
 
 static std::vector<PhoxPhoton> load_photons_txt(const std::string& path) {
     std::vector<PhoxPhoton> out;
@@ -56,34 +55,18 @@ int main(int argc, char** argv) {
         return 1;                                  // the reference fails without -p (tests/test_GPUPhotonFileSource.sh:108-118)
     }
     try {
-        using phoxnpy::load;
-        std::string fd = geom + "/CSGFoundry/", ss = fd + "SSim/stree/standard/";
-        auto solid = load(fd + "solid.npy"), prim = load(fd + "prim.npy"), node = load(fd + "node.npy"), itra = load(fd + "itra.npy");
-        auto inst = load(fd + "inst.npy"), plan = load(fd + "plan.npy", false);
-        auto bnd = load(ss + "bnd.npy"), optical = load(ss + "optical.npy"), icdf = load(ss + "icdf.npy", false);
-        if (bnd.dtype != "<f4" || bnd.shape.size() != 5) throw std::runtime_error("bnd.npy must be float32 (nbnd,4,2,nwl,4)");
         std::vector<PhoxPhoton> ph = load_photons_txt(photons);
         if (ph.empty()) { std::cerr << "ERROR: no photons loaded from " << photons << std::endl; return 1; }
         std::cout << "Loaded " << ph.size() << " photons from " << photons << std::endl;
 
-        PhoxSimulator* cx = PhoxSimulator::Create(solid.data.data(), solid.shape[0], prim.data.data(), prim.shape[0], node.data.data(), node.shape[0],
-                                                  plan.empty() ? nullptr : plan.data.data(), plan.empty() ? 0 : plan.shape[0], itra.data.data(),
-                                                  itra.shape[0], inst.data.data(), inst.shape[0], bnd.as<float>(), bnd.shape[0], bnd.shape[3], 60.f, 1.f,
-                                                  optical.as<int32_t>(), icdf.empty() ? nullptr : icdf.as<float>(), icdf.empty() ? 0 : 3,
-                                                  icdf.empty() ? 0 : icdf.count() / 3, 20, device);
+        PhoxSimulator* cx = phoxapp::create_from_geometry_dir(geom, device);
         std::cout << cx->desc() << std::endl;
         cx->setInputPhoton(ph.data(), (int64_t)ph.size());
         double dt = cx->simulate(0, false);
         unsigned nhit = cx->getNumHit();
         std::cout << "Simulation time: " << dt << " seconds" << std::endl;
         std::cout << "Opticks: NumHits:  " << nhit << std::endl;
-        std::ofstream of(out);
-        for (unsigned i = 0; i < nhit; i++) {
-            PhoxPhoton h;
-            cx->getHit(h, i);
-            of << h.q[3] << " " << h.q[11] << "  (" << h.q[0] << ", " << h.q[1] << ", " << h.q[2] << ")  (" << h.q[4] << ", " << h.q[5] << ", " << h.q[6]
-               << ")  (" << h.q[8] << ", " << h.q[9] << ", " << h.q[10] << ")" << std::endl;
-        }
+        phoxapp::write_hits_text(cx, out);
         cx->reset(0);
         delete cx;
     } catch (const std::exception& e) {

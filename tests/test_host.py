@@ -162,3 +162,27 @@ def test_cxx_adaptor_compiles_standalone_and_geometry_dir_roundtrip(tmp_path):
     assert (back["bnd"] == g["bnd"]).all() and (back["optical"] == g["optical"]).all() and (back["icdf"] == g["icdf"]).all()
     assert back["bnd_names"] == g["bnd_names"]
     assert os.path.exists(os.path.join(ROOT, "eic-opticks_b200", "apps", "PhoxPhotonFileSource"))
+
+
+def test_cxx_torch_driver_generates_the_reference_photons(tmp_path):
+    """apps/PhoxPhotonSourceMinimal.cpp: JSON config parsing (src/config.cpp:107-145) and host torch generation
+    (src/torch.cpp:8-30) against the python restatement, without a GPU (--dump-photons)"""
+    import subprocess
+    from eic_opticks_b200 import gensteps as G
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "eic-opticks_b200", "apps", "PhoxPhotonSourceMinimal")
+    assert os.path.exists(exe), "run __graft_entry__.build()"
+    cfg = os.path.join(root, "tests", "golden", "config_dev.json")
+    out = tmp_path / "photons.txt"
+    r = subprocess.run([exe, "-c", cfg, "--dump-photons", str(out)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    assert "Dumped 100 photons, event mode DebugLite maxslot 1000000" in r.stdout
+    a = np.loadtxt(out)
+    t, _ = G.torch_config(cfg)
+    ref = G.torch_photons(t, seed=0)
+    assert a.shape == (100, 16)
+    assert np.abs(a[:, :12] - ref.reshape(100, 16)[:, :12]).max() < 2e-5          # sinf/cosf of glibc vs numpy differ by ulps of a 15 mm radius
+    assert (a[:, 12] == 4).all() and (a[:, 15] == 4).all()
+    bad = tmp_path / "bad.json"; bad.write_text('{"torch": {"gentype": "TORCH"}}')
+    r2 = subprocess.run([exe, "-c", str(bad), "--dump-photons", str(out)], capture_output=True, text=True, timeout=60)
+    assert r2.returncode != 0 and "missing key" in r2.stderr

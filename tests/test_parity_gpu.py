@@ -405,6 +405,29 @@ def test_cxx_file_source_driver_known_answer(tmp_path):
     assert r2.returncode != 0
 
 
+def test_cxx_torch_driver_matches_python_path(tmp_path):
+    """apps/PhoxPhotonSourceMinimal.cpp (GPUPhotonSourceMinimal contract): config/dev.json torch on the raindrop"""
+    import subprocess
+    from eic_opticks_b200 import foundry as F
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "eic-opticks_b200", "apps", "PhoxPhotonSourceMinimal")
+    assert os.path.exists(exe), "run __graft_entry__.build()"
+    g = ph.geometries.raindrop()
+    F.save_geometry(g, str(tmp_path / "geom"))
+    cfg = os.path.join(root, "tests", "golden", "config_dev.json")
+    t, _ = G.torch_config(cfg)
+    sim = ph.Simulator.Create(g["foundry"], g["bnd"], g["optical"])
+    want_host = len(sim.simulate_np(G.input_photon_genstep(t["numphoton"]), 0, G.torch_photons(t, seed=0)))
+    want_gs = len(sim.simulate_np(G.torch_genstep(t), 0))
+    sim.close()
+    for extra, want in (([], want_host), (["--genstep"], want_gs)):
+        out = tmp_path / "hits.txt"
+        r = subprocess.run([exe, "-g", str(tmp_path / "geom"), "-c", cfg, "-o", str(out)] + extra, capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr
+        assert "Opticks: NumHits:  %d" % want in r.stdout, (r.stdout, want)
+        assert want > 50 and len(open(out).read().strip().split("\n")) == want
+
+
 def test_oracle_texture_emulation_vs_hardware():
     """the CPU oracle's restatement of CUDA linear texture filtering (8-bit fraction, lerp form) against the
     B200 texture unit on a dispersive boundary table at random fractional wavelengths"""
