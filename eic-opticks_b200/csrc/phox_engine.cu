@@ -106,6 +106,7 @@ struct phox_context {
     DevBuf<Photon> d_merged;                   // result of the last phox_merge_hits / phox_merge
     DevBuf<Photon> d_merge_in;
     MergeScratch merge_scratch;
+ DevBuf<float4> d_exact;                    // per CSGPrim: (sizes ; translation) of prims that are exactly a box
     DevBuf<float> d_slack;                     // per CSGPrim: exit-bound slack of prims that are exactly a box (0 = not such a prim)
     DevBuf<unsigned long long> d_counters;     // [0] rays, [1] hit total of the launch
     unsigned long long* h_counters = nullptr;  // pinned mirror
@@ -235,7 +236,7 @@ extern "C" void phox_destroy(phox_context* ctx) {
     ctx->d_genstep.release(); ctx->d_prefix.release(); ctx->d_input.release(); ctx->d_photon.release();
     ctx->d_record.release(); ctx->d_hit.release(); ctx->d_seq.release(); ctx->d_prd.release();
     ctx->d_block_hits.release(); ctx->d_block_off.release(); ctx->d_counters.release();
-    ctx->d_slack.release();
+    ctx->d_slack.release(); ctx->d_exact.release();
     ctx->d_lpos.release(); ctx->d_hitlite.release(); ctx->d_merged_lite.release();
     ctx->d_merged.release(); ctx->d_merge_in.release(); merge_scratch_free(ctx->merge_scratch);
     ctx->d_active[0].release(); ctx->d_active[1].release(); ctx->d_ndraw.release(); ctx->d_wave_count.release(); ctx->d_wave_hits.release();
@@ -352,6 +353,7 @@ extern "C" int phox_set_geometry(phox_context* ctx, const void* solid_, int64_t 
     // is the exit face, so the traversal may drop it once a nearer hit is known (phox_kernels.cuh, exit bound).
     // slack = distance by which the padded box must be shrunk to lie inside the true box with a pad to spare.
     std::vector<float> slack((size_t)nprim, 0.f);
+    std::vector<float> exact((size_t)nprim * 8, 0.f);
     const Node* hnode = (const Node*)node_;
     const Qat4* hitra = (const Qat4*)itra_;
     for (int64_t p = 0; p < nprim; p++) {
@@ -379,7 +381,12 @@ extern "C" int phox_set_geometry(phox_context* ctx, const void* solid_, int64_t 
             worst = std::max(worst, std::max(tlo - plo, phi - thi));
             m = std::max(m, std::max(std::fabs(plo), std::fabs(phi)));
         }
-        if (inside && nd.f[0] > 0.f && nd.f[1] > 0.f && nd.f[2] > 0.f) slack[p] = worst + 4e-6f * m;
+        if (inside && nd.f[0] > 0.f && nd.f[1] > 0.f && nd.f[2] > 0.f) {
+            slack[p] = worst + 4e-6f * m;
+            float* e = &exact[8 * (size_t)p];
+            e[0] = nd.f[0]; e[1] = nd.f[1]; e[2] = nd.f[2]; e[3] = 0.f;      // q0: full sizes, as leaf_box3 reads them
+            e[4] = -c[0]; e[5] = -c[1]; e[6] = -c[2]; e[7] = 0.f;            // row 3 of the inverse transform (0 without transform)
+        }
     }
     std::vector<float> solid_box((size_t)nsolid * 6);
     for (int64_t s = 0; s < nsolid; s++) {
@@ -442,6 +449,8 @@ extern "C" int phox_set_geometry(phox_context* ctx, const void* solid_, int64_t 
     CK(cudaMemcpyAsync(ctx->d_boxes.p, boxes.data(), boxes.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     CK(ctx->d_slack.reserve(std::max<size_t>(1, (size_t)nprim)));
     CK(cudaMemcpyAsync(ctx->d_slack.p, slack.data(), (size_t)nprim * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx->d_exact.reserve(std::max<size_t>(2, (size_t)nprim * 2)));
+    CK(cudaMemcpyAsync(ctx->d_exact.p, exact.data(), (size_t)nprim * 8 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
 
     ctx->build_kernels = 0;
@@ -597,7 +606,7 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
     SimParams P;
     std::memset(&P, 0, sizeof(P));
     P.scene.geo.node = ctx->d_node.p; P.scene.geo.plan = ctx->d_plan.p; P.scene.geo.itra = ctx->d_itra.p;
-    P.scene.prim = ctx->d_prim.p; P.scene.nodes = ctx->d_bvh.p; P.scene.inst = ctx->d_inst.p;
+    P.scene.prim = ctx->d_prim.p; P.scene.exact = ctx->d_exact.p; P.scene.nodes = ctx->d_bvh.p; P.scene.inst = ctx->d_inst.p;
     P.scene.ninst = ctx->ninst; P.scene.tlas_root = ctx->tlas_root; P.scene.accel = c.accel;
     P.tables.bnd_tex = ctx->bnd_tex; P.tables.icdf_tex = ctx->icdf_tex; P.tables.optical = ctx->d_optical.p;
     P.tables.nx = ctx->nx; P.tables.ny = ctx->ny; P.tables.nm0 = ctx->nm0; P.tables.nms = ctx->nms; P.tables.hd_factor = ctx->hd_factor;
@@ -933,7 +942,7 @@ extern "C" int phox_intersect(phox_context* ctx, const float* ray_o_tmin, const 
     CK(cudaMemcpyAsync(d_d, ray_d, (size_t)nray * 16, cudaMemcpyHostToDevice, ctx->stream));
     Scene sc;
     sc.geo.node = ctx->d_node.p; sc.geo.plan = ctx->d_plan.p; sc.geo.itra = ctx->d_itra.p;
-    sc.prim = ctx->d_prim.p; sc.nodes = ctx->d_bvh.p; sc.inst = ctx->d_inst.p;
+    sc.prim = ctx->d_prim.p; sc.exact = ctx->d_exact.p; sc.nodes = ctx->d_bvh.p; sc.inst = ctx->d_inst.p;
     sc.ninst = ctx->ninst; sc.tlas_root = ctx->tlas_root; sc.accel = accel;
     const int T = 128;
     cudaEventRecord(ctx->ev[0], ctx->stream);
@@ -986,7 +995,7 @@ extern "C" int64_t phox_simtrace(phox_context* ctx, const void* genstep, int64_t
         SimtraceParams S;
         std::memset(&S, 0, sizeof(S));
         S.scene.geo.node = ctx->d_node.p; S.scene.geo.plan = ctx->d_plan.p; S.scene.geo.itra = ctx->d_itra.p;
-        S.scene.prim = ctx->d_prim.p; S.scene.nodes = ctx->d_bvh.p; S.scene.inst = ctx->d_inst.p;
+        S.scene.prim = ctx->d_prim.p; S.scene.exact = ctx->d_exact.p; S.scene.nodes = ctx->d_bvh.p; S.scene.inst = ctx->d_inst.p;
         S.scene.ninst = ctx->ninst; S.scene.tlas_root = ctx->tlas_root; S.scene.accel = c.accel;
         S.genstep = d_gs; S.gs_prefix = d_prefix; S.num_genstep = (int)num_genstep;
         S.input = d_in; S.input_base = 0; S.photon_offset = 0; S.num = (unsigned)n;

@@ -36,6 +36,7 @@ namespace phox {
 struct Scene {
     Geo geo;
     const float4* prim;             // Prim[nprim] viewed as 4 x float4
+    const float4* exact;            // 2 x float4 per CSGPrim that is exactly a box (sizes ; translation), see intersect_exact_box
     const BvhNode* nodes;           // pool: instance tree first, then one tree per solid
     const InstanceRec* inst;
     int ninst;
@@ -92,6 +93,18 @@ PHOX_D void keep_nearest(Nearest& best, const float4& is, int prim_idx, int inst
         best.inst = inst_idx;
     }
 }
+
+// A CSGPrim that is one un-complemented box3 leaf without rotation (most world, mother and crystal volumes): the same
+// arithmetic as intersect_leaf's transform + leaf_box3 + normal back-transform, which for a pure translation reduce to
+// o + t, d, n exactly (products with the 0 / 1 matrix entries are exact), without the dependent loads of prim -> node ->
+// transform.  Out of line so that every kernel shares one compiled body, like intersect_prim_cold.
+__device__ __noinline__ bool intersect_exact_box(float4& is, const float4* rec, float tmin, const float3& ro, const float3& rd) {
+    float4 q0 = __ldg(rec), tr = __ldg(rec + 1);
+    float3 o = f3(ro.x + tr.x, ro.y + tr.y, ro.z + tr.z);
+    return leaf_box3(is, q0, tmin, o, rd);
+}
+constexpr int kLeafExactBox = 0x40000000;        // leaf item flag: the prim qualifies for intersect_exact_box
+constexpr int kLeafItemMask = 0x3fffffff;
 
 constexpr int kBvhStack = 64;
 constexpr int kTravReturn = (int)0x80000000;     // stack marker: leave the current solid, back to the instance tree
@@ -185,15 +198,25 @@ PHOX_D void traverse_bvh(Nearest& best, const Scene& sc, float tmin, const float
             continue;
         }
         {                                                      // a CSGPrim: the one intersect site
-            int prim_idx = ~cur;
-            float4 p0 = __ldg(sc.prim + 4 * prim_idx);
-            const float4* nroot = sc.geo.node + 4 * __float_as_int(p0.y);
+            int item = ~cur;
+            int prim_idx = item & kLeafItemMask;
             float4 is = make_float4(0.f, 0.f, 0.f, 0.f);
-#if PHOX_HOT_LEAF
-            if (intersect_prim(is, nroot, sc.geo, tmin, o, d)) keep_nearest(best, is, prim_idx, inst_idx, tmin);
-#else
-            if (intersect_prim_cold(is, nroot, sc.geo, tmin, o, d)) keep_nearest(best, is, prim_idx, inst_idx, tmin);
+            bool ok;
+#if PHOX_EXACT_BOX
+            if (item & kLeafExactBox) {
+                ok = intersect_exact_box(is, sc.exact + 2 * prim_idx, tmin, o, d);
+            } else
 #endif
+            {
+                float4 p0 = __ldg(sc.prim + 4 * prim_idx);
+                const float4* nroot = sc.geo.node + 4 * __float_as_int(p0.y);
+#if PHOX_HOT_LEAF
+                ok = intersect_prim(is, nroot, sc.geo, tmin, o, d);
+#else
+                ok = intersect_prim_cold(is, nroot, sc.geo, tmin, o, d);
+#endif
+            }
+            if (ok) keep_nearest(best, is, prim_idx, inst_idx, tmin);
         }
         cur = pop();
     }
@@ -588,10 +611,12 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
                     if (P.seq) { Seq seq = P.seq[idx]; seq_add(seq, (unsigned)bounce, p.flag(), p.boundary()); P.seq[idx] = seq; }
                 }
                 survive = !(command == FLOW_BREAK) && bounce < P.max_bounce && p.time < P.max_time;
-                if (P.lpos && !survive) P.lpos[idx] = pack_lpos(r.lposcost, r.lposfphi);      // the photon's last intersect
-            } else if (P.lpos) {
-                P.lpos[idx] = 0u;                           // the miss program clears the local position
             }
+        }
+        if (P.lpos && a < count && !survive) {              // lite mode: local position of the photon's last intersect, re-read from
+            const Prd* hp = W.hits + a;                     // the hit record so that nothing extra stays live across propagate();
+            unsigned pb = hp->prim_boundary;                // the miss program clears it
+            P.lpos[idx] = pb == kWaveNoHit ? 0u : pack_lpos(hp->lposcost, hp->lposfphi);
         }
         unsigned ballot = __ballot_sync(0xffffffffu, survive);
         // append the survivors of this chunk to the next list, in order within the chunk
@@ -619,6 +644,8 @@ __global__ void k_mark_exact_boxes(BvhNode* nodes, int nnode, const float* __res
     int4 d = nodes[i].d;
     d.z = (d.x < 0) ? __float_as_int(slack[~d.x]) : 0;
     d.w = (d.y < 0 && d.y != kBvhNoChild) ? __float_as_int(slack[~d.y]) : 0;
+    if (d.z != 0) d.x = ~((~d.x) | kLeafExactBox);
+    if (d.w != 0) d.y = ~((~d.y) | kLeafExactBox);
     nodes[i].d = d;
 }
 
