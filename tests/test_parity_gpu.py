@@ -331,6 +331,49 @@ def test_lite_hits_and_lite_merging():
     sim.close()
 
 
+def test_edge_cases_empty_ragged_offsets_and_limits():
+    """empty and ragged gensteps, a zero-bounce event, absolute photon indices beyond 2^32 (sphoton::set_index puts bits
+    32..39 into the top byte of identity, sysrap/sphoton.h:224-232), a genstep larger than max_slot"""
+    w = workloads.sipm8x8_scint(num_photon=20000, photons_per_genstep=100)
+    gs = w["gensteps"]
+    for mode in (ph.KERNEL_PERSISTENT, ph.KERNEL_WAVEFRONT):
+        sim = make_sim(w, event_mode=ph.MODE_HITPHOTONSEQ, kernel_mode=mode)
+        base = sim.simulate_np(gs, 0).copy()
+        p0 = sim.get_array("photon").copy()
+        # ragged: zero-photon gensteps interleaved do not move any photon index
+        empty = gs[:3].copy(); empty.view(np.uint32)[:, 0, 3] = 0
+        ragged = np.concatenate([empty[:1], gs[:50], empty[1:2], gs[50:], empty[2:]])
+        assert sim.simulate_np(ragged, 0).tobytes() == base.tobytes() and sim.get_array("photon").tobytes() == p0.tobytes()
+        # only empty gensteps: an event with no photons and no hits
+        h = sim.simulate_np(empty, 0)
+        assert h.shape == (0, 4, 4) and sim.num_hit() == 0 and len(sim.get_array("photon")) == 0
+        # one photon
+        one = gs[:1].copy(); one.view(np.uint32)[0, 0, 3] = 1
+        sim.simulate_np(one, 0)
+        assert sim.get_array("photon").shape == (1, 4, 4) and (sim.get_array("photon").view(np.uint32)[0, 3, 2] == 0)
+        # zero bounces: the generated photons themselves
+        sim.set_config(max_bounce=0)
+        assert len(sim.simulate_np(gs, 0)) == 0
+        g0 = sim.get_array("photon")
+        assert (g0.view(np.uint32)[:, 3, 0] & 0xffff).tolist().count(2) + (g0.view(np.uint32)[:, 3, 0] & 0xffff).tolist().count(1) == len(g0)   # SI or CK
+        assert (sim.get_array("seq")[:, 0, 0] < 16).all()
+        sim.set_config(max_bounce=w["config"].get("max_bounce", 31))
+        # absolute index beyond 2^32
+        off = (5 << 32) + 123
+        hb = sim.simulate_np(gs[:20], 0, None, off)
+        pb = sim.get_array("photon")
+        assert (pb.view(np.uint32)[:, 3, 2] == (np.arange(len(pb), dtype=np.uint64) + np.uint64(123)).astype(np.uint32)).all()
+        assert ((pb.view(np.uint32)[:, 3, 1] >> 24) == 5).all() and ((hb.view(np.uint32)[:, 3, 1] >> 24) == 5).all()
+        ref = Oracle().simulate(w["geom"], gs[:20], None, photon_offset=off, max_bounce=w["config"].get("max_bounce", 31))
+        same = (pb.view(np.uint32)[:, 3, :] == ref["photon"].view(np.uint32)[:, 3, :]).all(axis=1)
+        assert same.mean() > 0.99
+        # a genstep that does not fit max_slot is an error, not a truncation
+        sim.set_config(max_slot=50)
+        with pytest.raises(ph.lib.PhoxError):
+            sim.simulate_np(gs, 0)
+        sim.close()
+
+
 def test_event_index_skipahead_and_rng_sequence():
     w = workloads.sipm8x8_scint(num_photon=1000, photons_per_genstep=100)
     sim = make_sim(w)
