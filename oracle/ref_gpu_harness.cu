@@ -17,6 +17,7 @@
 #include <stdint.h>
 #include <string.h>
 #include <vector>
+#include <algorithm>
 #include <cuda_runtime.h>
 #include <curand_kernel.h>
 
@@ -165,6 +166,29 @@ __global__ void ref_intersect(RefParams P, const float4* o_tmin, const float4* d
     quad2 prd;
     ref_trace(P, make_float3(o_tmin[i].x, o_tmin[i].y, o_tmin[i].z), make_float3(dir[i].x, dir[i].y, dir[i].z), o_tmin[i].w, P.tmax, &prd);
     out[i] = prd;
+}
+
+// simtrace raygen (CSGOptiX7.cu:536-577) around the reference's own qsim::generate_photon_simtrace_frame
+// (qudarap/qsim.h:2459-2511) and sevent::add_simtrace (sysrap/sevent.h:670-697)
+__global__ void ref_simtrace(RefParams P, const quad6* genstep, const int* seed, unsigned n, quad4* out, unsigned long long seedv,
+                             unsigned long long offset) {
+    unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const quad6& gs = genstep[seed[idx]];
+    RNG rng;
+    curand_init(seedv, (unsigned long long)idx, offset, &rng);       // qrng<Philox>::init with event index 0 (qrng.h:131-137)
+    qsim sim;
+    quad4 p;
+    sim.generate_photon_simtrace_frame(p, rng, gs, idx, (unsigned)seed[idx]);
+    const float3& pos = (const float3&)p.q0.f;
+    const float3& mom = (const float3&)p.q1.f;
+    quad2 prd;
+    prd.zero();
+    ref_trace(P, pos, mom, P.tmin, P.tmax, &prd);
+    if (prd.boundary() == 0xffffu) { prd.q0.f.x = 0.6f; prd.q0.f.y = 0.6f; prd.q0.f.z = 0.6f; prd.q0.f.w = 1.f; }   // __miss__ms: SBT.cc:181-193 background
+    sevent evt;
+    evt.simtrace = out;
+    evt.add_simtrace(idx, p, &prd, P.tmin);
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -385,4 +409,61 @@ extern "C" int phoxref_intersect(const void* solid, int nsolid, const void* prim
     cudaFree(d_o); cudaFree(d_d); cudaFree(d_out);
     sc.release();
     return 0;
+}
+
+extern "C" int phoxref_simtrace(const void* solid, int nsolid, const void* prim, int nprim, const void* node, int nnode, const void* plan, int nplan,
+                                const void* itra, int nitra, const void* inst, int ninst, const void* genstep, int ngs, float tmin, float tmax,
+                                unsigned long long seedv, unsigned long long offset, void* out) {
+    g_err[0] = 0;
+    RefScene sc;
+    if (sc.setup(solid, nsolid, prim, nprim, node, nnode, plan, nplan, itra, nitra, inst, ninst)) return -1;
+    const quad6* gs = (const quad6*)genstep;
+    std::vector<int> seed;
+    for (int g = 0; g < ngs; g++) for (unsigned k = 0; k < gs[g].q0.u.w; k++) seed.push_back(g);
+    size_t n = seed.size();
+    quad6* d_gs; int* d_seed; quad4* d_out;
+    RCK(up(&d_gs, genstep, (size_t)ngs * sizeof(quad6)));
+    RCK(up(&d_seed, seed.data(), n * sizeof(int)));
+    RCK(up(&d_out, (const void*)nullptr, n * sizeof(quad4)));
+    RefParams P; memset(&P, 0, sizeof(P));
+    P.node = sc.d_node; P.plan = sc.d_plan; P.itra = sc.d_itra; P.prim = sc.d_prim; P.inst = sc.d_inst; P.ninst = sc.ninst; P.tmin = tmin; P.tmax = tmax;
+    RCK(cudaDeviceSetLimit(cudaLimitStackSize, 8192));
+    const int T = 64;
+    ref_simtrace<<<(unsigned)((n + T - 1) / T), T>>>(P, d_gs, d_seed, (unsigned)n, d_out, seedv, offset);
+    RCK(cudaGetLastError());
+    RCK(cudaDeviceSynchronize());
+    RCK(cudaMemcpy(out, d_out, n * sizeof(quad4), cudaMemcpyDeviceToHost));
+    cudaFree(d_gs); cudaFree(d_seed); cudaFree(d_out);
+    sc.release();
+    return (int)n;
+}
+
+// hit merging with the reference's own functors (sysrap/sphoton.h:277-304, sysrap/sphotonlite.h), driven on the host the way
+// SPM::merge_partial_select drives them on the device (sysrap/SPM.cu:153-290): select, key, stable sort by key, reduce by key.
+template <typename T> static int ref_merge_t(const T* in, int n, unsigned mask, float tw, T* out) {
+    typename T::select_pred sel{mask};
+    typename T::key_functor key{tw};
+    typename T::reduce_op red;
+    std::vector<T> v;
+    for (int i = 0; i < n; i++) if (mask == 0u || sel(in[i])) v.push_back(in[i]);
+    if (tw == 0.f) { for (size_t k = 0; k < v.size(); k++) out[k] = v[k]; return (int)v.size(); }
+    std::vector<int> order(v.size());
+    for (size_t k = 0; k < v.size(); k++) order[k] = (int)k;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key(v[a]) < key(v[b]); });
+    int m = 0;
+    for (size_t k = 0; k < order.size();) {
+        uint64_t k0 = key(v[order[k]]);
+        T r = v[order[k]];
+        size_t j = k + 1;
+        for (; j < order.size() && key(v[order[j]]) == k0; j++) r = red(r, v[order[j]]);
+        out[m++] = r;
+        k = j;
+    }
+    return m;
+}
+extern "C" int phoxref_merge(const void* photons, int n, unsigned mask, float tw, void* out) {
+    return ref_merge_t<sphoton>((const sphoton*)photons, n, mask, tw, (sphoton*)out);
+}
+extern "C" int phoxref_merge_lite(const void* lite, int n, unsigned mask, float tw, void* out) {
+    return ref_merge_t<sphotonlite>((const sphotonlite*)lite, n, mask, tw, (sphotonlite*)out);
 }

@@ -68,6 +68,33 @@ class RefGPU:
             raise RuntimeError("phoxref_simulate: " + self.lib.phoxref_last_error().decode())
         return dict(photon=photon, record=record, seq=seq, prd=prd, nray=nray.value)
 
+    def simtrace(self, geom, gensteps, tmin=0.05, tmax=1e6, seed=0, offset=0):
+        """the reference's generate_photon_simtrace_frame + add_simtrace around the brute-force trace (FRAME gensteps)"""
+        keep, gargs = self._geo(geom["foundry"])
+        gs = np.ascontiguousarray(gensteps, dtype=np.float32).reshape(-1, 6, 4)
+        n = int(gs.view(np.uint32)[:, 0, 3].sum())
+        out = np.zeros((n, 4, 4), dtype=np.float32)
+        self.lib.phoxref_simtrace.restype = C.c_int
+        rc = self.lib.phoxref_simtrace(*gargs, _p(gs), C.c_int(len(gs)), C.c_float(tmin), C.c_float(tmax), C.c_uint64(seed), C.c_uint64(offset), _p(out))
+        if rc != n:
+            raise RuntimeError("phoxref_simtrace: " + self.lib.phoxref_last_error().decode())
+        return out
+
+    def merge(self, photons, time_window, select_mask=0):
+        """sphoton::select_pred / key_functor / reduce_op of the reference, driven on the host (no GPU involved)"""
+        ph = np.ascontiguousarray(photons, dtype=np.float32).reshape(-1, 4, 4)
+        out = np.zeros_like(ph)
+        self.lib.phoxref_merge.restype = C.c_int
+        m = self.lib.phoxref_merge(_p(ph), C.c_int(len(ph)), C.c_uint(select_mask), C.c_float(time_window), _p(out))
+        return out[:m].copy()
+
+    def merge_lite(self, lite, time_window, select_mask=0):
+        a = np.ascontiguousarray(lite, dtype=np.uint32).reshape(-1, 4)
+        out = np.zeros_like(a)
+        self.lib.phoxref_merge_lite.restype = C.c_int
+        m = self.lib.phoxref_merge_lite(_p(a), C.c_int(len(a)), C.c_uint(select_mask), C.c_float(time_window), _p(out))
+        return out[:m].copy()
+
     def intersect(self, geom, origin, direction, tmin=0.0, tmax=1e6):
         keep, gargs = self._geo(geom["foundry"])
         o = np.zeros((len(origin), 4), dtype=np.float32); o[:, :3] = origin; o[:, 3] = tmin

@@ -255,6 +255,16 @@ def test_simtrace_matches_oracle_and_intersect():
         miss = su[:, 2, 3] == 0xffffffff
         if miss.any():                                                          # miss program: background colour, t = 1
             assert (st[miss, 0] == np.array([0.6, 0.6, 0.6, 1.0], dtype=np.float32)).all() and (su[miss, 3, 3] == 0xffffffff).all()
+        # against the reference's own generate_photon_simtrace_frame + add_simtrace compiled for the B200 (oracle/_ref)
+        rg = RefGPU("debugtag").simtrace(w["geom"], gs)
+        assert (st[:, 2, :3] == rg[:, 2, :3]).all()                              # origins: same transform arithmetic
+        assert np.abs(st[:, 3, :3] - rg[:, 3, :3]).max() < 2e-7                  # directions: same sincosf, at most an fma contraction apart
+        gu = rg.view(np.uint32)
+        same_g = (su[:, 2, 3] == gu[:, 2, 3]) & (su[:, 3, 3] == gu[:, 3, 3])
+        assert same_g.mean() > 0.998, (name, same_g.mean())
+        hg = same_g & (su[:, 2, 3] != 0xffffffff)
+        assert np.quantile(np.abs(st[hg, 0, 3] - rg[hg, 0, 3]) / np.maximum(1.0, rg[hg, 0, 3]), 0.999) < 1e-4
+        assert (st[:, 1, 3] == rg[:, 1, 3]).all()                                # tmin column
         # the same rays fed back as INPUT_PHOTON_SIMTRACE: bit-identical records, and t / identities equal to phox_intersect
         rays = np.zeros_like(st); rays[:, 0, :3] = st[:, 2, :3]; rays[:, 1, :3] = st[:, 3, :3]
         st2 = sim.simtrace(G.input_simtrace_genstep(len(rays)), rays)
