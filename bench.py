@@ -302,6 +302,14 @@ def main():
         else:
             kern_s, achieved, kernel_name, share = loop_s, cnt_r * bytes_per_photon / loop_s / 1e9, "k_simulate", st_dev["simulate_kernel_seconds"] / (ms_dev * 1e-3)
             rays_per_launch, ray_bytes = st_dev["num_ray"] / max(1, st_dev["num_launch"]), None
+        # DRAM traffic per launch of the dominant kernel: bytes per ray from the committed ncu --set full capture x rays per launch here
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "traffic_r1.json")
+        if wave and os.path.exists(tpath) and args.workload == "sipm8x8_scint":
+            with open(tpath) as f:
+                tj = json.load(f)
+            traffic = tj["k_wf_trace"]["dram_bytes_per_ray"] * rays_per_launch
+            traffic_src = "profiles/traffic_r1.json: %.0f DRAM bytes per ray (ncu dram__bytes_read+write of one k_wf_trace launch / its rays) x rays_per_launch" % tj["k_wf_trace"]["dram_bytes_per_ray"]
         out = {
             "metric": "photons propagated/sec", "value": value, "unit": "photons/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -315,7 +323,7 @@ def main():
                     "d2h_bytes_per_step": int(64 * st_e2e["num_hit"] / max(1, args.steps)), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(st_dev["num_kernel"] + st_e2e["num_kernel"]),
             "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_kind, "traffic": None, "kernel_ms": kern_s * 1e3,
+                         "peak_source": peak_kind, "traffic": traffic, "traffic_source": traffic_src, "kernel_ms": kern_s * 1e3,
                          "algorithmic_bytes_per_ray": ray_bytes, "rays_per_launch": rays_per_launch,
                          "kernel_share_of_bounce_loop": share,
                          "bounce_loop_ms": loop_s * 1e3, "bounce_loop_share_of_step": st_dev["simulate_kernel_seconds"] / (ms_dev * 1e-3),
