@@ -1,16 +1,17 @@
 // phox_kernels.cuh : the event kernels.
 //
-//   trace()        nearest CSGPrim along a ray: instance BVH -> per-solid BVH -> intersect_prim.
+//   trace_inline() / trace()   nearest CSGPrim along a ray: instance BVH -> per-solid BVH -> prim test -> hit_finish.
 //                  Replaces optixTrace + __intersection__is + __closesthit__ch + __miss__ms
 //                  (CSGOptiX/CSGOptiX7.cu:110-216, 655-682, 749-847, 869-940).
-//   k_simulate     one thread per photon: seed lookup, RNG init, generate, bounce loop, photon
-//                  write, per-block hit count.  Replaces the simulate raygen
-//                  (CSGOptiX7.cu:405-503) and the thrust seeding passes
-//                  (qudarap/QEvt.cu:181-237, sysrap/iexpand.h:86-142): the genstep of a photon
-//                  is found by binary search in the exclusive prefix sum of genstep.numphoton.
-//   k_hit_offsets  exclusive scan of the per-block hit counts (one block).
-//   k_hit_compact  stable stream compaction of hit photons, ascending photon index.  Replaces
-//                  thrust count_if + copy_if (sysrap/SU.cu:48-56, 91-92, 157-159).
+//   wavefront form of the simulate raygen (CSGOptiX7.cu:405-503), the default:
+//     k_wf_generate   seed lookup (binary search in the prefix sum of genstep.numphoton: no seed array, replaces
+//                     qudarap/QEvt.cu:181-237 + sysrap/iexpand.h:86-142), RNG init, generate, photon + list entry
+//     k_wf_trace      one ray per live photon -> 32 B hit record
+//     k_wf_propagate  hit record -> qsim::propagate -> photon; survivors appended, in order, to the next list
+//   k_simulate     persistent form: the whole loop per photon in one kernel, warps refill finished lanes.
+//   k_hit_count / k_hit_offsets / k_hit_compact   stable stream compaction of hit photons (and their sphotonlite
+//                  records), ascending photon index.  Replaces thrust count_if + copy_if (sysrap/SU.cu:48-56, 91-92, 157-159).
+//   k_simtrace, k_intersect, k_boundary_lookup, k_rng_sequence   simtrace mode and query kernels.
 #pragma once
 #include "phox_types.h"
 #include "phox_math.cuh"
