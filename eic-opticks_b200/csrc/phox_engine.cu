@@ -199,11 +199,11 @@ extern "C" phox_context* phox_create(int device) {
         int w[3] = {0, 0, 0};
         if (dbg) {
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[0], k_wf_generate<true>, kWaveThreads, 0);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[1], k_wf_trace<true>, kWaveThreads, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[1], k_wf_trace<true>, kTraceThreads, 0);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[2], k_wf_propagate<true>, kPropThreads, 0);
         } else {
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[0], k_wf_generate<false>, kWaveThreads, 0);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[1], k_wf_trace<false>, kWaveThreads, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[1], k_wf_trace<false>, kTraceThreads, 0);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[2], k_wf_propagate<false>, kPropThreads, 0);
         }
         for (int k = 0; k < 3; k++) ctx->wave_grid[k][dbg] = std::max(w[k], 1) * prop.multiProcessorCount;
@@ -669,16 +669,16 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
             W.bounce = b;
             if (prof) {        // same launches, with an event before each kernel
                 CK(cudaEventRecord(ctx->prof_ev[2 * b], ctx->stream));
-                if (dbg) k_wf_trace<true><<<grid(1), kWaveThreads, 0, ctx->stream>>>(W);
-                else k_wf_trace<false><<<grid(1), kWaveThreads, 0, ctx->stream>>>(W);
+                if (dbg) k_wf_trace<true><<<grid(1, kTraceThreads), kTraceThreads, 0, ctx->stream>>>(W);
+                else k_wf_trace<false><<<grid(1, kTraceThreads), kTraceThreads, 0, ctx->stream>>>(W);
                 CK(cudaEventRecord(ctx->prof_ev[2 * b + 1], ctx->stream));
                 if (dbg) k_wf_propagate<true><<<grid(2, kPropThreads), kPropThreads, 0, ctx->stream>>>(W);
                 else k_wf_propagate<false><<<grid(2, kPropThreads), kPropThreads, 0, ctx->stream>>>(W);
                 if (b == c.max_bounce - 1) CK(cudaEventRecord(ctx->prof_ev[2 * b + 2], ctx->stream));
                 continue;
             }
-            if (dbg) { k_wf_trace<true><<<grid(1), kWaveThreads, 0, ctx->stream>>>(W); k_wf_propagate<true><<<grid(2, kPropThreads), kPropThreads, 0, ctx->stream>>>(W); }
-            else { k_wf_trace<false><<<grid(1), kWaveThreads, 0, ctx->stream>>>(W); k_wf_propagate<false><<<grid(2, kPropThreads), kPropThreads, 0, ctx->stream>>>(W); }
+            if (dbg) { k_wf_trace<true><<<grid(1, kTraceThreads), kTraceThreads, 0, ctx->stream>>>(W); k_wf_propagate<true><<<grid(2, kPropThreads), kPropThreads, 0, ctx->stream>>>(W); }
+            else { k_wf_trace<false><<<grid(1, kTraceThreads), kTraceThreads, 0, ctx->stream>>>(W); k_wf_propagate<false><<<grid(2, kPropThreads), kPropThreads, 0, ctx->stream>>>(W); }
         }
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->ev[1], ctx->stream));

@@ -451,6 +451,10 @@ struct WaveParams {
 #define PHOX_WF_TRACE_MIN_BLOCKS 4      // resident 256-thread blocks per SM the trace kernel is compiled for (register cap 65536/(256*N))
 #endif
 constexpr int kWaveThreads = 256;
+#ifndef PHOX_WF_TRACE_THREADS
+#define PHOX_WF_TRACE_THREADS 256       // block of the trace kernel; with PHOX_WF_TRACE_MIN_BLOCKS it sets the register budget
+#endif
+constexpr int kTraceThreads = PHOX_WF_TRACE_THREADS;
 #ifndef PHOX_WF_PROP_THREADS
 #define PHOX_WF_PROP_THREADS 256        // block of the physics kernel = run length of the ordered survivor append
 #endif
@@ -502,7 +506,7 @@ __global__ void __launch_bounds__(kWaveThreads) k_wf_generate(const __grid_const
 }
 
 template <bool DEBUG>
-__global__ void __launch_bounds__(kWaveThreads, PHOX_WF_TRACE_MIN_BLOCKS) k_wf_trace(const __grid_constant__ WaveParams W) {
+__global__ void __launch_bounds__(kTraceThreads, PHOX_WF_TRACE_MIN_BLOCKS) k_wf_trace(const __grid_constant__ WaveParams W) {
     const SimParams& P = W.sim;
     const unsigned count = *W.count_in;
     unsigned nray = 0;
