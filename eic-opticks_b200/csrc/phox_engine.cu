@@ -137,6 +137,8 @@ struct phox_context {
 #define PHOX_KERNEL_AUTO_CHOICE PHOX_KERNEL_WAVEFRONT
 #endif
 
+static const int64_t kAutoWavefrontMinPhotons = 250000;     // photons per launch from which PHOX_KERNEL_AUTO picks the wavefront form
+
 extern "C" void phox_default_config(phox_config* c) {
     if (!c) return;
     std::memset(c, 0, sizeof(*c));
@@ -627,7 +629,10 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
     P.seed = c.rng_seed; P.rng_offset = c.rng_offset; P.skipahead = c.skipahead_event_offset;
     P.burn = c.rng_mode == PHOX_RNG_DEBUG_TAG ? 1 : 0;
 
-    const bool wavefront = (c.kernel_mode == PHOX_KERNEL_AUTO ? PHOX_KERNEL_AUTO_CHOICE : c.kernel_mode) == PHOX_KERNEL_WAVEFRONT;
+    // AUTO: the wavefront form wins once a launch fills the machine several times over; below that its ~65 kernels each
+    // run a single under-filled wave and the one persistent kernel is up to 2x quicker (profiles/r1_summary.md, small events)
+    const bool wavefront = (c.kernel_mode == PHOX_KERNEL_AUTO ? (n < kAutoWavefrontMinPhotons ? PHOX_KERNEL_PERSISTENT : PHOX_KERNEL_AUTO_CHOICE)
+                                                              : c.kernel_mode) == PHOX_KERNEL_WAVEFRONT;
     if (!wavefront) {
         CK(cudaMemsetAsync(ctx->d_counters.p + 3, 0, sizeof(unsigned long long), ctx->stream));
         // persistent grid: every SM gets as many resident blocks as the kernel's registers allow

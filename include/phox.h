@@ -51,7 +51,7 @@ enum {
 /* How the bounce loop is scheduled on the GPU.  Both forms call the same trace and propagate code and
  * give bit-identical results. */
 enum {
-    PHOX_KERNEL_AUTO = 0,       /* the faster form for the build (currently wavefront)                        */
+    PHOX_KERNEL_AUTO = 0,       /* by launch size: persistent below 250 k photons, wavefront above            */
     PHOX_KERNEL_PERSISTENT = 1, /* one fused kernel, persistent warps that refill idle lanes                  */
     PHOX_KERNEL_WAVEFRONT = 2   /* per bounce: trace kernel + physics kernel over the list of live photons    */
 };
