@@ -54,6 +54,16 @@ struct DevBuf {
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
+// per-call device scratch of the query entry points: freed on every return path
+template <typename T>
+struct TmpBuf {
+    T* p = nullptr;
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)); }
+    ~TmpBuf() { if (p) cudaFree(p); }
+    TmpBuf() = default;
+    TmpBuf(const TmpBuf&) = delete;
+    TmpBuf& operator=(const TmpBuf&) = delete;
+};
 }  // namespace
 
 struct phox_context {
@@ -938,11 +948,11 @@ extern "C" int phox_intersect(phox_context* ctx, const float* ray_o_tmin, const 
     if (!ray_o_tmin || !ray_d || !dst_prd || nray < 0) return ctx->fail(PHOX_E_ARG, "phox_intersect: bad arguments");
     if (nray == 0) return PHOX_OK;
     CK(cudaSetDevice(ctx->device));
-    float4 *d_o = nullptr, *d_d = nullptr;
-    Prd* d_out = nullptr;
-    CK(cudaMalloc(&d_o, (size_t)nray * 16));
-    CK(cudaMalloc(&d_d, (size_t)nray * 16));
-    CK(cudaMalloc(&d_out, (size_t)nray * 32));
+    TmpBuf<float4> b_o, b_d;
+    TmpBuf<Prd> b_out;
+    CK(b_o.alloc((size_t)nray)); CK(b_d.alloc((size_t)nray)); CK(b_out.alloc((size_t)nray));
+    float4 *d_o = b_o.p, *d_d = b_d.p;
+    Prd* d_out = b_out.p;
     CK(cudaMemcpyAsync(d_o, ray_o_tmin, (size_t)nray * 16, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_d, ray_d, (size_t)nray * 16, cudaMemcpyHostToDevice, ctx->stream));
     Scene sc;
@@ -950,19 +960,15 @@ extern "C" int phox_intersect(phox_context* ctx, const float* ray_o_tmin, const 
     sc.prim = ctx->d_prim.p; sc.exact = ctx->d_exact.p; sc.nodes = ctx->d_bvh.p; sc.inst = ctx->d_inst.p;
     sc.ninst = ctx->ninst; sc.tlas_root = ctx->tlas_root; sc.accel = accel;
     const int T = 128;
-    cudaEventRecord(ctx->ev[0], ctx->stream);
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     k_intersect<<<(unsigned)((nray + T - 1) / T), T, 0, ctx->stream>>>(sc, d_o, d_d, (unsigned)nray, ctx->cfg.tmax, d_out);
-    cudaEventRecord(ctx->ev[1], ctx->stream);
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess && cudaEventSynchronize(ctx->ev[1]) == cudaSuccess) {
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
-        ctx->stats.simulate_kernel_seconds = ms * 1e-3;          // device time of the query kernel
-    }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(dst_prd, d_out, (size_t)nray * 32, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_o); cudaFree(d_d); cudaFree(d_out);
-    if (e != cudaSuccess) return ctx->cuda_fail(e, "phox_intersect");
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CK(cudaMemcpyAsync(dst_prd, d_out, (size_t)nray * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    ctx->stats.simulate_kernel_seconds = ms * 1e-3;              // device time of the query kernel
     return PHOX_OK;
 }
 
@@ -1098,20 +1104,18 @@ extern "C" int phox_boundary_lookup(phox_context* ctx, const float* nm, const ui
     if (!ctx->have_tables) return ctx->fail(PHOX_E_STATE, "phox_boundary_lookup: tables not set");
     if (!nm || !line || !k || !dst || n <= 0) return ctx->fail(PHOX_E_ARG, "phox_boundary_lookup: bad arguments");
     CK(cudaSetDevice(ctx->device));
-    float* d_nm = nullptr; unsigned *d_line = nullptr, *d_k = nullptr; float4* d_out = nullptr;
-    CK(cudaMalloc(&d_nm, n * 4)); CK(cudaMalloc(&d_line, n * 4)); CK(cudaMalloc(&d_k, n * 4)); CK(cudaMalloc(&d_out, n * 16));
-    CK(cudaMemcpyAsync(d_nm, nm, n * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(d_line, line, n * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(d_k, k, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    TmpBuf<float> b_nm; TmpBuf<unsigned> b_line, b_k; TmpBuf<float4> b_out;
+    CK(b_nm.alloc((size_t)n)); CK(b_line.alloc((size_t)n)); CK(b_k.alloc((size_t)n)); CK(b_out.alloc((size_t)n));
+    CK(cudaMemcpyAsync(b_nm.p, nm, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(b_line.p, line, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(b_k.p, k, n * 4, cudaMemcpyHostToDevice, ctx->stream));
     Tables tb;
     tb.bnd_tex = ctx->bnd_tex; tb.icdf_tex = ctx->icdf_tex; tb.optical = ctx->d_optical.p;
     tb.nx = ctx->nx; tb.ny = ctx->ny; tb.nm0 = ctx->nm0; tb.nms = ctx->nms; tb.hd_factor = ctx->hd_factor;
-    k_boundary_lookup<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(tb, d_nm, d_line, d_k, (unsigned)n, d_out);
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(dst, d_out, n * 16, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_nm); cudaFree(d_line); cudaFree(d_k); cudaFree(d_out);
-    if (e != cudaSuccess) return ctx->cuda_fail(e, "phox_boundary_lookup");
+    k_boundary_lookup<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(tb, b_nm.p, b_line.p, b_k.p, (unsigned)n, b_out.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(dst, b_out.p, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return PHOX_OK;
 }
 
