@@ -20,7 +20,7 @@ G4MaterialPropertiesTable::CalculateGROUPVEL, G4GDMLRead rotation convention (ro
 placement with the inverse), G4Scintillation's trapezoid integral of the emission spectrum.
 
 Not covered (asserts, like the reference does for phi segments u4/U4Solid.h:555-561): phi/theta segments,
-polycone, trap, ellipsoid, assemblies, replicas, NIST materials by name, instancing (FREQ_CUT 500).
+trap, polyhedra, torus, assemblies, replicas, NIST materials by name, instancing (FREQ_CUT 500).
 """
 import math
 import re
@@ -209,6 +209,29 @@ class GDML:
             pl.append([0, 0, 1, hz]); pl.append([0, 0, -1, hz])
             xm, ym = max(x1, x2), max(y1, y2)
             return F.convexpolyhedron(pl, [-xm, -ym, -hz, xm, ym, hz])
+        if tag == "polycone":
+            assert g("deltaphi", 2 * math.pi / au) * au >= 2 * math.pi - 1e-9 and g("startphi") == 0, \
+                "polycone phi segments need the experimental phicut of u4/U4Polycone.h:331-346 and are not translated"
+            rz = [(self.ev(z.get("rmin"), 0.0) * lu, self.ev(z.get("rmax")) * lu, self.ev(z.get("z")) * lu) for z in el.findall("zplane")]
+            return polycone_tree(rz)
+        if tag == "ellipsoid":
+            # u4/U4Solid.h init_Ellipsoid: sphere of radius cz (z-sliced at the cuts, 0.1 mm safety on the uncut side), scaled in x and y
+            sx, sy, sz = g("ax") * lu, g("by") * lu, g("cz") * lu
+            zcut1, zcut2 = g("zcut1", 0.0) * lu, g("zcut2", 0.0) * lu
+            if zcut1 == 0.0 and zcut2 == 0.0:                 # G4Ellipsoid: both cuts zero = uncut
+                zcut1, zcut2 = -sz, sz
+            zmin, zmax = max(zcut1, -sz), min(zcut2, sz)
+            assert zmax > zmin
+            upper_cut, lower_cut = zmax < sz, zmin > -sz
+            if not upper_cut and not lower_cut:
+                leaf = F.sphere(sz)
+            elif upper_cut and lower_cut:
+                leaf = F.zsphere(sz, zmin, zmax)
+            elif lower_cut:
+                leaf = F.zsphere(sz, zmin, zmax + 0.1)
+            else:
+                leaf = F.zsphere(sz, zmin - 0.1, zmax)
+            return leaf.placed(F.scale(sx / sz, sy / sz, 1.0))
         if tag in ("subtraction", "union", "intersection"):
             a = self.solid_tree(el.find("first").get("ref"))
             b = self.solid_tree(el.find("second").get("ref"))
@@ -260,6 +283,77 @@ class GDML:
             elif el.tag == "bordersurface":
                 pv = [p.get("ref") for p in el.findall("physvolref")]
                 self.borders.append(dict(name=el.get("name"), surface=el.get("surfaceproperty"), pv1=pv[0], pv2=pv[1]))
+
+
+def polycone_tree(rz):
+    """U4Polycone (u4/U4Polycone.h:303-640): z-planes (rmin, rmax, z) -> union of cylinders / cones per z segment for the outside,
+    the same from rmin for the inside (subtracted), with the z nudges of sysrap/sn.h (ZNudgeOverlapJoints: at a coincident
+    joint the prim with the smaller radius there grows 1 mm into the other; ZNudgeExpandEnds: the inner sticks out 1 mm at
+    both ends) so that no faces coincide."""
+    rz = [tuple(float(v) for v in t) for t in rz]
+    if all(rz[i][2] >= rz[i + 1][2] for i in range(len(rz) - 1)) and rz[0][2] > rz[-1][2]:
+        rz = rz[::-1]
+    assert all(rz[i][2] <= rz[i + 1][2] for i in range(len(rz) - 1)), "polycone z-planes must be monotonic"
+    zmin, zmax = rz[0][2], rz[-1][2]
+    assert zmax > zmin
+
+    def collect(outside):
+        prims = []
+        for (a, b) in zip(rz[:-1], rz[1:]):
+            r1, r2 = (a[1], b[1]) if outside else (a[0], b[0])
+            z1, z2 = a[2], b[2]
+            if z1 == z2 or (not outside and r1 == 0.0 and r2 == 0.0):
+                continue
+            prims.append(dict(cone=r1 != r2, r1=r2 if r1 == r2 else r1, z1=z1, r2=r2, z2=z2))
+        return prims
+
+    def decrease_zmin(p, dz):
+        nz = p["z1"] - dz
+        if p["cone"]:
+            p["r1"] = max(p["r2"] + (p["r2"] - p["r1"]) * (nz - p["z2"]) / (p["z2"] - p["z1"]), 0.0)
+        p["z1"] = nz
+
+    def increase_zmax(p, dz):
+        nz = p["z2"] + dz
+        if p["cone"]:
+            p["r2"] = max(p["r1"] + (p["r2"] - p["r1"]) * (nz - p["z1"]) / (p["z2"] - p["z1"]), 0.0)
+        p["z2"] = nz
+
+    def overlap_joints(prims):
+        for lower, upper in zip(prims[:-1], prims[1:]):
+            if lower["z2"] != upper["z1"]:
+                continue
+            if lower["r2"] > upper["r1"]:
+                decrease_zmin(upper, 1.0)
+            else:
+                increase_zmax(lower, 1.0)
+
+    def tree(prims):
+        leaves = [F.cone(p["r1"], p["z1"], p["r2"], p["z2"]) if p["cone"] else F.cylinder(p["r2"], p["z1"], p["z2"]) for p in prims]
+        t = leaves[0]
+        for leaf in leaves[1:]:
+            t = F.union(t, leaf)                                # sn::UnionTree, VERSION 0: unbalanced, left deep
+        return t
+
+    router, rinner = {t[1] for t in rz}, {t[0] for t in rz}
+    if len(router) == 1:
+        outer = F.cylinder(rz[0][1], zmin, zmax)
+    else:
+        po = collect(True)
+        if len(po) > 1:
+            overlap_joints(po)
+        outer = tree(po)
+    if rinner == {0.0}:
+        return outer
+    if len(rinner) == 1:
+        inner = F.cylinder(rz[0][0], zmin, zmax)
+    else:
+        pi_ = collect(False)
+        decrease_zmin(pi_[0], 1.0); increase_zmax(pi_[-1], 1.0)
+        if len(pi_) > 1:
+            overlap_joints(pi_)
+        inner = tree(pi_)
+    return F.difference(outer, inner)
 
 
 def _place_tree(t, m):

@@ -176,6 +176,21 @@ class Oracle:
             raise RuntimeError("oracle_simtrace failed")
         return out
 
+    def intersect(self, geom, origin, direction, tmin=0.0, tmax=1e6, use_boxes=False):
+        """closest hit of each ray over all prims (quad2 per ray), CPU"""
+        fd = geom["foundry"]
+        a = {k: np.ascontiguousarray(fd[k], dtype=(np.int32 if k == "solid" else np.float32)) for k in ("solid", "prim", "node", "plan", "itra", "inst")}
+        o = np.zeros((len(origin), 4), dtype=np.float32); o[:, :3] = origin; o[:, 3] = tmin
+        d = np.zeros((len(origin), 4), dtype=np.float32); d[:, :3] = direction
+        out = np.zeros((len(o), 2, 4), dtype=np.float32)
+        self.lib.oracle_intersect.restype = C.c_int
+        rc = self.lib.oracle_intersect(_p(a["solid"]), C.c_int(len(a["solid"])), _p(a["prim"]), _p(a["node"]), _p(a["plan"]) if len(a["plan"]) else None,
+                                       _p(a["itra"]), C.c_int(len(a["itra"])), _p(a["inst"]), C.c_int(len(a["inst"])), _p(o), _p(d), C.c_int(len(o)),
+                                       C.c_float(tmax), _p(out), C.c_int(1 if use_boxes else 0))
+        if rc != 0:
+            raise RuntimeError("oracle_intersect failed")
+        return out
+
     def merge_lite(self, lite, time_window, select_mask=0):
         a = np.ascontiguousarray(lite, dtype=np.uint32).reshape(-1, 4)
         out = np.zeros_like(a)

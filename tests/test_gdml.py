@@ -101,3 +101,55 @@ def test_mini_detector_runs_and_bvh_matches_brute():
             fl.add(v & 0xf); v >>= 4
     assert {3, 7, 8}.issubset(fl)          # TO, SD (block skins), SA (implicit absorber on the steel plate)
     sim.close()
+
+
+def test_polycone_and_ellipsoid_follow_u4(tmp_path):
+    """U4Polycone (u4/U4Polycone.h) and U4Solid::init_Ellipsoid restated: tree shape, nudges, and ray distances from the oracle"""
+    from eic_opticks_b200 import gdml as GD, foundry as F
+    from _ref import Oracle
+    # outer: cylinder r50 z[-100,0], cone 50->20 z[0,60]; inner: r10 everywhere
+    t = GD.polycone_tree([(10, 50, -100), (10, 50, 0), (10, 20, 60)])
+    assert isinstance(t, F.Op) and t.typecode == F.CSG_DIFFERENCE
+    outer, inner = t.left, t.right
+    assert isinstance(outer, F.Op) and outer.typecode == F.CSG_UNION and isinstance(inner, F.Leaf) and inner.typecode == F.CSG_CYLINDER
+    cyl, cone = outer.left, outer.right
+    # joint at z = 0: both radii 50 -> "else" branch of ZNudgeOverlapJoint: the lower prim grows 1 mm upwards
+    assert cyl.typecode == F.CSG_CYLINDER and tuple(cyl.param[3:6]) == (50.0, -100.0, 1.0)
+    assert cone.typecode == F.CSG_CONE and tuple(cone.param[:4]) == (50.0, 0.0, 20.0, 60.0)
+    assert tuple(inner.param[3:6]) == (10.0, -100.0, 60.0)            # single-radius inner: plain cylinder over the z range
+    # varying inner radius: ends stick out by 1 mm, cone radii extrapolated along the slope
+    t2 = GD.polycone_tree([(5, 50, 0), (15, 50, 100)])
+    assert t2.left.typecode == F.CSG_CYLINDER and t2.right.typecode == F.CSG_CONE
+    assert np.allclose(t2.right.param[:4], (4.9, -1.0, 15.1, 101.0))
+    # descending z planes are reversed
+    t3 = GD.polycone_tree([(0, 20, 60), (0, 50, 0), (0, 50, -100)])
+    assert t3.typecode == F.CSG_UNION and t3.left.typecode == F.CSG_CYLINDER
+
+    gd = tmp_path / "pc.gdml"
+    gd.write_text("""<?xml version="1.0"?>
+<gdml><define/><materials>
+ <material name="Vac"><D value="1e-25"/><fraction n="1" ref="H"/></material><element name="H" formula="H" Z="1"><atom value="1"/></element>
+</materials><solids>
+ <box name="w" x="1000" y="1000" z="1000" lunit="mm"/>
+ <polycone name="pc" startphi="0" deltaphi="360" aunit="deg" lunit="mm">
+  <zplane rmin="10" rmax="50" z="-100"/><zplane rmin="10" rmax="50" z="0"/><zplane rmin="10" rmax="20" z="60"/></polycone>
+ <ellipsoid name="el" ax="30" by="40" cz="50" zcut1="-20" zcut2="0" lunit="mm"/>
+</solids><structure>
+ <volume name="pcl"><materialref ref="Vac"/><solidref ref="pc"/></volume>
+ <volume name="ell"><materialref ref="Vac"/><solidref ref="el"/></volume>
+ <volume name="W"><materialref ref="Vac"/><solidref ref="w"/>
+  <physvol name="a"><volumeref ref="pcl"/></physvol>
+  <physvol name="b"><volumeref ref="ell"/><position x="200" y="0" z="0" unit="mm"/></physvol></volume>
+</structure><setup name="Default" version="1.0"><world ref="W"/></setup></gdml>""")
+    geom = GD.translate(str(gd))
+    o = np.array([[200, 400, -10], [200, 0, -300]], dtype=np.float32)
+    d = np.array([[0, -1, 0], [0, 0, 1]], dtype=np.float32)
+    el = Oracle().intersect(geom, o, d)
+    # ellipsoid centre (200,0,0), semi axes 30,40,50, kept between z=-20 and z=0; ray down -y at z=-10: y = 40*sqrt(1-(10/50)^2)
+    assert abs(el[0, 0, 3] - (400 - 40 * np.sqrt(1 - 0.04))) < 1e-2
+    assert abs(el[1, 0, 3] - (300 - 20)) < 1e-3                                # from below: the z = -20 cut plane
+    pc = Oracle().intersect(geom, np.array([[0, 300, -50], [0, 300, 30], [30, 0, 300]], dtype=np.float32),
+                            np.array([[0, -1, 0], [0, -1, 0], [0, 0, -1]], dtype=np.float32))
+    assert abs(pc[0, 0, 3] - 250) < 1e-3                                       # cylinder part, r = 50
+    assert abs(pc[1, 0, 3] - (300 - 35)) < 1e-3                                # cone part: r(30) = 50 - 30/60*30 = 35
+    assert abs(pc[2, 0, 3] - (300 - 40)) < 1e-3                                # from above at r = 30: cone surface z = 60*(50-30)/30 = 40
