@@ -216,7 +216,7 @@ def main():
             hits = torch.empty((nh, 4, 4), dtype=torch.float32, device=dev)
             if nh:
                 sim.get_hits_device(hits.data_ptr())
-            parallel.gather_hits(hits)
+            parallel.gather_hits(hits, dst=0)          # the event's hits end up on one rank, like on the reference's one host process
 
     def step_e2e(event_id):
         gs_np = h_gs.numpy(); ip_np = h_ip.numpy() if h_ip is not None else None
@@ -316,7 +316,7 @@ def main():
             "config": {"workload": args.workload, "photons_per_gpu_per_step": cnt_r, "gensteps_per_gpu": int(len(gs_r)), "max_bounce": sim.cfg.max_bounce,
                        "event_mode": "Minimal", "rng_mode": "DEBUG_TAG", "accel": "two-level BVH", "kernel_mode": args.kernel_mode, "max_slot": args.max_slot,
                        "l2": "256 MB flush between timed steps",
-                       "sharding": "gensteps partitioned over ranks, absolute photon offsets, hits all-gathered (NCCL) each step" if world > 1 else "single GPU"},
+                       "sharding": "gensteps partitioned over ranks, absolute photon offsets, hits gathered to rank 0 (NCCL send/recv) each step" if world > 1 else "single GPU"},
             "rays_per_s": st_dev["num_ray"] * world / (ms_dev * 1e-3), "bounces_per_photon": st_dev["num_ray"] / max(1, cnt_r * args.steps),
             "hit_fraction": f_hit, "step_ms": st_dev["step_ms"], "e2e_step_ms": st_e2e["step_ms"],
             "e2e": {"value": e2e, "unit": "photons/s", "h2d_bytes_per_step": int(gs_r.nbytes + (ip_r.nbytes if ip_r is not None else 0)),

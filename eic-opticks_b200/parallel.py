@@ -33,10 +33,15 @@ def shard_event(gensteps, rank, world_size, input_photons=None):
     return np.ascontiguousarray(gs[s0:s1]), None, off, cnt
 
 
-def gather_hits(hits, group=None, device=None):
-    """all-gather variable-length hit arrays (n_r,4,4) float32 -> the whole event's hits in rank
-    order.  `hits` may be a numpy array (gloo / CPU) or a torch tensor on this rank's device (NCCL).
-    Two collectives: counts, then the records padded to the maximum count."""
+def gather_hits(hits, group=None, device=None, dst=None):
+    """gather variable-length hit arrays (n_r,4,4) float32 -> the whole event's hits in rank order.
+    `hits` may be a numpy array (gloo / CPU) or a torch tensor on this rank's device (NCCL).
+
+    dst=None : every rank receives the whole array (all-gather of the records padded to the maximum count).
+    dst=r    : only rank r receives it (the reference hands hits to ONE host process): every other rank sends its
+               records straight into its slice of r's output buffer (point-to-point, no padding, no extra copy) and
+               gets None back.
+    Returns (hits or None, counts per rank)."""
     import torch
     import torch.distributed as dist
 
@@ -46,14 +51,36 @@ def gather_hits(hits, group=None, device=None):
         t = t.to(device)
     t = t.reshape(-1, 16).contiguous()
     world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
     n_local = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
-    counts = [torch.zeros_like(n_local) for _ in range(world)]
-    dist.all_gather(counts, n_local, group=group)
-    counts = [int(c.item()) for c in counts]
+    all_counts = torch.zeros(world, dtype=torch.int64, device=t.device)
+    dist.all_gather_into_tensor(all_counts, n_local, group=group)
+    counts = [int(c) for c in all_counts.tolist()]
+    if dst is not None:
+        out = None
+        ops = []
+        if rank == dst:
+            out = torch.empty((sum(counts), 16), dtype=torch.float32, device=t.device)
+            off = 0
+            for r, c in enumerate(counts):
+                if r == rank:
+                    out[off:off + c] = t
+                elif c:
+                    ops.append(dist.P2POp(dist.irecv, out[off:off + c], dist.get_global_rank(group, r) if group is not None else r, group))
+                off += c
+        elif t.shape[0]:
+            ops.append(dist.P2POp(dist.isend, t, dist.get_global_rank(group, dst) if group is not None else dst, group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        if out is None:
+            return None, counts
+        out = out.reshape(-1, 4, 4)
+        return (out.cpu().numpy() if as_numpy else out), counts
     nmax = max(max(counts), 1)
     pad = torch.zeros((nmax, 16), dtype=torch.float32, device=t.device)
     pad[: t.shape[0]] = t
-    bufs = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(bufs, pad, group=group)
-    out = torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0).reshape(-1, 4, 4)
+    buf = torch.empty((world * nmax, 16), dtype=torch.float32, device=t.device)      # concatenation layout (gloo and NCCL both take it)
+    dist.all_gather_into_tensor(buf, pad, group=group)
+    out = torch.cat([buf[r * nmax: r * nmax + c] for r, c in enumerate(counts)], dim=0).reshape(-1, 4, 4)
     return (out.cpu().numpy() if as_numpy else out), counts

@@ -27,6 +27,16 @@ def _worker(rank, world, port, q):
     hits = np.zeros((len(sel), 4, 4), dtype=np.float32)
     hits.view(np.uint32)[:, 3, 2] = sel
     allhits, counts = parallel.gather_hits(hits)
+    # root-only gather (the reference hands the hits to one host process): same array on the root, None elsewhere
+    root, counts_r = parallel.gather_hits(hits, dst=1)
+    assert counts_r == counts
+    if rank == 1:
+        assert root.shape == allhits.shape and root.tobytes() == allhits.tobytes()
+    else:
+        assert root is None
+    empty, counts_e = parallel.gather_hits(hits[:0] if rank == 0 else hits, dst=0)     # a rank without hits
+    if rank == 0:
+        assert len(empty) == counts[1] and counts_e[0] == 0
     q.put((rank, off, cnt, counts, allhits.view(np.uint32)[:, 3, 2].copy()))
     dist.barrier()
     dist.destroy_process_group()
