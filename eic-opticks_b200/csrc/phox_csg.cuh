@@ -117,10 +117,16 @@ PHOX_D bool leaf_zsphere(float4& is, const float4& q0, const float4& q1, float t
     return ok;
 }
 
+// idir = 1 / rd, supplied by the caller (the traversal already holds it for its slab tests; IEEE division gives the same bits)
+PHOX_D bool leaf_box3_idir(float4& is, const float4& q0, float tmin, const float3& ro, const float3& rd, const float3& idir);
+
 PHOX_D bool leaf_box3(float4& is, const float4& q0, float tmin, const float3& ro, const float3& rd) {
+    return leaf_box3_idir(is, q0, tmin, ro, rd, f3(1.f / rd.x, 1.f / rd.y, 1.f / rd.z));
+}
+
+PHOX_D bool leaf_box3_idir(float4& is, const float4& q0, float tmin, const float3& ro, const float3& rd, const float3& idir) {
     float3 bmin = f3(-q0.x / 2.f, -q0.y / 2.f, -q0.z / 2.f);
     float3 bmax = f3(q0.x / 2.f, q0.y / 2.f, q0.z / 2.f);
-    float3 idir = f3(1.f / rd.x, 1.f / rd.y, 1.f / rd.z);
     float3 t0 = f3((bmin.x - ro.x) * idir.x, (bmin.y - ro.y) * idir.y, (bmin.z - ro.z) * idir.z);
     float3 t1 = f3((bmax.x - ro.x) * idir.x, (bmax.y - ro.y) * idir.y, (bmax.z - ro.z) * idir.z);
     float3 nr = f3(fminf(t0.x, t1.x), fminf(t0.y, t1.y), fminf(t0.z, t1.z));

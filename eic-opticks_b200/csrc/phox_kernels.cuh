@@ -99,10 +99,10 @@ PHOX_D void keep_nearest(Nearest& best, const float4& is, int prim_idx, int inst
 // arithmetic as intersect_leaf's transform + leaf_box3 + normal back-transform, which for a pure translation reduce to
 // o + t, d, n exactly (products with the 0 / 1 matrix entries are exact), without the dependent loads of prim -> node ->
 // transform.  Out of line so that every kernel shares one compiled body, like intersect_prim_cold.
-__device__ __noinline__ bool intersect_exact_box(float4& is, const float4* rec, float tmin, const float3& ro, const float3& rd) {
+__device__ __noinline__ bool intersect_exact_box(float4& is, const float4* rec, float tmin, const float3& ro, const float3& rd, const float3& idir) {
     float4 q0 = __ldg(rec), tr = __ldg(rec + 1);
     float3 o = f3(ro.x + tr.x, ro.y + tr.y, ro.z + tr.z);
-    return leaf_box3(is, q0, tmin, o, rd);
+    return leaf_box3_idir(is, q0, tmin, o, rd, idir);       // idir = 1 / rd as the traversal computed it: the direction is not transformed
 }
 constexpr int kLeafExactBox = 0x40000000;        // leaf item flag: the prim qualifies for intersect_exact_box
 constexpr int kLeafItemMask = 0x3fffffff;
@@ -205,7 +205,7 @@ PHOX_D void traverse_bvh(Nearest& best, const Scene& sc, float tmin, const float
             bool ok;
 #if PHOX_EXACT_BOX
             if (item & kLeafExactBox) {
-                ok = intersect_exact_box(is, sc.exact + 2 * prim_idx, tmin, o, d);
+                ok = intersect_exact_box(is, sc.exact + 2 * prim_idx, tmin, o, d, idir);
             } else
 #endif
             {
