@@ -641,6 +641,7 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
 
     // AUTO: the wavefront form wins once a launch fills the machine several times over; below that its ~65 kernels each
     // run a single under-filled wave and the one persistent kernel is up to 2x quicker (profiles/r1_summary.md, small events)
+    if (n > 0x7fffffffll) return ctx->fail(PHOX_E_NOMEM, "launch of more than 2^31 photons: lower max_slot");
     const bool wavefront = (c.kernel_mode == PHOX_KERNEL_AUTO ? (n < kAutoWavefrontMinPhotons ? PHOX_KERNEL_PERSISTENT : PHOX_KERNEL_AUTO_CHOICE)
                                                               : c.kernel_mode) == PHOX_KERNEL_WAVEFRONT;
     if (!wavefront) {

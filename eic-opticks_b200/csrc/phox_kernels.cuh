@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(kSimThreads, PHOX_SIM_MIN_BLOCKS) k_simulate(c
 // bodies the persistent kernel calls, so both forms give bit-identical results.
 struct WaveParams {
     SimParams sim;
-    unsigned* active_in;            // photon slots alive at this bounce
+    unsigned* active_in;            // photon slots alive at this bounce (bit 31: kListEps0)
     unsigned* active_out;           // survivors (next bounce)
     const unsigned* count_in;       // device-side length of active_in
     unsigned* count_out;            // device-side length of active_out (zeroed beforehand)
@@ -462,6 +462,8 @@ constexpr int kPropThreads = PHOX_WF_PROP_THREADS;
 #ifndef PHOX_WF_PROP_MIN_BLOCKS
 #define PHOX_WF_PROP_MIN_BLOCKS 5       // 48 registers
 #endif
+constexpr unsigned kListEps0 = 0x80000000u;     // list entry bit: the photon's last flag is in PropagateEpsilon0Mask (-> tmin0), so that
+constexpr unsigned kListSlotMask = 0x7fffffffu; // the trace kernel does not have to read the flag word of the photon record
 constexpr unsigned kWaveNoHit = 0xffffffffu;    // prim_boundary of a list entry whose photon is final (miss or time over)
 
 template <bool DEBUG>
@@ -489,11 +491,11 @@ __global__ void __launch_bounds__(kWaveThreads) k_wf_generate(const __grid_const
 #if PHOX_WF_STREAM
         p.store_cs(P.photon + idx);
         __stcs(W.ndraw + idx, rng.consumed(base));
-        __stcs(W.active_out + idx, idx);
+        __stcs(W.active_out + idx, idx | ((p.obf & P.eps0_mask) ? kListEps0 : 0u));
 #else
         p.store(P.photon + idx);
         W.ndraw[idx] = rng.consumed(base);
-        W.active_out[idx] = idx;
+        W.active_out[idx] = idx | ((p.obf & P.eps0_mask) ? kListEps0 : 0u);
 #endif
         if (P.lpos) P.lpos[idx] = 0u;
         if (DEBUG) {
@@ -513,20 +515,20 @@ __global__ void __launch_bounds__(kTraceThreads, PHOX_WF_TRACE_MIN_BLOCKS) k_wf_
     const unsigned stride = gridDim.x * blockDim.x;
     for (unsigned a = blockIdx.x * blockDim.x + threadIdx.x; a < count; a += stride) {
 #if PHOX_WF_STREAM
-        unsigned idx = __ldcs(W.active_in + a);
+        const unsigned entry = __ldcs(W.active_in + a);
+        const unsigned idx = entry & kListSlotMask;
         const float4* ph = reinterpret_cast<const float4*>(P.photon + idx);
         float4 q0 = __ldcs(ph), q1 = __ldcs(ph + 1);
-        unsigned obf = __ldcs(reinterpret_cast<const unsigned*>(ph + 3));
 #else
-        unsigned idx = W.active_in[a];
+        const unsigned entry = W.active_in[a];
+        const unsigned idx = entry & kListSlotMask;
         const float4* ph = reinterpret_cast<const float4*>(P.photon + idx);
         float4 q0 = ph[0], q1 = ph[1];
-        unsigned obf = __float_as_uint(ph[3].x);
 #endif
         Prd r;
         r.nx = r.ny = r.nz = 0.f; r.t = -1.f; r.lposcost = r.lposfphi = 0.f; r.iindex_identity = 0xffffffffu; r.prim_boundary = kWaveNoHit;
         if (q0.w < P.max_time) {                                // else the while-condition of the raygen loop fails: photon is final
-            float tmin = (obf & P.eps0_mask) ? P.tmin0 : P.tmin;
+            float tmin = (entry & kListEps0) ? P.tmin0 : P.tmin;   // the list entry carries (last flag & PropagateEpsilon0Mask) != 0
             float3 o = f3(q0.x, q0.y, q0.z), d = f3(q1.x, q1.y, q1.z);
             HitInfo h;
             bool ok;
@@ -572,10 +574,10 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
     for (unsigned base_a = blockIdx.x * blockDim.x; base_a < count; base_a += gridDim.x * blockDim.x) {
         unsigned a = base_a + threadIdx.x;
         bool survive = false;
-        unsigned idx = 0;
+        unsigned idx = 0, entry_out = 0;
         if (a < count) {
 #if PHOX_WF_STREAM
-            idx = __ldcs(W.active_in + a);
+            idx = __ldcs(W.active_in + a) & kListSlotMask;
             Prd r;
             {
                 const float4* hp = reinterpret_cast<const float4*>(W.hits + a);
@@ -584,7 +586,7 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
                 r.iindex_identity = __float_as_uint(h1.z); r.prim_boundary = __float_as_uint(h1.w);
             }
 #else
-            idx = W.active_in[a];
+            idx = W.active_in[a] & kListSlotMask;
             Prd r = W.hits[a];
 #endif
             if (r.prim_boundary != kWaveNoHit) {            // a miss (or time over) leaves the photon as it is: final
@@ -616,6 +618,7 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
                     if (P.seq) { Seq seq = P.seq[idx]; seq_add(seq, (unsigned)bounce, p.flag(), p.boundary()); P.seq[idx] = seq; }
                 }
                 survive = !(command == FLOW_BREAK) && bounce < P.max_bounce && p.time < P.max_time;
+                entry_out = idx | ((p.obf & P.eps0_mask) ? kListEps0 : 0u);
             }
         }
         if (P.lpos && a < count && !survive) {              // lite mode: local position of the photon's last intersect, re-read from
@@ -634,9 +637,9 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
         }
         __syncthreads();
 #if PHOX_WF_STREAM
-        if (survive) __stcs(W.active_out + s_base + s_warp[warp] + __popc(ballot & ((1u << lane) - 1u)), idx);
+        if (survive) __stcs(W.active_out + s_base + s_warp[warp] + __popc(ballot & ((1u << lane) - 1u)), entry_out);
 #else
-        if (survive) W.active_out[s_base + s_warp[warp] + __popc(ballot & ((1u << lane) - 1u))] = idx;
+        if (survive) W.active_out[s_base + s_warp[warp] + __popc(ballot & ((1u << lane) - 1u))] = entry_out;
 #endif
         __syncthreads();
     }

@@ -192,7 +192,10 @@ def test_wavefront_form_with_launch_slicing_and_time_cut():
     w = workloads.sipm8x8_scint(num_photon=50000, photons_per_genstep=100)
     res = []
     for mode in (ph.KERNEL_PERSISTENT, ph.KERNEL_WAVEFRONT):
-        sim = make_sim(w, event_mode=ph.MODE_HITPHOTONSEQ, kernel_mode=mode, max_slot=7000, max_time=3.0, max_bounce=9)
+        # distinct epsilons: tmin0 applies after the flags of epsilon0_mask (here SI|CK|SC|RE only: not after TORCH... the sources
+        # of this workload), the wavefront form carries that decision as a bit of the list entry
+        sim = make_sim(w, event_mode=ph.MODE_HITPHOTONSEQ, kernel_mode=mode, max_slot=7000, max_time=3.0, max_bounce=9,
+                       propagate_epsilon=0.07, propagate_epsilon0=0.001)
         h = sim.simulate_np(w["gensteps"], 1).copy()
         res.append((h, sim.get_array("photon").copy(), sim.get_array("seq").copy()))
         sim.close()
