@@ -118,16 +118,16 @@ constexpr int kTravDone = (int)0x80000001;
 // CSGPrim inside a solid) or one of the two markers.  Children are visited near-first; the far one is
 // parked on the stack with its entry distance so it is dropped once a nearer hit is known.
 PHOX_D void traverse_bvh(Nearest& best, const Scene& sc, float tmin, const float3& o_w, const float3& d_w) {
-    int stack[kBvhStack];
-    float stack_t[kBvhStack];
+    int2 stack[kBvhStack];                                   // (item, entry distance bits): one 8 B local store / load per push / pop
     int sp = 0;
     auto push = [&](int item, float t) {
-        if (sp < kBvhStack) { stack[sp] = item; stack_t[sp] = t; sp++; }
+        if (sp < kBvhStack) { stack[sp] = make_int2(item, __float_as_int(t)); sp++; }
     };
     auto pop = [&]() -> int {
         while (sp > 0) {
             sp--;
-            if (stack_t[sp] <= best.t) return stack[sp];
+            int2 e = stack[sp];
+            if (__int_as_float(e.y) <= best.t) return e.x;
         }
         return kTravDone;
     };
