@@ -71,6 +71,8 @@ struct phox_context {
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    double last_bounces_per_photon = 0.;    // rays per photon of the previous launch (PHOX_KERNEL_AUTO heuristic)
+    unsigned long long event_rays_seen = 0; // rays of the current event counted before this launch
     bool profiling = false;                 // phox_set_profiling: events between the kernels of the wavefront form
     std::vector<cudaEvent_t> prof_ev;
     std::string err;
@@ -147,7 +149,12 @@ struct phox_context {
 #define PHOX_KERNEL_AUTO_CHOICE PHOX_KERNEL_WAVEFRONT
 #endif
 
-static const int64_t kAutoWavefrontMinPhotons = 250000;     // photons per launch from which PHOX_KERNEL_AUTO picks the wavefront form
+// PHOX_KERNEL_AUTO: photons per launch from which the wavefront form is picked.  Long histories (the 8x8 crystals: 20 bounces per
+// photon) pay off from 250 k photons; when the previous launch of this context averaged fewer than 6 bounces per photon the live
+// list collapses after a few bounces and the persistent kernel stays ahead up to ~2 M photons (profiles/r1_summary.md, small events).
+static const int64_t kAutoWavefrontMinPhotons = 250000;
+static const int64_t kAutoWavefrontMinPhotonsShort = 2000000;
+static const double kAutoShortHistory = 6.0;
 
 extern "C" void phox_default_config(phox_config* c) {
     if (!c) return;
@@ -642,7 +649,9 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
     // AUTO: the wavefront form wins once a launch fills the machine several times over; below that its ~65 kernels each
     // run a single under-filled wave and the one persistent kernel is up to 2x quicker (profiles/r1_summary.md, small events)
     if (n > 0x7fffffffll) return ctx->fail(PHOX_E_NOMEM, "launch of more than 2^31 photons: lower max_slot");
-    const bool wavefront = (c.kernel_mode == PHOX_KERNEL_AUTO ? (n < kAutoWavefrontMinPhotons ? PHOX_KERNEL_PERSISTENT : PHOX_KERNEL_AUTO_CHOICE)
+    const int64_t auto_min = (ctx->last_bounces_per_photon > 0. && ctx->last_bounces_per_photon < kAutoShortHistory) ? kAutoWavefrontMinPhotonsShort
+                                                                                                                     : kAutoWavefrontMinPhotons;
+    const bool wavefront = (c.kernel_mode == PHOX_KERNEL_AUTO ? (n < auto_min ? PHOX_KERNEL_PERSISTENT : PHOX_KERNEL_AUTO_CHOICE)
                                                               : c.kernel_mode) == PHOX_KERNEL_WAVEFRONT;
     if (!wavefront) {
         CK(cudaMemsetAsync(ctx->d_counters.p + 3, 0, sizeof(unsigned long long), ctx->stream));
@@ -708,6 +717,8 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
     CK(cudaStreamSynchronize(ctx->stream));
     int64_t nhit = (int64_t)ctx->h_counters[1];
     ctx->stats.num_kernel += 3;
+    ctx->last_bounces_per_photon = double(ctx->h_counters[0] - ctx->event_rays_seen) / double(n);     // feeds PHOX_KERNEL_AUTO
+    ctx->event_rays_seen = ctx->h_counters[0];
     if (nhit > 0) {
         CK(ctx->d_hit.reserve((size_t)(ctx->num_hit + nhit), true, ctx->stream));
         if (lite) CK(ctx->d_hitlite.reserve((size_t)(ctx->num_hit + nhit), true, ctx->stream));
@@ -777,6 +788,7 @@ static int begin_event(phox_context* ctx) {
     std::memset(&ctx->stats, 0, sizeof(ctx->stats));
     ctx->event_max_record = ctx->cfg.max_record;
     CK(cudaMemsetAsync(ctx->d_counters.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    ctx->event_rays_seen = 0;
     ctx->have_event = false;
     return PHOX_OK;
 }

@@ -9,7 +9,7 @@ for wl in ("sipm8x8_scint", "pmt_wall_torch"):
         w = workloads.WORKLOADS[wl](num_photon=n)
         g = w["geom"]
         row = []
-        for mode in (ph.KERNEL_PERSISTENT, ph.KERNEL_WAVEFRONT):
+        for mode in (ph.KERNEL_PERSISTENT, ph.KERNEL_WAVEFRONT, ph.KERNEL_AUTO):
             sim = ph.Simulator.Create(g["foundry"], g["bnd"], g["optical"], g["icdf"], event_mode=ph.MODE_MINIMAL, kernel_mode=mode, **w["config"])
             ts, ks = [], []
             for k in range(9):
@@ -19,4 +19,4 @@ for wl in ("sipm8x8_scint", "pmt_wall_torch"):
                 ks.append(sim.stats()["simulate_kernel_seconds"])
             row.append((np.median(ts[2:]) * 1e3, np.median(ks[2:]) * 1e3))
             sim.close()
-        print("%-16s n %8d  persistent wall %8.3f ms loop %8.3f ms | wavefront wall %8.3f ms loop %8.3f ms" % (wl, n, row[0][0], row[0][1], row[1][0], row[1][1]), flush=True)
+        print("%-16s n %8d  persistent wall %8.3f ms loop %8.3f ms | wavefront wall %8.3f ms loop %8.3f ms | auto wall %8.3f ms loop %8.3f ms" % (wl, n, row[0][0], row[0][1], row[1][0], row[1][1], row[2][0], row[2][1]), flush=True)
