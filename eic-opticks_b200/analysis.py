@@ -60,8 +60,29 @@ def chi2_histories(seq_a, seq_b, cut=30):
     return chi2, max(ndf - 1, 1), rows
 
 
+TAG_NAMES = ["_", "to_sci", "to_bnd", "to_sca", "to_abs", "at_burn_sf_sd", "at_ref", "sf_burn", "sc", "to_ree", "re_wl", "re_mom_ph",
+             "re_mom_ct", "re_pol_ph", "re_pol_ct", "hp_ph"]                       # sysrap/stag.h:17-35
+
+
+def tag_slots(tag):
+    """(n,4) uint64 stag array -> (n,64) int array of the 4-bit consumption tags, slot order (stag::get, sysrap/stag.h:344-350)"""
+    tag = np.asarray(tag, dtype=np.uint64).reshape(-1, 4)
+    return np.stack([(tag[:, k // 16] >> np.uint64(4 * (k % 16))) & np.uint64(0xf) for k in range(64)], axis=1).astype(np.int64)
+
+
+def tag_desc(tag_row, flat_row=None):
+    """one photon's consumption record as text, e.g. 'to_sci:0.1234 to_bnd:0.5678 ...' (the stagr::desc role)"""
+    slots = tag_slots(np.asarray(tag_row).reshape(1, 4))[0]
+    out = []
+    for k, t in enumerate(slots):
+        if t == 0:
+            break
+        out.append(TAG_NAMES[t] if flat_row is None else "%s:%.4f" % (TAG_NAMES[t], flat_row[k]))
+    return " ".join(out)
+
+
 def save_event(folder, index, arrays, meta=None):
-    """arrays: dict name -> ndarray (photon, record, seq, prd, hit, genstep, inphoton ...).  Written as
+    """arrays: dict name -> ndarray (photon, record, seq, prd, tag, flat, hit, genstep, inphoton ...).  Written as
     <folder>/A%03d/<name>.npy plus NPFold_index.txt, like an SEvt save directory of the EGPU ("A") event."""
     d = os.path.join(folder, "A%03d" % index)
     os.makedirs(d, exist_ok=True)

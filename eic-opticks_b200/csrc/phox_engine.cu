@@ -112,6 +112,11 @@ struct phox_context {
     DevBuf<Prd> d_wave_hits;
     int wave_grid[3][2] = {{0, 0}, {0, 0}, {0, 0}};             // persistent grid sizes of generate/trace/propagate, <false/true>
     DevBuf<unsigned long long> d_block_off;
+    DevBuf<unsigned long long> d_tag;          // DebugHeavy: stag per photon (4 u64)
+    DevBuf<float> d_flat;                      // DebugHeavy: sflat per photon (64 floats)
+    DevBuf<unsigned> d_tagslot;
+    std::vector<unsigned long long> h_tag;
+    std::vector<float> h_flat;
     DevBuf<unsigned> d_lpos;                   // lite mode: packed local position of each photon's last intersect
     DevBuf<PhotonLite> d_hitlite;              // lite mode: sphotonlite of every hit, same order as d_hit
     DevBuf<PhotonLite> d_merged_lite;
@@ -256,6 +261,7 @@ extern "C" void phox_destroy(phox_context* ctx) {
     ctx->d_record.release(); ctx->d_hit.release(); ctx->d_seq.release(); ctx->d_prd.release();
     ctx->d_block_hits.release(); ctx->d_block_off.release(); ctx->d_counters.release();
     ctx->d_slack.release(); ctx->d_exact.release();
+    ctx->d_tag.release(); ctx->d_flat.release(); ctx->d_tagslot.release();
     ctx->d_lpos.release(); ctx->d_hitlite.release(); ctx->d_merged_lite.release();
     ctx->d_merged.release(); ctx->d_merge_in.release(); merge_scratch_free(ctx->merge_scratch);
     ctx->d_active[0].release(); ctx->d_active[1].release(); ctx->d_ndraw.release(); ctx->d_wave_count.release(); ctx->d_wave_hits.release();
@@ -616,6 +622,12 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
     if (mode_keeps_seq(mode)) CK(ctx->d_seq.reserve((size_t)n));
     if (mode_keeps_record(mode)) CK(ctx->d_record.reserve((size_t)n * c.max_record));
     if (mode_keeps_prd(mode)) CK(ctx->d_prd.reserve((size_t)n * c.max_record));
+    if (mode_keeps_prd(mode)) {        // DebugHeavy also keeps the tag / flat arrays (SEventConfig.cc:1590-1592: MaxTag = MaxFlat = 1)
+        CK(ctx->d_tag.reserve((size_t)n * 4)); CK(ctx->d_flat.reserve((size_t)n * 64)); CK(ctx->d_tagslot.reserve((size_t)n));
+        CK(cudaMemsetAsync(ctx->d_tag.p, 0, (size_t)n * 32, ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_flat.p, 0, (size_t)n * 256, ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_tagslot.p, 0, (size_t)n * 4, ctx->stream));
+    }
     const bool lite = c.mode_lite != 0;
     if (lite) CK(ctx->d_lpos.reserve((size_t)n));
     // record / prd slots past the end of a history read as zero (debug modes only, so not on the production path)
@@ -637,6 +649,9 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
     P.record = mode_keeps_record(mode) ? ctx->d_record.p : nullptr;
     P.prd = mode_keeps_prd(mode) ? ctx->d_prd.p : nullptr;
     P.lpos = lite ? ctx->d_lpos.p : nullptr;
+    P.tag = mode_keeps_prd(mode) ? ctx->d_tag.p : nullptr;
+    P.flat = mode_keeps_prd(mode) ? ctx->d_flat.p : nullptr;
+    P.tagslot = mode_keeps_prd(mode) ? ctx->d_tagslot.p : nullptr;
     P.max_record = c.max_record;
     P.work_counter = reinterpret_cast<unsigned*>(ctx->d_counters.p + 3);
     P.counters = ctx->d_counters.p;
@@ -774,6 +789,11 @@ static int gather_debug(phox_context* ctx, int64_t n) {
         size_t o = ctx->h_prd.size();
         ctx->h_prd.resize(o + (size_t)n * mr);
         CK(cudaMemcpyAsync(ctx->h_prd.data() + o, ctx->d_prd.p, (size_t)n * mr * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        size_t ot = ctx->h_tag.size(), of = ctx->h_flat.size();
+        ctx->h_tag.resize(ot + (size_t)n * 4);
+        ctx->h_flat.resize(of + (size_t)n * 64);
+        CK(cudaMemcpyAsync(ctx->h_tag.data() + ot, ctx->d_tag.p, (size_t)n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_flat.data() + of, ctx->d_flat.p, (size_t)n * 256, cudaMemcpyDeviceToHost, ctx->stream));
     }
     CK(cudaStreamSynchronize(ctx->stream));
     return PHOX_OK;
@@ -784,7 +804,7 @@ static int begin_event(phox_context* ctx) {
     if (!ctx->have_tables) return ctx->fail(PHOX_E_STATE, "phox_simulate: tables not set");
     CK(cudaSetDevice(ctx->device));
     ctx->num_photon = 0; ctx->num_hit = 0;
-    ctx->h_photon.clear(); ctx->h_record.clear(); ctx->h_seq.clear(); ctx->h_prd.clear();
+    ctx->h_photon.clear(); ctx->h_record.clear(); ctx->h_seq.clear(); ctx->h_prd.clear(); ctx->h_tag.clear(); ctx->h_flat.clear();
     std::memset(&ctx->stats, 0, sizeof(ctx->stats));
     ctx->event_max_record = ctx->cfg.max_record;
     CK(cudaMemsetAsync(ctx->d_counters.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
@@ -928,6 +948,8 @@ extern "C" int64_t phox_get_array(phox_context* ctx, const char* name, void* dst
     else if (n == "record") { src = ctx->h_record.data(); bytes = (int64_t)ctx->h_record.size() * 64; }
     else if (n == "seq") { src = ctx->h_seq.data(); bytes = (int64_t)ctx->h_seq.size() * 32; }
     else if (n == "prd") { src = ctx->h_prd.data(); bytes = (int64_t)ctx->h_prd.size() * 32; }
+    else if (n == "tag") { src = ctx->h_tag.data(); bytes = (int64_t)ctx->h_tag.size() * 8; }
+    else if (n == "flat") { src = ctx->h_flat.data(); bytes = (int64_t)ctx->h_flat.size() * 4; }
     else if (n == "hit") {
         bytes = ctx->num_hit * 64;
         if (!dst) return bytes;
@@ -951,7 +973,7 @@ extern "C" void phox_reset(phox_context* ctx) {
     if (!ctx) return;
     ctx->have_event = false;
     ctx->num_photon = 0; ctx->num_hit = 0;
-    ctx->h_photon.clear(); ctx->h_record.clear(); ctx->h_seq.clear(); ctx->h_prd.clear();
+    ctx->h_photon.clear(); ctx->h_record.clear(); ctx->h_seq.clear(); ctx->h_prd.clear(); ctx->h_tag.clear(); ctx->h_flat.clear();
     ctx->h_photon.shrink_to_fit(); ctx->h_record.shrink_to_fit(); ctx->h_seq.shrink_to_fit(); ctx->h_prd.shrink_to_fit();
 }
 

@@ -62,6 +62,9 @@ struct SimParams {
     Seq* seq;
     Photon* record;
     Prd* prd;
+    unsigned long long* tag;                // stag[N]: 4 u64 per slot (DebugHeavy), zeroed before the launch
+    float* flat;                            // sflat[N]: 64 floats per slot
+    unsigned* tagslot;                      // per slot: tagged draws so far (wavefront form: the recorder is parked between kernels)
     unsigned* lpos;                         // per slot, lite mode: packed local position of the photon's last intersect (sphotonlite::set_lpos)
     int max_record;
     unsigned* work_counter;                 // next unclaimed photon slot of this launch
@@ -331,6 +334,7 @@ __global__ void __launch_bounds__(kSimThreads, PHOX_SIM_MIN_BLOCKS) k_simulate(c
     PhotonState p;
     Philox rng;
     Seq seq;
+    unsigned tag_slot = 0u;              // DebugHeavy: tagged draws of this photon so far
     unsigned last_lpos = 0u;             // lite mode: packed lposcost/lposfphi of the last trace (0 after a miss, like the miss program)
     const unsigned hit_flags = ((DEBUG && P.prd != nullptr) || P.lpos != nullptr) ? kHitFphi : 0u;
 
@@ -364,6 +368,7 @@ __global__ void __launch_bounds__(kSimThreads, PHOX_SIM_MIN_BLOCKS) k_simulate(c
                 bounce = 0;
                 active = true;
                 last_lpos = 0u;
+                tag_slot = 0u;
                 if (DEBUG) {
                     seq.seqhis[0] = seq.seqhis[1] = seq.seqbnd[0] = seq.seqbnd[1] = 0ull;
                     if (P.record && 0 < P.max_record) p.store(P.record + (size_t)P.max_record * idx);
@@ -404,7 +409,15 @@ __global__ void __launch_bounds__(kSimThreads, PHOX_SIM_MIN_BLOCKS) k_simulate(c
                             P.prd[(size_t)P.max_record * idx + bounce] = r;
                         }
                     }
-                    int command = propagate(p, rng, h, P.tables, P.burn != 0);
+                    int command;
+                    if (DEBUG && P.tag) {
+                        Tagr tg;
+                        tg.tag = P.tag + 4 * (size_t)idx; tg.flat = P.flat + 64 * (size_t)idx; tg.slot = tag_slot;
+                        command = propagate_t<true>(p, rng, h, P.tables, P.burn != 0, &tg);
+                        tag_slot = tg.slot;
+                    } else {
+                        command = propagate(p, rng, h, P.tables, P.burn != 0);
+                    }
                     bounce++;
                     if (DEBUG) {
                         if (P.record && bounce < P.max_record) p.store(P.record + (size_t)P.max_record * idx + bounce);
@@ -604,7 +617,15 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
                 HitInfo h;
                 h.normal = f3(r.nx, r.ny, r.nz); h.t = r.t; h.lposcost = r.lposcost; h.lposfphi = r.lposfphi;
                 h.iindex_identity = r.iindex_identity; h.prim_boundary = r.prim_boundary;
-                int command = propagate(p, rng, h, P.tables, P.burn != 0);
+                int command;
+                if (DEBUG && P.tag) {
+                    Tagr tg;
+                    tg.tag = P.tag + 4 * (size_t)idx; tg.flat = P.flat + 64 * (size_t)idx; tg.slot = P.tagslot[idx];
+                    command = propagate_t<true>(p, rng, h, P.tables, P.burn != 0, &tg);
+                    P.tagslot[idx] = tg.slot;
+                } else {
+                    command = propagate(p, rng, h, P.tables, P.burn != 0);
+                }
                 int bounce = W.bounce + 1;
 #if PHOX_WF_STREAM
                 p.store_cs(P.photon + idx);

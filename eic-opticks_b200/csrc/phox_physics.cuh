@@ -106,6 +106,25 @@ struct HitInfo {                    // quad2 prd in registers
     PHOX_D unsigned iindex() const { return iindex_identity >> 16; }
 };
 
+// stagr (sysrap/stag.h:231-262): which random draw was consumed where, for aligning the stream with Geant4 (DebugHeavy mode,
+// as-built DEBUG_TAG flag): 4-bit tag per draw, 16 per u64, 4 u64 (stag) + the 64 uniforms themselves (sflat).
+enum : unsigned {
+    TAG_to_sci = 1, TAG_to_bnd = 2, TAG_to_sca = 3, TAG_to_abs = 4, TAG_at_burn_sf_sd = 5, TAG_at_ref = 6, TAG_sf_burn = 7, TAG_sc = 8,
+    TAG_to_ree = 9, TAG_re_wl = 10, TAG_re_mom_ph = 11, TAG_re_mom_ct = 12, TAG_re_pol_ph = 13, TAG_re_pol_ct = 14
+};
+struct Tagr {
+    unsigned long long* tag;        // [4] of this photon (zeroed before the event)
+    float* flat;                    // [64] of this photon
+    unsigned slot;
+    PHOX_D void add(unsigned t, float f) {
+        if (slot < 64u) {
+            tag[slot >> 4] |= (unsigned long long)(t & 0xfu) << (4u * (slot & 15u));
+            flat[slot] = f;
+        }
+        slot += 1u;
+    }
+};
+
 // ---- tables ----------------------------------------------------------------------------------
 PHOX_D float4 bnd_lookup(const Tables& tb, float nm, unsigned line, unsigned k) {
     float fx = (nm - tb.nm0) / tb.nms;
@@ -375,11 +394,13 @@ PHOX_D void marsaglia_direction(float3& dir, Philox& rng) {
     dir = f3(a * u, a * v, 2.f * b - 1.f);
 }
 
-PHOX_D void rayleigh_scatter(PhotonState& p, Philox& rng) {
+template <bool TAG>
+PHOX_D void rayleigh_scatter(PhotonState& p, Philox& rng, Tagr* tg) {
     float3 direction, polarization;
     bool looping = true;
     do {
         float u0 = rng.uniform(), u1 = rng.uniform(), u2 = rng.uniform(), u3 = rng.uniform(), u4 = rng.uniform();
+        if (TAG) { tg->add(TAG_sc, u0); tg->add(TAG_sc, u1); tg->add(TAG_sc, u2); tg->add(TAG_sc, u3); tg->add(TAG_sc, u4); }
         float cosTheta = u0;
         float sinTheta = sqrtf(1.0f - u0 * u0);
         if (u1 < 0.5f) cosTheta = -cosTheta;
@@ -408,7 +429,10 @@ PHOX_D void rayleigh_scatter(PhotonState& p, Philox& rng) {
 // One bounce: the photon has a ray hit `h` (normal normalised, world frame).  Returns the flow
 // command; on BREAK the photon is finished.  `burn` selects the DEBUG_TAG consumption pattern.
 // out of line: ONE compiled body for every kernel instantiation, so event modes cannot differ by FMA contraction
-__device__ __noinline__ int propagate(PhotonState& p, Philox& rng, const HitInfo& h, const Tables& tb, bool burn) {
+// TAG = true is a second compiled body that also records every tagged draw (qsim.h tagr.add sites); it runs only in the
+// DebugHeavy event mode, the production body carries no trace of it.
+template <bool TAG>
+__device__ __noinline__ int propagate_t(PhotonState& p, Philox& rng, const HitInfo& h, const Tables& tb, bool burn, Tagr* tg) {
     const unsigned boundary = h.boundary();
     const float3 normal = h.normal;
     float cosTheta = dot(p.mom, normal);
@@ -430,9 +454,13 @@ __device__ __noinline__ int propagate(PhotonState& p, Philox& rng, const HitInfo
         const float absorption_length = material1.y, scattering_length = material1.z, reemission_prob = material1.w;
         const float distance_to_boundary = h.t;
         rng.align();
-        if (burn) { rng.uniform(); rng.uniform(); }
+        if (burn) {
+            float u_to_sci = rng.uniform(), u_to_bnd = rng.uniform();
+            if (TAG) { tg->add(TAG_to_sci, u_to_sci); tg->add(TAG_to_bnd, u_to_bnd); }
+        }
         float u_scattering = rng.uniform();
         float u_absorption = rng.uniform();
+        if (TAG) { tg->add(TAG_to_sca, u_scattering); tg->add(TAG_to_abs, u_absorption); }
         float scattering_distance = -scattering_length * logf(u_scattering);
         float absorption_distance = -absorption_length * logf(u_absorption);
 
@@ -442,10 +470,15 @@ __device__ __noinline__ int propagate(PhotonState& p, Philox& rng, const HitInfo
                 p.time += absorption_distance / group_velocity;
                 p.pos = p.pos + absorption_distance * p.mom;
                 float u_reemit = reemission_prob == 0.f ? 2.f : rng.uniform();
+                if (TAG) { if (u_reemit != 2.f) tg->add(TAG_to_ree, u_reemit); }
                 if (u_reemit < reemission_prob) {
                     float u_re_wavelength = rng.uniform();
                     float u_re_mom_ph = rng.uniform(), u_re_mom_ct = rng.uniform();
                     float u_re_pol_ph = rng.uniform(), u_re_pol_ct = rng.uniform();
+                    if (TAG) {
+                        tg->add(TAG_re_wl, u_re_wavelength); tg->add(TAG_re_mom_ph, u_re_mom_ph); tg->add(TAG_re_mom_ct, u_re_mom_ct);
+                        tg->add(TAG_re_pol_ph, u_re_pol_ph); tg->add(TAG_re_pol_ct, u_re_pol_ct);
+                    }
                     p.wavelength = icdf_wavelength(tb, u_re_wavelength);
                     p.mom = uniform_sphere(u_re_mom_ph, u_re_mom_ct);
                     p.pol = normalize(cross(uniform_sphere(u_re_pol_ph, u_re_pol_ct), p.mom));
@@ -460,7 +493,7 @@ __device__ __noinline__ int propagate(PhotonState& p, Philox& rng, const HitInfo
             if (scattering_distance <= distance_to_boundary) {
                 p.time += scattering_distance / group_velocity;
                 p.pos = p.pos + scattering_distance * p.mom;
-                rayleigh_scatter(p, rng);
+                rayleigh_scatter<TAG>(p, rng, tg);
                 flag = F_BULK_SCATTER;
                 command = FLOW_CONTINUE;
             }
@@ -500,8 +533,12 @@ __device__ __noinline__ int propagate(PhotonState& p, Philox& rng, const HitInfo
             const float2 TT = normalize2(E2_t);
             const float TransCoeff = (tir || n1c1 == 0.f) ? 0.f : n2c2 * dot2(E2_t, E2_t) / n1c1;
 
-            if (burn) rng.uniform();
+            if (burn) {
+                const float u_boundary_burn = rng.uniform();
+                if (TAG) tg->add(TAG_at_burn_sf_sd, u_boundary_burn);
+            }
             const float u_reflect = rng.uniform();
+            if (TAG) tg->add(TAG_at_ref, u_reflect);
             const bool reflect = u_reflect > TransCoeff;
 
             p.mom = reflect ? p.mom + 2.0f * c1 * on : eta * (p.mom) + (eta * c1 - c2) * on;
@@ -511,7 +548,10 @@ __device__ __noinline__ int propagate(PhotonState& p, Philox& rng, const HitInfo
                         : (reflect ? (tir ? -p.pol + 2.f * EdotN * on : RR.x * A_trans + RR.y * A_paral)
                                    : TT.x * A_trans + TT.y * A_paral);
             flag = reflect ? F_BOUNDARY_REFLECT : F_BOUNDARY_TRANSMIT;
-            if (burn && reflect) { rng.uniform(); rng.uniform(); rng.uniform(); rng.uniform(); }
+            if (burn && reflect) {
+                const float a0 = rng.uniform(), a1 = rng.uniform(), a2 = rng.uniform(), a3 = rng.uniform();
+                if (TAG) { tg->add(TAG_to_sci, a0); tg->add(TAG_to_bnd, a1); tg->add(TAG_to_sca, a2); tg->add(TAG_to_abs, a3); }
+            }
             command = FLOW_CONTINUE;
         } else if (ems == EMS_Surface) {
             at_surface = true;
@@ -530,7 +570,11 @@ __device__ __noinline__ int propagate(PhotonState& p, Philox& rng, const HitInfo
             const float4 surface = bnd_lookup(tb, p.wavelength, su_line, 0);     // detect, absorb, specular, diffuse
             const float detect = surface.x, absorb = surface.y, diffuse = surface.w;
             float u_surface = rng.uniform();
-            if (burn) rng.uniform();
+            if (TAG) tg->add(TAG_at_burn_sf_sd, u_surface);
+            if (burn) {
+                const float u_surface_burn = rng.uniform();
+                if (TAG) tg->add(TAG_sf_burn, u_surface_burn);
+            }
             command = u_surface < absorb + detect ? FLOW_BREAK : FLOW_CONTINUE;
             if (command == FLOW_BREAK) {
                 flag = u_surface < absorb ? F_SURFACE_ABSORB : F_SURFACE_DETECT;
@@ -566,6 +610,11 @@ __device__ __noinline__ int propagate(PhotonState& p, Philox& rng, const HitInfo
     }
     p.set_flag(flag);
     return command;
+}
+
+// the production body
+PHOX_D int propagate(PhotonState& p, Philox& rng, const HitInfo& h, const Tables& tb, bool burn) {
+    return propagate_t<false>(p, rng, h, tb, burn, nullptr);
 }
 
 }  // namespace phox

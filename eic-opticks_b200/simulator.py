@@ -217,6 +217,10 @@ class Simulator:
             out = np.empty((n, nbytes // 32 // max(n, 1), 2, 4), dtype=np.float32)
         elif name == "hit":
             out = np.empty((nbytes // 64, 4, 4), dtype=np.float32)
+        elif name == "tag":                                     # stag: 4 x u64 per photon, 16 4-bit tags each
+            out = np.empty((nbytes // 32, 4), dtype=np.uint64)
+        elif name == "flat":                                    # sflat: the first 64 tagged uniforms per photon
+            out = np.empty((nbytes // 256, 64), dtype=np.float32)
         else:
             raise KeyError(name)
         if nbytes:

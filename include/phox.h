@@ -169,7 +169,8 @@ int     phox_get_hits_device(phox_context* ctx, void* d_dst);      /* device dst
 
 /* Named arrays of the last event, when the event mode keeps them:
  * "photon" (64 B/photon), "record" (64 B * max_record), "seq" (32 B), "prd" (32 B * max_record),
- * "hit".  Returns the byte size when dst is NULL. */
+ * "tag" (stag, 32 B: 4-bit consumption tag of each of the first 64 tagged random draws, sysrap/stag.h) and "flat"
+ * (sflat, 256 B: those 64 uniforms) in the DebugHeavy mode, "hit".  Returns the byte size when dst is NULL. */
 int64_t phox_get_array(phox_context* ctx, const char* name, void* dst, int64_t dst_bytes);
 
 /* Counters of the last event: total bounces (= intersect queries), launches, kernels launched. */

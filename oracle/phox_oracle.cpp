@@ -91,6 +91,17 @@ struct Rng {
     float uniform() { return next() * 2.3283064365386963e-10f + (2.3283064365386963e-10f / 2.0f); }   // curand_uniform
 };
 
+// stagr (sysrap/stag.h:231-262, set :333-337): 4-bit tag per random draw + the uniform itself, first 64 draws
+struct OTagr {
+    uint64_t* tag; float* flat; unsigned slot;
+    void add(unsigned t, float f) {
+        if (slot < 64u) { tag[slot / 16u] |= (uint64_t)(t & 0xfu) << (4u * (slot % 16u)); flat[slot] = f; }
+        slot += 1u;
+    }
+};
+static thread_local OTagr* g_tagr = nullptr;      // set per photon by oracle_simulate when tag / flat outputs were asked for
+#define OTAG(t, u) do { if (g_tagr) g_tagr->add((t), (u)); } while (0)
+
 // ---- geometry views --------------------------------------------------------------------------
 struct Node { union { float f[16]; unsigned u[16]; int i[16]; }; };
 struct Prim { union { float f[16]; unsigned u[16]; int i[16]; }; };
@@ -871,6 +882,7 @@ void rayleigh_scatter(Photon& p, Rng& rng) {           // qsim.h:601-689
     v3 direction, polarization; bool looping = true;
     do {
         float u0 = rng.uniform(), u1 = rng.uniform(), u2 = rng.uniform(), u3 = rng.uniform(), u4 = rng.uniform();
+        OTAG(8, u0); OTAG(8, u1); OTAG(8, u2); OTAG(8, u3); OTAG(8, u4);                 // stag_sc (qsim.h:618-622)
         float cosTheta = u0, sinTheta = sqrtf(1.0f - u0 * u0);
         if (u1 < 0.5f) cosTheta = -cosTheta;
         float ang = 2.f * PI_F * u2, sinPhi = sinf(ang), cosPhi = cosf(ang);
@@ -911,8 +923,9 @@ int propagate(Photon& p, Rng& rng, const Prd& prd, const Tables& tb, bool debug_
     {   // propagate_to_boundary
         float absorption_length = s.material1.y, scattering_length = s.material1.z, reemission_prob = s.material1.w, group_velocity = s.m1group2.x;
         float distance_to_boundary = prd.t;
-        if (debug_tag) { rng.uniform(); rng.uniform(); }
+        if (debug_tag) { float u_to_sci = rng.uniform(), u_to_bnd = rng.uniform(); OTAG(1, u_to_sci); OTAG(2, u_to_bnd); }
         float u_scattering = rng.uniform(), u_absorption = rng.uniform();
+        OTAG(3, u_scattering); OTAG(4, u_absorption);                                    // qsim.h:739-742
         float scattering_distance = -scattering_length * logf(u_scattering), absorption_distance = -absorption_length * logf(u_absorption);
         command = BOUNDARY;
         if (absorption_distance <= scattering_distance) {
@@ -920,8 +933,10 @@ int propagate(Photon& p, Rng& rng, const Prd& prd, const Tables& tb, bool debug_
                 p.time += absorption_distance / group_velocity;
                 p.pos = p.pos + absorption_distance * p.mom;
                 float u_reemit = reemission_prob == 0.f ? 2.f : rng.uniform();
+                if (u_reemit != 2.f) OTAG(9, u_reemit);
                 if (u_reemit < reemission_prob) {
                     float u_re_wavelength = rng.uniform(), u_re_mom_ph = rng.uniform(), u_re_mom_ct = rng.uniform(), u_re_pol_ph = rng.uniform(), u_re_pol_ct = rng.uniform();
+                    OTAG(10, u_re_wavelength); OTAG(11, u_re_mom_ph); OTAG(12, u_re_mom_ct); OTAG(13, u_re_pol_ph); OTAG(14, u_re_pol_ct);
                     p.wavelength = scint_wavelength(tb, u_re_wavelength);
                     p.mom = uniform_sphere(u_re_mom_ph, u_re_mom_ct);
                     p.pol = normalize(cross(uniform_sphere(u_re_pol_ph, u_re_pol_ct), p.mom));
@@ -960,15 +975,16 @@ int propagate(Photon& p, Rng& rng, const Prd& prd, const Tables& tb, bool debug_
             float rinv = 1.0f / sqrtf(E2rx * E2rx + E2ry * E2ry), tinv = 1.0f / sqrtf(E2tx * E2tx + E2ty * E2ty);
             float RRx = E2rx * rinv, RRy = E2ry * rinv, TTx = E2tx * tinv, TTy = E2ty * tinv;
             float TransCoeff = (tir || n1c1 == 0.f) ? 0.f : n2c2 * (E2tx * E2tx + E2ty * E2ty) / n1c1;
-            if (debug_tag) rng.uniform();
+            if (debug_tag) { float u_boundary_burn = rng.uniform(); OTAG(5, u_boundary_burn); }
             float u_reflect = rng.uniform();
+            OTAG(6, u_reflect);
             bool reflect = u_reflect > TransCoeff;
             p.mom = reflect ? p.mom + 2.0f * c1 * oriented_normal : eta * p.mom + (eta * c1 - c2) * oriented_normal;
             v3 A_paral = normalize(cross(p.mom, A_trans));
             p.pol = normal_incidence ? (reflect ? p.pol * (n2 > n1 ? -1.f : 1.f) : p.pol)
                                      : (reflect ? (tir ? -p.pol + 2.f * EdotN * oriented_normal : RRx * A_trans + RRy * A_paral) : TTx * A_trans + TTy * A_paral);
             flag = reflect ? BOUNDARY_REFLECT : BOUNDARY_TRANSMIT;
-            if (debug_tag && reflect) { rng.uniform(); rng.uniform(); rng.uniform(); rng.uniform(); }
+            if (debug_tag && reflect) { float a0 = rng.uniform(), a1 = rng.uniform(), a2 = rng.uniform(), a3 = rng.uniform(); OTAG(1, a0); OTAG(2, a1); OTAG(3, a2); OTAG(4, a3); }
             command = CONTINUE;
         } else if (ems == 2) at_surface = true;
         else if (prd.lposcost < 0.f) at_surface = true;
@@ -976,7 +992,8 @@ int propagate(Photon& p, Rng& rng, const Prd& prd, const Tables& tb, bool debug_
         if (at_surface) {   // propagate_at_surface
             float detect = s.surface.x, absorb = s.surface.y, reflect_diffuse_ = s.surface.w;
             float u_surface = rng.uniform();
-            if (debug_tag) rng.uniform();
+            OTAG(5, u_surface);
+            if (debug_tag) { float u_surface_burn = rng.uniform(); OTAG(7, u_surface_burn); }
             command = u_surface < absorb + detect ? BREAK : CONTINUE;
             if (command == BREAK) flag = u_surface < absorb ? SURFACE_ABSORB : SURFACE_DETECT;
             else {
@@ -1068,10 +1085,13 @@ static unsigned pack_lpos(float lposcost, float lposfphi) {
     return (u16(lposcost) << 16) | u16(lposfphi);
 }
 static unsigned* g_lite_out = nullptr;      // optional sphotonlite[n] output of the next oracle_simulate call
+static uint64_t* g_tag_out = nullptr;       // optional stag[n] (4 u64) / sflat[n] (64 f32) outputs, zeroed by the caller
+static float* g_flat_out = nullptr;
 
 extern "C" {
 
 void oracle_set_lite_out(unsigned* p) { g_lite_out = p; }
+void oracle_set_tag_out(uint64_t* tag, float* flat) { g_tag_out = tag; g_flat_out = flat; }
 
 // CSGOptiX/CSGOptiX7.cu:405-503 per photon; seeding = QEvt.cu:181-237 (seed[i] = owning genstep)
 int oracle_simulate(const int* solid, int nsolid, const void* prim, int nprim, const void* node, int nnode, const void* plan, int nplan,
@@ -1107,6 +1127,8 @@ int oracle_simulate(const int* solid, int nsolid, const void* prim, int nprim, c
         Seq seq = {{0, 0}, {0, 0}};
         int bounce = 0;
         unsigned last_lpos = 0u;
+        OTagr tagr = {g_tag_out ? g_tag_out + 4 * idx : nullptr, g_flat_out ? g_flat_out + 64 * idx : nullptr, 0u};
+        g_tagr = g_tag_out ? &tagr : nullptr;              // generation draws are not tagged (no tagr.add in the generators)
         if (rec && 0 < mr) rec[(size_t)mr * idx] = p;                          // sctx::point sysrap/sctx.h:134-140
         if (seqo) seq_add_nibble(seq, 0, p.flag(), p.boundary());
         while (bounce < cfg->max_bounce && p.time < cfg->max_time) {
@@ -1124,6 +1146,7 @@ int oracle_simulate(const int* solid, int nsolid, const void* prim, int nprim, c
             if (seqo) seq_add_nibble(seq, (unsigned)bounce, p.flag(), p.boundary());
             if (command == BREAK) break;
         }
+        g_tagr = nullptr;
         if (seqo) seqo[idx] = seq;
         if (pout) pout[idx] = p;
         if (g_lite_out) {                                                      // sphotonlite::init + set_lpos, CSGOptiX7.cu:455-463

@@ -278,6 +278,9 @@ struct RefScene {
     void release() { cudaFree(d_node); cudaFree(d_plan); cudaFree(d_itra); cudaFree(d_prim); cudaFree(d_inst); }
 };
 
+static void* g_tag_out = nullptr;      // optional stag[n] / sflat[n] host outputs of the next phoxref_simulate (DEBUG_TAG build)
+static void* g_flat_out = nullptr;
+extern "C" void phoxref_set_tag_out(void* tag, void* flat) { g_tag_out = tag; g_flat_out = flat; }
 extern "C" const char* phoxref_last_error() { return g_err; }
 extern "C" int phoxref_is_production() {
 #ifdef PRODUCTION
@@ -347,6 +350,13 @@ extern "C" int phoxref_simulate(const void* solid, int nsolid, const void* prim,
     if (record_out && cfg->max_record > 0) { h_evt.max_record = cfg->max_record; RCK(up(&h_evt.record, (const void*)nullptr, n * cfg->max_record * sizeof(sphoton))); RCK(cudaMemset(h_evt.record, 0, n * cfg->max_record * sizeof(sphoton))); }
     if (prd_out && cfg->max_record > 0) { h_evt.max_prd = cfg->max_record; RCK(up(&h_evt.prd, (const void*)nullptr, n * cfg->max_record * sizeof(quad2))); RCK(cudaMemset(h_evt.prd, 0, n * cfg->max_record * sizeof(quad2))); }
     if (seq_out) { h_evt.max_seq = 1; RCK(up(&h_evt.seq, (const void*)nullptr, n * sizeof(sseq))); }
+#ifdef DEBUG_TAG
+    if (g_tag_out && g_flat_out) {      // sctx::end writes evt->tag / evt->flat (sysrap/sctx.h:181-182)
+        h_evt.max_tag = 1; h_evt.max_flat = 1;
+        RCK(up(&h_evt.tag, (const void*)nullptr, n * sizeof(stag))); RCK(cudaMemset(h_evt.tag, 0, n * sizeof(stag)));
+        RCK(up(&h_evt.flat, (const void*)nullptr, n * sizeof(sflat))); RCK(cudaMemset(h_evt.flat, 0, n * sizeof(sflat)));
+    }
+#endif
 #endif
     sevent* d_evt; RCK(up(&d_evt, &h_evt, sizeof(h_evt)));
 
@@ -374,6 +384,12 @@ extern "C" int phoxref_simulate(const void* solid, int nsolid, const void* prim,
     if (record_out && h_evt.record) RCK(cudaMemcpy(record_out, h_evt.record, n * cfg->max_record * sizeof(sphoton), cudaMemcpyDeviceToHost));
     if (prd_out && h_evt.prd) RCK(cudaMemcpy(prd_out, h_evt.prd, n * cfg->max_record * sizeof(quad2), cudaMemcpyDeviceToHost));
     if (seq_out && h_evt.seq) RCK(cudaMemcpy(seq_out, h_evt.seq, n * sizeof(sseq), cudaMemcpyDeviceToHost));
+#ifdef DEBUG_TAG
+    if (g_tag_out && h_evt.tag) RCK(cudaMemcpy(g_tag_out, h_evt.tag, n * sizeof(stag), cudaMemcpyDeviceToHost));
+    if (g_flat_out && h_evt.flat) RCK(cudaMemcpy(g_flat_out, h_evt.flat, n * sizeof(sflat), cudaMemcpyDeviceToHost));
+    if (h_evt.tag) cudaFree(h_evt.tag);
+    if (h_evt.flat) cudaFree(h_evt.flat);
+#endif
 #endif
     if (nray_out) RCK(cudaMemcpy(nray_out, d_nray, 8, cudaMemcpyDeviceToHost));
 

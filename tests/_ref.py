@@ -43,7 +43,7 @@ class RefGPU:
         return a, args
 
     def simulate(self, geom, gensteps, input_photons=None, event_id=0, photon_offset=0, max_bounce=31, max_record=32,
-                 tmin=0.05, tmin0=0.05, tmax=1e6, max_time=1e27, eps0mask=0x37, seed=0, offset=0, skipahead=100000, hd_factor=20):
+                 tmin=0.05, tmin0=0.05, tmax=1e6, max_time=1e27, eps0mask=0x37, seed=0, offset=0, skipahead=100000, hd_factor=20, tags=False):
         fd = geom["foundry"]
         keep, gargs = self._geo(fd)
         bnd = np.ascontiguousarray(geom["bnd"], dtype=np.float32)
@@ -60,13 +60,17 @@ class RefGPU:
         seq = np.zeros((n, 2, 2), dtype=np.uint64) if dbg else None
         prd = np.zeros((n, max_record, 2, 4), dtype=np.float32) if dbg else None
         nray = C.c_uint64(0)
+        tag = np.zeros((n, 4), dtype=np.uint64) if (tags and dbg) else None
+        flat = np.zeros((n, 64), dtype=np.float32) if (tags and dbg) else None
+        self.lib.phoxref_set_tag_out(_p(tag), _p(flat))
         rc = self.lib.phoxref_simulate(*gargs, _p(bnd), C.c_int(bnd.shape[0]), C.c_int(bnd.shape[3]), C.c_float(60.0), C.c_float(1.0), _p(optical),
                                        _p(icdf), C.c_int(0 if icdf is None else icdf.shape[1]), C.c_int(hd_factor),
                                        _p(gs), C.c_int(len(gs)), _p(ip), C.c_int(0 if ip is None else len(ip)), C.byref(cfg),
                                        _p(photon), _p(record), _p(seq), _p(prd), C.byref(nray))
+        self.lib.phoxref_set_tag_out(None, None)
         if rc != 0:
             raise RuntimeError("phoxref_simulate: " + self.lib.phoxref_last_error().decode())
-        return dict(photon=photon, record=record, seq=seq, prd=prd, nray=nray.value)
+        return dict(photon=photon, record=record, seq=seq, prd=prd, nray=nray.value, tag=tag, flat=flat)
 
     def simtrace(self, geom, gensteps, tmin=0.05, tmax=1e6, seed=0, offset=0):
         """the reference's generate_photon_simtrace_frame + add_simtrace around the brute-force trace (FRAME gensteps)"""
@@ -130,7 +134,7 @@ class Oracle:
 
     def simulate(self, geom, gensteps, input_photons=None, event_id=0, photon_offset=0, max_bounce=31, max_record=32,
                  tmin=0.05, tmin0=0.05, tmax=1e6, max_time=1e27, eps0mask=0x37, hit_mask=0x40, seed=0, offset=0, skipahead=100000,
-                 hd_factor=20, debug_tag=True, use_boxes=False, nthreads=0, arrays=True, lite=False):
+                 hd_factor=20, debug_tag=True, use_boxes=False, nthreads=0, arrays=True, lite=False, tags=False):
         fd = geom["foundry"]
         a = {k: np.ascontiguousarray(fd[k], dtype=(np.int32 if k == "solid" else np.float32)) for k in ("solid", "prim", "node", "plan", "itra", "inst")}
         bnd = np.ascontiguousarray(geom["bnd"], dtype=np.float32)
@@ -149,6 +153,9 @@ class Oracle:
         nray, nhit = C.c_uint64(0), C.c_uint64(0)
         lite_arr = np.zeros((n, 4), dtype=np.uint32) if lite else None
         self.lib.oracle_set_lite_out(_p(lite_arr))
+        tag = np.zeros((n, 4), dtype=np.uint64) if tags else None
+        flat = np.zeros((n, 64), dtype=np.float32) if tags else None
+        self.lib.oracle_set_tag_out(_p(tag), _p(flat))
         rc = self.lib.oracle_simulate(_p(a["solid"]), C.c_int(len(a["solid"])), _p(a["prim"]), C.c_int(len(a["prim"])), _p(a["node"]), C.c_int(len(a["node"])),
                                       _p(a["plan"]) if len(a["plan"]) else None, C.c_int(len(a["plan"])), _p(a["itra"]), C.c_int(len(a["itra"])),
                                       _p(a["inst"]), C.c_int(len(a["inst"])),
@@ -157,9 +164,10 @@ class Oracle:
                                       _p(gs), C.c_int(len(gs)), _p(ip), C.c_int(0 if ip is None else len(ip)), C.byref(cfg),
                                       _p(photon), _p(record), _p(seq), _p(prd), C.byref(nray), C.byref(nhit))
         self.lib.oracle_set_lite_out(None)
+        self.lib.oracle_set_tag_out(None, None)
         if rc != 0:
             raise RuntimeError("oracle_simulate failed")
-        return dict(photon=photon, record=record, seq=seq, prd=prd, nray=nray.value, nhit=nhit.value, lite=lite_arr)
+        return dict(photon=photon, record=record, seq=seq, prd=prd, nray=nray.value, nhit=nhit.value, lite=lite_arr, tag=tag, flat=flat)
 
     def simtrace(self, geom, gensteps, input_simtrace=None, tmin=0.05, tmax=1e6, seed=0, offset=0, use_boxes=True):
         fd = geom["foundry"]

@@ -39,3 +39,16 @@ def test_rng_sequence_file_naming(tmp_path):
     p = A.save_rng_sequence(str(tmp_path), u)
     assert p.endswith("rng_sequence_f_ni100_nj16_nk16_tranche100/rng_sequence_f_ni100_nj16_nk16_ioffset000000.npy")
     assert np.load(p).shape == (100, 16, 16)
+
+
+def test_tag_decoding():
+    from eic_opticks_b200 import analysis as A
+    tag = np.zeros((1, 4), dtype=np.uint64)
+    seq = [1, 2, 3, 4, 5, 7] + [1, 2, 3, 4, 5, 6] * 2 + [8] * 5           # 23 slots: spills into the second u64
+    for k, t in enumerate(seq):
+        tag[0, k // 16] |= np.uint64(t) << np.uint64(4 * (k % 16))
+    s = A.tag_slots(tag)
+    assert s.shape == (1, 64) and s[0, :len(seq)].tolist() == seq and (s[0, len(seq):] == 0).all()
+    txt = A.tag_desc(tag[0])
+    assert txt.startswith("to_sci to_bnd to_sca to_abs at_burn_sf_sd sf_burn") and txt.endswith("sc sc sc sc sc")
+    assert A.tag_desc(tag[0], np.linspace(0, 1, 64)).split()[1] == "to_bnd:%.4f" % (1 / 63)

@@ -387,6 +387,36 @@ def test_edge_cases_empty_ragged_offsets_and_limits():
         sim.close()
 
 
+@pytest.mark.parametrize("name,kw", [CASES[0], CASES[5], CASES[3]])
+def test_tag_and_flat_arrays_equal_the_reference_tagr(name, kw):
+    """DebugHeavy tag / flat arrays (sysrap/stag.h, written by sctx::end) against the reference's own stagr running inside its
+    qsim.h on the B200 (as-built DEBUG_TAG build), for both forms of the loop: integer work, so bit-exact on every photon whose
+    history agrees"""
+    w = workloads.WORKLOADS[name](**dict(kw, num_photon=10000))
+    ref = RefGPU("debugtag").simulate(w["geom"], w["gensteps"], w["input_photons"], max_bounce=w["config"].get("max_bounce", 31), tags=True)
+    orc = Oracle().simulate(w["geom"], w["gensteps"], w["input_photons"], max_bounce=w["config"].get("max_bounce", 31), tags=True)
+    got = {}
+    for mode in (ph.KERNEL_PERSISTENT, ph.KERNEL_WAVEFRONT):
+        sim = make_sim(w, event_mode=ph.MODE_DEBUGHEAVY, kernel_mode=mode)
+        sim.simulate_np(w["gensteps"], 0, w["input_photons"])
+        tag, flat, seq = sim.get_array("tag").copy(), sim.get_array("flat").copy(), sim.get_array("seq").copy()
+        assert tag.shape == (10000, 4) and flat.shape == (10000, 64)
+        same = (seq == ref["seq"]).all(axis=(1, 2))
+        assert same.mean() > 0.995
+        assert (tag[same] == ref["tag"][same]).all(), name
+        assert (flat[same].view(np.uint32) == ref["flat"][same].view(np.uint32)).all(), name
+        same_o = (seq == orc["seq"]).all(axis=(1, 2))
+        assert (tag[same_o] == orc["tag"][same_o]).all() and (flat[same_o].view(np.uint32) == orc["flat"][same_o].view(np.uint32)).all()
+        got[mode] = (tag, flat)
+        sim.close()
+    assert got[ph.KERNEL_PERSISTENT][0].tobytes() == got[ph.KERNEL_WAVEFRONT][0].tobytes()
+    assert got[ph.KERNEL_PERSISTENT][1].tobytes() == got[ph.KERNEL_WAVEFRONT][1].tobytes()
+    sim = make_sim(w, event_mode=ph.MODE_DEBUGLITE)
+    sim.simulate_np(w["gensteps"], 0, w["input_photons"])
+    assert len(sim.get_array("tag")) == 0 and len(sim.get_array("flat")) == 0                  # only DebugHeavy keeps them
+    sim.close()
+
+
 def test_event_index_skipahead_and_rng_sequence():
     w = workloads.sipm8x8_scint(num_photon=1000, photons_per_genstep=100)
     sim = make_sim(w)
