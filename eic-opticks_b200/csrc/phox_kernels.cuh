@@ -29,6 +29,18 @@
 #ifndef PHOX_EXACT_BOX
 #define PHOX_EXACT_BOX 1           // exit-distance bound for prims that are exactly their box (see traverse_bvh)
 #endif
+#ifndef PHOX_PROP_SSA
+#define PHOX_PROP_SSA 1            // the physics body works on private copies of photon / stream / hit (see propagate_body)
+#endif
+#ifndef PHOX_PROP_INLINE_ALL
+#define PHOX_PROP_INLINE_ALL 1     // propagate() is compiled into its (single) call site of every kernel; 0: one out-of-line body
+#endif
+#ifndef PHOX_WF_PROP_INLINE
+#define PHOX_WF_PROP_INLINE 1      // same for k_wf_propagate alone (what PHOX_PROP_INLINE_ALL = 0 builds compare against)
+#endif
+#ifndef PHOX_TRAV_SPLIT
+#define PHOX_TRAV_SPLIT 1          // exact-box leaves inline, node-loop state parked by hand around the out-of-line prim test
+#endif
 #include "phox_bvh.cuh"
 #include "phox_physics.cuh"
 
@@ -121,6 +133,9 @@ constexpr int kTravDone = (int)0x80000001;
 // CSGPrim inside a solid) or one of the two markers.  Children are visited near-first; the far one is
 // parked on the stack with its entry distance so it is dropped once a nearer hit is known.
 PHOX_D void traverse_bvh(Nearest& best, const Scene& sc, float tmin, const float3& o_w, const float3& d_w) {
+#if PHOX_TRAV_SPLIT
+    volatile float park[10];
+#endif
     int2 stack[kBvhStack];                                   // (item, entry distance bits): one 8 B local store / load per push / pop
     int sp = 0;
     auto push = [&](int item, float t) {
@@ -206,7 +221,13 @@ PHOX_D void traverse_bvh(Nearest& best, const Scene& sc, float tmin, const float
             int prim_idx = item & kLeafItemMask;
             float4 is = make_float4(0.f, 0.f, 0.f, 0.f);
             bool ok;
-#if PHOX_EXACT_BOX
+#if PHOX_EXACT_BOX && PHOX_TRAV_SPLIT
+            if (item & kLeafExactBox) {                        // inlined: no call, nothing to preserve
+                const float4* rec = sc.exact + 2 * prim_idx;
+                float4 q0 = __ldg(rec), tr = __ldg(rec + 1);
+                ok = leaf_box3_idir(is, q0, tmin, f3(o.x + tr.x, o.y + tr.y, o.z + tr.z), d, idir);
+            } else
+#elif PHOX_EXACT_BOX
             if (item & kLeafExactBox) {
                 ok = intersect_exact_box(is, sc.exact + 2 * prim_idx, tmin, o, d, idir);
             } else
@@ -214,7 +235,20 @@ PHOX_D void traverse_bvh(Nearest& best, const Scene& sc, float tmin, const float
             {
                 float4 p0 = __ldg(sc.prim + 4 * prim_idx);
                 const float4* nroot = sc.geo.node + 4 * __float_as_int(p0.y);
-#if PHOX_HOT_LEAF
+#if PHOX_TRAV_SPLIT
+                // The values the node loop reads every visit are parked by hand around the one out-of-line call and come
+                // back as NEW values: their live ranges end at the call, so the register allocator has no reason to keep
+                // them in spill slots - which it otherwise reloads at the head of every node visit (9 local loads per
+                // visit at 64 registers, profiles/r1_summary.md).
+                park[0] = o.x; park[1] = o.y; park[2] = o.z; park[3] = idir.x; park[4] = idir.y; park[5] = idir.z;
+                park[6] = tmin; park[7] = best.t; park[8] = __int_as_float(root); park[9] = __int_as_float(sp);
+                float4 is_c = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float3 o_c = o, d_c = d;
+                ok = intersect_prim_cold(is_c, nroot, sc.geo, tmin, o_c, d_c);
+                is = is_c;
+                o = f3(park[0], park[1], park[2]); idir = f3(park[3], park[4], park[5]);
+                tmin = park[6]; best.t = park[7]; root = __float_as_int(park[8]); sp = __float_as_int(park[9]);
+#elif PHOX_HOT_LEAF
                 ok = intersect_prim(is, nroot, sc.geo, tmin, o, d);
 #else
                 ok = intersect_prim_cold(is, nroot, sc.geo, tmin, o, d);
@@ -624,7 +658,13 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
                     command = propagate_t<true>(p, rng, h, P.tables, P.burn != 0, &tg);
                     P.tagslot[idx] = tg.slot;
                 } else {
+                    {
+#if PHOX_WF_PROP_INLINE
+                    command = propagate_body<false>(p, rng, h, P.tables, P.burn != 0, nullptr);
+#else
                     command = propagate(p, rng, h, P.tables, P.burn != 0);
+#endif
+                    }
                 }
                 int bounce = W.bounce + 1;
 #if PHOX_WF_STREAM

