@@ -507,7 +507,7 @@ constexpr int kTraceThreads = PHOX_WF_TRACE_THREADS;
 #endif
 constexpr int kPropThreads = PHOX_WF_PROP_THREADS;
 #ifndef PHOX_WF_PROP_MIN_BLOCKS
-#define PHOX_WF_PROP_MIN_BLOCKS 5       // 48 registers
+#define PHOX_WF_PROP_MIN_BLOCKS 4       // 64 registers: the inlined physics body fits without spills (5 blocks = 48 registers: 0.509 vs 0.490 ms per launch)
 #endif
 constexpr unsigned kListEps0 = 0x80000000u;     // list entry bit: the photon's last flag is in PropagateEpsilon0Mask (-> tmin0), so that
 constexpr unsigned kListSlotMask = 0x7fffffffu; // the trace kernel does not have to read the flag word of the photon record
@@ -613,8 +613,9 @@ __global__ void __launch_bounds__(kTraceThreads, PHOX_WF_TRACE_MIN_BLOCKS) k_wf_
 
 template <bool DEBUG>
 __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_propagate(const __grid_constant__ WaveParams W) {
-    __shared__ unsigned s_warp[kPropThreads / 32];
-    __shared__ unsigned s_base;
+    __shared__ unsigned s_warp[2][kPropThreads / 32];      // double-buffered by chunk parity: two barriers per chunk instead of three
+    __shared__ unsigned s_base[2];
+    unsigned par = 0;
     const SimParams& P = W.sim;
     const unsigned count = *W.count_in;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -689,20 +690,20 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
         }
         unsigned ballot = __ballot_sync(0xffffffffu, survive);
         // append the survivors of this chunk to the next list, in order within the chunk
-        if (lane == 0) s_warp[warp] = __popc(ballot);
+        if (lane == 0) s_warp[par][warp] = __popc(ballot);
         __syncthreads();
         if (threadIdx.x == 0) {
             unsigned tot = 0;
-            for (int w = 0; w < kPropThreads / 32; w++) { unsigned c = s_warp[w]; s_warp[w] = tot; tot += c; }
-            s_base = tot ? atomicAdd(W.count_out, tot) : 0u;
+            for (int w = 0; w < kPropThreads / 32; w++) { unsigned c = s_warp[par][w]; s_warp[par][w] = tot; tot += c; }
+            s_base[par] = tot ? atomicAdd(W.count_out, tot) : 0u;
         }
         __syncthreads();
 #if PHOX_WF_STREAM
-        if (survive) __stcs(W.active_out + s_base + s_warp[warp] + __popc(ballot & ((1u << lane) - 1u)), entry_out);
+        if (survive) __stcs(W.active_out + s_base[par] + s_warp[par][warp] + __popc(ballot & ((1u << lane) - 1u)), entry_out);
 #else
-        if (survive) W.active_out[s_base + s_warp[warp] + __popc(ballot & ((1u << lane) - 1u))] = entry_out;
+        if (survive) W.active_out[s_base[par] + s_warp[par][warp] + __popc(ballot & ((1u << lane) - 1u))] = entry_out;
 #endif
-        __syncthreads();
+        par ^= 1u;
     }
 }
 

@@ -1,0 +1,17 @@
+mkdir -p gpurun_out/tune5
+O=gpurun_out/tune5
+for v in default p64 p40 pt128 pt128r64 pt128r56 t128; do
+  if [ $v = default ]; then unset PHOX_LIB; else export PHOX_LIB=/root/repo/tune/$v.so; fi
+  for wl in sipm8x8_scint:12500000 scintillator_tank:4000000; do
+    timeout 300 python bench.py --no-cpu-baseline --steps 3 --workload ${wl%%:*} --photons ${wl#*:} > $O/${v}_${wl%%:*}.json 2> $O/${v}_${wl%%:*}.err
+  done
+done
+unset PHOX_LIB
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob('gpurun_out/tune5/*.json')):
+    try:
+        j=json.loads(open(f).read().strip().splitlines()[-1]); r=j.get('roofline',{})
+        print(f.split('/')[-1], '%.1f M/s'%(j['value']/1e6), 'trace %.4f ms prop %.4f ms'%(r.get('kernel_ms',0), r.get('propagate_kernel_ms',0)))
+    except Exception as e: print(f,'ERR',e)
+PY
