@@ -64,6 +64,18 @@ __device__ __forceinline__ float box_entry(float lox, float loy, float loz, floa
     texit = tf;
     return tn <= tf ? tn : CUDART_INF_F;
 }
+// same test, the verdict as a predicate (tentry is only meaningful for a hit)
+__device__ __forceinline__ bool box_hit(float lox, float loy, float loz, float hix, float hiy, float hiz,
+                                        const float3& o, const float3& idir, float tmin, float tbest, float& tentry, float& texit) {
+    float tx0 = (lox - o.x) * idir.x, tx1 = (hix - o.x) * idir.x;
+    float ty0 = (loy - o.y) * idir.y, ty1 = (hiy - o.y) * idir.y;
+    float tz0 = (loz - o.z) * idir.z, tz1 = (hiz - o.z) * idir.z;
+    float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), tmin));
+    float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), tbest));
+    tf *= 1.0000004f;
+    tentry = tn; texit = tf;
+    return tn <= tf;
+}
 
 // For a box that IS the prim (box3 leaf without rotation) whose padded copy is (lo, hi): when the ray origin lies
 // inside the box shrunk by `slack` on every entering side, the prim's own answer is its exit face, which cannot be

@@ -38,6 +38,9 @@
 #ifndef PHOX_WF_PROP_INLINE
 #define PHOX_WF_PROP_INLINE 1      // same for k_wf_propagate alone (what PHOX_PROP_INLINE_ALL = 0 builds compare against)
 #endif
+#ifndef PHOX_HITFIN_INLINE
+#define PHOX_HITFIN_INLINE 0
+#endif
 #ifndef PHOX_TRAV_SPLIT
 #define PHOX_TRAV_SPLIT 1          // exact-box leaves inline, node-loop state parked by hand around the out-of-line prim test
 #endif
@@ -152,19 +155,19 @@ PHOX_D void traverse_bvh(Nearest& best, const Scene& sc, float tmin, const float
     float3 o = o_w, d = d_w;
     float3 idir = f3(1.f / d.x, 1.f / d.y, 1.f / d.z);
     int root = sc.tlas_root;
+    const BvhNode* tree = sc.nodes + root;                   // root of the tree being walked
     bool in_solid = false;
     int inst_idx = 0;
     int cur = sc.ninst == 1 ? ~0 : 0;
 
     while (true) {
         while (cur >= 0) {                                     // internal nodes
-            const float4* np = reinterpret_cast<const float4*>(sc.nodes + root + cur);
+            const float4* np = reinterpret_cast<const float4*>(tree + cur);
             float4 a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2);
             int4 ch = __ldg(reinterpret_cast<const int4*>(np + 3));
-            float e0, e1 = 0.f;
-            float t0 = box_entry(a.x, a.y, a.z, a.w, b.x, b.y, o, idir, tmin, best.t, e0);
-            float t1 = ch.y == kBvhNoChild ? CUDART_INF_F : box_entry(b.z, b.w, c.x, c.y, c.z, c.w, o, idir, tmin, best.t, e1);
-            bool h0 = t0 < CUDART_INF_F, h1 = t1 < CUDART_INF_F;
+            float t0, t1 = 0.f, e0, e1 = 0.f;
+            bool h0 = box_hit(a.x, a.y, a.z, a.w, b.x, b.y, o, idir, tmin, best.t, t0, e0);
+            bool h1 = ch.y != kBvhNoChild && box_hit(b.z, b.w, c.x, c.y, c.z, c.w, o, idir, tmin, best.t, t1, e1);
 #if PHOX_EXACT_BOX
             // c0/c1: no hit of the child can be nearer than this.  Normally the entry distance; for a prim that
             // is exactly its box and holds the ray origin, (a lower bound of) the exit distance - which lets the
@@ -197,6 +200,7 @@ PHOX_D void traverse_bvh(Nearest& best, const Scene& sc, float tmin, const float
             }
             in_solid = false;
             root = sc.tlas_root;
+            tree = sc.nodes + root;
             cur = pop();
             continue;
         }
@@ -211,6 +215,7 @@ PHOX_D void traverse_bvh(Nearest& best, const Scene& sc, float tmin, const float
                 idir = f3(1.f / d.x, 1.f / d.y, 1.f / d.z);
             }
             root = meta.w;
+            tree = sc.nodes + root;
             in_solid = true;
             if (sc.ninst > 1) push(kTravReturn, -CUDART_INF_F);
             cur = 0;
@@ -248,6 +253,7 @@ PHOX_D void traverse_bvh(Nearest& best, const Scene& sc, float tmin, const float
                 is = is_c;
                 o = f3(park[0], park[1], park[2]); idir = f3(park[3], park[4], park[5]);
                 tmin = park[6]; best.t = park[7]; root = __float_as_int(park[8]); sp = __float_as_int(park[9]);
+                tree = sc.nodes + root;
 #elif PHOX_HOT_LEAF
                 ok = intersect_prim(is, nroot, sc.geo, tmin, o, d);
 #else
@@ -288,7 +294,7 @@ __device__ __noinline__ void traverse_brute(Nearest& best, const Scene& sc, floa
 // what keeps the persistent and the wavefront form, and the debug and production kernels, bit-identical.
 constexpr unsigned kHitFphi = 1u;          // fill lposfphi (only the prd debug array and simtrace read it)
 constexpr unsigned kHitRawNormal = 2u;     // leave the normal as the closest-hit program delivers it (simtrace); the simulate raygen normalises
-__device__ __noinline__ bool hit_finish(HitInfo& h, const Scene& sc, const Nearest& best, const float3& o, const float3& d, unsigned flags) {
+PHOX_D bool hit_finish_core(HitInfo& h, const Scene& sc, const Nearest& best, const float3& o, const float3& d, unsigned flags) {
     if (best.prim < 0) {
         h.normal = f3(0.f, 0.f, 0.f); h.t = 1.f; h.lposcost = 0.f; h.lposfphi = 0.f;
         h.iindex_identity = 0xffffffffu; h.prim_boundary = 0xffffffffu;
@@ -316,6 +322,19 @@ __device__ __noinline__ bool hit_finish(HitInfo& h, const Scene& sc, const Neare
     return true;
 }
 
+// value copies in, value copy out: the same expression graph wherever it is compiled (see propagate_body)
+PHOX_D bool hit_finish_body(HitInfo& h_out, const Scene& sc, const Nearest& best_in, const float3& o_in, const float3& d_in, unsigned flags) {
+    const Nearest best = best_in;
+    const float3 o = o_in, d = d_in;
+    HitInfo h;
+    const bool ok = hit_finish_core(h, sc, best, o, d, flags);
+    h_out = h;
+    return ok;
+}
+__device__ __noinline__ bool hit_finish(HitInfo& h, const Scene& sc, const Nearest& best, const float3& o, const float3& d, unsigned flags) {
+    return hit_finish_body(h, sc, best, o, d, flags);
+}
+
 // nearest intersect in (tmin, tmax]; fills the prd-equivalent.  Returns false on a miss (the reference's miss
 // program sets boundary 0xffff).  Inline form: the traversal is compiled into the calling kernel, where the scene
 // pointers are kernel parameters (constant bank) instead of loads through a reference.  The boxes only cull; hit
@@ -325,7 +344,11 @@ PHOX_D bool trace_inline(HitInfo& h, const Scene& sc, const float3& o, const flo
     best.t = tmax; best.prim = -1; best.inst = 0; best.n = f3(0.f, 0.f, 0.f);
     if (sc.accel == 0) traverse_bvh(best, sc, tmin, o, d);
     else traverse_brute(best, sc, tmin, o, d);
+#if PHOX_HITFIN_INLINE
+    return hit_finish_body(h, sc, best, o, d, flags);
+#else
     return hit_finish(h, sc, best, o, d, flags);
+#endif
 }
 
 // out-of-line form for kernels with several trace sites (persistent kernel, geometry queries)
