@@ -386,6 +386,7 @@ extern "C" int phox_set_geometry(phox_context* ctx, const void* solid_, int64_t 
         int no = prim[p].node_offset();
         if (no < 0 || no >= nnode) continue;
         const Node& nd = hnode[no];
+        if (nd.typecode() >= CSG_LEAF) slack[p] = -1.f;      // a single leaf node: kLeafSingle (overwritten below when it is an exact box)
         if (nd.typecode() != CSG_BOX3 || nd.complement()) continue;
         float c[3] = {0.f, 0.f, 0.f};
         unsigned ti = nd.transform_idx();

@@ -38,6 +38,9 @@
 #ifndef PHOX_WF_PROP_INLINE
 #define PHOX_WF_PROP_INLINE 1      // same for k_wf_propagate alone (what PHOX_PROP_INLINE_ALL = 0 builds compare against)
 #endif
+#ifndef PHOX_LEAF_DIRECT
+#define PHOX_LEAF_DIRECT 0          // single-leaf prims: 1 = call the leaf dispatcher directly, 2 = compile it in place (measured: mixed, profiles/r1_summary.md)
+#endif
 #ifndef PHOX_HITFIN_INLINE
 #define PHOX_HITFIN_INLINE 0
 #endif
@@ -123,7 +126,8 @@ __device__ __noinline__ bool intersect_exact_box(float4& is, const float4* rec, 
     return leaf_box3_idir(is, q0, tmin, o, rd, idir);       // idir = 1 / rd as the traversal computed it: the direction is not transformed
 }
 constexpr int kLeafExactBox = 0x40000000;        // leaf item flag: the prim qualifies for intersect_exact_box
-constexpr int kLeafItemMask = 0x3fffffff;
+constexpr int kLeafSingle = 0x20000000;          // leaf item flag: the prim is one leaf node (no tree, no list): the leaf dispatcher is called directly
+constexpr int kLeafItemMask = 0x1fffffff;
 
 constexpr int kBvhStack = 64;
 constexpr int kTravReturn = (int)0x80000000;     // stack marker: leave the current solid, back to the instance tree
@@ -240,6 +244,14 @@ PHOX_D void traverse_bvh(Nearest& best, const Scene& sc, float tmin, const float
             {
                 float4 p0 = __ldg(sc.prim + 4 * prim_idx);
                 const float4* nroot = sc.geo.node + 4 * __float_as_int(p0.y);
+#if PHOX_TRAV_SPLIT && PHOX_LEAF_DIRECT == 2
+                if (item & kLeafSingle) {                      // leaf dispatcher compiled in place, on value copies
+                    const float3 o_c = o, d_c = d;
+                    float4 is_c;
+                    ok = intersect_leaf(is_c, nroot, sc.geo, tmin, o_c, d_c);
+                    is = is_c;
+                } else {
+#endif
 #if PHOX_TRAV_SPLIT
                 // The values the node loop reads every visit are parked by hand around the one out-of-line call and come
                 // back as NEW values: their live ranges end at the call, so the register allocator has no reason to keep
@@ -249,6 +261,10 @@ PHOX_D void traverse_bvh(Nearest& best, const Scene& sc, float tmin, const float
                 park[6] = tmin; park[7] = best.t; park[8] = __int_as_float(root); park[9] = __int_as_float(sp);
                 float4 is_c = make_float4(0.f, 0.f, 0.f, 0.f);
                 const float3 o_c = o, d_c = d;
+#if PHOX_LEAF_DIRECT
+                if (item & kLeafSingle) ok = intersect_leaf_cold(is_c, nroot, sc.geo, tmin, o_c, d_c);    // what intersect_prim_cold would call
+                else
+#endif
                 ok = intersect_prim_cold(is_c, nroot, sc.geo, tmin, o_c, d_c);
                 is = is_c;
                 o = f3(park[0], park[1], park[2]); idir = f3(park[3], park[4], park[5]);
@@ -258,6 +274,9 @@ PHOX_D void traverse_bvh(Nearest& best, const Scene& sc, float tmin, const float
                 ok = intersect_prim(is, nroot, sc.geo, tmin, o, d);
 #else
                 ok = intersect_prim_cold(is, nroot, sc.geo, tmin, o, d);
+#endif
+#if PHOX_TRAV_SPLIT && PHOX_LEAF_DIRECT == 2
+                }
 #endif
             }
             if (ok) keep_nearest(best, is, prim_idx, inst_idx, tmin);
@@ -731,14 +750,17 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
 }
 
 // after a solid's BVH is built: leaf children whose CSGPrim is exactly its box get that prim's slack in d.z / d.w
+// slack < 0 marks a prim that is a single leaf node but not an exact box (kLeafSingle)
 __global__ void k_mark_exact_boxes(BvhNode* nodes, int nnode, const float* __restrict__ slack) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nnode) return;
     int4 d = nodes[i].d;
-    d.z = (d.x < 0) ? __float_as_int(slack[~d.x]) : 0;
-    d.w = (d.y < 0 && d.y != kBvhNoChild) ? __float_as_int(slack[~d.y]) : 0;
-    if (d.z != 0) d.x = ~((~d.x) | kLeafExactBox);
-    if (d.w != 0) d.y = ~((~d.y) | kLeafExactBox);
+    float s0 = (d.x < 0) ? slack[~d.x] : 0.f;
+    float s1 = (d.y < 0 && d.y != kBvhNoChild) ? slack[~d.y] : 0.f;
+    d.z = s0 > 0.f ? __float_as_int(s0) : 0;
+    d.w = s1 > 0.f ? __float_as_int(s1) : 0;
+    if (s0 > 0.f) d.x = ~((~d.x) | kLeafExactBox); else if (s0 < 0.f) d.x = ~((~d.x) | kLeafSingle);
+    if (s1 > 0.f) d.y = ~((~d.y) | kLeafExactBox); else if (s1 < 0.f) d.y = ~((~d.y) | kLeafSingle);
     nodes[i].d = d;
 }
 
