@@ -173,13 +173,25 @@ class GDML:
         if tag == "box":
             return F.box3(g("x") * lu, g("y") * lu, g("z") * lu)
         if tag in ("sphere", "orb"):
+            # u4/U4Solid.h:494-561 : orb = sphere ; G4Sphere = outer [ minus inner ], each layer a zsphere when the theta range
+            # is cut (zmin = r cos(theta0 + dtheta), zmax = r cos(theta0)) ; phi segments are refused there too (assert :555-557)
             rmax = (g("rmax") if tag == "sphere" else g("r")) * lu
             rmin = g("rmin") * lu if tag == "sphere" else 0.0
-            dphi, dtheta = g("deltaphi", 2 * math.pi / au) * au, g("deltatheta", math.pi / au) * au
-            assert dphi >= 2 * math.pi - 1e-9 and dtheta >= math.pi - 1e-9 and g("startphi") == 0 and g("starttheta") == 0, \
-                "sphere phi/theta segments are not translated (u4/U4Solid.h:555-561 asserts too)"
-            outer = F.sphere(rmax)
-            return outer if rmin <= 0 else F.difference(outer, F.sphere(rmin))
+            dphi = g("deltaphi", 2 * math.pi / au) * au
+            theta0 = g("starttheta") * au if tag == "sphere" else 0.0
+            dtheta = min(g("deltatheta", math.pi / au) * au, math.pi - theta0) if tag == "sphere" else math.pi
+            assert dphi >= 2 * math.pi - 1e-9 and g("startphi") == 0, "sphere phi segments are not translated (u4/U4Solid.h:555-557 asserts too)"
+            assert 0.0 <= theta0 <= math.pi and 0.0 < dtheta
+            z_slice = theta0 > 0.0 or dtheta < math.pi - 1e-12
+
+            def layer(r):
+                if not z_slice:
+                    return F.sphere(r)
+                zmin, zmax = r * math.cos(theta0 + dtheta), r * math.cos(theta0)
+                assert zmax > zmin
+                return F.zsphere(r, zmin, zmax)
+            outer = layer(rmax)
+            return outer if rmin <= 0 else F.difference(outer, layer(rmin))
         if tag == "tube":
             rmax, rmin, hz = g("rmax") * lu, g("rmin") * lu, g("z") * lu / 2.0
             assert g("deltaphi", 2 * math.pi / au) * au >= 2 * math.pi - 1e-9, "tube phi segments are not translated"
@@ -189,15 +201,13 @@ class GDML:
             nudge = hz * 0.01                                # u4/U4Solid.h:813-821 : inner lengthened by 1 % of hz each end
             return F.difference(outer, F.cylinder(rmin, -(hz + nudge), hz + nudge))
         if tag == "cone":
+            # u4/U4Solid.h:903-941 : outer cone [ minus inner cone ], both over the full z range, no end nudge, phi ignored
             hz = g("z") * lu / 2.0
-            assert g("deltaphi", 2 * math.pi / au) * au >= 2 * math.pi - 1e-9, "cone phi segments are not translated"
             outer = F.cone(g("rmax1") * lu, -hz, g("rmax2") * lu, hz)
-            if g("rmin1") <= 0 and g("rmin2") <= 0:
-                return outer
-            nudge = hz * 0.01
             r1, r2 = g("rmin1") * lu, g("rmin2") * lu
-            slope = (r2 - r1) / (2 * hz)
-            return F.difference(outer, F.cone(max(r1 - slope * nudge, 0.0), -(hz + nudge), max(r2 + slope * nudge, 0.0), hz + nudge))
+            if r1 == 0.0 and r2 == 0.0:
+                return outer
+            return F.difference(outer, F.cone(r1, -hz, r2, hz))
         if tag == "trd":
             x1, x2, y1, y2, hz = g("x1") * lu / 2, g("x2") * lu / 2, g("y1") * lu / 2, g("y2") * lu / 2, g("z") * lu / 2
             pl = []
@@ -232,6 +242,17 @@ class GDML:
             else:
                 leaf = F.zsphere(sz, zmin - 0.1, zmax)
             return leaf.placed(F.scale(sx / sz, sy / sz, 1.0))
+        if tag == "multiUnion":
+            # u4/U4Solid.h:672-727 : list node (CSG_CONTIGUOUS unless the name hints CSG_DISCONTIGUOUS) of the placed subs,
+            # which must be single primitives (the reference puts a "notsupported" placeholder otherwise)
+            subs = []
+            for nd in el.findall("multiUnionNode"):
+                sub = self.solid_tree(nd.find("solid").get("ref"))
+                if not isinstance(sub, F.Leaf):
+                    raise NotImplementedError("multiUnion %s: sub-solid %s is not a primitive (sn::Notsupported in the reference)" % (name, nd.find("solid").get("ref")))
+                subs.append(_place_tree(sub, placement_matrix(self._inline_or_ref(nd, "position"), self._inline_or_ref(nd, "rotation"))))
+            kind = F.CSG_DISCONTIGUOUS if "CSG_DISCONTIGUOUS" in name else F.CSG_CONTIGUOUS
+            return F.ListNode(kind, subs)
         if tag in ("subtraction", "union", "intersection"):
             a = self.solid_tree(el.find("first").get("ref"))
             b = self.solid_tree(el.find("second").get("ref"))

@@ -153,3 +153,50 @@ def test_polycone_and_ellipsoid_follow_u4(tmp_path):
     assert abs(pc[0, 0, 3] - 250) < 1e-3                                       # cylinder part, r = 50
     assert abs(pc[1, 0, 3] - (300 - 35)) < 1e-3                                # cone part: r(30) = 50 - 30/60*30 = 35
     assert abs(pc[2, 0, 3] - (300 - 40)) < 1e-3                                # from above at r = 30: cone surface z = 60*(50-30)/30 = 40
+
+
+def test_sphere_theta_cone_and_multiunion_follow_u4(tmp_path):
+    """U4Solid::init_Sphere_ theta slices (zsphere layers), init_Cons (no inner nudge), init_MultiUnion (contiguous list node)"""
+    from eic_opticks_b200 import gdml as GD, foundry as F
+    from _ref import Oracle
+    gd = tmp_path / "s.gdml"
+    gd.write_text("""<?xml version="1.0"?>
+<gdml><define/><materials>
+ <material name="Vac"><D value="1e-25"/><fraction n="1" ref="H"/></material><element name="H" formula="H" Z="1"><atom value="1"/></element>
+</materials><solids>
+ <box name="w" x="2000" y="2000" z="2000" lunit="mm"/>
+ <sphere name="cap" rmin="40" rmax="50" starttheta="0" deltatheta="60" startphi="0" deltaphi="360" aunit="deg" lunit="mm"/>
+ <cone name="co" rmin1="10" rmax1="30" rmin2="20" rmax2="60" z="100" startphi="0" deltaphi="360" aunit="deg" lunit="mm"/>
+ <orb name="o1" r="30" lunit="mm"/><box name="b1" x="40" y="40" z="100" lunit="mm"/>
+ <multiUnion name="mu">
+  <multiUnionNode name="n1"><solid ref="o1"/></multiUnionNode>
+  <multiUnionNode name="n2"><solid ref="b1"/><position x="0" y="0" z="60" unit="mm"/></multiUnionNode>
+ </multiUnion>
+</solids><structure>
+ <volume name="capl"><materialref ref="Vac"/><solidref ref="cap"/></volume>
+ <volume name="col"><materialref ref="Vac"/><solidref ref="co"/></volume>
+ <volume name="mul"><materialref ref="Vac"/><solidref ref="mu"/></volume>
+ <volume name="W"><materialref ref="Vac"/><solidref ref="w"/>
+  <physvol name="a"><volumeref ref="capl"/></physvol>
+  <physvol name="b"><volumeref ref="col"/><position x="300" y="0" z="0" unit="mm"/></physvol>
+  <physvol name="c"><volumeref ref="mul"/><position x="-300" y="0" z="0" unit="mm"/></physvol></volume>
+</structure><setup name="Default" version="1.0"><world ref="W"/></setup></gdml>""")
+    g = GD.GDML(str(gd))
+    cap = g.solid_tree("cap")
+    assert isinstance(cap, F.Op) and cap.typecode == F.CSG_DIFFERENCE
+    assert cap.left.typecode == F.CSG_ZSPHERE and cap.right.typecode == F.CSG_ZSPHERE
+    assert np.allclose(cap.left.param[3:6], (50.0, 25.0, 50.0)) and np.allclose(cap.right.param[3:6], (40.0, 20.0, 40.0))   # r, zmin = r cos 60, zmax = r
+    co = g.solid_tree("co")
+    assert co.typecode == F.CSG_DIFFERENCE and tuple(co.left.param[:4]) == (30.0, -50.0, 60.0, 50.0) and tuple(co.right.param[:4]) == (10.0, -50.0, 20.0, 50.0)
+    mu = g.solid_tree("mu")
+    assert isinstance(mu, F.ListNode) and mu.typecode == F.CSG_CONTIGUOUS and [s.typecode for s in mu.subs] == [F.CSG_SPHERE, F.CSG_BOX3]
+
+    geom = GD.translate(str(gd))
+    o = np.array([[0, 0, 500], [10, 0, -500], [300, 500, 0], [-300, 0, 500], [-300, 500, 0]], dtype=np.float32)
+    d = np.array([[0, 0, -1], [0, 0, 1], [0, -1, 0], [0, 0, -1], [0, -1, 0]], dtype=np.float32)
+    r = Oracle().intersect(geom, o, d)
+    assert abs(r[0, 0, 3] - 450) < 1e-3                                        # top of the cap, r = 50
+    assert abs(r[1, 0, 3] - (500 + np.sqrt(1600 - 100))) < 1e-3                # from below at x = 10: the outer layer's cut plane (z = 25) lies inside the subtracted inner layer -> first surface is the r = 40 sphere
+    assert abs(r[2, 0, 3] - (500 - 45)) < 1e-3                                 # cone centred at x = 300: outer radius at z = 0 is 45
+    assert abs(r[3, 0, 3] - (500 - 110)) < 1e-3                                # multi-union: box top at z = 60 + 50
+    assert abs(r[4, 0, 3] - (500 - 30)) < 1e-3                                 # ... and the orb's equator
