@@ -310,6 +310,7 @@ extern "C" int phox_set_geometry(phox_context* ctx, const void* solid_, int64_t 
     if (!solid_ || !prim_ || !node_ || nsolid <= 0 || nprim <= 0 || nnode <= 0) return ctx->fail(PHOX_E_ARG, "phox_set_geometry: solid/prim/node arrays are required");
     if ((nitra > 0 && !itra_) || (nplan > 0 && !plan_)) return ctx->fail(PHOX_E_ARG, "phox_set_geometry: null itra/plan with non-zero count");
     if (nprim > 0xffff + 1) { /* globalPrimIdx is truncated to 16 bits in prd, like the reference (CSGOptiX7.cu:899) */ }
+    if (nprim > (int64_t)kLeafItemMask) return ctx->fail(PHOX_E_ARG, "phox_set_geometry: more than 2^29 prims (BVH leaf items carry two flag bits)");
     CK(cudaSetDevice(ctx->device));
     const Solid* solid = (const Solid*)solid_;
     const Prim* prim = (const Prim*)prim_;
