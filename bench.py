@@ -303,13 +303,21 @@ def main():
             kern_s, achieved, kernel_name, share = loop_s, cnt_r * bytes_per_photon / loop_s / 1e9, "k_simulate", st_dev["simulate_kernel_seconds"] / (ms_dev * 1e-3)
             rays_per_launch, ray_bytes = st_dev["num_ray"] / max(1, st_dev["num_launch"]), None
         # DRAM traffic per launch of the dominant kernel: bytes per ray from the committed ncu --set full capture x rays per launch here
-        traffic, traffic_src = None, None
+        traffic, traffic_src, tj = None, None, None
         tpath = os.path.join(ROOT, "profiles", "traffic_r1.json")
         if wave and os.path.exists(tpath) and args.workload == "sipm8x8_scint":
             with open(tpath) as f:
                 tj = json.load(f)
             traffic = tj["k_wf_trace"]["dram_bytes_per_ray"] * rays_per_launch
             traffic_src = "profiles/traffic_r1.json: %.0f DRAM bytes per ray (ncu dram__bytes_read+write of one k_wf_trace launch / its rays) x rays_per_launch" % tj["k_wf_trace"]["dram_bytes_per_ray"]
+        # the other kernel of the bounce loop, k_wf_propagate: 176 algorithmic bytes per live photon (104 read + 72 written)
+        second = None
+        if wave and prof["propagate_kernel_seconds"] > 0:
+            prop_s = prof["propagate_kernel_seconds"] / prof["num_trace_launch"]
+            prop_gbs = rays_per_launch * 176.0 / prop_s / 1e9
+            second = {"kernel": "k_wf_propagate", "bound": "hbm", "achieved": prop_gbs, "peak": peak, "unit": "GB/s", "frac": prop_gbs / peak,
+                      "algorithmic_bytes_per_photon": 176.0, "kernel_ms": prop_s * 1e3,
+                      "traffic": (tj["k_wf_propagate"]["dram_bytes_per_ray"] * rays_per_launch) if tj else None}
         out = {
             "metric": "photons propagated/sec", "value": value, "unit": "photons/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -329,6 +337,7 @@ def main():
                          "bounce_loop_ms": loop_s * 1e3, "bounce_loop_share_of_step": st_dev["simulate_kernel_seconds"] / (ms_dev * 1e-3),
                          "path_algorithmic_bytes_per_photon": bytes_per_photon, "path_achieved_gbs": cnt_r * bytes_per_photon / loop_s / 1e9,
                          "propagate_kernel_ms": (prof["propagate_kernel_seconds"] / prof["num_trace_launch"] * 1e3) if wave else None,
+                         "second_kernel": second,
                          "note": "the bounce loop is latency/issue bound, not HBM bound (geometry and tables are cache resident); "
                                  "ncu traffic and stall breakdown in profiles/"},
             "clocks": clocks,
