@@ -186,3 +186,24 @@ def test_cxx_torch_driver_generates_the_reference_photons(tmp_path):
     bad = tmp_path / "bad.json"; bad.write_text('{"torch": {"gentype": "TORCH"}}')
     r2 = subprocess.run([exe, "-c", str(bad), "--dump-photons", str(out)], capture_output=True, text=True, timeout=60)
     assert r2.returncode != 0 and "missing key" in r2.stderr
+
+
+def test_committed_bench_record_carries_the_contract_keys():
+    """profiles/bench_r1_default.json is one line of `python bench.py` on a B200: the keys the driver and the judge read must be there
+    and mutually consistent (value = photons per step / ms_per_step, roofline.achieved = algorithmic bytes / kernel time)."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "profiles", "bench_r1_default.json")) as f:
+        d = json.loads(f.read().strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "e2e", "gpu_launches", "roofline", "clocks", "cpu_baseline"):
+        assert k in d, k
+    assert d["unit"] == "photons/s" and d["n_gpus"] == 1 and d["warmup"] >= 3 and d["vs_baseline"] is None and d["config"]["workload"] == "sipm8x8_scint"
+    assert abs(d["value"] - d["config"]["photons_per_gpu_per_step"] / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]
+    assert d["gpu_launches"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] < d["value"] * 1.01
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert abs(r["achieved"] - r["rays_per_launch"] * r["algorithmic_bytes_per_ray"] / (r["kernel_ms"] * 1e-3) / 1e9) < 1e-6 * r["achieved"]
+    assert r["traffic"] > r["rays_per_launch"] * r["algorithmic_bytes_per_ray"]          # ncu DRAM bytes per launch, above the algorithmic bytes
+    assert d["clocks"]["reasons"] == [] and d["clocks"]["sm_mhz"] >= 0.9 * d["clocks"]["sm_max_mhz"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
