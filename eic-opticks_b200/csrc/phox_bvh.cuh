@@ -10,6 +10,8 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
+#include <utility>
+#include <vector>
 
 namespace phox {
 
@@ -45,6 +47,27 @@ struct BvhScratch {
 };
 cudaError_t bvh_build(const float* d_boxes, int n, int base_item, BvhNode* d_out, BvhScratch& scratch, cudaStream_t stream, int* kernel_count);
 void bvh_scratch_free(BvhScratch& scratch);
+
+// Host: number of internal nodes on the longest root-to-leaf path of a tree laid out in nodes[0 .. nnode), or -1 when the
+// array does not describe a tree (index out of range, more visits than nodes).  The traversal parks at most one entry per
+// internal node of the current path, so `depth(instance tree) + 1 + depth(deepest solid tree)` bounds its stack.
+inline int bvh_tree_depth(const BvhNode* nodes, int nnode) {
+    if (!nodes || nnode <= 0) return -1;
+    std::vector<std::pair<int, int>> todo;
+    todo.emplace_back(0, 1);
+    int deepest = 0;
+    long long visited = 0;
+    while (!todo.empty()) {
+        const std::pair<int, int> e = todo.back();
+        todo.pop_back();
+        if (e.first < 0 || e.first >= nnode || ++visited > (long long)nnode) return -1;
+        if (e.second > deepest) deepest = e.second;
+        const int c0 = nodes[e.first].d.x, c1 = nodes[e.first].d.y;
+        if (c0 >= 0 && c0 != kBvhNoChild) todo.emplace_back(c0, e.second + 1);
+        if (c1 >= 0 && c1 != kBvhNoChild) todo.emplace_back(c1, e.second + 1);
+    }
+    return deepest;
+}
 
 #if defined(__CUDACC__)
 // slab test against a box given as lo/hi ; returns entry distance, or +inf when missed, and the exit

@@ -495,6 +495,21 @@ extern "C" int phox_set_geometry(phox_context* ctx, const void* solid_, int64_t 
         CK(cudaStreamSynchronize(ctx->stream));     // scratch is reused by the next build
     }
     CK(cudaStreamSynchronize(ctx->stream));
+    {   // the traversal stack holds kBvhStack entries and drops pushes beyond that: refuse trees that could overflow it
+        std::vector<BvhNode> hn((size_t)pool);
+        CK(cudaMemcpyAsync(hn.data(), ctx->d_bvh.p, (size_t)pool * sizeof(BvhNode), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        const int dt = bvh_tree_depth(hn.data() + ctx->tlas_root, std::max<int>((int)ninst - 1, 1));
+        int ds = 0;
+        bool known = dt >= 0;
+        for (int64_t s = 0; s < nsolid && known; s++) {
+            if (solid[s].num_prim == 0) continue;
+            const int d = bvh_tree_depth(hn.data() + solid_root[s], std::max(solid[s].num_prim - 1, 1));
+            if (d < 0) known = false; else ds = std::max(ds, d);
+        }
+        if (known && dt + 1 + ds > kBvhStack)
+            return ctx->fail(PHOX_E_ARG, "phox_set_geometry: BVH deeper than the traversal stack (instance tree + solid tree > 63 levels)");
+    }
     ctx->have_geometry = true;
     return PHOX_OK;
 }

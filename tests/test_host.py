@@ -207,3 +207,36 @@ def test_committed_bench_record_carries_the_contract_keys():
     assert r["traffic"] > r["rays_per_launch"] * r["algorithmic_bytes_per_ray"]          # ncu DRAM bytes per launch, above the algorithmic bytes
     assert d["clocks"]["reasons"] == [] and d["clocks"]["sm_mhz"] >= 0.9 * d["clocks"]["sm_max_mhz"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+
+
+def test_bvh_depth_guard_function(tmp_path):
+    """phox_bvh.cuh bvh_tree_depth (host): what phox_set_geometry uses to refuse trees deeper than the traversal stack"""
+    import subprocess
+    src = tmp_path / "d.cpp"
+    src.write_text(r'''
+#include "phox_bvh.cuh"
+#include <cstdio>
+using namespace phox;
+static BvhNode mk(int c0, int c1) { BvhNode n{}; n.d.x = c0; n.d.y = c1; return n; }
+int main() {
+    // one item
+    BvhNode one[1] = {mk(~5, kBvhNoChild)};
+    // chain: node i -> (leaf, node i+1), 6 internal nodes ; leaves carry the flag bits the engine sets (still negative)
+    BvhNode chain[6];
+    for (int i = 0; i < 6; i++) chain[i] = mk(~(i | 0x40000000), i < 5 ? i + 1 : ~(99 | 0x20000000));
+    // balanced over 4 items: root(1,2), 1(l,l), 2(l,l)
+    BvhNode bal[3] = {mk(1, 2), mk(~0, ~1), mk(~2, ~3)};
+    // malformed: cycle, and child out of range
+    BvhNode cyc[2] = {mk(1, ~0), mk(0, ~1)};
+    BvhNode oor[1] = {mk(7, ~0)};
+    std::printf("%d %d %d %d %d %d\n", bvh_tree_depth(one, 1), bvh_tree_depth(chain, 6), bvh_tree_depth(bal, 3), bvh_tree_depth(cyc, 2),
+                bvh_tree_depth(oor, 1), bvh_tree_depth(nullptr, 0));
+    return 0;
+}
+''')
+    exe = tmp_path / "d"
+    r = subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "eic-opticks_b200", "csrc"), "-I", "/usr/local/cuda/include",
+                        "-o", str(exe), str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()
+    assert out == ["1", "6", "2", "-1", "-1", "-1"], out
