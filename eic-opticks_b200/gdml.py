@@ -288,7 +288,7 @@ class GDML:
 
     def _read_structure(self, st):
         for el in st:
-            if el.tag == "volume":
+            if el.tag in ("volume", "assembly"):
                 phys = []
                 for ch in self._expand(el):
                     if ch.tag != "physvol":
@@ -298,6 +298,9 @@ class GDML:
                     phys.append(dict(name=name, volume=ch.find("volumeref").get("ref"), pos=self._inline_or_ref(ch, "position"),
                                      rot=self._inline_or_ref(ch, "rotation"), copynumber=int(ch.get("copynumber", "0"))))
                 aux = {a.get("auxtype"): a.get("auxvalue") for a in el.findall("auxiliary")}
+                if el.tag == "assembly":       # G4AssemblyVolume: no solid, no material; its daughters are imprinted into the mother
+                    self.volumes[el.get("name")] = dict(assembly=True, phys=phys, aux=aux)
+                    continue
                 self.volumes[el.get("name")] = dict(material=el.find("materialref").get("ref"), solid=el.find("solidref").get("ref"), phys=phys, aux=aux)
             elif el.tag == "skinsurface":
                 self.skins.append(dict(name=el.get("name"), surface=el.get("surfaceproperty"), volume=el.find("volumeref").get("ref")))
@@ -459,8 +462,18 @@ def translate(path):
         info["prim_names"].append(strip_ptr(pv_name))
         if "SensDet" in vol["aux"]:
             info["sensitive_prims"].append(len(info["prim_names"]) - 1)
-        for ph in vol["phys"]:
-            visit(ph["name"], ph["volume"], me, placement_matrix(ph["pos"], ph["rot"]) @ frame)
+        place(vol["phys"], me, frame, "")
+
+    def place(phys, me, frame, prefix):
+        """daughters of a volume; a daughter that is an assembly contributes its own daughters, placed through it
+        (G4AssemblyVolume::MakeImprint: the assembly itself leaves no volume in the tree)"""
+        for ph in phys:
+            m = placement_matrix(ph["pos"], ph["rot"]) @ frame
+            child = g.volumes[ph["volume"]]
+            if child.get("assembly"):
+                place(child["phys"], me, m, prefix + ph["name"] + "_")
+            else:
+                visit(prefix + ph["name"], ph["volume"], me, m)
 
     visit(g.world + "_PV", g.world, None, np.eye(4))
     fd.end_solid()

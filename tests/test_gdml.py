@@ -200,3 +200,38 @@ def test_sphere_theta_cone_and_multiunion_follow_u4(tmp_path):
     assert abs(r[2, 0, 3] - (500 - 45)) < 1e-3                                 # cone centred at x = 300: outer radius at z = 0 is 45
     assert abs(r[3, 0, 3] - (500 - 110)) < 1e-3                                # multi-union: box top at z = 60 + 50
     assert abs(r[4, 0, 3] - (500 - 30)) < 1e-3                                 # ... and the orb's equator
+
+
+def test_assembly_daughters_are_imprinted_into_the_mother(tmp_path):
+    """<assembly> (G4AssemblyVolume): its daughters land in the mother volume with the composed placement; same arrays as placing them directly"""
+    from eic_opticks_b200 import gdml as GD
+    head = """<?xml version="1.0"?>
+<gdml><define/><materials>
+ <material name="Vac"><D value="1e-25"/><fraction n="1" ref="H"/></material><element name="H" formula="H" Z="1"><atom value="1"/></element>
+</materials><solids>
+ <box name="w" x="2000" y="2000" z="2000" lunit="mm"/><box name="b" x="10" y="20" z="30" lunit="mm"/><orb name="o" r="5" lunit="mm"/>
+</solids><structure>
+ <volume name="bl"><materialref ref="Vac"/><solidref ref="b"/></volume>
+ <volume name="ol"><materialref ref="Vac"/><solidref ref="o"/></volume>
+"""
+    tail = """</structure><setup name="Default" version="1.0"><world ref="W"/></setup></gdml>"""
+    a = tmp_path / "a.gdml"
+    a.write_text(head + """
+ <assembly name="asm">
+  <physvol name="p1"><volumeref ref="bl"/><position x="100" y="0" z="0" unit="mm"/></physvol>
+  <physvol name="p2"><volumeref ref="ol"/><position x="0" y="50" z="0" unit="mm"/><rotation x="0" y="0" z="90" unit="deg"/></physvol>
+ </assembly>
+ <volume name="W"><materialref ref="Vac"/><solidref ref="w"/>
+  <physvol name="A1"><volumeref ref="asm"/><position x="0" y="0" z="200" unit="mm"/><rotation x="0" y="0" z="90" unit="deg"/></physvol>
+  <physvol name="A2"><volumeref ref="asm"/><position x="0" y="0" z="-200" unit="mm"/></physvol>
+ </volume>""" + tail)
+    ga = GD.translate(str(a))
+    assert ga["prim_names"] == ["W_PV", "A1_p1", "A1_p2", "A2_p1", "A2_p2"]
+    fa = ga["foundry"]
+    assert fa["prim"].shape[0] == 5
+    # second imprint is a pure translation: box centre at (100, 0, -200), orb at (0, 50, -200)
+    bb = fa["prim"].reshape(-1, 16)[:, 8:14]
+    assert np.allclose(bb[3], (95, -10, -215, 105, 10, -185), atol=1e-3) and np.allclose(bb[4], (-5, 45, -205, 5, 55, -195), atol=1e-3)
+    # first imprint is rotated about z by 90 degrees (frame rotation): the box's x offset turns into a y offset, extents swap
+    c = 0.5 * (bb[1, :3] + bb[1, 3:]); e = bb[1, 3:] - bb[1, :3]
+    assert np.allclose(np.abs(c), (0, 100, 200), atol=1e-3) and np.allclose(e, (20, 10, 30), atol=1e-3)
