@@ -388,8 +388,9 @@ def _place_tree(t, m):
     return F.Op(t.typecode, _place_tree(t.left, m), _place_tree(t.right, m))
 
 
-def translate(path):
-    """GDML file -> dict(foundry, bnd, optical, icdf, bnd_names, ...) in the layout of geometries.py builders"""
+def translate(path, freq_cut=500):
+    """GDML file -> dict(foundry, bnd, optical, icdf, bnd_names, ...) in the layout of geometries.py builders.
+    freq_cut = stree::FREQ_CUT (sysrap/stree.h:293-294, envvar stree__FREQ_CUT in the reference): subtrees repeated at least that often are instanced."""
     g = GDML(path)
     bt = T.BoundaryTable()
 
@@ -435,13 +436,13 @@ def translate(path):
                 return skin_lookup[lv]
         return ""
 
-    fd = F.Foundry()
-    fd.begin_solid("r0")
-    info = dict(prim_names=[], sensitive_prims=[])
+    # ---- pass 1: structural nodes in preorder (U4Tree::initNodes_r), boundaries in order of first use ------------
+    nds = []
     implicit_added = set()
+    lv_index = {name: k for k, name in enumerate(g.volumes)}
 
-    def visit(pv_name, lv_name, mother, frame):
-        """preorder walk (U4Tree::initNodes_r): mother = (pv name, lv name, its mother lv name) or None"""
+    def visit(pv_name, lv_name, mother, frame, local, parent, copyno):
+        """mother = (pv name, lv name, its mother lv name) or None ; frame = global placement, local = placement in the mother"""
         vol = g.volumes[lv_name]
         imat = vol["material"]
         omat = g.volumes[mother[1]]["material"] if mother else imat
@@ -453,33 +454,101 @@ def translate(path):
             osur = "Implicit_RINDEX_NoRINDEX_%s_%s" % (strip_ptr(mother[0]), strip_ptr(pv_name))
         if not isur and i_r and not o_r and mother:            # implicit_isur
             isur = "Implicit_RINDEX_NoRINDEX_%s_%s" % (strip_ptr(pv_name), strip_ptr(mother[0]))
-        for s in (osur, isur):
-            if s.startswith("Implicit_") and s not in implicit_added:
-                bt.add_surface(T.implicit_surface(s))
-                implicit_added.add(s)
+        for s_ in (osur, isur):
+            if s_.startswith("Implicit_") and s_ not in implicit_added:
+                bt.add_surface(T.implicit_surface(s_))
+                implicit_added.add(s_)
         boundary = bt.boundary(strip_ptr(omat), osur, isur, strip_ptr(imat))
-        fd.add_prim(g.solid_tree(vol["solid"]), boundary, frame, name=strip_ptr(vol["solid"]))
-        info["prim_names"].append(strip_ptr(pv_name))
-        if "SensDet" in vol["aux"]:
-            info["sensitive_prims"].append(len(info["prim_names"]) - 1)
-        place(vol["phys"], me, frame, "")
+        idx = len(nds)
+        nd = dict(pv=pv_name, lv=lv_name, parent=parent, frame=frame, local=local, boundary=boundary, copyno=copyno,
+                  solid=vol["solid"], sensitive="SensDet" in vol["aux"], end=idx + 1, ridx=0)
+        nds.append(nd)
+        place(vol["phys"], me, frame, np.eye(4), "", idx)
+        nd["end"] = len(nds)                                   # preorder: the subtree of a node is the index range [idx, end)
 
-    def place(phys, me, frame, prefix):
+    def place(phys, me, frame, local, prefix, parent):
         """daughters of a volume; a daughter that is an assembly contributes its own daughters, placed through it
         (G4AssemblyVolume::MakeImprint: the assembly itself leaves no volume in the tree)"""
         for ph in phys:
-            m = placement_matrix(ph["pos"], ph["rot"]) @ frame
+            m_local = placement_matrix(ph["pos"], ph["rot"]) @ local
             child = g.volumes[ph["volume"]]
             if child.get("assembly"):
-                place(child["phys"], me, m, prefix + ph["name"] + "_")
+                place(child["phys"], me, frame, m_local, prefix + ph["name"] + "_", parent)
             else:
-                visit(prefix + ph["name"], ph["volume"], me, m)
+                visit(prefix + ph["name"], ph["volume"], me, m_local @ frame, m_local, parent, ph["copynumber"])
 
-    visit(g.world + "_PV", g.world, None, np.eye(4))
+    visit(g.world + "_PV", g.world, None, np.eye(4), np.eye(4), -1, 0)
+
+    # ---- pass 2: factorize (sysrap/stree.h:5263-5545) -----------------------------------------------------------
+    # subtree digest = lvid of the top + (lvid, local transform) of every node of its progeny (stree.h:4419-4428, U4Tree.h:839);
+    # digests repeated >= FREQ_CUT times whose parent's digest is not itself that frequent become instanced solids.
+    import hashlib
+    N = len(nds)
+    digs = [hashlib.md5(np.int32(lv_index[n["lv"]]).tobytes() + np.ascontiguousarray(n["local"], dtype=np.float64).tobytes()).digest() for n in nds]
+    subs = [hashlib.md5(np.int32(lv_index[n["lv"]]).tobytes() + b"".join(digs[k + 1:n["end"]])).digest() for k, n in enumerate(nds)]
+    first, freq = {}, {}
+    for k, sub in enumerate(subs):
+        first.setdefault(sub, k)
+        freq[sub] = freq.get(sub, 0) + 1
+    disqualified = set()
+    for sub, f_ in freq.items():                               # stree::disqualifyContainedRepeats / is_contained_repeat
+        if f_ < freq_cut:
+            continue
+        parent = nds[first[sub]]["parent"]
+        if parent >= 0 and freq[subs[parent]] >= freq_cut:
+            disqualified.add(sub)
+    ranked = sorted(freq, key=lambda sub: (-(freq[sub] if sub not in disqualified else -freq[sub]), first[sub]))     # stree_subs_freq_ordering
+    factors = [sub for sub in ranked if sub not in disqualified and freq[sub] >= freq_cut]                          # stree::enumerateFactors
+    outers = []
+    for f_, sub in enumerate(factors):                         # stree::labelFactorSubtrees
+        out_nodes = [k for k in range(N) if subs[k] == sub]
+        assert len({nds[k]["end"] - k for k in out_nodes}) == 1 and len({nds[k]["lv"] for k in out_nodes}) == 1
+        for k in out_nodes:
+            for q in range(k, nds[k]["end"]):
+                nds[q]["ridx"] = f_ + 1
+        outers.append(out_nodes)
+
+    # sensors of instances (U4Tree::identifySensitiveInstances + U4SensorIdentifierDefault::getInstanceIdentity: the copy number of an
+    # outer volume whose name contains "PMT" and whose subtree holds a sensitive volume), indices in preorder (stree::reorderSensors)
+    sensor = {}
+    for out_nodes in outers:
+        for k in out_nodes:
+            has_sd = any(nds[q]["sensitive"] for q in range(k, nds[k]["end"]))
+            sensor[k] = nds[k]["copyno"] if (has_sd and "PMT" in nds[k]["pv"]) else -1
+    sensor_index = {k: r for r, k in enumerate(sorted(k for k, v in sensor.items() if v > -1))}
+
+    # ---- pass 3: CSGFoundry arrays (CSG/CSGImport.cc:151-260): solid 0 = remainder, solid f + 1 = first instance of factor f ----------
+    fd = F.Foundry()
+    info = dict(prim_names=[], sensitive_prims=[])
+
+    def emit(k, frame):
+        nd = nds[k]
+        fd.add_prim(g.solid_tree(nd["solid"]), nd["boundary"], frame, name=strip_ptr(nd["solid"]))
+        info["prim_names"].append(strip_ptr(nd["pv"]))
+        if nd["sensitive"]:
+            info["sensitive_prims"].append(len(info["prim_names"]) - 1)
+
+    fd.begin_solid("r0")
+    for k in range(N):
+        if nds[k]["ridx"] == 0:
+            emit(k, nds[k]["frame"])
     fd.end_solid()
+    for f_, out_nodes in enumerate(outers):
+        k0 = out_nodes[0]
+        fd.begin_solid("f%d" % (f_ + 1))
+        rel = {k0: np.eye(4)}                                  # placement relative to the outer volume: product of the local transforms below it
+        for k in range(k0, nds[k0]["end"]):
+            if k != k0:
+                rel[k] = nds[k]["local"] @ rel[nds[k]["parent"]]
+            emit(k, rel[k])
+        fd.end_solid()
+    fd.add_instance(np.eye(4), 0, -1, -1)                      # stree::add_inst: the global instance first, then factor by factor
+    for f_, out_nodes in enumerate(outers):
+        for k in out_nodes:
+            fd.add_instance(nds[k]["frame"], f_ + 1, sensor[k], sensor_index.get(k, -1))
 
     icdf = None
-    extra = dict(gdml=g, prim_names=info["prim_names"], sensitive_prims=info["sensitive_prims"], table=bt)
+    extra = dict(gdml=g, prim_names=info["prim_names"], sensitive_prims=info["sensitive_prims"], table=bt, num_factor=len(factors))
     if scint is not None:
         name, spectrum, tau = scint
         icdf = T.make_icdf(spectrum[0], spectrum[1])

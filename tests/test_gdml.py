@@ -235,3 +235,61 @@ def test_assembly_daughters_are_imprinted_into_the_mother(tmp_path):
     # first imprint is rotated about z by 90 degrees (frame rotation): the box's x offset turns into a y offset, extents swap
     c = 0.5 * (bb[1, :3] + bb[1, 3:]); e = bb[1, 3:] - bb[1, :3]
     assert np.allclose(np.abs(c), (0, 100, 200), atol=1e-3) and np.allclose(e, (20, 10, 30), atol=1e-3)
+
+
+def test_repeated_subtrees_become_instanced_solids(tmp_path):
+    """stree::factorize restated (sysrap/stree.h:5263-5545) + stree::add_inst + the default sensor identifier: 600 placements of a
+    two-volume PMT become one compound solid and 600 instance transforms; the nested repeat is not a factor of its own;
+    the rays see the same surfaces as in the flat translation."""
+    from eic_opticks_b200 import gdml as GD
+    from _ref import Oracle
+    pvs = []
+    for i in range(24):
+        for j in range(25):
+            k = i * 25 + j
+            pvs.append('<physvol name="PMT_%d" copynumber="%d"><volumeref ref="glassl"/><position x="%g" y="%g" z="0" unit="mm"/></physvol>'
+                       % (k, 1000 + k, (i - 11.5) * 250.0, (j - 12.0) * 250.0))
+    gd = tmp_path / "wall.gdml"
+    gd.write_text("""<?xml version="1.0"?>
+<gdml><define>
+ <matrix name="RI" coldim="2" values="1.55*eV 1.4 6.2*eV 1.4"/><matrix name="RW" coldim="2" values="1.55*eV 1.33 6.2*eV 1.33"/>
+ <matrix name="RV" coldim="2" values="1.55*eV 1.0 6.2*eV 1.0"/>
+</define><materials>
+ <element name="H" formula="H" Z="1"><atom value="1"/></element>
+ <material name="Water"><property name="RINDEX" ref="RW"/><D value="1"/><fraction n="1" ref="H"/></material>
+ <material name="Glass"><property name="RINDEX" ref="RI"/><D value="2"/><fraction n="1" ref="H"/></material>
+ <material name="Vac"><property name="RINDEX" ref="RV"/><D value="1e-25"/><fraction n="1" ref="H"/></material>
+</materials><solids>
+ <box name="w" x="8000" y="8000" z="2000" lunit="mm"/><orb name="glass" r="100" lunit="mm"/><orb name="vac" r="95" lunit="mm"/>
+</solids><structure>
+ <volume name="vacl"><materialref ref="Vac"/><solidref ref="vac"/><auxiliary auxtype="SensDet" auxvalue="PhotonDetector"/></volume>
+ <volume name="glassl"><materialref ref="Glass"/><solidref ref="glass"/><physvol name="inner"><volumeref ref="vacl"/></physvol></volume>
+ <volume name="W"><materialref ref="Water"/><solidref ref="w"/>
+""" + "\n".join(pvs) + """
+ </volume>
+</structure><setup name="Default" version="1.0"><world ref="W"/></setup></gdml>""")
+    t = GD.translate(str(gd))
+    flat = GD.translate(str(gd), freq_cut=10 ** 9)
+    assert t["num_factor"] == 1 and flat["num_factor"] == 0
+    fd, ff = t["foundry"], flat["foundry"]
+    assert fd["solid"].shape[0] == 2 and fd["prim"].shape[0] == 3 and ff["prim"].shape[0] == 1201
+    si = fd["solid"][:, 1]
+    assert tuple(si[0, :2]) == (1, 0) and tuple(si[1, :2]) == (2, 1)                     # numPrim, primOffset
+    assert bytes(fd["solid"][1].reshape(-1).view(np.uint8)[:2]) == b"f1"
+    inst = fd["inst"]
+    ii = inst.view(np.int32)
+    assert inst.shape[0] == 601 and tuple(ii[0, :, 3]) == (0, 0, 0, -1) and (ii[1:, 1, 3] == 1).all() and (ii[:, 0, 3] == np.arange(601)).all()
+    assert (ii[1:, 2, 3] == 1000 + np.arange(600) + 1).all() and (ii[1:, 3, 3] == np.arange(600)).all()      # copy number + 1 ; sensor index in preorder
+    assert np.allclose(inst[1, 3, :3], (-11.5 * 250, -12 * 250, 0)) and np.allclose(inst[600, 3, :3], (11.5 * 250, 12 * 250, 0))
+    # prims of the compound solid are in the frame of its outer volume
+    bb = fd["prim"].reshape(-1, 16)[:, 8:14]
+    assert np.allclose(bb[1], (-100, -100, -100, 100, 100, 100)) and np.allclose(bb[2], (-95, -95, -95, 95, 95, 95))
+    assert t["bnd_names"] == flat["bnd_names"]
+    # same surfaces along random rays (distance and normal), instanced vs flat
+    rng = np.random.default_rng(5)
+    o = np.stack([rng.uniform(-3000, 3000, 400), rng.uniform(-3000, 3000, 400), np.full(400, 900.0)], axis=1).astype(np.float32)
+    d = np.stack([rng.normal(0, 0.3, 400), rng.normal(0, 0.3, 400), -np.ones(400)], axis=1)
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    a, b = Oracle().intersect(t, o, d), Oracle().intersect(flat, o, d)
+    assert np.allclose(a[:, 0, 3], b[:, 0, 3], rtol=1e-5, atol=1e-3) and np.allclose(a[:, 0, :3], b[:, 0, :3], atol=1e-4)
+    assert ((a[:, 0, 3] < 1500).sum() > 100)                                              # a good share of the rays do hit PMTs (the rest reach the world box)
