@@ -293,3 +293,17 @@ def test_repeated_subtrees_become_instanced_solids(tmp_path):
     a, b = Oracle().intersect(t, o, d), Oracle().intersect(flat, o, d)
     assert np.allclose(a[:, 0, 3], b[:, 0, 3], rtol=1e-5, atol=1e-3) and np.allclose(a[:, 0, :3], b[:, 0, :3], atol=1e-4)
     assert ((a[:, 0, 3] < 1500).sum() > 100)                                              # a good share of the rays do hit PMTs (the rest reach the world box)
+
+
+def test_gdml2geom_cli_writes_a_loadable_geometry_directory(tmp_path):
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "geom"
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "gdml2geom.py"), os.path.join(GOLD, "mini_detector.gdml"), str(out)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0 and "7 prims" in r.stdout, r.stdout + r.stderr
+    back = F.load_geometry(str(out))
+    t = gdml.translate(os.path.join(GOLD, "mini_detector.gdml"))
+    for k in ("solid", "prim", "node", "itra", "inst"):
+        assert (back["foundry"][k].view(np.uint8) == t["foundry"][k].view(np.uint8)).all(), k
+    assert back["bnd_names"] == t["bnd_names"] and (back["bnd"] == t["bnd"].astype(np.float32)).all()
