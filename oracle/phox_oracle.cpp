@@ -13,7 +13,8 @@
 // linear texture filter, so float results agree with the GPU to ~1e-6 relative, not bitwise.
 //
 // Each function names the reference lines it follows.  One scalar photon at a time, brute-force
-// loop over instances and prims (an optional prim-box pre-test speeds up the timed baseline).
+// loop over instances and prims (use_boxes = 1: prim-box pre-test; use_boxes = 2: median-split box trees over instances and
+// prims, which only cull and leave every output byte unchanged - that is the form bench.py times as the CPU arm).
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -107,10 +108,48 @@ struct Node { union { float f[16]; unsigned u[16]; int i[16]; }; };
 struct Prim { union { float f[16]; unsigned u[16]; int i[16]; }; };
 struct Inst { float inv[16]; int solid, identity, is_identity, prim_offset, num_prim; };
 
+// Timing aid only (use_boxes == 2, the bench's CPU arm): median-split box trees over the instances and over the prims of each
+// solid.  They only cull; the answer is the same as the plain loops' (nearest t, ties to the lower (instance, prim) pair).
+struct CpuBvhNode { float bb[6]; int left, right; };          // left < 0 : leaf holding item ~left
+struct CpuBvh {
+    std::vector<CpuBvhNode> nodes;
+    int build(std::vector<int>& items, int lo, int hi, const std::vector<float>& boxes) {
+        CpuBvhNode nd;
+        for (int a = 0; a < 3; a++) { nd.bb[a] = INFINITY; nd.bb[a + 3] = -INFINITY; }
+        for (int k = lo; k < hi; k++) for (int a = 0; a < 3; a++) {
+            nd.bb[a] = fminf(nd.bb[a], boxes[6 * (size_t)items[k] + a]); nd.bb[a + 3] = fmaxf(nd.bb[a + 3], boxes[6 * (size_t)items[k] + 3 + a]);
+        }
+        int me = (int)nodes.size();
+        nodes.push_back(nd);
+        if (hi - lo == 1) { nodes[me].left = ~items[lo]; nodes[me].right = 0; return me; }
+        int ax = 0; float ext = -1.f;
+        for (int a = 0; a < 3; a++) { float e = nd.bb[a + 3] - nd.bb[a]; if (e > ext) { ext = e; ax = a; } }
+        int mid = (lo + hi) / 2;
+        std::nth_element(items.begin() + lo, items.begin() + mid, items.begin() + hi, [&](int x, int y) {
+            float cx = boxes[6 * (size_t)x + ax] + boxes[6 * (size_t)x + 3 + ax], cy = boxes[6 * (size_t)y + ax] + boxes[6 * (size_t)y + 3 + ax];
+            return cx < cy || (cx == cy && x < y);
+        });
+        int l = build(items, lo, mid, boxes), r = build(items, mid, hi, boxes);
+        nodes[me].left = l; nodes[me].right = r;
+        return me;
+    }
+    void make(int n, const std::vector<float>& boxes) {
+        nodes.clear();
+        if (n <= 0) return;
+        std::vector<int> items(n);
+        for (int i = 0; i < n; i++) items[i] = i;
+        nodes.reserve(2 * (size_t)n);
+        build(items, 0, n, boxes);
+    }
+};
+
 struct Scene {
     const Node* node; const v4* plan; std::vector<float> itra; const Prim* prim;
     std::vector<Inst> inst;
     bool use_boxes;
+    bool use_bvh = false;
+    CpuBvh tlas;                       // over the world boxes of the instances
+    std::vector<CpuBvh> blas;          // per solid, over its prim boxes (items = prim index within the solid)
 };
 
 inline v3 right_multiply(const float* m, v3 v, float w) {        // sysrap/sqat4.h:45-52
@@ -610,8 +649,74 @@ bool box_hit(const float* bb, v3 o, v3 d, float tmin, float tbest) {
     return tn <= tf * 1.000001f;
 }
 
+// slab test with a precomputed 1/d (same padding and tolerance as box_hit)
+inline bool box_hit_inv(const float* bb, const float* oo, const float* inv, float tmin, float tbest) {
+    float tn = tmin, tf = tbest;
+    for (int a = 0; a < 3; a++) {
+        float pad = 4e-6f * fmaxf(1.f, fmaxf(fabsf(bb[a]), fabsf(bb[a + 3])));
+        float t0 = (bb[a] - pad - oo[a]) * inv[a], t1 = (bb[a + 3] + pad - oo[a]) * inv[a];
+        if (t0 != t0 || t1 != t1) continue;
+        tn = fmaxf(tn, fminf(t0, t1)); tf = fminf(tf, fmaxf(t0, t1));
+    }
+    return tn <= tf * 1.000001f;
+}
+
+struct Best { float t; bool found; v3 n; int inst, prim; unsigned boundary; };
+
+// prims of one instance through the solid's box tree; order independent: ties go to the lower (instance, prim) pair
+static void trace_solid_bvh(Best& b, const Scene& sc, int i, v3 oo, v3 dd, float tmin) {
+    const Inst& ri = sc.inst[i];
+    const CpuBvh& bv = sc.blas[ri.solid];
+    if (bv.nodes.empty()) return;
+    const float o3[3] = {oo.x, oo.y, oo.z}, inv[3] = {1.f / dd.x, 1.f / dd.y, 1.f / dd.z};
+    int stack[128], sp = 0;
+    stack[sp++] = 0;
+    while (sp > 0) {
+        const CpuBvhNode& nd = bv.nodes[stack[--sp]];
+        if (!box_hit_inv(nd.bb, o3, inv, tmin, b.t)) continue;
+        if (nd.left < 0) {
+            int pidx = ri.prim_offset + ~nd.left;
+            const Prim& pr = sc.prim[pidx];
+            const Node* root = sc.node + pr.i[1];
+            v4 isect = {0, 0, 0, 0};
+            bool valid = intersect_prim(isect, root, sc, tmin, oo, dd);
+            if (valid && isect.w > tmin) {
+                bool closer = isect.w < b.t || (isect.w == b.t && (!b.found || i < b.inst || (i == b.inst && pidx < b.prim)));
+                if (closer) { b.t = isect.w; b.found = true; b.n = mk(isect.x, isect.y, isect.z); b.inst = i; b.prim = pidx; b.boundary = root->u[6]; }
+            }
+            continue;
+        }
+        if (sp + 2 <= 128) { stack[sp++] = nd.right; stack[sp++] = nd.left; }
+    }
+}
+
+static void trace_bvh(Best& b, const Scene& sc, v3 o, v3 d, float tmin) {
+    if (sc.tlas.nodes.empty()) return;
+    const float o3[3] = {o.x, o.y, o.z}, inv[3] = {1.f / d.x, 1.f / d.y, 1.f / d.z};
+    int stack[128], sp = 0;
+    stack[sp++] = 0;
+    while (sp > 0) {
+        const CpuBvhNode& nd = sc.tlas.nodes[stack[--sp]];
+        if (!box_hit_inv(nd.bb, o3, inv, tmin, b.t)) continue;
+        if (nd.left < 0) {
+            int i = ~nd.left;
+            const Inst& ri = sc.inst[i];
+            v3 oo = ri.is_identity ? o : right_multiply(ri.inv, o, 1.f);
+            v3 dd = ri.is_identity ? d : right_multiply(ri.inv, d, 0.f);
+            trace_solid_bvh(b, sc, i, oo, dd, tmin);
+            continue;
+        }
+        if (sp + 2 <= 128) { stack[sp++] = nd.right; stack[sp++] = nd.left; }
+    }
+}
+
 bool trace(Prd& prd, const Scene& sc, v3 o, v3 d, float tmin, float tmax) {
     float best_t = tmax; bool found = false; v3 best_n = mk(0, 0, 0); int best_inst = 0, best_prim = 0; unsigned best_boundary = 0;
+    if (sc.use_bvh) {
+        Best b; b.t = tmax; b.found = false; b.n = mk(0, 0, 0); b.inst = 0; b.prim = 0; b.boundary = 0;
+        trace_bvh(b, sc, o, d, tmin);
+        best_t = b.t; found = b.found; best_n = b.n; best_inst = b.inst; best_prim = b.prim; best_boundary = b.boundary;
+    } else
     for (size_t i = 0; i < sc.inst.size(); i++) {
         const Inst& ri = sc.inst[i];
         v3 oo = ri.is_identity ? o : right_multiply(ri.inv, o, 1.f);
@@ -1052,6 +1157,7 @@ bool invert_affine(const float* m, float* out) {
 int make_scene(Scene& sc, const int* solid, int nsolid, const void* prim, const void* node, const void* plan, const float* itra, int nitra,
                const float* inst, int ninst, int use_boxes) {
     sc.node = (const Node*)node; sc.prim = (const Prim*)prim; sc.plan = (const v4*)plan; sc.use_boxes = use_boxes != 0;
+    sc.use_bvh = false;
     sc.itra.assign(itra, itra + (size_t)nitra * 16);
     for (int i = 0; i < nitra; i++) { sc.itra[16 * i + 3] = 0.f; sc.itra[16 * i + 7] = 0.f; sc.itra[16 * i + 11] = 0.f; sc.itra[16 * i + 15] = 1.f; }
     if (ninst <= 0 || !inst) {
@@ -1073,6 +1179,41 @@ int make_scene(Scene& sc, const int* solid, int nsolid, const void* prim, const 
         if (!invert_affine(m, r.inv)) return -1;
         r.solid = gas; r.num_prim = solid[12 * gas + 4]; r.prim_offset = solid[12 * gas + 5];
         sc.inst.push_back(r);
+    }
+    if (use_boxes == 2) {              // box trees for the timed CPU arm
+        sc.blas.assign(nsolid, CpuBvh());
+        std::vector<float> sbox((size_t)nsolid * 6);
+        for (int s_ = 0; s_ < nsolid; s_++) {
+            int np = solid[12 * s_ + 4], po = solid[12 * s_ + 5];
+            std::vector<float> boxes((size_t)np * 6);
+            for (int a = 0; a < 3; a++) { sbox[6 * s_ + a] = INFINITY; sbox[6 * s_ + 3 + a] = -INFINITY; }
+            for (int k = 0; k < np; k++) for (int a = 0; a < 6; a++) {
+                float v = sc.prim[po + k].f[8 + a];
+                boxes[6 * (size_t)k + a] = v;
+                if (a < 3) sbox[6 * s_ + a] = fminf(sbox[6 * s_ + a], v); else sbox[6 * s_ + a] = fmaxf(sbox[6 * s_ + a], v);
+            }
+            sc.blas[s_].make(np, boxes);
+        }
+        std::vector<float> ibox((size_t)ninst * 6);
+        for (int i = 0; i < ninst; i++) {
+            float m[16]; memcpy(m, inst + 16 * i, 64);
+            m[3] = m[7] = m[11] = 0.f; m[15] = 1.f;
+            const float* sb = &sbox[6 * (size_t)sc.inst[i].solid];
+            float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+            for (int c = 0; c < 8; c++) {
+                float v[3] = {(c & 1) ? sb[3] : sb[0], (c & 2) ? sb[4] : sb[1], (c & 4) ? sb[5] : sb[2]};
+                for (int a = 0; a < 3; a++) {
+                    float w = m[a] * v[0] + m[4 + a] * v[1] + m[8 + a] * v[2] + m[12 + a];
+                    lo[a] = fminf(lo[a], w); hi[a] = fmaxf(hi[a], w);
+                }
+            }
+            for (int a = 0; a < 3; a++) {
+                float pad = 1e-4f * fmaxf(1.f, fmaxf(fabsf(lo[a]), fabsf(hi[a])));
+                ibox[6 * (size_t)i + a] = lo[a] - pad; ibox[6 * (size_t)i + 3 + a] = hi[a] + pad;
+            }
+        }
+        sc.tlas.make(ninst, ibox);
+        sc.use_bvh = true;
     }
     return 0;
 }

@@ -145,7 +145,7 @@ class Oracle:
         n = int(gs.view(np.uint32)[:, 0, 3].sum())
         ip = None if input_photons is None else np.ascontiguousarray(input_photons, dtype=np.float32)
         cfg = OracleConfig(max_bounce, max_record, event_id, 1 if debug_tag else 0, tmin, tmin0, tmax, max_time, eps0mask, hit_mask,
-                           seed, offset, skipahead, photon_offset, 1 if use_boxes else 0, nthreads)
+                           seed, offset, skipahead, photon_offset, int(use_boxes), nthreads)
         photon = np.zeros((n, 4, 4), dtype=np.float32)
         record = np.zeros((n, max_record, 4, 4), dtype=np.float32) if arrays else None
         seq = np.zeros((n, 2, 2), dtype=np.uint64) if arrays else None
@@ -179,7 +179,7 @@ class Oracle:
         self.lib.oracle_simtrace.restype = C.c_int
         rc = self.lib.oracle_simtrace(_p(a["solid"]), C.c_int(len(a["solid"])), _p(a["prim"]), _p(a["node"]), _p(a["plan"]) if len(a["plan"]) else None,
                                       _p(a["itra"]), C.c_int(len(a["itra"])), _p(a["inst"]), C.c_int(len(a["inst"])), _p(gs), C.c_int(len(gs)),
-                                      _p(ip), C.c_float(tmin), C.c_float(tmax), C.c_uint64(seed), C.c_uint64(offset), _p(out), C.c_int(1 if use_boxes else 0))
+                                      _p(ip), C.c_float(tmin), C.c_float(tmax), C.c_uint64(seed), C.c_uint64(offset), _p(out), C.c_int(int(use_boxes)))
         if rc != n:
             raise RuntimeError("oracle_simtrace failed")
         return out
@@ -194,7 +194,7 @@ class Oracle:
         self.lib.oracle_intersect.restype = C.c_int
         rc = self.lib.oracle_intersect(_p(a["solid"]), C.c_int(len(a["solid"])), _p(a["prim"]), _p(a["node"]), _p(a["plan"]) if len(a["plan"]) else None,
                                        _p(a["itra"]), C.c_int(len(a["itra"])), _p(a["inst"]), C.c_int(len(a["inst"])), _p(o), _p(d), C.c_int(len(o)),
-                                       C.c_float(tmax), _p(out), C.c_int(1 if use_boxes else 0))
+                                       C.c_float(tmax), _p(out), C.c_int(int(use_boxes)))
         if rc != 0:
             raise RuntimeError("oracle_intersect failed")
         return out
