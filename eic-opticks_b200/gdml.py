@@ -23,6 +23,7 @@ Not covered (asserts, like the reference does for phi segments u4/U4Solid.h:555-
 trap, polyhedra, torus, assemblies, replicas, NIST materials by name, instancing (FREQ_CUT 500).
 """
 import math
+import os
 import re
 import xml.etree.ElementTree as ET
 
@@ -388,9 +389,11 @@ def _place_tree(t, m):
     return F.Op(t.typecode, _place_tree(t.left, m), _place_tree(t.right, m))
 
 
-def translate(path, freq_cut=500):
+def translate(path, freq_cut=None):
     """GDML file -> dict(foundry, bnd, optical, icdf, bnd_names, ...) in the layout of geometries.py builders.
     freq_cut = stree::FREQ_CUT (sysrap/stree.h:293-294, envvar stree__FREQ_CUT in the reference): subtrees repeated at least that often are instanced."""
+    if freq_cut is None:
+        freq_cut = int(os.environ.get("stree__FREQ_CUT", "500"))
     g = GDML(path)
     bt = T.BoundaryTable()
 

@@ -18,7 +18,7 @@ def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__.split("\n")[0])
     ap.add_argument("gdml")
     ap.add_argument("out")
-    ap.add_argument("--freq-cut", type=int, default=500, help="stree::FREQ_CUT: subtrees repeated at least this often are instanced")
+    ap.add_argument("--freq-cut", type=int, default=None, help="stree::FREQ_CUT: subtrees repeated at least this often are instanced")
     a = ap.parse_args(argv)
     from eic_opticks_b200 import gdml, foundry
     g = gdml.translate(a.gdml, freq_cut=a.freq_cut)
