@@ -127,3 +127,15 @@ def save_rng_sequence(folder, uniforms, ioffset=0, nj=16, nk=16):
     path = os.path.join(sub, "rng_sequence_f_ni%d_nj%d_nk%d_ioffset%06d.npy" % (ni, nj, nk, ioffset))
     np.save(path, u.reshape(ni, nj, nk))
     return path
+
+
+def compare_ab(record_a, record_b, atol=1e-5, shifted=True):
+    """tests/compare_ab.py of the reference: photon indices whose step records differ between the GPU event (A) and the Geant4 event (B).
+    With `shifted` the A records are compared from step 1 on against the B records up to the last but one (the U4Recorder B side
+    has no separate generation point: compare_ab.py:11), otherwise step for step."""
+    a, b = np.asarray(record_a), np.asarray(record_b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    if shifted:
+        a, b = a[:, 1:], b[:, :-1]
+    close = np.isclose(a, b, rtol=0.0, atol=atol).reshape(len(a), -1).all(axis=1)
+    return [int(i) for i in np.nonzero(~close)[0]]

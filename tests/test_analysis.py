@@ -52,3 +52,22 @@ def test_tag_decoding():
     txt = A.tag_desc(tag[0])
     assert txt.startswith("to_sci to_bnd to_sca to_abs at_burn_sf_sd sf_burn") and txt.endswith("sc sc sc sc sc")
     assert A.tag_desc(tag[0], np.linspace(0, 1, 64)).split()[1] == "to_bnd:%.4f" % (1 / 63)
+
+
+def test_compare_ab_lists_the_photons_whose_records_differ(tmp_path):
+    """tests/compare_ab.py of the reference, as analysis.compare_ab and scripts/compare_ab.py"""
+    import os, subprocess, sys
+    orc = Oracle()
+    w = workloads.scintillator_tank(num_photon=2000, photons_per_genstep=100)
+    a = orc.simulate(w["geom"], w["gensteps"])
+    rec = a["record"]
+    b = np.zeros_like(rec)
+    b[:, :-1] = rec[:, 1:]                          # a B side without the generation point, like the U4Recorder arrays
+    b[[14, 22, 81], 0, 0, 0] += 1e-3                # three photons moved by a micron at their first step
+    assert A.compare_ab(rec, b) == [14, 22, 81]
+    assert A.compare_ab(rec, rec, shifted=False) == []
+    da = A.save_event(str(tmp_path / "a"), 0, dict(record=rec, seq=a["seq"]))
+    db = A.save_event(str(tmp_path / "b"), 0, dict(record=b, seq=a["seq"]))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "compare_ab.py"), da, db], capture_output=True, text=True)
+    assert r.returncode == 0 and "[14, 22, 81]" in r.stdout and "chi2/ndf 0.00" in r.stdout, r.stdout + r.stderr
