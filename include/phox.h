@@ -104,7 +104,9 @@ const char*   phox_desc(const phox_context* ctx);         /* SSimulator::desc   
  *   inst  : qat4[ninst] instance transforms, 4th column ints = (ins_idx, gas_idx,
  *           sensor_identifier+1, sensor_index) (sysrap/sqat4.h:345-407)
  * Builds the two-level BVH on the device (replaces SBT::createGAS/createIAS,
- * CSGOptiX/SBT.cc:277-370). */
+ * CSGOptiX/SBT.cc:277-370).  PHOX_E_ARG for inconsistent arrays, a singular instance transform,
+ * more than 2^29 prims, or trees deeper than the traversal stack (instance tree + deepest
+ * solid tree > 63 levels) - never a silently truncated traversal. */
 int phox_set_geometry(phox_context* ctx,
                       const void* solid, int64_t nsolid,
                       const void* prim,  int64_t nprim,
