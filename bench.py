@@ -143,7 +143,7 @@ def main():
     ap.add_argument("--impl", default="phox", choices=["phox", "reference"])
     ap.add_argument("--workload", default="sipm8x8_scint")
     ap.add_argument("--photons", type=int, default=12_500_000, help="photons per GPU per step")
-    ap.add_argument("--cpu-sample", type=int, default=4_000_000, help="photons of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=6_000_000, help="photons of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="diagnosis: do not sample NVML clocks during the timed region")
     ap.add_argument("--max-slot", type=int, default=0, help="photons per launch (0 = library default); an event is sliced at genstep granularity")

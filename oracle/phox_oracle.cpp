@@ -109,8 +109,8 @@ struct Prim { union { float f[16]; unsigned u[16]; int i[16]; }; };
 struct Inst { float inv[16]; int solid, identity, is_identity, prim_offset, num_prim; };
 
 // Timing aid only (use_boxes == 2, the bench's CPU arm): median-split box trees over the instances and over the prims of each
-// solid.  They only cull; the answer is the same as the plain loops' (nearest t, ties to the lower (instance, prim) pair).
-struct CpuBvhNode { float bb[6]; int left, right; };          // left < 0 : leaf holding item ~left
+// solid (padded boxes, near child first, enclosing volumes in a subtree of their own).  They only cull; the answer is the same as the plain loops' (nearest t, ties to the lower (instance, prim) pair).
+struct CpuBvhNode { float bb[6]; int left, right, axis; };    // left < 0 : leaf holding item ~left ; bb already padded ; axis of the split
 struct CpuBvh {
     std::vector<CpuBvhNode> nodes;
     int build(std::vector<int>& items, int lo, int hi, const std::vector<float>& boxes) {
@@ -119,11 +119,16 @@ struct CpuBvh {
         for (int k = lo; k < hi; k++) for (int a = 0; a < 3; a++) {
             nd.bb[a] = fminf(nd.bb[a], boxes[6 * (size_t)items[k] + a]); nd.bb[a + 3] = fmaxf(nd.bb[a + 3], boxes[6 * (size_t)items[k] + 3 + a]);
         }
+        int ax = 0; float ext = -1.f;
+        for (int a = 0; a < 3; a++) { float e = nd.bb[a + 3] - nd.bb[a]; if (e > ext) { ext = e; ax = a; } }
+        for (int a = 0; a < 3; a++) {          // the padding of box_hit, applied once here
+            float pad = 4e-6f * fmaxf(1.f, fmaxf(fabsf(nd.bb[a]), fabsf(nd.bb[a + 3])));
+            nd.bb[a] -= pad; nd.bb[a + 3] += pad;
+        }
+        nd.axis = ax; nd.left = nd.right = 0;
         int me = (int)nodes.size();
         nodes.push_back(nd);
         if (hi - lo == 1) { nodes[me].left = ~items[lo]; nodes[me].right = 0; return me; }
-        int ax = 0; float ext = -1.f;
-        for (int a = 0; a < 3; a++) { float e = nd.bb[a + 3] - nd.bb[a]; if (e > ext) { ext = e; ax = a; } }
         int mid = (lo + hi) / 2;
         std::nth_element(items.begin() + lo, items.begin() + mid, items.begin() + hi, [&](int x, int y) {
             float cx = boxes[6 * (size_t)x + ax] + boxes[6 * (size_t)x + 3 + ax], cy = boxes[6 * (size_t)y + ax] + boxes[6 * (size_t)y + 3 + ax];
@@ -133,13 +138,28 @@ struct CpuBvh {
         nodes[me].left = l; nodes[me].right = r;
         return me;
     }
+    // Geant4 geometries nest: a few enclosing volumes (world, mother boxes) span everything and would inflate every node of a
+    // median-split tree.  Items much larger than the typical one get a subtree of their own next to the tree of the rest.
     void make(int n, const std::vector<float>& boxes) {
         nodes.clear();
         if (n <= 0) return;
         std::vector<int> items(n);
         for (int i = 0; i < n; i++) items[i] = i;
-        nodes.reserve(2 * (size_t)n);
-        build(items, 0, n, boxes);
+        nodes.reserve(2 * (size_t)n + 2);
+        auto diag2 = [&](int i) { float d = 0.f; for (int a = 0; a < 3; a++) { float e = boxes[6 * (size_t)i + 3 + a] - boxes[6 * (size_t)i + a]; d += e * e; } return d; };
+        std::vector<float> dd(n);
+        for (int i = 0; i < n; i++) dd[i] = diag2(i);
+        std::vector<float> sorted_dd(dd);
+        std::nth_element(sorted_dd.begin(), sorted_dd.begin() + n / 2, sorted_dd.end());
+        const float cut = 16.f * sorted_dd[n / 2];                       // diagonal more than 4 x the median one
+        int nlarge = (int)(std::stable_partition(items.begin(), items.end(), [&](int i) { return dd[i] > cut; }) - items.begin());
+        if (nlarge == 0 || nlarge == n || n < 8) { build(items, 0, n, boxes); return; }
+        CpuBvhNode root;
+        for (int a = 0; a < 3; a++) { root.bb[a] = -INFINITY; root.bb[a + 3] = INFINITY; }
+        root.axis = 0; root.left = root.right = 0;
+        nodes.push_back(root);
+        int l = build(items, nlarge, n, boxes), r = build(items, 0, nlarge, boxes);     // the ordinary items are looked at first
+        nodes[0].left = l; nodes[0].right = r;
     }
 };
 
@@ -653,8 +673,7 @@ bool box_hit(const float* bb, v3 o, v3 d, float tmin, float tbest) {
 inline bool box_hit_inv(const float* bb, const float* oo, const float* inv, float tmin, float tbest) {
     float tn = tmin, tf = tbest;
     for (int a = 0; a < 3; a++) {
-        float pad = 4e-6f * fmaxf(1.f, fmaxf(fabsf(bb[a]), fabsf(bb[a + 3])));
-        float t0 = (bb[a] - pad - oo[a]) * inv[a], t1 = (bb[a + 3] + pad - oo[a]) * inv[a];
+        float t0 = (bb[a] - oo[a]) * inv[a], t1 = (bb[a + 3] - oo[a]) * inv[a];          // bb is padded at build time
         if (t0 != t0 || t1 != t1) continue;
         tn = fmaxf(tn, fminf(t0, t1)); tf = fminf(tf, fmaxf(t0, t1));
     }
@@ -686,7 +705,10 @@ static void trace_solid_bvh(Best& b, const Scene& sc, int i, v3 oo, v3 dd, float
             }
             continue;
         }
-        if (sp + 2 <= 128) { stack[sp++] = nd.right; stack[sp++] = nd.left; }
+        if (sp + 2 <= 128) {                                   // near child on top: the split axis orders the children along the ray
+            const bool left_first = inv[nd.axis] >= 0.f;
+            stack[sp++] = left_first ? nd.right : nd.left; stack[sp++] = left_first ? nd.left : nd.right;
+        }
     }
 }
 
@@ -706,7 +728,10 @@ static void trace_bvh(Best& b, const Scene& sc, v3 o, v3 d, float tmin) {
             trace_solid_bvh(b, sc, i, oo, dd, tmin);
             continue;
         }
-        if (sp + 2 <= 128) { stack[sp++] = nd.right; stack[sp++] = nd.left; }
+        if (sp + 2 <= 128) {
+            const bool left_first = inv[nd.axis] >= 0.f;
+            stack[sp++] = left_first ? nd.right : nd.left; stack[sp++] = left_first ? nd.left : nd.right;
+        }
     }
 }
 
