@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(kSimThreads, PHOX_SIM_MIN_BLOCKS) k_simulate(c
                 HitInfo h;
                 bool ok = trace(h, P.scene, p.pos, p.mom, tmin, P.tmax, hit_flags);
                 nray++;
-                if (P.refine && ok) {
+                if (P.refine) {                                 // trace<true>: decided by 0.99 x prd distance, which is 1 after a miss (CSGOptiX7.cu:165-184)
                     float t_approx = 0.99f * h.t;
                     if (t_approx > P.refine_distance) {
                         float3 closer = p.pos + t_approx * p.mom;
@@ -627,8 +627,8 @@ __global__ void __launch_bounds__(kTraceThreads, PHOX_WF_TRACE_MIN_BLOCKS) k_wf_
                 ok = trace_inline(h, P.scene, from, d, tmin, P.tmax, ((DEBUG && P.prd != nullptr) || P.lpos != nullptr) ? kHitFphi : 0u);
                 nray++;
                 if (pass == 1) { h.t += t_add; break; }
-                if (!(P.refine && ok)) break;
-                t_add = 0.99f * h.t;
+                if (!P.refine) break;
+                t_add = 0.99f * h.t;                            // h.t is 1 after a miss, like the miss program's prd (CSGOptiX7.cu:165-184, 667)
                 if (!(t_add > P.refine_distance)) break;
                 from = o + t_add * d;
             }
@@ -937,7 +937,7 @@ __global__ void k_simtrace(const __grid_constant__ SimtraceParams S) {
     }
     HitInfo h;
     bool ok = trace(h, S.scene, pos, mom, S.tmin, S.tmax, kHitFphi | kHitRawNormal);
-    if (S.refine && ok) {
+    if (S.refine) {
         float t_approx = 0.99f * h.t;
         if (t_approx > S.refine_distance) {
             float3 closer = pos + t_approx * mom;

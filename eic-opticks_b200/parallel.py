@@ -84,3 +84,84 @@ def gather_hits(hits, group=None, device=None, dst=None):
     dist.all_gather_into_tensor(buf, pad, group=group)
     out = torch.cat([buf[r * nmax: r * nmax + c] for r, c in enumerate(counts)], dim=0).reshape(-1, 4, 4)
     return (out.cpu().numpy() if as_numpy else out), counts
+
+
+class PipelinedHitGather:
+    """Root-only gather of each event's hits, overlapped with the following events (GPU ranks, NCCL).
+
+    push(sim) after every simulate: the event's hits are copied into one of two staging buffers on the simulator's
+    stream, and the gather of the PREVIOUS event is posted on a second stream - by then every rank has long finished that
+    event, so the exchange of the counts does not make a fast rank wait for a slow one, and the records travel while the
+    next event's kernels run.  drain() posts the last gather and waits for it.  The root's receive buffer only grows.
+    result() -> (hits (n,4,4) device tensor on the root | None, counts per rank) of the last completed gather."""
+
+    def __init__(self, capacity, device, dst=0, group=None):
+        import torch
+        self.torch = torch
+        self.device, self.dst, self.group = device, dst, group
+        self.stream = torch.cuda.Stream(device)
+        self.bufs = [torch.empty((max(int(capacity), 1), 16), dtype=torch.float32, device=device) for _ in range(2)]
+        self.staged = None              # (buffer index, hit count, event recorded after the staging copy)
+        self.k = 0
+        self.out = None
+        self.last = (None, None)
+
+    def _post(self):
+        import torch.distributed as dist
+        torch = self.torch
+        b, n, ev = self.staged
+        self.staged = None
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ev)
+            t = self.bufs[b][:n]
+            n_local = torch.tensor([n], dtype=torch.int64, device=self.device)
+            all_counts = torch.zeros(world, dtype=torch.int64, device=self.device)
+            dist.all_gather_into_tensor(all_counts, n_local, group=self.group)
+            counts = [int(c) for c in all_counts.tolist()]
+            ops, out = [], None
+            if rank == self.dst:
+                tot = sum(counts)
+                if self.out is None or self.out.shape[0] < tot:
+                    self.out = torch.empty((tot + tot // 4 + 1024, 16), dtype=torch.float32, device=self.device)
+                out = self.out[:tot]
+                off = 0
+                for r, c in enumerate(counts):
+                    if r == rank:
+                        out[off:off + c].copy_(t, non_blocking=True)
+                    elif c:
+                        ops.append(dist.P2POp(dist.irecv, out[off:off + c], dist.get_global_rank(self.group, r) if self.group is not None else r, self.group))
+                    off += c
+            elif n:
+                ops.append(dist.P2POp(dist.isend, t, dist.get_global_rank(self.group, self.dst) if self.group is not None else self.dst, self.group))
+            if ops:
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()                  # orders the gather stream after the transfer; the host does not block
+            self.last = (None if out is None else out.reshape(-1, 4, 4), counts)
+
+    def push(self, sim):
+        torch = self.torch
+        if self.staged is not None:
+            self._post()
+        b = self.k & 1
+        self.k += 1
+        n = int(sim.num_hit())
+        if n > self.bufs[b].shape[0]:
+            # the transfer that last read this buffer was posted two events ago; wait for it before replacing the buffer
+            self.stream.synchronize()
+            self.bufs[b] = torch.empty((n + n // 4, 16), dtype=torch.float32, device=self.device)
+        if n:
+            sim.get_hits_device(self.bufs[b].data_ptr())        # async copy on the simulator's stream
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        # the next event may only overwrite this staging buffer's twin; this one is read by the gather posted at the next push
+        self.staged = (b, n, ev)
+
+    def drain(self):
+        if self.staged is not None:
+            self._post()
+        self.stream.synchronize()
+        return self.last
+
+    def result(self):
+        return self.last

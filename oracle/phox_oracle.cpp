@@ -1161,6 +1161,7 @@ struct Config {
     unsigned eps0mask, hit_mask;
     uint64_t seed, offset, skipahead, photon_offset;
     int use_boxes, nthreads;
+    unsigned refine; float refine_distance;          // PropagateRefine / PropagateRefineDistance (CSGOptiX/CSGOptiX7.cu:454-458)
 };
 
 bool invert_affine(const float* m, float* out) {
@@ -1302,6 +1303,15 @@ int oracle_simulate(const int* solid, int nsolid, const void* prim, int nprim, c
             Prd prd;
             bool ok = trace(prd, sc, p.pos, p.mom, tmin, cfg->tmax);
             nray++;
+            if (cfg->refine) {                                                 // trace<true> CSGOptiX/CSGOptiX7.cu:146-185 (distance is 1 after a miss)
+                float t_approx = 0.99f * prd.t;
+                if (t_approx > cfg->refine_distance) {
+                    v3 closer = p.pos + t_approx * p.mom;
+                    ok = trace(prd, sc, closer, p.mom, tmin, cfg->tmax);
+                    nray++;
+                    prd.t += t_approx;
+                }
+            }
             last_lpos = ok ? pack_lpos(prd.lposcost, prd.lposfphi) : 0u;
             if (!ok) break;
             prd.normal = normalize(prd.normal);

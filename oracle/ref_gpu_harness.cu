@@ -58,6 +58,8 @@ struct RefParams {
     unsigned long long photon_slot_offset;
     float tmin, tmin0, tmax, max_time;
     unsigned eps0mask;
+    unsigned refine;                 // params.PropagateRefine
+    float refine_distance;           // params.PropagateRefineDistance
     unsigned long long* nray;
 };
 
@@ -140,6 +142,15 @@ __global__ void ref_simulate(RefParams P) {
         float tmin = (ctx.p.orient_boundary_flag & P.eps0mask) ? P.tmin0 : P.tmin;
         ref_trace(P, ctx.p.pos, ctx.p.mom, tmin, P.tmax, prd);
         nray++;
+        if (P.refine) {                                  // trace<true> (CSGOptiX7.cu:146-185), the same statements around ref_trace
+            float t_approx = 0.99f * prd->distance();
+            if (t_approx > P.refine_distance) {
+                float3 closer_ray_origin = ctx.p.pos + t_approx * ctx.p.mom;
+                ref_trace(P, closer_ray_origin, ctx.p.mom, tmin, P.tmax, prd);
+                nray++;
+                prd->distance_add(t_approx);
+            }
+        }
         if (prd->boundary() == 0xffffu) break;
         float3* normal = prd->normal();
         *normal = normalize(*normal);
@@ -295,6 +306,7 @@ struct RefConfig {
     float tmin, tmin0, tmax, max_time;
     unsigned eps0mask, pad1;
     unsigned long long seed, offset, skipahead, photon_offset;
+    unsigned refine; float refine_distance;
 };
 
 extern "C" int phoxref_simulate(const void* solid, int nsolid, const void* prim, int nprim, const void* node, int nnode, const void* plan, int nplan,
@@ -372,6 +384,7 @@ extern "C" int phoxref_simulate(const void* solid, int nsolid, const void* prim,
     P.sim = d_sim; P.evt = d_evt; P.photon_slot_offset = cfg->photon_offset;
     P.tmin = cfg->tmin; P.tmin0 = cfg->tmin0; P.tmax = cfg->tmax; P.max_time = cfg->max_time; P.eps0mask = cfg->eps0mask;
     P.nray = d_nray;
+    P.refine = cfg->refine; P.refine_distance = cfg->refine_distance;
 
     RCK(cudaDeviceSetLimit(cudaLimitStackSize, 8192));
     const int T = 64;

@@ -16,7 +16,8 @@ class RefConfig(C.Structure):
     _fields_ = [("max_bounce", C.c_int), ("max_record", C.c_int), ("event_index", C.c_int), ("pad", C.c_int),
                 ("tmin", C.c_float), ("tmin0", C.c_float), ("tmax", C.c_float), ("max_time", C.c_float),
                 ("eps0mask", C.c_uint), ("pad1", C.c_uint),
-                ("seed", C.c_uint64), ("offset", C.c_uint64), ("skipahead", C.c_uint64), ("photon_offset", C.c_uint64)]
+                ("seed", C.c_uint64), ("offset", C.c_uint64), ("skipahead", C.c_uint64), ("photon_offset", C.c_uint64),
+                ("refine", C.c_uint), ("refine_distance", C.c_float)]
 
 
 def _p(a):
@@ -43,7 +44,8 @@ class RefGPU:
         return a, args
 
     def simulate(self, geom, gensteps, input_photons=None, event_id=0, photon_offset=0, max_bounce=31, max_record=32,
-                 tmin=0.05, tmin0=0.05, tmax=1e6, max_time=1e27, eps0mask=0x37, seed=0, offset=0, skipahead=100000, hd_factor=20, tags=False):
+                 tmin=0.05, tmin0=0.05, tmax=1e6, max_time=1e27, eps0mask=0x37, seed=0, offset=0, skipahead=100000, hd_factor=20, tags=False,
+                 refine=0, refine_distance=5000.0):
         fd = geom["foundry"]
         keep, gargs = self._geo(fd)
         bnd = np.ascontiguousarray(geom["bnd"], dtype=np.float32)
@@ -53,7 +55,8 @@ class RefGPU:
         gs = np.ascontiguousarray(gensteps, dtype=np.float32).reshape(-1, 6, 4)
         n = int(gs.view(np.uint32)[:, 0, 3].sum())
         ip = None if input_photons is None else np.ascontiguousarray(input_photons, dtype=np.float32)
-        cfg = RefConfig(max_bounce, max_record, event_id, 0, tmin, tmin0, tmax, max_time, eps0mask, 0, seed, offset, skipahead, photon_offset)
+        cfg = RefConfig(max_bounce, max_record, event_id, 0, tmin, tmin0, tmax, max_time, eps0mask, 0, seed, offset, skipahead, photon_offset,
+                        refine, refine_distance)
         photon = np.zeros((n, 4, 4), dtype=np.float32)
         dbg = not self.production
         record = np.zeros((n, max_record, 4, 4), dtype=np.float32) if dbg else None
@@ -115,7 +118,7 @@ class OracleConfig(C.Structure):
                 ("tmin", C.c_float), ("tmin0", C.c_float), ("tmax", C.c_float), ("max_time", C.c_float),
                 ("eps0mask", C.c_uint), ("hit_mask", C.c_uint),
                 ("seed", C.c_uint64), ("offset", C.c_uint64), ("skipahead", C.c_uint64), ("photon_offset", C.c_uint64),
-                ("use_boxes", C.c_int), ("nthreads", C.c_int)]
+                ("use_boxes", C.c_int), ("nthreads", C.c_int), ("refine", C.c_uint), ("refine_distance", C.c_float)]
 
 
 class Oracle:
@@ -134,7 +137,7 @@ class Oracle:
 
     def simulate(self, geom, gensteps, input_photons=None, event_id=0, photon_offset=0, max_bounce=31, max_record=32,
                  tmin=0.05, tmin0=0.05, tmax=1e6, max_time=1e27, eps0mask=0x37, hit_mask=0x40, seed=0, offset=0, skipahead=100000,
-                 hd_factor=20, debug_tag=True, use_boxes=False, nthreads=0, arrays=True, lite=False, tags=False):
+                 hd_factor=20, debug_tag=True, use_boxes=False, nthreads=0, arrays=True, lite=False, tags=False, refine=0, refine_distance=5000.0):
         fd = geom["foundry"]
         a = {k: np.ascontiguousarray(fd[k], dtype=(np.int32 if k == "solid" else np.float32)) for k in ("solid", "prim", "node", "plan", "itra", "inst")}
         bnd = np.ascontiguousarray(geom["bnd"], dtype=np.float32)
@@ -145,7 +148,7 @@ class Oracle:
         n = int(gs.view(np.uint32)[:, 0, 3].sum())
         ip = None if input_photons is None else np.ascontiguousarray(input_photons, dtype=np.float32)
         cfg = OracleConfig(max_bounce, max_record, event_id, 1 if debug_tag else 0, tmin, tmin0, tmax, max_time, eps0mask, hit_mask,
-                           seed, offset, skipahead, photon_offset, int(use_boxes), nthreads)
+                           seed, offset, skipahead, photon_offset, int(use_boxes), nthreads, refine, refine_distance)
         photon = np.zeros((n, 4, 4), dtype=np.float32)
         record = np.zeros((n, max_record, 4, 4), dtype=np.float32) if arrays else None
         seq = np.zeros((n, 2, 2), dtype=np.uint64) if arrays else None

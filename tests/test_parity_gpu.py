@@ -4,10 +4,17 @@
    (3) itself across launch slicing / rank sharding / BVH vs brute force / host vs device-resident paths.
 
 Tolerances (north_star): history flags, boundaries, identities, indices bit-exact; positions, times,
-wavelengths within 1e-4 relative.  Photons whose float arithmetic lands on the other side of a branch
-(nvcc contracts a*b+c differently in different inlining contexts, so even two builds of the SAME
-reference source differ in the last ulp of quadratic roots) take a different history; the tests bound
-their fraction (<= 0.2 %) and compare floats only on photons with identical histories.
+wavelengths within 1e-4 relative.
+
+* With FMA contraction off on both sides (csrc/libphox_nofma.so against oracle/_ref/libphoxref_*_nofma.so, `make parity`)
+  EVERY photon of every workload is identical - integer data AND every float bit
+  (test_nofma_builds_are_bit_identical_to_reference_headers): the two code bases evaluate the same expressions in the
+  same order.
+* In the default build (the reference's own flags: no -fmad option, CSGOptiX/CMakeLists.txt:47-57) nvcc fuses a*b+c
+  differently in the two code bases - it does so even between two inlining contexts of ONE code base - so a photon whose
+  branch variable lies within the last bit of its threshold takes the other branch.  Measured (profiles/parity_r2.json,
+  with the bounce, the decision and the distance of every such photon): 0 to 8 photons of 30 000; the tests bound the
+  fraction at 5e-4 and check the floats of ALL matching photons (max, not a quantile) against a per-workload bound.
 """
 import os
 
@@ -39,20 +46,25 @@ def rel_err(a, b):
     return np.abs(a[:, :3, :] - b[:, :3, :]) / scale
 
 
-def float_tol(name):
-    # sphere_leak is a chaotic billiard: 31 specular reflections inside a sphere amplify 1-ulp differences
-    # exponentially; only there the end-of-history tolerance is loosened, per-step records stay at 1e-4
-    return 5e-3 if name.startswith("sphere_leak") else 1e-4
+# Largest float error over ALL photons with matching histories, default build (profiles/parity_r2.json).  Beyond 1e-4 the
+# gap opens at a grazing intersect with a curved surface (sqrt of a tiny discriminant: one ulp in, 1e-3 of t out) and, in
+# the sphere_leak billiard, is then amplified by 31 specular bounces; flat-faced geometry stays at 1e-5.  The bound that
+# holds everywhere is the one of the nofma pair: 0.
+MAX_FLOAT_ERR = {"sipm8x8_scint": 1e-4, "raindrop_cerenkov": 1e-6, "sphere_leak_torch": 3e-2, "pmt_wall_torch": 3e-2,
+                 "boolean_zoo_torch": 5e-2, "scintillator_tank": 1e-2}
+MIN_SAME = 0.9995            # measured: >= 0.99973 on every workload, both RNG modes
 
 
-def check_against(name, p, seq, ref_p, ref_seq, min_same=0.998, float_q=0.9995):
+def check_against(name, p, seq, ref_p, ref_seq, min_same=MIN_SAME, float_q=0.9995, max_err=None, q_tol=1e-4):
     pu, ru = p.view(np.uint32), ref_p.view(np.uint32)
     same = (pu[:, 3, :] == ru[:, 3, :]).all(axis=1) & (pu[:, 1, 3] == ru[:, 1, 3])          # q3 flags/identity/index + hitcount_iindex
     if seq is not None and ref_seq is not None:
         same &= (seq == ref_seq).all(axis=(1, 2))                                            # seqhis AND seqbnd
     assert same.mean() >= min_same, "%s: identical integer data for only %.5f of photons" % (name, same.mean())
     r = rel_err(p[same], ref_p[same])
-    assert np.quantile(r, float_q) < float_tol(name), "%s: float q%.4f rel err %.3g" % (name, float_q, np.quantile(r, float_q))
+    assert np.quantile(r, float_q) < q_tol, "%s: float q%.4f rel err %.3g" % (name, float_q, np.quantile(r, float_q))
+    if max_err is not None:
+        assert r.max() <= max_err, "%s: max float rel err over all matching photons %.3g" % (name, r.max())
     return same.mean()
 
 
@@ -68,7 +80,11 @@ def test_photon_by_photon_vs_reference_headers(name, kw, variant):
         sim.set_config(accel=accel)
         hits = sim.simulate_np(w["gensteps"], 0, w["input_photons"])
         p, seq = sim.get_array("photon"), sim.get_array("seq")
-        frac = check_against("%s/%s/accel%d" % (name, variant, accel), p, seq, ref["photon"], ref["seq"])
+        # the production build of the reference keeps no seq array: photons that part and end on the same final flags cannot be
+        # told from matching ones there, so the max over "matching" photons is only asserted where histories are compared
+        frac = check_against("%s/%s/accel%d" % (name, variant, accel), p, seq, ref["photon"], ref["seq"],
+                             max_err=MAX_FLOAT_ERR[name] if variant == "debugtag" else None,
+                             q_tol=5e-4 if name.startswith("sphere_leak") else 1e-4)
         # hits = stable compaction of the photon array
         fm = p.view(np.uint32)[:, 3, 3]
         sel = (fm & 0x40) == 0x40
@@ -79,9 +95,37 @@ def test_photon_by_photon_vs_reference_headers(name, kw, variant):
             ns = 4 if name.startswith("sphere_leak") else rec.shape[1]          # step records: first bounces of the billiard
             rr = np.abs(rec[same][:, :ns, :3, :] - ref["record"][same][:, :ns, :3, :]) / np.maximum(1.0, np.abs(ref["record"][same][:, :ns, :3, :]))
             assert np.quantile(rr, 0.9995) < 1e-4
+            assert rr.max() <= MAX_FLOAT_ERR[name]
             assert (prd.view(np.uint32)[same][:, :, 1, 2:] == ref["prd"].view(np.uint32)[same][:, :, 1, 2:]).mean() > 0.9999   # identity, prim|boundary
         print(name, variant, accel, "identical fraction %.5f" % frac, "hits", len(hits), "rays", sim.stats()["num_ray"], ref["nray"])
     sim.close()
+
+
+def test_nofma_builds_are_bit_identical_to_reference_headers(tmp_path):
+    """with -fmad=false on both sides the engine and the reference's device headers agree on EVERY photon
+    of all six workloads x both RNG-consumption modes x brute force / BVH - history flags, boundaries, identities, seqhis,
+    seqbnd, and every bit of every float.  Runs tests/_parity.py in a process of its own (the library is chosen at import)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "eic-opticks_b200", "csrc", "libphox_nofma.so")
+    assert os.path.exists(lib), "run __graft_entry__.build() (make -C eic-opticks_b200/csrc parity)"
+    for v in ("debugtag", "production"):
+        assert os.path.exists(os.path.join(ORACLE, "_ref", "libphoxref_%s_nofma.so" % v)), "oracle/_ref/*_nofma.so missing: build where /root/reference exists"
+    out = tmp_path / "parity_nofma.json"
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "_parity.py"), "--build", "nofma", "--out", str(out)],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    rep = json.load(open(out))
+    assert len(rep["entries"]) == 6 * 2 * 2
+    for e in rep["entries"]:
+        tag = (e["workload"], e["rng_mode"], e["accel"])
+        assert e["identical_integer_data"] == e["photons"], tag
+        assert e["float_bits_identical_fraction_of_matching"] == 1.0 and e["max_ulp_matching"] == 0, tag
+        if e["rng_mode"] == "debugtag":
+            assert e["max_rel_err_step_records"] == 0.0, tag
+    assert rep["all_identical"]
 
 
 @pytest.mark.parametrize("name,kw", CASES)
@@ -95,7 +139,8 @@ def test_photon_by_photon_vs_cpu_oracle(name, kw):
     # dispersive tables: the oracle's emulation of the texture filter matches the hardware bit for bit on 97.4 % of
     # fetches (see test_oracle_texture_emulation_vs_hardware); the others move lengths by up to 1/256 of a table step
     fq = 0.98 if name == "scintillator_tank" else 0.9995
-    check_against(name + "/oracle", p, seq, orc["photon"], orc["seq"], min_same=0.99 if name == "scintillator_tank" else 0.995, float_q=fq)
+    check_against(name + "/oracle", p, seq, orc["photon"], orc["seq"], min_same=0.99 if name == "scintillator_tank" else 0.995, float_q=fq,
+                  q_tol=5e-3 if name.startswith("sphere_leak") else 1e-4)      # host libm (sinf, logf ...) differs from CUDA's by ulps: the billiard amplifies them
     assert abs(len(hits) - orc["nhit"]) <= max(5, 0.005 * len(p))
     sim.close()
 
