@@ -112,6 +112,15 @@ class ClockSampler:
                 "samples": len(self.sm), "power_w_max": max(self.power) if self.power else None}
 
 
+def host_threads():
+    """host threads this process may run on.  Asked for explicitly: under torch.distributed.run the environment carries
+    OMP_NUM_THREADS=1, which would otherwise turn the CPU arm into a single-thread run (SCALE_r01: 41 k photons/s, timeouts)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def oracle_throughput(w, sample_photons, nthreads=0):
     """time the CPU oracle on the first gensteps of the workload holding ~sample_photons photons"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -128,7 +137,7 @@ def oracle_throughput(w, sample_photons, nthreads=0):
         sub, ipn = gs[:k], None
         n = int(num[:k].sum())
     orc = Oracle()
-    threads = orc.num_threads() if nthreads <= 0 else nthreads
+    threads = host_threads() if nthreads <= 0 else nthreads
     t0 = time.perf_counter()
     r = orc.simulate(w["geom"], sub, ipn, max_bounce=w["config"].get("max_bounce", 31), use_boxes=2, nthreads=threads, arrays=False)
     dt = time.perf_counter() - t0
@@ -171,8 +180,10 @@ def main():
         print(json.dumps({
             "impl": "reference", "metric": "photons propagated/sec", "value": value, "unit": "photons/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / len(vals), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": {"workload": args.workload, "photons_per_step": vals[0]["photons"], "max_bounce": w["config"].get("max_bounce", 31),
-                                                            "note": "CPU oracle port of the reference path (Geant4 and the OptiX build cannot be installed here)"},
+            "dtype": "f32", "data": "synthetic", "config": {"workload": args.workload, "photons_per_gpu_per_step": args.photons, "cpu_sample_photons_per_step": vals[0]["photons"],
+                                                            "max_bounce": w["config"].get("max_bounce", 31), "host_threads": vals[0]["cores"],
+                                                            "note": "CPU oracle port of the reference path (Geant4 and the OptiX build cannot be installed here); each step is a bounded sample "
+                                                                    "of the GPU arm's workload (its first gensteps), the rate is per photon"},
             "cpu_baseline": {"value": value, "unit": "photons/s", "cores": vals[0]["cores"], "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "photons/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}))
@@ -209,14 +220,14 @@ def main():
     h_hits = torch.empty((max(cnt_r, 1), 4, 4), dtype=torch.float32).pin_memory()
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)     # 256 MB > 126 MB L2
 
+    # N > 1: every event's hits end up on rank 0 (the reference hands hits to one host process).  The gather of event k is posted
+    # on a second stream after event k+1 was launched and travels while it runs; staging and receive buffers are allocated once.
+    gather = parallel.PipelinedHitGather(max(1024, cnt_r // 4), dev, dst=0) if world > 1 else None
+
     def step_device(event_id):
         sim.simulate_device(d_gs.data_ptr(), len(gs_r), d_ip.data_ptr() if d_ip is not None else 0, 0 if ip_r is None else len(ip_r), event_id, off_r)
-        if world > 1:
-            nh = sim.num_hit()
-            hits = torch.empty((nh, 4, 4), dtype=torch.float32, device=dev)
-            if nh:
-                sim.get_hits_device(hits.data_ptr())
-            parallel.gather_hits(hits, dst=0)          # the event's hits end up on one rank, like on the reference's one host process
+        if gather is not None:
+            gather.push(sim)
 
     def step_e2e(event_id):
         gs_np = h_gs.numpy(); ip_np = h_ip.numpy() if h_ip is not None else None
@@ -247,6 +258,13 @@ def main():
             st = sim.stats()
             for key in st_sum:
                 st_sum[key] += st[key]
+        if gather is not None and fn is step_device:
+            # the last event's gather is part of the job: post it and wait for it inside the timed region
+            t0 = time.perf_counter()
+            gather.drain()                             # posts the gather of the last event and synchronises its stream
+            drain_ms = 1e3 * (time.perf_counter() - t0)
+            ms += drain_ms
+            st_sum["gather_drain_ms"] = round(drain_ms, 3)
         barrier()
         clocks = sampler.stop() if sampler else None
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -324,7 +342,8 @@ def main():
             "config": {"workload": args.workload, "photons_per_gpu_per_step": cnt_r, "gensteps_per_gpu": int(len(gs_r)), "max_bounce": sim.cfg.max_bounce,
                        "event_mode": "Minimal", "rng_mode": "DEBUG_TAG", "accel": "two-level BVH", "kernel_mode": args.kernel_mode, "max_slot": args.max_slot,
                        "l2": "256 MB flush between timed steps",
-                       "sharding": "gensteps partitioned over ranks, absolute photon offsets, hits gathered to rank 0 (NCCL send/recv) each step" if world > 1 else "single GPU"},
+                       "sharding": "gensteps partitioned over ranks, absolute photon offsets, every event's hits gathered to rank 0 (NCCL send/recv on a second stream, "
+                                   "overlapped with the next event; the last gather is drained inside the timed region)" if world > 1 else "single GPU"},
             "rays_per_s": st_dev["num_ray"] * world / (ms_dev * 1e-3), "bounces_per_photon": st_dev["num_ray"] / max(1, cnt_r * args.steps),
             "hit_fraction": f_hit, "step_ms": st_dev["step_ms"], "e2e_step_ms": st_e2e["step_ms"],
             "e2e": {"value": e2e, "unit": "photons/s", "h2d_bytes_per_step": int(gs_r.nbytes + (ip_r.nbytes if ip_r is not None else 0)),
@@ -342,7 +361,7 @@ def main():
                                  "ncu traffic and stall breakdown in profiles/"},
             "clocks": clocks,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:         # N = 1 only: at N > 1 the other ranks would idle in a barrier behind a CPU loop
             wc = workloads.WORKLOADS[args.workload](num_photon=min(args.photons, args.cpu_sample * 2))
             cb = oracle_throughput(wc, args.cpu_sample)
             out["cpu_baseline"] = {"value": cb["value"], "unit": "photons/s", "cores": cb["cores"], "kind": "port",

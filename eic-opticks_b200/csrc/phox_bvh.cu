@@ -113,6 +113,9 @@ __global__ void __launch_bounds__(1024) k_ploc(const float* __restrict__ boxes, 
                 float a = merged_area(cb + 6 * i, cb + 6 * j);
                 if (a < best) { best = a; bj = j; }
             }
+            // boxes are validated as finite before the build; should an area still come out inf / NaN, fall back to the
+            // neighbour in Morton order so that every round merges at least one pair and the loop terminates
+            if (bj < 0) bj = i + 1 < count ? i + 1 : i - 1;
             nn[i] = bj;
         }
         __syncthreads();

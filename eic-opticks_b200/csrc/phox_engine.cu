@@ -203,8 +203,8 @@ extern "C" phox_context* phox_create(int device) {
     e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     ctx->stream = ctx->own_stream;
     for (int k = 0; k < 4 && e == cudaSuccess; k++) e = cudaEventCreate(&ctx->ev[k]);
-    if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_counters, 4 * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = ctx->d_counters.reserve(4);
+    if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_counters, 8 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = ctx->d_counters.reserve(8);
     if (e != cudaSuccess) {
         g_create_error = std::string("phox_create: ") + cudaGetErrorString(e);
         delete ctx;
@@ -332,6 +332,33 @@ extern "C" int phox_set_geometry(phox_context* ctx, const void* solid_, int64_t 
         if (node[n].typecode() == CSG_CONVEXPOLYHEDRON && (int64_t)node[n].u[0] + node[n].u[1] > nplan)
             return ctx->fail(PHOX_E_ARG, "phox_set_geometry: convexpolyhedron planes outside plan array");
     }
+    // The BVH builder needs finite, ordered boxes (a NaN / inf box never finds a merge partner), and the CSG evaluators index
+    // nodes relative to the prim's root: check both here so that a malformed foundry is an error code, not a hung or faulting GPU.
+    for (int64_t p = 0; p < nprim; p++) {
+        for (int k = 0; k < 3; k++) {
+            float lo = prim[p].f[8 + k], hi = prim[p].f[11 + k];
+            if (!std::isfinite(lo) || !std::isfinite(hi) || !(lo <= hi))
+                return ctx->fail(PHOX_E_ARG, "phox_set_geometry: prim bounding box is not finite or has lo > hi");
+        }
+        const int nn = prim[p].num_node(), no = prim[p].node_offset();
+        const Node& root = node[no];
+        const unsigned tc = root.typecode();
+        if (tc < CSG_NODE && tc != CSG_ZERO) {                       // boolean tree: complete binary tree of subNum nodes, list nodes may follow it
+            const unsigned sub = root.sub_num();
+            if (sub < 1u || sub > (unsigned)nn || ((sub + 1u) & sub) != 0u || sub > 255u)
+                return ctx->fail(PHOX_E_ARG, "phox_set_geometry: tree root subNum is not 2^h - 1 within the prim's nodes (h <= 7)");
+        }
+        for (int k = 0; k < nn; k++) {
+            const Node& nd = node[no + k];
+            const unsigned t = nd.typecode();
+            if (t == CSG_CONTIGUOUS || t == CSG_DISCONTIGUOUS || t == CSG_OVERLAP) {
+                if ((uint64_t)nd.sub_offset() + nd.sub_num() > (uint64_t)nn || nd.sub_num() == 0u)
+                    return ctx->fail(PHOX_E_ARG, "phox_set_geometry: list node sub range outside the prim's nodes");
+                if (t == CSG_CONTIGUOUS && nd.sub_num() > 8u)
+                    return ctx->fail(PHOX_E_ARG, "phox_set_geometry: contiguous list node with more than 8 subs (csg_intersect_node.h enter sort)");
+            }
+        }
+    }
 
     // instances: default to one identity instance of solid 0 (what CSGFoundry::addInstance does for
     // the global remainder solid, sysrap/stree.h:6737-6747)
@@ -436,6 +463,9 @@ extern "C" int phox_set_geometry(phox_context* ctx, const void* solid_, int64_t 
         const Qat4& q = inst[i];
         int gas = q.i[7];
         if (gas < 0 || gas >= nsolid) return ctx->fail(PHOX_E_ARG, "phox_set_geometry: instance gas_idx outside solid array");
+        if (solid[gas].num_prim <= 0) return ctx->fail(PHOX_E_ARG, "phox_set_geometry: instance of a solid without prims");
+        for (int k = 0; k < 16; k++)
+            if (k % 4 != 3 && !std::isfinite(q.f[k])) return ctx->fail(PHOX_E_ARG, "phox_set_geometry: instance transform is not finite");
         float m[16];
         std::memcpy(m, q.f, 64);
         m[3] = m[7] = m[11] = 0.f; m[15] = 1.f;
@@ -850,9 +880,14 @@ static int check_gensteps(phox_context* ctx, const Genstep* gs, int64_t ngs, int
 extern "C" int phox_simulate(phox_context* ctx, const void* genstep_, int64_t ngs, const void* input_photon, int64_t ninput, int32_t event_id,
                              uint64_t photon_offset, double* launch_seconds) {
     if (!ctx) return PHOX_E_ARG;
-    if (!genstep_ || ngs <= 0) return ctx->fail(PHOX_E_ARG, "phox_simulate: no gensteps");       // QSim::simulate returns -1. here
+    if (ngs < 0 || (ngs > 0 && !genstep_)) return ctx->fail(PHOX_E_ARG, "phox_simulate: null genstep array");
     int rc = begin_event(ctx);
     if (rc) return rc;
+    if (ngs == 0) {          // a valid empty event (e.g. the share of a rank when an event has fewer gensteps than ranks): no launch, no hits
+        if (launch_seconds) *launch_seconds = 0.;
+        ctx->have_event = true;
+        return PHOX_OK;
+    }
     const Genstep* gs = (const Genstep*)genstep_;
     rc = check_gensteps(ctx, gs, ngs, ninput, input_photon != nullptr);
     if (rc) return rc;
@@ -902,20 +937,33 @@ extern "C" int phox_simulate(phox_context* ctx, const void* genstep_, int64_t ng
 extern "C" int phox_simulate_device(phox_context* ctx, const void* d_genstep, int64_t ngs, const void* d_input_photon, int64_t ninput,
                                     int32_t event_id, uint64_t photon_offset, double* launch_seconds) {
     if (!ctx) return PHOX_E_ARG;
-    if (!d_genstep || ngs <= 0) return ctx->fail(PHOX_E_ARG, "phox_simulate_device: no gensteps");
+    if (ngs < 0 || (ngs > 0 && !d_genstep)) return ctx->fail(PHOX_E_ARG, "phox_simulate_device: null genstep array");
     int rc = begin_event(ctx);
     if (rc) return rc;
+    if (ngs == 0) { if (launch_seconds) *launch_seconds = 0.; ctx->have_event = true; return PHOX_OK; }      // empty event, like phox_simulate
     double t0 = now_s();
     CK(ctx->d_prefix.reserve((size_t)ngs + 1));
-    k_genstep_prefix<<<1, 1024, 0, ctx->stream>>>((const Genstep*)d_genstep, (int)ngs, ctx->d_prefix.p);
+    // the prefix kernel reads every genstep anyway: it also reports what check_gensteps looks at on the host path
+    // ([0] bit 0 scintillation genstep, bit 1 input-photon genstep; [1] input-photon gensteps; [2] their numphoton)
+    unsigned* d_gsinfo = reinterpret_cast<unsigned*>(ctx->d_counters.p + 4);       // slots 4-5; 0 rays, 1 hit total, 3 work counter
+    CK(cudaMemsetAsync(d_gsinfo, 0, 16, ctx->stream));
+    k_genstep_prefix<<<1, 1024, 0, ctx->stream>>>((const Genstep*)d_genstep, (int)ngs, ctx->d_prefix.p, d_gsinfo);
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(ctx->h_counters + 2, ctx->d_prefix.p + ngs, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_counters + 4, d_gsinfo, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_counters + 6, ctx->d_prefix.p + ngs, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    int64_t n = (int64_t)ctx->h_counters[2];
+    int64_t n = (int64_t)ctx->h_counters[6];
+    unsigned gsinfo[4];
+    std::memcpy(gsinfo, ctx->h_counters + 4, 16);
     ctx->stats.num_kernel += 1;
-    if (n <= 0) return ctx->fail(PHOX_E_ARG, "phox_simulate_device: gensteps hold no photons");
     if (n > effective_max_slot(ctx)) return ctx->fail(PHOX_E_NOMEM, "phox_simulate_device: event exceeds max_slot; the device-resident path is single-launch");
-    (void)ninput;
+    if ((gsinfo[0] & 1u) && !ctx->icdf_tex) return ctx->fail(PHOX_E_STATE, "phox_simulate_device: scintillation genstep but no icdf table was set");
+    if (gsinfo[0] & 2u) {
+        if (!d_input_photon) return ctx->fail(PHOX_E_ARG, "phox_simulate_device: INPUT_PHOTON genstep without input photons");
+        if (gsinfo[1] != 1u || ngs != 1 || (int64_t)gsinfo[2] != ninput)
+            return ctx->fail(PHOX_E_ARG, "phox_simulate_device: input photons ride on exactly one INPUT_PHOTON genstep with numphoton == ninput");
+    }
+    if (n == 0) { if (launch_seconds) *launch_seconds = now_s() - t0; ctx->have_event = true; return PHOX_OK; }
     rc = run_launch(ctx, (const Genstep*)d_genstep, ctx->d_prefix.p, (int)ngs, (const Photon*)d_input_photon, photon_offset, photon_offset, n, event_id);
     if (rc) return rc;
     if (mode_keeps_photon(ctx->cfg.event_mode)) { rc = gather_debug(ctx, n); if (rc) return rc; }

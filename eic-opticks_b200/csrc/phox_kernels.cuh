@@ -840,7 +840,9 @@ __global__ void __launch_bounds__(kHitTile) k_hit_compact(const Photon* __restri
 }
 
 // numphoton prefix of device-resident gensteps (one block)
-__global__ void k_genstep_prefix(const Genstep* __restrict__ gs, int n, unsigned long long* __restrict__ prefix) {
+// info (zeroed by the caller): [0] bit 0 = a scintillation genstep is present, bit 1 = an input-photon genstep is present,
+// [1] = number of input-photon gensteps, [2] = numphoton of (the last) one - the device-path form of check_gensteps
+__global__ void k_genstep_prefix(const Genstep* __restrict__ gs, int n, unsigned long long* __restrict__ prefix, unsigned* __restrict__ info) {
     __shared__ unsigned long long s[1024];
     __shared__ unsigned long long carry;
     if (threadIdx.x == 0) { carry = 0ull; prefix[0] = 0ull; }
@@ -848,6 +850,11 @@ __global__ void k_genstep_prefix(const Genstep* __restrict__ gs, int n, unsigned
     for (int base = 0; base < n; base += 1024) {
         int i = base + threadIdx.x;
         unsigned long long v = i < n ? (unsigned long long)gs[i].u[3] : 0ull;
+        if (i < n && info) {
+            int code = gs[i].gencode();
+            if (code == GS_SCINTILLATION || code == GS_DsG4Scintillation_r4695) atomicOr(info, 1u);
+            if (code == GS_INPUT_PHOTON) { atomicOr(info, 2u); atomicAdd(info + 1, 1u); info[2] = gs[i].u[3]; }
+        }
         s[threadIdx.x] = v;
         __syncthreads();
         for (int off = 1; off < 1024; off <<= 1) {

@@ -19,10 +19,13 @@ from its published algorithms: G4PhysicsVector::Value (linear interpolation, cla
 G4MaterialPropertiesTable::CalculateGROUPVEL, G4GDMLRead rotation convention (rotateX, rotateY, rotateZ,
 placement with the inverse), G4Scintillation's trapezoid integral of the emission spectrum.
 
-Not covered (asserts, like the reference does for phi segments u4/U4Solid.h:555-561): phi/theta segments,
-trap, polyhedra, torus, assemblies, replicas, NIST materials by name, instancing (FREQ_CUT 500).
+Covered beyond plain placements: <assembly> imprints, instancing by repeated subtree digests (stree::factorize, FREQ_CUT 500).
+Not covered (asserts, like the reference does for phi segments u4/U4Solid.h:555-561): phi segments of tubs / sphere,
+trap, polyhedra, torus, cut tubs, replicas, NIST materials by name.
 """
+import ast
 import math
+import operator
 import os
 import re
 import xml.etree.ElementTree as ET
@@ -64,7 +67,28 @@ class Evaluator:
             return default
         e = e.replace("^", "**")
         e = re.sub(r"\[([^\]]+)\]", r"_\1", e)           # name[i] style indexing -> name_i
-        return float(eval(e, {"__builtins__": {}}, self.ns))
+        return float(self._eval(ast.parse(e, mode="eval").body))
+
+    _BIN = {ast.Add: operator.add, ast.Sub: operator.sub, ast.Mult: operator.mul, ast.Div: operator.truediv, ast.Pow: operator.pow,
+            ast.Mod: operator.mod, ast.FloorDiv: operator.floordiv}
+    _UN = {ast.UAdd: operator.pos, ast.USub: operator.neg}
+
+    def _eval(self, node):
+        """arithmetic only: numbers, names of the GDML namespace, + - * / ** % unary +-, calls of the math functions.  GDML files are
+        input data, so attribute strings never reach Python's eval (an empty __builtins__ is not a sandbox)"""
+        if isinstance(node, ast.Constant) and isinstance(node.value, (int, float)) and not isinstance(node.value, bool):
+            return node.value
+        if isinstance(node, ast.Name):
+            if node.id not in self.ns or callable(self.ns[node.id]):
+                raise ValueError("GDML expression: unknown name %r" % node.id)
+            return self.ns[node.id]
+        if isinstance(node, ast.BinOp) and type(node.op) in self._BIN:
+            return self._BIN[type(node.op)](self._eval(node.left), self._eval(node.right))
+        if isinstance(node, ast.UnaryOp) and type(node.op) in self._UN:
+            return self._UN[type(node.op)](self._eval(node.operand))
+        if isinstance(node, ast.Call) and isinstance(node.func, ast.Name) and node.func.id in MATH and not node.keywords:
+            return MATH[node.func.id](*[self._eval(a) for a in node.args])
+        raise ValueError("GDML expression: %s is not allowed" % type(node).__name__)
 
     def set(self, name, value):
         self.ns[name] = value

@@ -114,7 +114,7 @@ def sipm8x8():
                                            scintillation_time=21.5))
 
 
-def pmt_wall(nx=100, ny=100, pitch=250.0):
+def pmt_wall(nx=100, ny=100, pitch=250.0, sensor_a=False):
     """Synthetic instanced PMT wall (BASELINE config 4): solid 0 = water world box, solid 1 = one
     PMT (glass bulb = sphere union neck cylinder, inner vacuum sphere behind a photocathode
     surface), instanced nx*ny times on a grid with sensor identifiers 0..n-1."""
@@ -123,7 +123,10 @@ def pmt_wall(nx=100, ny=100, pitch=250.0):
     bt.add_material(T.Material("Water", RINDEX=(en, [1.333, 1.333]), ABSLENGTH=(en, [30000.0, 30000.0]), RAYLEIGH=(en, [50000.0, 50000.0])))
     bt.add_material(T.Material("Pyrex", RINDEX=(en, [1.47, 1.47]), ABSLENGTH=(en, [1000.0, 1000.0])))
     bt.add_material(T.Material("Vacuum", RINDEX=(en, [1.0, 1.0])))
-    bt.add_surface(T.Surface("Photocathode", EFFICIENCY=(en, [0.25, 0.25])))
+    # sensor_a: the optical surface is named '#...' so that its optical row carries ems 3 (smatsur_Surface_zplus_sensor_A,
+    # sysrap/smatsur.h:8-16, sstandard.h:311-441): hits on the upper hemisphere of the bulb (lposcost >= 0) detect
+    # unconditionally (qsim::propagate_at_surface_Detect), the lower hemisphere falls back to the ordinary surface model
+    bt.add_surface(T.Surface("Photocathode", EFFICIENCY=(en, [0.25, 0.25]), optical_surface_name="#Photocathode" if sensor_a else None))
     b_world = bt.boundary("Water", "", "", "Water")
     b_glass = bt.boundary("Water", "", "", "Pyrex")
     b_vac = bt.boundary("Pyrex", "Photocathode", "Photocathode", "Vacuum")
@@ -236,3 +239,60 @@ def scintillator_tank():
     e = np.linspace(2.0, 4.0, 41)
     icdf = T.make_icdf(e, np.exp(-0.5 * ((e - 2.9) / 0.25) ** 2))
     return _finish(fd, bt, icdf, extra=dict(ls_line=bt.material_line("LS"), scintillation_time=4.5))
+
+
+def far_wall(distance=12000.0):
+    """Large scene for PropagateRefine (CSGOptiX/CSGOptiX7.cu:146-185): intersect distances well beyond the default
+    PropagateRefineDistance of 5000 mm.  A 30 m water box with a glass sphere, a tubs and a sensor slab ~2 x distance
+    away from the source plane."""
+    bt = T.BoundaryTable()
+    en = [1.55, 6.2]
+    bt.add_material(T.Material("Rock"))
+    bt.add_material(T.Material("Water", RINDEX=(en, [1.333, 1.35]), ABSLENGTH=(en, [60000.0, 40000.0]), RAYLEIGH=(en, [80000.0, 40000.0])))
+    bt.add_material(T.Material("Glass", RINDEX=(en, [1.48, 1.52]), ABSLENGTH=(en, [5000.0, 3000.0])))
+    bt.add_surface(T.implicit_surface("Implicit_RINDEX_NoRINDEX_water_rock"))
+    bt.add_surface(T.Surface("SensorSkin", EFFICIENCY=(en, [0.5, 0.5])))
+    fd = F.Foundry()
+    fd.begin_solid("r0")
+    fd.add_prim(F.box3(32000, 32000, 32000), bt.boundary("Rock", "", "", "Rock"), name="Rock")
+    fd.add_prim(F.box3(30000, 30000, 30000), bt.boundary("Rock", "Implicit_RINDEX_NoRINDEX_water_rock", "Implicit_RINDEX_NoRINDEX_water_rock", "Water"), name="Water")
+    fd.add_prim(F.sphere(1500.0), bt.boundary("Water", "", "", "Glass"), F.translate(0, 0, -distance), name="FarSphere")
+    fd.add_prim(F.difference(F.cylinder(1200.0, -400.0, 400.0), F.cylinder(900.0, -404.0, 404.0)), bt.boundary("Water", "", "", "Glass"),
+                F.rotate_x(20.0) @ F.translate(2500.0, 0, -distance + 2000.0), name="FarTubs")
+    fd.add_prim(F.box3(6000, 6000, 100), bt.boundary("Water", "SensorSkin", "SensorSkin", "Glass"), F.translate(-3000.0, 1000.0, -distance - 2000.0), name="FarSensor")
+    fd.end_solid()
+    return _finish(fd, bt)
+
+
+def halfspace_zoo():
+    """Solids cut by CSG_HALFSPACE leaves (CSG/csg_intersect_leaf_halfspace.h:156-193): the unbounded leaf, its
+    'exit at infinity' signalling (isect.y = -0.f) inside intersections, a complemented halfspace (difference) and a
+    transformed one, all glass in water inside an absorbing rock box."""
+    bt = T.BoundaryTable()
+    en = [1.55, 6.2]
+    bt.add_material(T.Material("Rock"))
+    bt.add_material(T.Material("Water", RINDEX=(en, [1.333, 1.35]), ABSLENGTH=(en, [2000.0, 1500.0]), RAYLEIGH=(en, [800.0, 400.0])))
+    bt.add_material(T.Material("Glass", RINDEX=(en, [1.48, 1.52]), ABSLENGTH=(en, [500.0, 300.0])))
+    bt.add_surface(T.implicit_surface("Implicit_RINDEX_NoRINDEX_water_rock"))
+    bt.add_surface(T.Surface("SensorSkin", EFFICIENCY=(en, [0.5, 0.5])))
+    b_water = bt.boundary("Rock", "Implicit_RINDEX_NoRINDEX_water_rock", "Implicit_RINDEX_NoRINDEX_water_rock", "Water")
+    b_glass = bt.boundary("Water", "", "", "Glass")
+    b_sens = bt.boundary("Water", "SensorSkin", "SensorSkin", "Glass")
+    fd = F.Foundry()
+    fd.begin_solid("r0")
+    fd.add_prim(F.box3(1400, 1400, 1400), bt.boundary("Rock", "", "", "Rock"), name="Rock")
+    fd.add_prim(F.box3(1200, 1200, 1200), b_water, name="Water")
+    s3 = 1.0 / np.sqrt(3.0)
+    shapes = [
+        ("sphere_cut_z", F.intersection(F.sphere(120), F.halfspace(0, 0, 1, 40.0)), b_glass),
+        ("box_minus_halfspace", F.difference(F.box3(200, 200, 200), F.halfspace(s3, s3, s3, 20.0)), b_sens),
+        ("cyl_two_cuts", F.intersection(F.intersection(F.cylinder(90, -120, 120), F.halfspace(1, 0, 0, 30.0)), F.halfspace(0, -1, 0, 50.0)), b_glass),
+        ("sphere_cut_rotated", F.intersection(F.sphere(110), F.halfspace(0, 0, 1, 0.0).placed(F.rotate_x(40.0) @ F.translate(0, 0, 25.0))), b_glass),
+    ]
+    centers = []
+    for k, (name, shape, b) in enumerate(shapes):
+        c = (-250.0 + (k % 2) * 500.0, -250.0 + (k // 2) * 500.0, 0.0)
+        centers.append(c)
+        fd.add_prim(shape, b, F.rotate_z(15.0 * k) @ F.translate(*c), mesh_idx=k + 2, name=name)
+    fd.end_solid()
+    return _finish(fd, bt, extra=dict(shape_centers=np.array(centers, dtype=np.float32), shape_names=[s[0] for s in shapes]))

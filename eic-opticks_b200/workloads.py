@@ -131,3 +131,80 @@ def scintillator_tank(num_photon=1_000_000, photons_per_genstep=500, seed=SEED):
 
 
 WORKLOADS["scintillator_tank"] = scintillator_tank
+
+
+# ---- workloads for the arms of the path the BASELINE configs do not reach -----------------------------
+def far_wall_torch(num_photon=100_000):
+    """PropagateRefine scene: torch disc 24 m from the solids it lights, so 0.99 t exceeds the default 5000 mm refine distance"""
+    geom = GEO.far_wall()
+    t = dict(pos=[0.0, 0.0, 12000.0], time=0.0, mom=[0.0, 0.0, -1.0], pol=[1.0, 0.0, 0.0], wavelength=430.0, radius=4000.0, numphoton=num_photon,
+             type="disc")
+    return dict(name="far_wall_torch", geom=geom, gensteps=G.torch_genstep(t, num_photon), input_photons=None,
+                config=dict(propagate_refine=1, refine_distance=5000.0), num_photon=num_photon)
+
+
+# rectangle first: its side index is photon_id / (numphoton / 4) with the ABSOLUTE photon id, so only a genstep that
+# starts the event (ids 0 .. numphoton-1) lands on sides 0..3 (sysrap/storch.h:470-510)
+TORCH_SHAPES = ("rectangle", "disc", "sphere", "sphere_marsaglia", "line", "point", "circle")
+
+
+def torch_shapes(num_photon=20_000, shapes=TORCH_SHAPES):
+    """one on-device storch genstep per source type (sysrap/storch.h:189-516) inside the boolean zoo; the index-driven types
+    (line, circle, rectangle) take their fraction from the ABSOLUTE photon id over the genstep's numphoton like the reference"""
+    geom = GEO.boolean_zoo()
+    per = max(4, num_photon // len(shapes)) // 4 * 4
+    gss = []
+    for k, ty in enumerate(shapes):
+        t = dict(pos=[30.0 * k, -20.0 * k, 250.0], time=0.1 * k, mom=G._normalize_f32([0.2, -0.1, -1.0]), pol=[1.0, 0.0, 0.0], wavelength=400.0 + 20.0 * k,
+                 radius=150.0, numphoton=per, type=ty, zenith=[0.1, 0.9], azimuth=[0.05, 0.95], distance=0.3)
+        if ty == "rectangle":
+            t["zenith"], t["azimuth"] = [-300.0, 300.0], [-400.0, 400.0]           # z and x extents of the frame
+        if ty in ("sphere", "sphere_marsaglia"):
+            t["radius"] = -900.0 if ty == "sphere" else 60.0
+            t["pos"] = [0.0, 0.0, 0.0]
+        gss.append(G.torch_genstep(t, per))
+    gs = np.ascontiguousarray(np.concatenate(gss))
+    return dict(name="torch_shapes", geom=geom, gensteps=gs, input_photons=None, config=dict(), num_photon=per * len(shapes))
+
+
+def carrier_photons(num_photon=150):
+    """scarrier gensteps (sysrap/scarrier.h:47-58): the photon is carried in the genstep itself, y displaced by 10 mm per photon id"""
+    geom = GEO.boolean_zoo()
+    gs = G.empty_gensteps(2)
+    u = gs.view(np.uint32)
+    for k, (pos, mom, pol, wl) in enumerate((((-900.0, -800.0, 10.0), (1.0, 0.0, 0.0), (0.0, 1.0, 0.0), 500.0),
+                                             ((-900.0, -1500.0, -40.0), G._normalize_f32([1.0, 0.05, 0.02]), (0.0, 0.0, 1.0), 430.0))):
+        u[k, 0] = (G.GS_CARRIER, 0, 0, num_photon // 2)
+        gs[k, 2] = (pos[0], pos[1], pos[2], 0.5 * k)
+        gs[k, 3, :3] = mom; u[k, 3, 3] = 0
+        gs[k, 4] = (pol[0], pol[1], pol[2], wl)
+    return dict(name="carrier_photons", geom=geom, gensteps=gs, input_photons=None, config=dict(), num_photon=2 * (num_photon // 2))
+
+
+def pmt_wall_sensor_a(num_photon=40_000, nx=12, ny=12):
+    """ems 3 (zplus_sensor_A) photocathode: photons from above hit the upper hemisphere (lposcost >= 0: unconditional detect,
+    qsim.h:2184-2327, 1749-1755), photons from below reach the lower hemisphere through the glass (lposcost < 0: ordinary
+    surface model with the same optical row)"""
+    geom = GEO.pmt_wall(nx, ny, sensor_a=True)
+    hx, hy = geom["half"]
+    half = num_photon // 2
+    r = float(min(hx, hy) - 600.0)
+    top = G.torch_photons(dict(pos=[0.0, 0.0, 1500.0], time=0.0, mom=[0.0, 0.0, -1.0], pol=[1.0, 0.0, 0.0], wavelength=420.0, radius=r, numphoton=half, type="disc"), half, seed=0)
+    bot = G.torch_photons(dict(pos=[0.0, 0.0, -1500.0], time=0.0, mom=G._normalize_f32([0.05, 0.02, 1.0]), pol=[1.0, 0.0, 0.0], wavelength=450.0, radius=r, numphoton=half, type="disc"),
+                          half, seed=1)
+    ph = np.ascontiguousarray(np.concatenate([top, bot]))
+    ph.view(np.uint32)[:, 3, :] = 0
+    return dict(name="pmt_wall_sensor_a", geom=geom, gensteps=G.input_photon_genstep(len(ph)), input_photons=ph, config=dict(), num_photon=len(ph))
+
+
+def halfspace_zoo_torch(num_photon=30_000):
+    """halfspace-cut solids lit from an inward-facing sphere source"""
+    geom = GEO.halfspace_zoo()
+    t = dict(pos=[0.0, 0.0, 0.0], time=0.0, mom=[0.0, 0.0, 1.0], pol=[1.0, 0.0, 0.0], wavelength=440.0, radius=-580.0, numphoton=num_photon,
+             type="sphere", zenith=[0.0, 1.0], azimuth=[0.0, 1.0])
+    return dict(name="halfspace_zoo_torch", geom=geom, gensteps=G.torch_genstep(t, num_photon), input_photons=None, config=dict(), num_photon=num_photon)
+
+
+ARM_WORKLOADS = dict(far_wall_torch=far_wall_torch, torch_shapes=torch_shapes, carrier_photons=carrier_photons, pmt_wall_sensor_a=pmt_wall_sensor_a,
+                     halfspace_zoo_torch=halfspace_zoo_torch)
+WORKLOADS.update(ARM_WORKLOADS)

@@ -143,6 +143,9 @@ int phox_get_config(const phox_context* ctx, phox_config* cfg);
  *                  use absolute indices: CSGOptiX/CSGOptiX7.cu:415-419), so that a rank handling
  *                  a slice of a bigger event gives results identical to the whole-event run
  * Events bigger than max_slot run as several launches (sysrap/SGenstep.h:249-323).
+ * ngenstep == 0 (or gensteps that hold no photons) is a valid EMPTY event - no launch, zero hits, PHOX_OK: what a rank
+ * gets when an event has fewer gensteps than ranks.  (The SSimulator adaptor still answers -1. without gensteps like
+ * QSim::simulate, qudarap/QSim.cc:446.)
  * On return the launch seconds are in *launch_seconds (may be NULL). */
 int phox_simulate(phox_context* ctx,
                   const void* genstep, int64_t ngenstep,

@@ -27,6 +27,15 @@ CASES = [("sipm8x8_scint", dict(num_photon=30000, photons_per_genstep=100)),
          ("pmt_wall_torch", dict(num_photon=30000, nx=20, ny=20)),
          ("boolean_zoo_torch", dict(num_photon=40000)),
          ("scintillator_tank", dict(num_photon=30000, photons_per_genstep=100))]
+# arms of the path the six workloads above do not reach: PropagateRefine beyond 5000 mm, every torch
+# source type on the device, carrier gensteps, the zplus_sensor_A surface arm incl. lposcost < 0, halfspace-cut solids
+ARM_CASES = [("far_wall_torch", dict(num_photon=20000)),
+             ("torch_shapes", dict(num_photon=21000)),
+             # carrier: PRODUCTION build only.  scarrier::generate stores float4s through (quad4&)sphoton (sysrap/scarrier.h:49-56); in the
+             # as-built DEBUG_TAG layout offsetof(sctx, p) is 36, so those stores are misaligned and the reference kernel itself faults
+             ("carrier_photons", dict(num_photon=150, variants=("production",))),
+             ("pmt_wall_sensor_a", dict(num_photon=30000)),
+             ("halfspace_zoo_torch", dict(num_photon=30000))]
 
 FLAG_NAMES = {1: "CK", 2: "SI", 4: "TO", 8: "AB", 16: "RE", 32: "SC", 64: "SD", 128: "SA", 256: "DR", 512: "SR", 1024: "BR", 2048: "BT", 0: "--"}
 
@@ -105,11 +114,14 @@ def compare_case(name, kw, build, accels=(1, 0), max_listed=40):
     from eic_opticks_b200 import workloads
     from _ref import RefGPU
     sfx = "_nofma" if build == "nofma" else ""
+    kw = dict(kw)
+    variants = kw.pop("variants", ("debugtag", "production"))
     w = workloads.WORKLOADS[name](**kw)
     g = w["geom"]
     entries = []
-    for variant in ("debugtag", "production"):
-        ref = RefGPU(variant + sfx).simulate(g, w["gensteps"], w["input_photons"], max_bounce=w["config"].get("max_bounce", 31))
+    for variant in variants:
+        ref = RefGPU(variant + sfx).simulate(g, w["gensteps"], w["input_photons"], max_bounce=w["config"].get("max_bounce", 31),
+                                             refine=w["config"].get("propagate_refine", 0), refine_distance=w["config"].get("refine_distance", 5000.0))
         kwc = dict(w["config"])
         kwc.update(event_mode=ph.MODE_DEBUGHEAVY, rng_mode=(ph.RNG_DEBUG_TAG if variant == "debugtag" else ph.RNG_PRODUCTION))
         sim = ph.Simulator.Create(g["foundry"], g["bnd"], g["optical"], g["icdf"], **kwc)
@@ -120,6 +132,7 @@ def compare_case(name, kw, build, accels=(1, 0), max_listed=40):
             same = integer_identity(got["photon"], got["seq"], ref["photon"], ref["seq"])
             n = len(same)
             e = {"workload": name, "photons": int(n), "rng_mode": variant, "accel": "bvh" if accel == 0 else "brute",
+                 "rays_phox": int(sim.stats()["num_ray"]), "rays_ref": int(ref["nray"]),
                  "identical_integer_data": int(same.sum()), "identical_fraction": float(same.mean())}
             fa, fb = got["photon"][same][:, :3, :], ref["photon"][same][:, :3, :]
             ulp = ulp_distance(fa, fb)
@@ -181,7 +194,7 @@ def main():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     want = [c for c in args.cases.split(",") if c]
     entries = []
-    for name, kw in CASES:
+    for name, kw in CASES + ARM_CASES:
         if want and name not in want:
             continue
         entries += compare_case(name, kw, args.build)
