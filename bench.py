@@ -156,6 +156,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="diagnosis: do not sample NVML clocks during the timed region")
     ap.add_argument("--max-slot", type=int, default=0, help="photons per launch (0 = library default); an event is sliced at genstep granularity")
+    ap.add_argument("--accel", default="bvh", choices=["bvh", "nohome", "brute"], help="bvh = two-level BVH + home cells (default); nohome = BVH alone (A/B); brute = validation loop")
     ap.add_argument("--kernel-mode", default="auto", choices=["auto", "persistent", "wavefront"], help="form of the bounce loop (include/phox.h PHOX_KERNEL_*)")
     args = ap.parse_args()
 
@@ -210,6 +211,8 @@ def main():
     sim = ph.Simulator.Create(g["foundry"], g["bnd"], g["optical"], g["icdf"], device=local_rank, event_mode=ph.MODE_MINIMAL, kernel_mode=kmode, **w["config"])
     if args.max_slot > 0:
         sim.set_config(max_slot=args.max_slot)
+    if args.accel != "bvh":
+        sim.set_config(accel={"nohome": ph.ACCEL_BVH_NOHOME, "brute": ph.ACCEL_BRUTE}[args.accel])
     stream = torch.cuda.current_stream(dev)
     sim.set_stream(stream.cuda_stream)
 
@@ -239,7 +242,7 @@ def main():
         torch.cuda.synchronize(dev)
 
     def timed(fn, steps, sampler=None):
-        st_sum = dict(num_kernel=0, simulate_kernel_seconds=0.0, compact_kernel_seconds=0.0, num_ray=0, num_hit=0, num_launch=0)
+        st_sum = dict(num_kernel=0, simulate_kernel_seconds=0.0, compact_kernel_seconds=0.0, num_ray=0, num_hit=0, num_launch=0, num_home_ray=0)
         barrier()
         if sampler:
             sampler.begin()
@@ -292,7 +295,7 @@ def main():
 
     # per-kernel pass (not part of `value`): CUDA events between the kernels of the bounce loop, on the launch stream
     sim.set_profiling(True)
-    prof = dict(trace_kernel_seconds=0.0, propagate_kernel_seconds=0.0, num_trace_launch=0, num_ray=0, simulate_kernel_seconds=0.0)
+    prof = dict(trace_kernel_seconds=0.0, propagate_kernel_seconds=0.0, home_kernel_seconds=0.0, num_trace_launch=0, num_ray=0, num_home_ray=0, simulate_kernel_seconds=0.0)
     for k in range(min(args.steps, 3)):
         flush.fill_(float(k)); torch.cuda.synchronize(dev)
         step_device(100 + k)
@@ -340,12 +343,12 @@ def main():
             "metric": "photons propagated/sec", "value": value, "unit": "photons/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "photons_per_gpu_per_step": cnt_r, "gensteps_per_gpu": int(len(gs_r)), "max_bounce": sim.cfg.max_bounce,
-                       "event_mode": "Minimal", "rng_mode": "DEBUG_TAG", "accel": "two-level BVH", "kernel_mode": args.kernel_mode, "max_slot": args.max_slot,
+                       "event_mode": "Minimal", "rng_mode": "DEBUG_TAG", "accel": {"bvh": "two-level BVH + home cells", "nohome": "two-level BVH", "brute": "brute force"}[args.accel], "kernel_mode": args.kernel_mode, "max_slot": args.max_slot,
                        "l2": "256 MB flush between timed steps",
                        "sharding": "gensteps partitioned over ranks, absolute photon offsets, every event's hits gathered to rank 0 (NCCL send/recv on a second stream, "
                                    "overlapped with the next event; the last gather is drained inside the timed region)" if world > 1 else "single GPU"},
             "rays_per_s": st_dev["num_ray"] * world / (ms_dev * 1e-3), "bounces_per_photon": st_dev["num_ray"] / max(1, cnt_r * args.steps),
-            "hit_fraction": f_hit, "step_ms": st_dev["step_ms"], "e2e_step_ms": st_e2e["step_ms"],
+            "hit_fraction": f_hit, "home_ray_fraction": st_dev["num_home_ray"] / max(1, st_dev["num_ray"]), "step_ms": st_dev["step_ms"], "e2e_step_ms": st_e2e["step_ms"],
             "e2e": {"value": e2e, "unit": "photons/s", "h2d_bytes_per_step": int(gs_r.nbytes + (ip_r.nbytes if ip_r is not None else 0)),
                     "d2h_bytes_per_step": int(64 * st_e2e["num_hit"] / max(1, args.steps)), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(st_dev["num_kernel"] + st_e2e["num_kernel"]),
@@ -356,6 +359,7 @@ def main():
                          "bounce_loop_ms": loop_s * 1e3, "bounce_loop_share_of_step": st_dev["simulate_kernel_seconds"] / (ms_dev * 1e-3),
                          "path_algorithmic_bytes_per_photon": bytes_per_photon, "path_achieved_gbs": cnt_r * bytes_per_photon / loop_s / 1e9,
                          "propagate_kernel_ms": (prof["propagate_kernel_seconds"] / prof["num_trace_launch"] * 1e3) if wave else None,
+                         "home_kernel_ms": (prof["home_kernel_seconds"] / prof["num_trace_launch"] * 1e3) if wave else None,
                          "second_kernel": second,
                          "note": "the bounce loop is latency/issue bound, not HBM bound (geometry and tables are cache resident); "
                                  "ncu traffic and stall breakdown in profiles/"},

@@ -10,7 +10,7 @@ from . import lib                       # noqa: F401  ctypes binding (no CPU fal
 from . import foundry, tables, gensteps, geometries   # noqa: F401
 from .simulator import Simulator, Event  # noqa: F401
 from .lib import (PhoxError, MODE_MINIMAL, MODE_HITPHOTON, MODE_HITPHOTONSEQ, MODE_DEBUGLITE, MODE_DEBUGHEAVY,  # noqa: F401
-                  RNG_PRODUCTION, RNG_DEBUG_TAG, ACCEL_BVH, ACCEL_BRUTE,
+                  RNG_PRODUCTION, RNG_DEBUG_TAG, ACCEL_BVH, ACCEL_BRUTE, ACCEL_BVH_NOHOME,
                   KERNEL_AUTO, KERNEL_PERSISTENT, KERNEL_WAVEFRONT)
 
 __all__ = ["Simulator", "Event", "PhoxError", "lib", "foundry", "tables", "gensteps", "geometries"]

@@ -124,7 +124,9 @@ PHOX_D bool leaf_box3(float4& is, const float4& q0, float tmin, const float3& ro
     return leaf_box3_idir(is, q0, tmin, ro, rd, f3(1.f / rd.x, 1.f / rd.y, 1.f / rd.z));
 }
 
-PHOX_D bool leaf_box3_idir(float4& is, const float4& q0, float tmin, const float3& ro, const float3& rd, const float3& idir) {
+// The box leaf in two halves, so that a caller with several boxes to compare (the home-cell pass) can settle the
+// nearest distance first and work out one normal, for the winner.  box3_t: does the ray meet the box beyond tmin, and where.
+PHOX_D bool box3_t(float& t_out, const float4& q0, float tmin, const float3& ro, const float3& rd, const float3& idir) {
     float3 bmin = f3(-q0.x / 2.f, -q0.y / 2.f, -q0.z / 2.f);
     float3 bmax = f3(q0.x / 2.f, q0.y / 2.f, q0.z / 2.f);
     float3 t0 = f3((bmin.x - ro.x) * idir.x, (bmin.y - ro.y) * idir.y, (bmin.z - ro.z) * idir.z);
@@ -146,22 +148,30 @@ PHOX_D bool leaf_box3_idir(float4& is, const float4& q0, float tmin, const float
     else if (along_y) has = in_x && in_z;
     else if (along_z) has = in_x && in_y;
     else has = (t_far > t_near && t_far > 0.f);
+    if (!has) return false;
+    float t = tmin < t_near ? t_near : (tmin < t_far ? t_far : tmin);
+    t_out = t;
+    return t > tmin;
+}
+// ... and the face normal at distance t along the ray
+PHOX_D float3 box3_normal(const float4& q0, const float3& ro, const float3& rd, float t) {
+    float3 bmin = f3(-q0.x / 2.f, -q0.y / 2.f, -q0.z / 2.f);
+    float3 bmax = f3(q0.x / 2.f, q0.y / 2.f, q0.z / 2.f);
+    float3 p = f3(ro.x + t * rd.x - 0.f, ro.y + t * rd.y - 0.f, ro.z + t * rd.z - 0.f);
+    float3 pa = f3(fabsf(p.x) / (bmax.x - bmin.x), fabsf(p.y) / (bmax.y - bmin.y), fabsf(p.z) / (bmax.z - bmin.z));
+    float3 n = f3(0.f, 0.f, 0.f);
+    if (pa.x >= pa.y && pa.x >= pa.z) n.x = copysignf(1.f, p.x);
+    else if (pa.y >= pa.x && pa.y >= pa.z) n.y = copysignf(1.f, p.y);
+    else if (pa.z >= pa.x && pa.z >= pa.y) n.z = copysignf(1.f, p.z);
+    return n;
+}
 
-    bool ok = false;
-    if (has) {
-        float t = tmin < t_near ? t_near : (tmin < t_far ? t_far : tmin);
-        float3 p = f3(ro.x + t * rd.x - 0.f, ro.y + t * rd.y - 0.f, ro.z + t * rd.z - 0.f);
-        float3 pa = f3(fabsf(p.x) / (bmax.x - bmin.x), fabsf(p.y) / (bmax.y - bmin.y), fabsf(p.z) / (bmax.z - bmin.z));
-        float3 n = f3(0.f, 0.f, 0.f);
-        if (pa.x >= pa.y && pa.x >= pa.z) n.x = copysignf(1.f, p.x);
-        else if (pa.y >= pa.x && pa.y >= pa.z) n.y = copysignf(1.f, p.y);
-        else if (pa.z >= pa.x && pa.z >= pa.y) n.z = copysignf(1.f, p.z);
-        if (t > tmin) {
-            ok = true;
-            is.x = n.x; is.y = n.y; is.z = n.z; is.w = t;
-        }
-    }
-    return ok;
+PHOX_D bool leaf_box3_idir(float4& is, const float4& q0, float tmin, const float3& ro, const float3& rd, const float3& idir) {
+    float t;
+    if (!box3_t(t, q0, tmin, ro, rd, idir)) return false;
+    float3 n = box3_normal(q0, ro, rd, t);
+    is.x = n.x; is.y = n.y; is.z = n.z; is.w = t;
+    return true;
 }
 
 PHOX_D bool leaf_cylinder(float4& is, const float4& q0, const float4& q1, float tmin, const float3& ro, const float3& rd) {

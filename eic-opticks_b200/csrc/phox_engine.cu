@@ -123,9 +123,15 @@ struct phox_context {
     DevBuf<Photon> d_merged;                   // result of the last phox_merge_hits / phox_merge
     DevBuf<Photon> d_merge_in;
     MergeScratch merge_scratch;
- DevBuf<float4> d_exact;                    // per CSGPrim: (sizes ; translation) of prims that are exactly a box
+    DevBuf<float4> d_exact;                    // per CSGPrim: (sizes ; translation) of prims that are exactly a box
+    DevBuf<float4> d_home;                     // per CSGPrim: HomeRec (box, candidate count, offset), see traverse_bvh
+    DevBuf<int2> d_cand;                       // candidate lists of the home cells
+    DevBuf<unsigned> d_home_state;             // wavefront form, per slot: home cell of the photon
+    DevBuf<unsigned> d_pending, d_pending_count;   // wavefront form: list positions k_wf_home left to k_wf_trace, and their count per bounce
+    int home_grid[2] = {0, 0};
+    int num_home = 0;                          // prims that have a candidate list
     DevBuf<float> d_slack;                     // per CSGPrim: exit-bound slack of prims that are exactly a box (0 = not such a prim)
-    DevBuf<unsigned long long> d_counters;     // [0] rays, [1] hit total of the launch
+    DevBuf<unsigned long long> d_counters;     // [0] rays, [1] hit total of the launch, [2] rays settled by their home cell, [3] work counter, [4-5] genstep info
     unsigned long long* h_counters = nullptr;  // pinned mirror
     std::vector<Photon> h_photon;              // concatenated per-launch arrays in debug modes
     std::vector<Photon> h_record;
@@ -231,6 +237,10 @@ extern "C" phox_context* phox_create(int device) {
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[2], k_wf_propagate<false>, kPropThreads, 0);
         }
         for (int k = 0; k < 3; k++) ctx->wave_grid[k][dbg] = std::max(w[k], 1) * prop.multiProcessorCount;
+        int wh = 0;
+        if (dbg) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wh, k_wf_home<true>, kWaveThreads, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wh, k_wf_home<false>, kWaveThreads, 0);
+        ctx->home_grid[dbg] = std::max(wh, 1) * prop.multiProcessorCount;
     }
     cudaGetLastError();
     char buf[256];
@@ -261,6 +271,7 @@ extern "C" void phox_destroy(phox_context* ctx) {
     ctx->d_record.release(); ctx->d_hit.release(); ctx->d_seq.release(); ctx->d_prd.release();
     ctx->d_block_hits.release(); ctx->d_block_off.release(); ctx->d_counters.release();
     ctx->d_slack.release(); ctx->d_exact.release();
+    ctx->d_home.release(); ctx->d_cand.release(); ctx->d_home_state.release(); ctx->d_pending.release(); ctx->d_pending_count.release();
     ctx->d_tag.release(); ctx->d_flat.release(); ctx->d_tagslot.release();
     ctx->d_lpos.release(); ctx->d_hitlite.release(); ctx->d_merged_lite.release();
     ctx->d_merged.release(); ctx->d_merge_in.release(); merge_scratch_free(ctx->merge_scratch);
@@ -499,6 +510,68 @@ extern "C" int phox_set_geometry(phox_context* ctx, const void* solid_, int64_t 
         }
     }
 
+    // Home cells (phox_kernels.cuh, traverse_bvh): for every prim of a solid that is placed exactly once, untransformed
+    // (the remainder solid 0 of a CSGFoundry), the list of all prims whose padded box comes within a pad of its box.
+    // A prim has no list when more than kHomeMaxCand prims do, or when the box of a transformed instance does.
+    std::vector<float> home((size_t)nprim * 8, 0.f);
+    std::vector<int2> cand;
+    ctx->num_home = 0;
+    {
+        std::vector<int> solid_inst_count((size_t)nsolid, 0), solid_inst((size_t)nsolid, -1);
+        for (int64_t i = 0; i < ninst; i++) { solid_inst_count[recs[i].solid]++; solid_inst[recs[i].solid] = (int)i; }
+        struct WorldPrim { int item, inst; };
+        std::vector<WorldPrim> wp;                       // prims of untransformed instances: their boxes are world boxes
+        std::vector<int> moved;                          // transformed instances
+        for (int64_t i = 0; i < ninst; i++) {
+            if (!recs[i].is_identity) { moved.push_back((int)i); continue; }
+            for (int k = 0; k < recs[i].num_prim; k++) {
+                int q = recs[i].prim_offset + k;
+                int item = q | (slack[q] > 0.f ? kLeafExactBox : (slack[q] < 0.f ? kLeafSingle : 0));
+                wp.push_back({item, (int)i});
+            }
+        }
+        size_t nelig = 0;
+        for (int64_t sidx = 0; sidx < nsolid; sidx++)
+            if (solid_inst_count[sidx] == 1 && recs[solid_inst[sidx]].is_identity) nelig += (size_t)solid[sidx].num_prim;
+        const bool affordable = (double)nelig * (double)(wp.size() + moved.size()) < 4e9;      // host loop, early exit at kHomeMaxCand + 1
+        for (int64_t sidx = 0; sidx < nsolid && affordable; sidx++) {
+            if (solid_inst_count[sidx] != 1 || !recs[solid_inst[sidx]].is_identity) continue;
+            for (int k = 0; k < solid[sidx].num_prim; k++) {
+                const int p = solid[sidx].prim_offset + k;
+                float m = 1.f;
+                for (int a = 0; a < 6; a++) m = std::max(m, std::fabs(prim[p].f[8 + a]));
+                for (int a = 0; a < 3; a++) m = std::max(m, prim[p].f[11 + a] - prim[p].f[8 + a]);
+                const float hp = 2e-5f * m;
+                float in_lo[3], in_hi[3], out_lo[3], out_hi[3];
+                for (int a = 0; a < 3; a++) {
+                    in_lo[a] = prim[p].f[8 + a] - hp; in_hi[a] = prim[p].f[11 + a] + hp;
+                    out_lo[a] = in_lo[a] - hp; out_hi[a] = in_hi[a] + hp;
+                }
+                auto overlaps = [&](const float* b) {
+                    return b[0] <= out_hi[0] && b[3] >= out_lo[0] && b[1] <= out_hi[1] && b[4] >= out_lo[1] && b[2] <= out_hi[2] && b[5] >= out_lo[2];
+                };
+                bool ok = true;
+                for (size_t j = 0; j < moved.size() && ok; j++) ok = !overlaps(&boxes[6 * (size_t)(nprim + moved[j])]);
+                const size_t first = cand.size();
+                for (size_t j = 0; j < wp.size() && ok; j++) {
+                    if (!overlaps(&boxes[6 * (size_t)(wp[j].item & kLeafItemMask)])) continue;
+                    if (cand.size() - first == (size_t)kHomeMaxCand) { ok = false; break; }
+                    cand.push_back(make_int2(wp[j].item, wp[j].inst));
+                }
+                if (!ok || cand.size() == first) { cand.resize(first); continue; }
+                float* h = &home[8 * (size_t)p];
+                h[0] = in_lo[0]; h[1] = in_lo[1]; h[2] = in_lo[2]; h[3] = in_hi[0]; h[4] = in_hi[1]; h[5] = in_hi[2];
+                int cnt = (int)(cand.size() - first), off = (int)first;
+                std::memcpy(&h[6], &cnt, 4); std::memcpy(&h[7], &off, 4);
+                ctx->num_home++;
+            }
+        }
+    }
+    CK(ctx->d_home.reserve(std::max<size_t>(2, (size_t)nprim * 2)));
+    CK(cudaMemcpyAsync(ctx->d_home.p, home.data(), (size_t)nprim * 8 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx->d_cand.reserve(std::max<size_t>(1, cand.size())));
+    if (!cand.empty()) CK(cudaMemcpyAsync(ctx->d_cand.p, cand.data(), cand.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+
     CK(ctx->d_inst.reserve((size_t)ninst));
     CK(ctx->d_boxes.reserve(boxes.size()));
     CK(ctx->d_bvh.reserve((size_t)pool));
@@ -685,7 +758,9 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
     std::memset(&P, 0, sizeof(P));
     P.scene.geo.node = ctx->d_node.p; P.scene.geo.plan = ctx->d_plan.p; P.scene.geo.itra = ctx->d_itra.p;
     P.scene.prim = ctx->d_prim.p; P.scene.exact = ctx->d_exact.p; P.scene.nodes = ctx->d_bvh.p; P.scene.inst = ctx->d_inst.p;
-    P.scene.ninst = ctx->ninst; P.scene.tlas_root = ctx->tlas_root; P.scene.accel = c.accel;
+    P.scene.ninst = ctx->ninst; P.scene.tlas_root = ctx->tlas_root;
+    P.scene.accel = c.accel == PHOX_ACCEL_BVH_NOHOME ? PHOX_ACCEL_BVH : c.accel;
+    P.scene.home = (c.accel == PHOX_ACCEL_BVH && ctx->num_home > 0) ? ctx->d_home.p : nullptr; P.scene.cand = ctx->d_cand.p;
     P.tables.bnd_tex = ctx->bnd_tex; P.tables.icdf_tex = ctx->icdf_tex; P.tables.optical = ctx->d_optical.p;
     P.tables.nx = ctx->nx; P.tables.ny = ctx->ny; P.tables.nm0 = ctx->nm0; P.tables.nms = ctx->nms; P.tables.hd_factor = ctx->hd_factor;
     P.genstep = d_gs; P.gs_prefix = d_prefix; P.num_genstep = ngs;
@@ -731,6 +806,14 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
         // list lengths stay on the device, so there is no host synchronisation inside the loop
         CK(ctx->d_active[0].reserve((size_t)n)); CK(ctx->d_active[1].reserve((size_t)n));
         CK(ctx->d_ndraw.reserve((size_t)n)); CK(ctx->d_wave_hits.reserve((size_t)n));
+        const bool homes = P.scene.home != nullptr;
+        const bool home_pass = homes && !c.propagate_refine;       // PropagateRefine re-traces from 0.99 t: those rays take the tree
+        if (homes) CK(ctx->d_home_state.reserve((size_t)n));
+        if (home_pass) {
+            CK(ctx->d_pending.reserve((size_t)n));
+            CK(ctx->d_pending_count.reserve((size_t)c.max_bounce + 2));
+            CK(cudaMemsetAsync(ctx->d_pending_count.p, 0, ((size_t)c.max_bounce + 2) * sizeof(unsigned), ctx->stream));
+        }
         CK(ctx->d_wave_count.reserve((size_t)c.max_bounce + 2));
         CK(cudaMemsetAsync(ctx->d_wave_count.p, 0, ((size_t)c.max_bounce + 2) * sizeof(unsigned), ctx->stream));
         ctx->h_counters[3] = (unsigned long long)n;              // pinned staging for the first list length (low word)
@@ -739,6 +822,7 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
         std::memset(&W, 0, sizeof(W));
         W.sim = P;
         W.ndraw = ctx->d_ndraw.p; W.hits = ctx->d_wave_hits.p;
+        W.home = P.scene.home ? ctx->d_home_state.p : nullptr;
         const int d = dbg ? 1 : 0;
         auto grid = [&](int k, int threads = kWaveThreads) {
             return (unsigned)std::max<int64_t>(1, std::min<int64_t>(ctx->wave_grid[k][d], (n + threads - 1) / threads));
@@ -749,27 +833,31 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
         else k_wf_generate<false><<<grid(0), kWaveThreads, 0, ctx->stream>>>(W);
         CK(cudaGetLastError());
         const bool prof = ctx->profiling;
-        if (prof) while (ctx->prof_ev.size() < 2 * (size_t)c.max_bounce + 1) { cudaEvent_t e; CK(cudaEventCreate(&e)); ctx->prof_ev.push_back(e); }
+        if (prof) while (ctx->prof_ev.size() < 3 * (size_t)c.max_bounce + 1) { cudaEvent_t e; CK(cudaEventCreate(&e)); ctx->prof_ev.push_back(e); }
+        const unsigned home_blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ctx->home_grid[d], (n + kWaveThreads - 1) / kWaveThreads));
         for (int b = 0; b < c.max_bounce; b++) {
             W.active_in = ctx->d_active[b & 1].p; W.active_out = ctx->d_active[(b + 1) & 1].p;
             W.count_in = ctx->d_wave_count.p + b; W.count_out = ctx->d_wave_count.p + b + 1;
+            W.pending = home_pass ? ctx->d_pending.p : nullptr;
+            W.pending_count = home_pass ? ctx->d_pending_count.p + b : nullptr;
             W.bounce = b;
-            if (prof) {        // same launches, with an event before each kernel
-                CK(cudaEventRecord(ctx->prof_ev[2 * b], ctx->stream));
-                if (dbg) k_wf_trace<true><<<grid(1, kTraceThreads), kTraceThreads, 0, ctx->stream>>>(W);
-                else k_wf_trace<false><<<grid(1, kTraceThreads), kTraceThreads, 0, ctx->stream>>>(W);
-                CK(cudaEventRecord(ctx->prof_ev[2 * b + 1], ctx->stream));
-                if (dbg) k_wf_propagate<true><<<grid(2, kPropThreads), kPropThreads, 0, ctx->stream>>>(W);
-                else k_wf_propagate<false><<<grid(2, kPropThreads), kPropThreads, 0, ctx->stream>>>(W);
-                if (b == c.max_bounce - 1) CK(cudaEventRecord(ctx->prof_ev[2 * b + 2], ctx->stream));
-                continue;
+            // per bounce: [k_wf_home ->] k_wf_trace -> k_wf_propagate ; with profiling on, an event before each kernel
+            if (prof) CK(cudaEventRecord(ctx->prof_ev[3 * b], ctx->stream));
+            if (home_pass) {
+                if (dbg) k_wf_home<true><<<home_blocks, kWaveThreads, 0, ctx->stream>>>(W);
+                else k_wf_home<false><<<home_blocks, kWaveThreads, 0, ctx->stream>>>(W);
             }
-            if (dbg) { k_wf_trace<true><<<grid(1, kTraceThreads), kTraceThreads, 0, ctx->stream>>>(W); k_wf_propagate<true><<<grid(2, kPropThreads), kPropThreads, 0, ctx->stream>>>(W); }
-            else { k_wf_trace<false><<<grid(1, kTraceThreads), kTraceThreads, 0, ctx->stream>>>(W); k_wf_propagate<false><<<grid(2, kPropThreads), kPropThreads, 0, ctx->stream>>>(W); }
+            if (prof) CK(cudaEventRecord(ctx->prof_ev[3 * b + 1], ctx->stream));
+            if (dbg) k_wf_trace<true><<<grid(1, kTraceThreads), kTraceThreads, 0, ctx->stream>>>(W);
+            else k_wf_trace<false><<<grid(1, kTraceThreads), kTraceThreads, 0, ctx->stream>>>(W);
+            if (prof) CK(cudaEventRecord(ctx->prof_ev[3 * b + 2], ctx->stream));
+            if (dbg) k_wf_propagate<true><<<grid(2, kPropThreads), kPropThreads, 0, ctx->stream>>>(W);
+            else k_wf_propagate<false><<<grid(2, kPropThreads), kPropThreads, 0, ctx->stream>>>(W);
+            if (prof && b == c.max_bounce - 1) CK(cudaEventRecord(ctx->prof_ev[3 * b + 3], ctx->stream));
         }
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-        ctx->stats.num_kernel += 1 + 2 * (uint64_t)c.max_bounce;
+        ctx->stats.num_kernel += 1 + (home_pass ? 3 : 2) * (uint64_t)c.max_bounce;
     }
     k_hit_count<<<nblock, T, 0, ctx->stream>>>(ctx->d_photon.p, (unsigned)n, c.hit_mask, ctx->d_block_hits.p);
     CK(cudaGetLastError());
@@ -801,9 +889,11 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
         CK(cudaMemcpy(live.data(), ctx->d_wave_count.p, live.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
         for (int b = 0; b < c.max_bounce; b++) {
             if (live[b] == 0) break;                // later kernels found an empty list
-            float ms_t = 0.f, ms_p = 0.f;
-            CK(cudaEventElapsedTime(&ms_t, ctx->prof_ev[2 * b], ctx->prof_ev[2 * b + 1]));
-            CK(cudaEventElapsedTime(&ms_p, ctx->prof_ev[2 * b + 1], ctx->prof_ev[2 * b + 2]));
+            float ms_h = 0.f, ms_t = 0.f, ms_p = 0.f;
+            CK(cudaEventElapsedTime(&ms_h, ctx->prof_ev[3 * b], ctx->prof_ev[3 * b + 1]));
+            CK(cudaEventElapsedTime(&ms_t, ctx->prof_ev[3 * b + 1], ctx->prof_ev[3 * b + 2]));
+            CK(cudaEventElapsedTime(&ms_p, ctx->prof_ev[3 * b + 2], ctx->prof_ev[3 * b + 3]));
+            ctx->stats.home_kernel_seconds += ms_h * 1e-3;
             ctx->stats.trace_kernel_seconds += ms_t * 1e-3;
             ctx->stats.propagate_kernel_seconds += ms_p * 1e-3;
             ctx->stats.num_trace_launch += 1;
@@ -926,8 +1016,8 @@ extern "C" int phox_simulate(phox_context* ctx, const void* genstep_, int64_t ng
         ctx->num_photon += sl.ph_count;
     }
     CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaMemcpy(ctx->h_counters, ctx->d_counters.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    ctx->stats.num_photon = (uint64_t)ctx->num_photon; ctx->stats.num_hit = (uint64_t)ctx->num_hit; ctx->stats.num_ray = ctx->h_counters[0];
+    CK(cudaMemcpy(ctx->h_counters, ctx->d_counters.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    ctx->stats.num_photon = (uint64_t)ctx->num_photon; ctx->stats.num_hit = (uint64_t)ctx->num_hit; ctx->stats.num_ray = ctx->h_counters[0]; ctx->stats.num_home_ray = ctx->h_counters[2];
     ctx->stats.launch_seconds = t_launch; ctx->stats.upload_seconds = t_up; ctx->stats.gather_seconds = t_gather;
     if (launch_seconds) *launch_seconds = t_launch;
     ctx->have_event = true;
@@ -968,10 +1058,10 @@ extern "C" int phox_simulate_device(phox_context* ctx, const void* d_genstep, in
     if (rc) return rc;
     if (mode_keeps_photon(ctx->cfg.event_mode)) { rc = gather_debug(ctx, n); if (rc) return rc; }
     CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaMemcpy(ctx->h_counters, ctx->d_counters.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(ctx->h_counters, ctx->d_counters.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     ctx->num_photon = n;
     double dt = now_s() - t0;
-    ctx->stats.num_photon = (uint64_t)n; ctx->stats.num_hit = (uint64_t)ctx->num_hit; ctx->stats.num_ray = ctx->h_counters[0];
+    ctx->stats.num_photon = (uint64_t)n; ctx->stats.num_hit = (uint64_t)ctx->num_hit; ctx->stats.num_ray = ctx->h_counters[0]; ctx->stats.num_home_ray = ctx->h_counters[2];
     ctx->stats.launch_seconds = dt;
     if (launch_seconds) *launch_seconds = dt;
     ctx->have_event = true;
@@ -1058,7 +1148,8 @@ extern "C" int phox_intersect(phox_context* ctx, const float* ray_o_tmin, const 
     Scene sc;
     sc.geo.node = ctx->d_node.p; sc.geo.plan = ctx->d_plan.p; sc.geo.itra = ctx->d_itra.p;
     sc.prim = ctx->d_prim.p; sc.exact = ctx->d_exact.p; sc.nodes = ctx->d_bvh.p; sc.inst = ctx->d_inst.p;
-    sc.ninst = ctx->ninst; sc.tlas_root = ctx->tlas_root; sc.accel = accel;
+    sc.ninst = ctx->ninst; sc.tlas_root = ctx->tlas_root; sc.accel = accel == PHOX_ACCEL_BVH_NOHOME ? PHOX_ACCEL_BVH : accel;
+    sc.home = nullptr; sc.cand = nullptr;            // single rays carry no home
     const int T = 128;
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     k_intersect<<<(unsigned)((nray + T - 1) / T), T, 0, ctx->stream>>>(sc, d_o, d_d, (unsigned)nray, ctx->cfg.tmax, d_out);
@@ -1107,7 +1198,8 @@ extern "C" int64_t phox_simtrace(phox_context* ctx, const void* genstep, int64_t
         std::memset(&S, 0, sizeof(S));
         S.scene.geo.node = ctx->d_node.p; S.scene.geo.plan = ctx->d_plan.p; S.scene.geo.itra = ctx->d_itra.p;
         S.scene.prim = ctx->d_prim.p; S.scene.exact = ctx->d_exact.p; S.scene.nodes = ctx->d_bvh.p; S.scene.inst = ctx->d_inst.p;
-        S.scene.ninst = ctx->ninst; S.scene.tlas_root = ctx->tlas_root; S.scene.accel = c.accel;
+        S.scene.ninst = ctx->ninst; S.scene.tlas_root = ctx->tlas_root; S.scene.accel = c.accel == PHOX_ACCEL_BVH_NOHOME ? PHOX_ACCEL_BVH : c.accel;
+        S.scene.home = nullptr; S.scene.cand = nullptr;
         S.genstep = d_gs; S.gs_prefix = d_prefix; S.num_genstep = (int)num_genstep;
         S.input = d_in; S.input_base = 0; S.photon_offset = 0; S.num = (unsigned)n;
         S.tmin = c.propagate_epsilon; S.tmax = c.tmax; S.refine_distance = c.refine_distance; S.refine = c.propagate_refine;

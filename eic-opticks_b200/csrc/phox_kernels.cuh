@@ -61,6 +61,8 @@ struct Scene {
     int ninst;
     int tlas_root;                  // node index of the instance tree
     int accel;                      // PHOX_ACCEL_*
+    const float4* home;             // 2 x float4 per CSGPrim (HomeRec, see traverse_bvh); null = home cells off
+    const int2* cand;               // candidate lists of the home cells: (leaf item with its flag bits, instance)
 };
 
 struct SimParams {
@@ -163,7 +165,6 @@ PHOX_D void traverse_bvh(Nearest& best, const Scene& sc, float tmin, const float
     bool in_solid = false;
     int inst_idx = 0;
     int cur = sc.ninst == 1 ? ~0 : 0;
-
     while (true) {
         while (cur >= 0) {                                     // internal nodes
             const float4* np = reinterpret_cast<const float4*>(tree + cur);
@@ -285,6 +286,107 @@ PHOX_D void traverse_bvh(Nearest& best, const Scene& sc, float tmin, const float
     }
 }
 
+//
+// Home cells.  A photon in a detector spends most of its bounces inside one small volume (a crystal, a fibre, a
+// light guide), and from inside a box the nearest surface can only belong to a prim whose box reaches into it.
+// `home` names a CSGPrim (of an identity-transform, single-instance solid: in practice the flattened remainder
+// solid 0) whose HomeRec holds its box HB, grown by a pad, and the list of EVERY prim whose padded box overlaps
+// HB grown once more (built in phox_set_geometry; prims with more than kHomeMaxCand neighbours, or whose box is
+// touched by a transformed instance, have no list).  When the ray origin lies in HB, the candidates are tested
+// first (k_wf_home).  If the nearest answer ends before the ray leaves HB
+// (best.t * 1.000001 < exit distance of HB, the slab expressions of box_hit) the search is over: for any other
+// prim Q some axis k has Q.lo_k > HB.hi_k + pad (or the mirror image), float subtraction and multiplication by
+// idir_k are monotonic, so Q's slab entry is >= HB's slab exit > best.t * 1.0000004 and box_hit(Q) - the test
+// the BVH culls with - is false as well.  Otherwise the ray goes to the full traversal (k_wf_trace over the pending list).  The home
+// only culls; results are those of the brute-force loop, bit for bit (tests: BVH == brute, home on == off).
+// On the way out the home becomes the prim that was hit if that prim has a list (the photon now sits on its
+// surface, i.e. inside its padded box), else it is kept.
+constexpr unsigned kNoHome = 0xffffffffu;
+constexpr int kHomeMaxCand = 16;
+
+// the home a photon takes along from a hit: the prim it hit if that prim has a candidate list, else the one it had
+PHOX_D void home_update(unsigned& home, const Scene& sc, int hit_prim) {
+    if (sc.home != nullptr && hit_prim >= 0 && (unsigned)hit_prim != home) {
+        if (__float_as_int(__ldg(sc.home + 2 * hit_prim + 1).z) > 0) home = (unsigned)hit_prim;
+    }
+}
+
+// A candidate that is not an exact box: the general prim evaluator, behind a by-value interface so that the one call
+// site of the home pass hands over and takes back plain values.
+__device__ __noinline__ float4 home_cold_candidate(const Scene* sc, int prim_idx, float tmin, float ox, float oy, float oz, float dx, float dy, float dz) {
+    const float4 p0 = __ldg(sc->prim + 4 * prim_idx);
+    const float3 o = f3(ox, oy, oz), d = f3(dx, dy, dz);
+    float4 is = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool ok = intersect_prim_cold(is, sc->geo.node + 4 * __float_as_int(p0.y), sc->geo, tmin, o, d);
+    if (!ok) is.w = -1.f;                                      // below every tmin: "no report"
+    return is;
+}
+
+// Candidates of `home` against the ray; true when they settle it (best is then the answer of the whole geometry).
+// Box candidates - the common case - only have their distance worked out in the loop; the normal is computed once,
+// for the winner (the same expressions as leaf_box3_idir, which is these two halves back to back).
+PHOX_D bool home_search(Nearest& best, const Scene& sc, float tmin, const float3& o, const float3& d, unsigned home) {
+    if (home == kNoHome) return false;
+    const float4* hr = sc.home + 2 * home;
+    const float4 ha = __ldg(hr), hb = __ldg(hr + 1);           // lo.xyz hi.x | hi.y hi.z count offset
+    const int n = __float_as_int(hb.z);
+    if (!(n > 0 && o.x >= ha.x && o.x <= ha.w && o.y >= ha.y && o.y <= hb.x && o.z >= ha.z && o.z <= hb.y)) return false;
+    const float3 idir = f3(1.f / d.x, 1.f / d.y, 1.f / d.z);
+    const float tx0 = (ha.x - o.x) * idir.x, tx1 = (ha.w - o.x) * idir.x;
+    const float ty0 = (ha.y - o.y) * idir.y, ty1 = (hb.x - o.y) * idir.y;
+    const float tz0 = (ha.z - o.z) * idir.z, tz1 = (hb.y - o.z) * idir.z;
+    const float t_home = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fmaxf(tz0, tz1));
+    const int2* cand = sc.cand + __float_as_int(hb.w);
+    // Everything the loop reads is parked by hand around the one out-of-line call and comes back as NEW values (see
+    // traverse_bvh): box candidates then run in registers alone, instead of out of the spill slots the register
+    // allocator would otherwise give every value that is live across the call.
+    volatile float park[20];
+    float ox = o.x, oy = o.y, oz = o.z, dx = d.x, dy = d.y, dz = d.z, ix = idir.x, iy = idir.y, iz = idir.z, t_home_v = t_home;
+    float bt = best.t, bnx = 0.f, bny = 0.f, bnz = 0.f;
+    int bprim = -1, binst = 0, nn = n;
+    bool bbox = false;                                         // the winner is a box whose normal is still to be computed
+    for (int i = 0; i < nn; i++) {
+        const int2 e = __ldg(cand + i);
+        const int prim_idx = e.x & kLeafItemMask;
+        float t = -1.f, nx = 0.f, ny = 0.f, nz = 0.f;
+        bool ok, isbox = false;
+#if PHOX_EXACT_BOX
+        if (e.x & kLeafExactBox) {
+            const float4* rec = sc.exact + 2 * prim_idx;
+            const float4 q0 = __ldg(rec), tr = __ldg(rec + 1);
+            ok = box3_t(t, q0, tmin, f3(ox + tr.x, oy + tr.y, oz + tr.z), f3(dx, dy, dz), f3(ix, iy, iz));
+            isbox = true;
+        } else
+#endif
+        {
+            park[0] = ox; park[1] = oy; park[2] = oz; park[3] = dx; park[4] = dy; park[5] = dz; park[6] = ix; park[7] = iy; park[8] = iz;
+            park[9] = tmin; park[10] = bt; park[11] = bnx; park[12] = bny; park[13] = bnz; park[14] = __int_as_float(bprim);
+            park[15] = __int_as_float(binst | (bbox ? 0x40000000 : 0)); park[16] = __int_as_float(i); park[17] = __int_as_float(nn); park[18] = t_home_v;
+            park[19] = __int_as_float((int)(cand - sc.cand));
+            const float4 is = home_cold_candidate(&sc, prim_idx, tmin, ox, oy, oz, dx, dy, dz);
+            ox = park[0]; oy = park[1]; oz = park[2]; dx = park[3]; dy = park[4]; dz = park[5]; ix = park[6]; iy = park[7]; iz = park[8];
+            tmin = park[9]; bt = park[10]; bnx = park[11]; bny = park[12]; bnz = park[13]; bprim = __float_as_int(park[14]);
+            binst = __float_as_int(park[15]); bbox = (binst & 0x40000000) != 0; binst &= 0x3fffffff;
+            i = __float_as_int(park[16]); nn = __float_as_int(park[17]); t_home_v = park[18];
+            cand = sc.cand + __float_as_int(park[19]);
+            t = is.w; nx = is.x; ny = is.y; nz = is.z;
+            ok = true;                                         // t = -1 when there was no report
+        }
+        if (ok && t > tmin) {                                  // keep_nearest, on plain values
+            const bool closer = t < bt || (t == bt && (bprim < 0 || e.y < binst || (e.y == binst && prim_idx < bprim)));
+            if (closer) { bt = t; bnx = nx; bny = ny; bnz = nz; bprim = prim_idx; binst = e.y; bbox = isbox; }
+        }
+    }
+    if (bbox) {
+        const float4* rec = sc.exact + 2 * bprim;
+        const float4 q0 = __ldg(rec), tr = __ldg(rec + 1);
+        const float3 nb = box3_normal(q0, f3(ox + tr.x, oy + tr.y, oz + tr.z), f3(dx, dy, dz), bt);
+        bnx = nb.x; bny = nb.y; bnz = nb.z;
+    }
+    best.t = bt; best.n = f3(bnx, bny, bnz); best.prim = bprim; best.inst = binst;
+    return bt * 1.000001f < t_home_v;
+}
+
 // validation path: every prim of every instance, no boxes involved
 __device__ __noinline__ void traverse_brute(Nearest& best, const Scene& sc, float tmin, const float3& o_w, const float3& d_w) {
     for (int i = 0; i < sc.ninst; i++) {
@@ -358,11 +460,12 @@ __device__ __noinline__ bool hit_finish(HitInfo& h, const Scene& sc, const Neare
 // program sets boundary 0xffff).  Inline form: the traversal is compiled into the calling kernel, where the scene
 // pointers are kernel parameters (constant bank) instead of loads through a reference.  The boxes only cull; hit
 // distances and normals come from the out-of-line prim evaluators and hit_finish.
-PHOX_D bool trace_inline(HitInfo& h, const Scene& sc, const float3& o, const float3& d, float tmin, float tmax, unsigned flags) {
+PHOX_D bool trace_inline(HitInfo& h, const Scene& sc, const float3& o, const float3& d, float tmin, float tmax, unsigned flags, unsigned& home) {
     Nearest best;
     best.t = tmax; best.prim = -1; best.inst = 0; best.n = f3(0.f, 0.f, 0.f);
     if (sc.accel == 0) traverse_bvh(best, sc, tmin, o, d);
     else traverse_brute(best, sc, tmin, o, d);
+    home_update(home, sc, best.prim);
 #if PHOX_HITFIN_INLINE
     return hit_finish_body(h, sc, best, o, d, flags);
 #else
@@ -372,7 +475,8 @@ PHOX_D bool trace_inline(HitInfo& h, const Scene& sc, const float3& o, const flo
 
 // out-of-line form for kernels with several trace sites (persistent kernel, geometry queries)
 __device__ __noinline__ bool trace(HitInfo& h, const Scene& sc, const float3& o, const float3& d, float tmin, float tmax, unsigned flags) {
-    return trace_inline(h, sc, o, d, tmin, tmax, flags);
+    unsigned home = kNoHome;
+    return trace_inline(h, sc, o, d, tmin, tmax, flags, home);
 }
 
 PHOX_D void seq_add(Seq& s, unsigned slot, unsigned flag, unsigned boundary) {      // sseq::add_nibble
@@ -531,11 +635,20 @@ struct WaveParams {
     const unsigned* count_in;       // device-side length of active_in
     unsigned* count_out;            // device-side length of active_out (zeroed beforehand)
     unsigned* ndraw;                // per slot: uniforms consumed so far
+    unsigned* home;                 // per slot: home cell (CSGPrim index or kNoHome), read and kept up by the trace kernels alone
+    unsigned* pending;              // list positions k_wf_home could not settle (null: k_wf_trace takes the whole list)
+    unsigned* pending_count;        // device-side length of pending (zeroed beforehand)
     Seq* seq_state;                 // per slot history being built (debug modes)
     Prd* hits;                      // per list position: hit of this bounce
     int bounce;                     // bounces done so far by every photon of active_in
 };
 
+#ifndef PHOX_HOME_HITFIN_INLINE
+#define PHOX_HOME_HITFIN_INLINE 1       // k_wf_home compiles the closest-hit arithmetic in place (value-copy body, see hit_finish_body)
+#endif
+#ifndef PHOX_WF_HOME_MIN_BLOCKS
+#define PHOX_WF_HOME_MIN_BLOCKS 4       // k_wf_home: 64 registers
+#endif
 #ifndef PHOX_WF_TRACE_MIN_BLOCKS
 #define PHOX_WF_TRACE_MIN_BLOCKS 4      // resident 256-thread blocks per SM the trace kernel is compiled for (register cap 65536/(256*N))
 #endif
@@ -581,10 +694,12 @@ __global__ void __launch_bounds__(kWaveThreads) k_wf_generate(const __grid_const
         p.store_cs(P.photon + idx);
         __stcs(W.ndraw + idx, rng.consumed(base));
         __stcs(W.active_out + idx, idx | ((p.obf & P.eps0_mask) ? kListEps0 : 0u));
+        if (W.home) __stcs(W.home + idx, kNoHome);
 #else
         p.store(P.photon + idx);
         W.ndraw[idx] = rng.consumed(base);
         W.active_out[idx] = idx | ((p.obf & P.eps0_mask) ? kListEps0 : 0u);
+        if (W.home) W.home[idx] = kNoHome;
 #endif
         if (P.lpos) P.lpos[idx] = 0u;
         if (DEBUG) {
@@ -596,27 +711,128 @@ __global__ void __launch_bounds__(kWaveThreads) k_wf_generate(const __grid_const
     }
 }
 
+// hit record of list position a (streaming store: the physics kernel reads it once)
+PHOX_D void wave_store_hit(Prd* hits, unsigned a, const Prd& r) {
+#if PHOX_WF_STREAM
+    float4* hp = reinterpret_cast<float4*>(hits + a);
+    __stcs(hp, make_float4(r.nx, r.ny, r.nz, r.t));
+    __stcs(hp + 1, make_float4(r.lposcost, r.lposfphi, __uint_as_float(r.iindex_identity), __uint_as_float(r.prim_boundary)));
+#else
+    hits[a] = r;
+#endif
+}
+PHOX_D void wave_no_hit(Prd& r) {
+    r.nx = r.ny = r.nz = 0.f; r.t = -1.f; r.lposcost = r.lposfphi = 0.f; r.iindex_identity = 0xffffffffu; r.prim_boundary = kWaveNoHit;
+}
+PHOX_D void wave_hit_record(Prd& r, const HitInfo& h) {
+    r.nx = h.normal.x; r.ny = h.normal.y; r.nz = h.normal.z; r.t = h.t;
+    r.lposcost = h.lposcost; r.lposfphi = h.lposfphi;
+    r.iindex_identity = h.iindex_identity; r.prim_boundary = h.prim_boundary;
+}
+
+// First pass of a bounce when the geometry has home cells: every live photon tries the candidate list of its home
+// (a handful of box / prim tests, no tree, no stack).  Settled rays get their hit record here; the others - no home
+// yet, origin outside it, nearest candidate hit beyond the home box - are appended to the pending list, which
+// k_wf_trace then walks with full warps.  Splitting the two matters because in one kernel a warp is only as fast as
+// its slowest lane: with 18 % of the rays needing the tree, practically every warp would still pay for it.
+template <bool DEBUG>
+__global__ void __launch_bounds__(kWaveThreads, PHOX_WF_HOME_MIN_BLOCKS) k_wf_home(const __grid_constant__ WaveParams W) {
+    const SimParams& P = W.sim;
+    const unsigned count = *W.count_in;
+    constexpr unsigned kHomeFlush = 3u * kWaveThreads;
+    __shared__ unsigned s_q[4 * kWaveThreads];
+    __shared__ unsigned s_n, s_base;
+    if (threadIdx.x == 0) s_n = 0u;
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned nray = 0;
+    const unsigned stride = gridDim.x * blockDim.x;
+    const unsigned rounds = (count + stride - 1) / stride;
+    for (unsigned k = 0; k < rounds; k++) {
+        const unsigned a = k * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        bool pending = false;
+        if (a < count) {
+            const unsigned entry = __ldcs(W.active_in + a);
+            const unsigned idx = entry & kListSlotMask;
+            const float4* ph = reinterpret_cast<const float4*>(P.photon + idx);
+            const float4 q0 = __ldcs(ph), q1 = __ldcs(ph + 1);
+            if (!(q0.w < P.max_time)) {                           // the while-condition of the raygen loop fails: photon is final
+                Prd r;
+                wave_no_hit(r);
+                wave_store_hit(W.hits, a, r);
+            } else {
+                unsigned home = __ldcs(W.home + idx);
+                const float tmin = (entry & kListEps0) ? P.tmin0 : P.tmin;
+                const float3 o = f3(q0.x, q0.y, q0.z), d = f3(q1.x, q1.y, q1.z);
+                Nearest best;
+                best.t = P.tmax; best.prim = -1; best.inst = 0; best.n = f3(0.f, 0.f, 0.f);
+                if (home_search(best, P.scene, tmin, o, d, home)) {
+                    const unsigned home_in = home;
+                    home_update(home, P.scene, best.prim);
+                    if (home != home_in) __stcs(W.home + idx, home);
+                    HitInfo h;
+                    {
+                        const Nearest best_c = best;
+                        const float3 o_c = o, d_c = d;
+                        HitInfo h_c;
+#if PHOX_HOME_HITFIN_INLINE
+                        hit_finish_body(h_c, P.scene, best_c, o_c, d_c, ((DEBUG && P.prd != nullptr) || P.lpos != nullptr) ? kHitFphi : 0u);
+#else
+                        hit_finish(h_c, P.scene, best_c, o_c, d_c, ((DEBUG && P.prd != nullptr) || P.lpos != nullptr) ? kHitFphi : 0u);     // a candidate answered: never a miss
+#endif
+                        h = h_c;
+                    }
+                    Prd r;
+                    wave_hit_record(r, h);
+                    if (DEBUG) { if (P.prd && W.bounce < P.max_record) P.prd[(size_t)P.max_record * idx + W.bounce] = r; }
+                    wave_store_hit(W.hits, a, r);
+                    nray++;
+                } else pending = true;
+            }
+        }
+        // pending rays queue up in shared memory and reach the global list in runs of >= kHomeFlush entries: one atomic on
+        // the list length per run (one per warp and round - a quarter of a million per launch - serialises on that one word)
+        const unsigned ballot = __ballot_sync(0xffffffffu, pending);
+        if (ballot) {
+            unsigned base = 0;
+            const int leader = __ffs(ballot) - 1;
+            if ((int)lane == leader) base = atomicAdd(&s_n, (unsigned)__popc(ballot));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (pending) s_q[base + __popc(ballot & ((1u << lane) - 1u))] = a;
+        }
+        __syncthreads();
+        const unsigned queued = s_n;
+        if (queued >= kHomeFlush || (k + 1 == rounds && queued > 0)) {
+            if (threadIdx.x == 0) s_base = atomicAdd(W.pending_count, queued);
+            __syncthreads();
+            for (unsigned i = threadIdx.x; i < queued; i += blockDim.x) W.pending[s_base + i] = s_q[i];
+            __syncthreads();
+            if (threadIdx.x == 0) s_n = 0u;
+        }
+        __syncthreads();
+    }
+    for (int off = 16; off > 0; off >>= 1) nray += __shfl_down_sync(0xffffffffu, nray, off);
+    if (lane == 0 && nray) { atomicAdd(P.counters, (unsigned long long)nray); atomicAdd(P.counters + 2, (unsigned long long)nray); }
+}
+
+// One ray per live photon (W.pending == null) or per entry of the pending list k_wf_home left behind.
 template <bool DEBUG>
 __global__ void __launch_bounds__(kTraceThreads, PHOX_WF_TRACE_MIN_BLOCKS) k_wf_trace(const __grid_constant__ WaveParams W) {
     const SimParams& P = W.sim;
-    const unsigned count = *W.count_in;
+    const unsigned count = W.pending ? *W.pending_count : *W.count_in;
     unsigned nray = 0;
     const unsigned stride = gridDim.x * blockDim.x;
-    for (unsigned a = blockIdx.x * blockDim.x + threadIdx.x; a < count; a += stride) {
-#if PHOX_WF_STREAM
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        const unsigned a = W.pending ? __ldcs(W.pending + i) : i;
         const unsigned entry = __ldcs(W.active_in + a);
         const unsigned idx = entry & kListSlotMask;
         const float4* ph = reinterpret_cast<const float4*>(P.photon + idx);
         float4 q0 = __ldcs(ph), q1 = __ldcs(ph + 1);
-#else
-        const unsigned entry = W.active_in[a];
-        const unsigned idx = entry & kListSlotMask;
-        const float4* ph = reinterpret_cast<const float4*>(P.photon + idx);
-        float4 q0 = ph[0], q1 = ph[1];
-#endif
         Prd r;
-        r.nx = r.ny = r.nz = 0.f; r.t = -1.f; r.lposcost = r.lposfphi = 0.f; r.iindex_identity = 0xffffffffu; r.prim_boundary = kWaveNoHit;
+        wave_no_hit(r);
         if (q0.w < P.max_time) {                                // else the while-condition of the raygen loop fails: photon is final
+            const unsigned home_in = W.home ? __ldcs(W.home + idx) : kNoHome;
+            unsigned home = home_in;
             float tmin = (entry & kListEps0) ? P.tmin0 : P.tmin;   // the list entry carries (last flag & PropagateEpsilon0Mask) != 0
             float3 o = f3(q0.x, q0.y, q0.z), d = f3(q1.x, q1.y, q1.z);
             HitInfo h;
@@ -624,7 +840,7 @@ __global__ void __launch_bounds__(kTraceThreads, PHOX_WF_TRACE_MIN_BLOCKS) k_wf_
             float3 from = o;
             float t_add = 0.f;
             for (int pass = 0;; pass++) {                       // one inlined trace site; pass 1 = PropagateRefine re-trace from 0.99 t
-                ok = trace_inline(h, P.scene, from, d, tmin, P.tmax, ((DEBUG && P.prd != nullptr) || P.lpos != nullptr) ? kHitFphi : 0u);
+                ok = trace_inline(h, P.scene, from, d, tmin, P.tmax, ((DEBUG && P.prd != nullptr) || P.lpos != nullptr) ? kHitFphi : 0u, home);
                 nray++;
                 if (pass == 1) { h.t += t_add; break; }
                 if (!P.refine) break;
@@ -632,22 +848,13 @@ __global__ void __launch_bounds__(kTraceThreads, PHOX_WF_TRACE_MIN_BLOCKS) k_wf_
                 if (!(t_add > P.refine_distance)) break;
                 from = o + t_add * d;
             }
+            if (home != home_in) __stcs(W.home + idx, home);
             if (ok) {
-                r.nx = h.normal.x; r.ny = h.normal.y; r.nz = h.normal.z; r.t = h.t;
-                r.lposcost = h.lposcost; r.lposfphi = h.lposfphi;
-                r.iindex_identity = h.iindex_identity; r.prim_boundary = h.prim_boundary;
+                wave_hit_record(r, h);
                 if (DEBUG) { if (P.prd && W.bounce < P.max_record) P.prd[(size_t)P.max_record * idx + W.bounce] = r; }
             }
         }
-#if PHOX_WF_STREAM
-        {
-            float4* hp = reinterpret_cast<float4*>(W.hits + a);
-            __stcs(hp, make_float4(r.nx, r.ny, r.nz, r.t));
-            __stcs(hp + 1, make_float4(r.lposcost, r.lposfphi, __uint_as_float(r.iindex_identity), __uint_as_float(r.prim_boundary)));
-        }
-#else
-        W.hits[a] = r;
-#endif
+        wave_store_hit(W.hits, a, r);
     }
     for (int off = 16; off > 0; off >>= 1) nray += __shfl_down_sync(0xffffffffu, nray, off);
     if ((threadIdx.x & 31u) == 0 && nray) atomicAdd(P.counters, (unsigned long long)nray);

@@ -201,6 +201,34 @@ def _transform_aabb(aabb, m):
     return np.concatenate([w.min(0), w.max(0)])
 
 
+def affine_inverse(m):
+    """Inverse of a 4x4 affine transform in the row-vector convention (linear part in rows 0-2, translation in row 3),
+    by cofactors in double precision like glm::inverse (sysrap/stran.h Tran<double>): a pure translation - and any
+    linear part made of 0 / +-1 entries - inverts EXACTLY, where an LU factorisation (np.linalg.inv) leaves 1e-17-sized
+    entries off the diagonal that a CSGFoundry written by the reference does not have."""
+    m = np.asarray(m, dtype=np.float64)
+    a = m[:3, :3]
+    c = np.empty((3, 3), dtype=np.float64)
+    c[0, 0] = a[1, 1] * a[2, 2] - a[1, 2] * a[2, 1]
+    c[0, 1] = a[0, 2] * a[2, 1] - a[0, 1] * a[2, 2]
+    c[0, 2] = a[0, 1] * a[1, 2] - a[0, 2] * a[1, 1]
+    c[1, 0] = a[1, 2] * a[2, 0] - a[1, 0] * a[2, 2]
+    c[1, 1] = a[0, 0] * a[2, 2] - a[0, 2] * a[2, 0]
+    c[1, 2] = a[0, 2] * a[1, 0] - a[0, 0] * a[1, 2]
+    c[2, 0] = a[1, 0] * a[2, 1] - a[1, 1] * a[2, 0]
+    c[2, 1] = a[0, 1] * a[2, 0] - a[0, 0] * a[2, 1]
+    c[2, 2] = a[0, 0] * a[1, 1] - a[0, 1] * a[1, 0]
+    det = a[0, 0] * c[0, 0] + a[0, 1] * c[1, 0] + a[0, 2] * c[2, 0]
+    if det == 0.0 or not np.isfinite(det):
+        raise ValueError("singular transform")
+    inv = np.zeros((4, 4), dtype=np.float64)
+    inv[:3, :3] = c / det
+    inv[3, :3] = -(m[3, 0] * inv[0, :3] + m[3, 1] * inv[1, :3] + m[3, 2] * inv[2, :3])
+    inv[3, 3] = 1.0
+    inv[np.abs(inv) == 0.0] = 0.0          # no negative zeros
+    return inv
+
+
 class Foundry:
     """Accumulates solids / prims / nodes and emits the CSGFoundry arrays."""
 
@@ -328,7 +356,7 @@ class Foundry:
             pi[i, 3, 3] = i                      # globalPrimIdx
         node = np.array(self.nodes, dtype=np.float32).reshape(nn, 4, 4)
         tran = np.array(self.trans, dtype=np.float64).reshape(-1, 4, 4)
-        itra = np.array([np.linalg.inv(t) for t in tran]).reshape(-1, 4, 4)
+        itra = np.array([affine_inverse(t) for t in tran]).reshape(-1, 4, 4)
         plan = np.array(self.planes, dtype=np.float32).reshape(-1, 4)
         insts = self.insts or [(np.eye(4), 0, 0, 0, -1)]
         inst = np.zeros((len(insts), 4, 4), dtype=np.float32)

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("PHOX_LIB") or os.path.join(CSRC, "libphox.so")   # PH
 PHOX_OK = 0
 MODE_MINIMAL, MODE_HITPHOTON, MODE_HITPHOTONSEQ, MODE_DEBUGLITE, MODE_DEBUGHEAVY = range(5)
 RNG_PRODUCTION, RNG_DEBUG_TAG = 0, 1
-ACCEL_BVH, ACCEL_BRUTE = 0, 1
+ACCEL_BVH, ACCEL_BRUTE, ACCEL_BVH_NOHOME = 0, 1, 2
 KERNEL_AUTO, KERNEL_PERSISTENT, KERNEL_WAVEFRONT = 0, 1, 2
 
 
@@ -47,6 +47,7 @@ class Stats(C.Structure):
         ("launch_seconds", C.c_double), ("upload_seconds", C.c_double), ("gather_seconds", C.c_double),
         ("simulate_kernel_seconds", C.c_double), ("compact_kernel_seconds", C.c_double),
         ("trace_kernel_seconds", C.c_double), ("propagate_kernel_seconds", C.c_double), ("num_trace_launch", C.c_uint64),
+        ("num_home_ray", C.c_uint64), ("home_kernel_seconds", C.c_double),
     ]
 
 

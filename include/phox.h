@@ -60,7 +60,8 @@ enum {
 /* How rays find their nearest CSGPrim. */
 enum {
     PHOX_ACCEL_BVH = 0,       /* two-level BVH built on the GPU (instances, then prims per solid) */
-    PHOX_ACCEL_BRUTE = 1      /* loop over every instance and prim: validation of the BVH only   */
+    PHOX_ACCEL_BRUTE = 1,     /* loop over every instance and prim: validation of the BVH only   */
+    PHOX_ACCEL_BVH_NOHOME = 2 /* the BVH without the home-cell shortcut (validation / A-B timing) */
 };
 
 /* Defaults are the reference's: sysrap/SEventConfig.cc:37-115, CSGOptiX/CSGOptiX.cc:651-668,
@@ -188,6 +189,8 @@ typedef struct phox_stats {
     double   trace_kernel_seconds;      /* sum over the trace kernels of the event */
     double   propagate_kernel_seconds;  /* sum over the physics kernels of the event */
     uint64_t num_trace_launch;          /* trace kernels that had live photons */
+    uint64_t num_home_ray;              /* rays of the event settled by the candidate list of their home cell, without the BVH */
+    double   home_kernel_seconds;       /* profiling: sum over the home-cell kernels of the event (trace_kernel_seconds: the BVH kernels) */
 } phox_stats;
 int phox_get_stats(const phox_context* ctx, phox_stats* st);
 

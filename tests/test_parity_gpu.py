@@ -368,6 +368,42 @@ def test_wavefront_form_is_bit_identical_to_persistent_form(name, kw):
     assert len(out[(ph.KERNEL_WAVEFRONT, ph.MODE_MINIMAL)]["hit"]) > 0
 
 
+HOME_CASES = CASES + [("far_wall_torch", dict(num_photon=20000)), ("halfspace_zoo_torch", dict(num_photon=20000)),
+                      ("pmt_wall_sensor_a", dict(num_photon=20000))]
+
+
+@pytest.mark.parametrize("name,kw", HOME_CASES)
+def test_home_cells_only_cull(name, kw):
+    """The home-cell shortcut of the traversal (phox_kernels.cuh traverse_bvh: candidate list of the prim the photon sits in,
+    accepted when the nearest candidate hit ends inside that prim's box) must give the bytes of the plain BVH and of the
+    brute-force loop (the persistent form of the loop has no home pass and serves as one more reference); and it has to be
+    exercised, not just compiled."""
+    w = workloads.WORKLOADS[name](**kw)
+    out, home_rays = {}, {}
+    for mode in (ph.KERNEL_WAVEFRONT, ph.KERNEL_PERSISTENT):
+        for accel in (ph.ACCEL_BVH, ph.ACCEL_BVH_NOHOME, ph.ACCEL_BRUTE):
+            sim = make_sim(w, event_mode=ph.MODE_DEBUGLITE, kernel_mode=mode, accel=accel, max_record=8)
+            h = sim.simulate_np(w["gensteps"], 1, w["input_photons"]).copy()
+            out[(mode, accel)] = {"hit": h, "photon": sim.get_array("photon").copy(), "seq": sim.get_array("seq").copy(),
+                                  "record": sim.get_array("record").copy()}
+            st = sim.stats()
+            home_rays[(mode, accel)] = (st["num_home_ray"], st["num_ray"])
+            sim.close()
+    for mode in (ph.KERNEL_WAVEFRONT, ph.KERNEL_PERSISTENT):
+        ref = out[(mode, ph.ACCEL_BRUTE)]
+        for accel in (ph.ACCEL_BVH, ph.ACCEL_BVH_NOHOME):
+            for k in ref:
+                assert out[(mode, accel)][k].tobytes() == ref[k].tobytes(), (name, "mode", mode, "accel", accel, k)
+    for k in out[(ph.KERNEL_WAVEFRONT, ph.ACCEL_BRUTE)]:
+        assert out[(ph.KERNEL_WAVEFRONT, ph.ACCEL_BRUTE)][k].tobytes() == out[(ph.KERNEL_PERSISTENT, ph.ACCEL_BRUTE)][k].tobytes(), (name, "wavefront vs persistent", k)
+    for mode in (ph.KERNEL_WAVEFRONT, ph.KERNEL_PERSISTENT):
+        assert home_rays[(mode, ph.ACCEL_BVH_NOHOME)][0] == 0 and home_rays[(mode, ph.ACCEL_BRUTE)][0] == 0
+        assert home_rays[(mode, ph.ACCEL_BVH)][1] == home_rays[(mode, ph.ACCEL_BRUTE)][1]          # same rays traced
+    print(name, "rays settled by their home cell: %d of %d" % home_rays[(ph.KERNEL_WAVEFRONT, ph.ACCEL_BVH)])
+    if name in ("sipm8x8_scint", "boolean_zoo_torch"):
+        assert home_rays[(ph.KERNEL_WAVEFRONT, ph.ACCEL_BVH)][0] > 0.3 * home_rays[(ph.KERNEL_WAVEFRONT, ph.ACCEL_BVH)][1]
+
+
 def test_wavefront_form_with_launch_slicing_and_time_cut():
     w = workloads.sipm8x8_scint(num_photon=50000, photons_per_genstep=100)
     res = []
