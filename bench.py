@@ -295,7 +295,7 @@ def main():
 
     # per-kernel pass (not part of `value`): CUDA events between the kernels of the bounce loop, on the launch stream
     sim.set_profiling(True)
-    prof = dict(trace_kernel_seconds=0.0, propagate_kernel_seconds=0.0, home_kernel_seconds=0.0, num_trace_launch=0, num_ray=0, num_home_ray=0, simulate_kernel_seconds=0.0)
+    prof = dict(trace_kernel_seconds=0.0, propagate_kernel_seconds=0.0, num_trace_launch=0, num_ray=0, num_home_ray=0, simulate_kernel_seconds=0.0)
     for k in range(min(args.steps, 3)):
         flush.fill_(float(k)); torch.cuda.synchronize(dev)
         step_device(100 + k)
@@ -359,7 +359,6 @@ def main():
                          "bounce_loop_ms": loop_s * 1e3, "bounce_loop_share_of_step": st_dev["simulate_kernel_seconds"] / (ms_dev * 1e-3),
                          "path_algorithmic_bytes_per_photon": bytes_per_photon, "path_achieved_gbs": cnt_r * bytes_per_photon / loop_s / 1e9,
                          "propagate_kernel_ms": (prof["propagate_kernel_seconds"] / prof["num_trace_launch"] * 1e3) if wave else None,
-                         "home_kernel_ms": (prof["home_kernel_seconds"] / prof["num_trace_launch"] * 1e3) if wave else None,
                          "second_kernel": second,
                          "note": "the bounce loop is latency/issue bound, not HBM bound (geometry and tables are cache resident); "
                                  "ncu traffic and stall breakdown in profiles/"},

@@ -127,8 +127,8 @@ struct phox_context {
     DevBuf<float4> d_home;                     // per CSGPrim: HomeRec (box, candidate count, offset), see traverse_bvh
     DevBuf<int2> d_cand;                       // candidate lists of the home cells
     DevBuf<unsigned> d_home_state;             // wavefront form, per slot: home cell of the photon
-    DevBuf<unsigned> d_pending, d_pending_count;   // wavefront form: list positions k_wf_home left to k_wf_trace, and their count per bounce
-    int home_grid[2] = {0, 0};
+    DevBuf<unsigned> d_pending, d_pending_count;   // wavefront form: list positions the home cells left to k_wf_trace, and their count per bounce
+    DevBuf<Prd> d_wave_hits2;                      // second hit buffer: the physics kernel fills the next bounce's records while it reads this bounce's
     int num_home = 0;                          // prims that have a candidate list
     DevBuf<float> d_slack;                     // per CSGPrim: exit-bound slack of prims that are exactly a box (0 = not such a prim)
     DevBuf<unsigned long long> d_counters;     // [0] rays, [1] hit total of the launch, [2] rays settled by their home cell, [3] work counter, [4-5] genstep info
@@ -230,17 +230,14 @@ extern "C" phox_context* phox_create(int device) {
         if (dbg) {
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[0], k_wf_generate<true>, kWaveThreads, 0);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[1], k_wf_trace<true>, kTraceThreads, 0);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[2], k_wf_propagate<true>, kPropThreads, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[2], k_wf_propagate<true, true>, kPropThreads, 0);
         } else {
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[0], k_wf_generate<false>, kWaveThreads, 0);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[1], k_wf_trace<false>, kTraceThreads, 0);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[2], k_wf_propagate<false>, kPropThreads, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[2], k_wf_propagate<false, true>, kPropThreads, 0);
         }
         for (int k = 0; k < 3; k++) ctx->wave_grid[k][dbg] = std::max(w[k], 1) * prop.multiProcessorCount;
-        int wh = 0;
-        if (dbg) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wh, k_wf_home<true>, kWaveThreads, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wh, k_wf_home<false>, kWaveThreads, 0);
-        ctx->home_grid[dbg] = std::max(wh, 1) * prop.multiProcessorCount;
+
     }
     cudaGetLastError();
     char buf[256];
@@ -271,7 +268,7 @@ extern "C" void phox_destroy(phox_context* ctx) {
     ctx->d_record.release(); ctx->d_hit.release(); ctx->d_seq.release(); ctx->d_prd.release();
     ctx->d_block_hits.release(); ctx->d_block_off.release(); ctx->d_counters.release();
     ctx->d_slack.release(); ctx->d_exact.release();
-    ctx->d_home.release(); ctx->d_cand.release(); ctx->d_home_state.release(); ctx->d_pending.release(); ctx->d_pending_count.release();
+    ctx->d_home.release(); ctx->d_cand.release(); ctx->d_home_state.release(); ctx->d_pending.release(); ctx->d_pending_count.release(); ctx->d_wave_hits2.release();
     ctx->d_tag.release(); ctx->d_flat.release(); ctx->d_tagslot.release();
     ctx->d_lpos.release(); ctx->d_hitlite.release(); ctx->d_merged_lite.release();
     ctx->d_merged.release(); ctx->d_merge_in.release(); merge_scratch_free(ctx->merge_scratch);
@@ -810,6 +807,7 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
         const bool home_pass = homes && !c.propagate_refine;       // PropagateRefine re-traces from 0.99 t: those rays take the tree
         if (homes) CK(ctx->d_home_state.reserve((size_t)n));
         if (home_pass) {
+            CK(ctx->d_wave_hits2.reserve((size_t)n));
             CK(ctx->d_pending.reserve((size_t)n));
             CK(ctx->d_pending_count.reserve((size_t)c.max_bounce + 2));
             CK(cudaMemsetAsync(ctx->d_pending_count.p, 0, ((size_t)c.max_bounce + 2) * sizeof(unsigned), ctx->stream));
@@ -833,31 +831,36 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
         else k_wf_generate<false><<<grid(0), kWaveThreads, 0, ctx->stream>>>(W);
         CK(cudaGetLastError());
         const bool prof = ctx->profiling;
-        if (prof) while (ctx->prof_ev.size() < 3 * (size_t)c.max_bounce + 1) { cudaEvent_t e; CK(cudaEventCreate(&e)); ctx->prof_ev.push_back(e); }
-        const unsigned home_blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ctx->home_grid[d], (n + kWaveThreads - 1) / kWaveThreads));
+        if (prof) while (ctx->prof_ev.size() < 2 * (size_t)c.max_bounce + 1) { cudaEvent_t e; CK(cudaEventCreate(&e)); ctx->prof_ev.push_back(e); }
+        Prd* hit_buf[2] = {ctx->d_wave_hits.p, home_pass ? ctx->d_wave_hits2.p : ctx->d_wave_hits.p};
         for (int b = 0; b < c.max_bounce; b++) {
             W.active_in = ctx->d_active[b & 1].p; W.active_out = ctx->d_active[(b + 1) & 1].p;
             W.count_in = ctx->d_wave_count.p + b; W.count_out = ctx->d_wave_count.p + b + 1;
-            W.pending = home_pass ? ctx->d_pending.p : nullptr;
-            W.pending_count = home_pass ? ctx->d_pending_count.p + b : nullptr;
+            W.hits = hit_buf[b & 1]; W.hits_next = hit_buf[(b + 1) & 1];
             W.bounce = b;
-            // per bounce: [k_wf_home ->] k_wf_trace -> k_wf_propagate ; with profiling on, an event before each kernel
-            if (prof) CK(cudaEventRecord(ctx->prof_ev[3 * b], ctx->stream));
-            if (home_pass) {
-                if (dbg) k_wf_home<true><<<home_blocks, kWaveThreads, 0, ctx->stream>>>(W);
-                else k_wf_home<false><<<home_blocks, kWaveThreads, 0, ctx->stream>>>(W);
-            }
-            if (prof) CK(cudaEventRecord(ctx->prof_ev[3 * b + 1], ctx->stream));
+            // per bounce: k_wf_trace -> k_wf_propagate ; with profiling on, an event before each kernel.
+            // With home cells the physics kernel of bounce b - 1 has already written the hit records of the rays their home
+            // settled; the trace kernel takes the rest, the pending list (everything at bounce 0: nobody has a home yet).
+            if (prof) CK(cudaEventRecord(ctx->prof_ev[2 * b], ctx->stream));
+            W.pending = (home_pass && b > 0) ? ctx->d_pending.p : nullptr;
+            W.pending_count = home_pass ? ctx->d_pending_count.p + b : nullptr;
             if (dbg) k_wf_trace<true><<<grid(1, kTraceThreads), kTraceThreads, 0, ctx->stream>>>(W);
             else k_wf_trace<false><<<grid(1, kTraceThreads), kTraceThreads, 0, ctx->stream>>>(W);
-            if (prof) CK(cudaEventRecord(ctx->prof_ev[3 * b + 2], ctx->stream));
-            if (dbg) k_wf_propagate<true><<<grid(2, kPropThreads), kPropThreads, 0, ctx->stream>>>(W);
-            else k_wf_propagate<false><<<grid(2, kPropThreads), kPropThreads, 0, ctx->stream>>>(W);
-            if (prof && b == c.max_bounce - 1) CK(cudaEventRecord(ctx->prof_ev[3 * b + 3], ctx->stream));
+            if (prof) CK(cudaEventRecord(ctx->prof_ev[2 * b + 1], ctx->stream));
+            W.pending = home_pass ? ctx->d_pending.p : nullptr;
+            W.pending_count = home_pass ? ctx->d_pending_count.p + b + 1 : nullptr;
+            if (home_pass) {
+                if (dbg) k_wf_propagate<true, true><<<grid(2, kPropThreads), kPropThreads, 0, ctx->stream>>>(W);
+                else k_wf_propagate<false, true><<<grid(2, kPropThreads), kPropThreads, 0, ctx->stream>>>(W);
+            } else {
+                if (dbg) k_wf_propagate<true, false><<<grid(2, kPropThreads), kPropThreads, 0, ctx->stream>>>(W);
+                else k_wf_propagate<false, false><<<grid(2, kPropThreads), kPropThreads, 0, ctx->stream>>>(W);
+            }
+            if (prof && b == c.max_bounce - 1) CK(cudaEventRecord(ctx->prof_ev[2 * b + 2], ctx->stream));
         }
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-        ctx->stats.num_kernel += 1 + (home_pass ? 3 : 2) * (uint64_t)c.max_bounce;
+        ctx->stats.num_kernel += 1 + 2 * (uint64_t)c.max_bounce;
     }
     k_hit_count<<<nblock, T, 0, ctx->stream>>>(ctx->d_photon.p, (unsigned)n, c.hit_mask, ctx->d_block_hits.p);
     CK(cudaGetLastError());
@@ -889,11 +892,9 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
         CK(cudaMemcpy(live.data(), ctx->d_wave_count.p, live.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
         for (int b = 0; b < c.max_bounce; b++) {
             if (live[b] == 0) break;                // later kernels found an empty list
-            float ms_h = 0.f, ms_t = 0.f, ms_p = 0.f;
-            CK(cudaEventElapsedTime(&ms_h, ctx->prof_ev[3 * b], ctx->prof_ev[3 * b + 1]));
-            CK(cudaEventElapsedTime(&ms_t, ctx->prof_ev[3 * b + 1], ctx->prof_ev[3 * b + 2]));
-            CK(cudaEventElapsedTime(&ms_p, ctx->prof_ev[3 * b + 2], ctx->prof_ev[3 * b + 3]));
-            ctx->stats.home_kernel_seconds += ms_h * 1e-3;
+            float ms_t = 0.f, ms_p = 0.f;
+            CK(cudaEventElapsedTime(&ms_t, ctx->prof_ev[2 * b], ctx->prof_ev[2 * b + 1]));
+            CK(cudaEventElapsedTime(&ms_p, ctx->prof_ev[2 * b + 1], ctx->prof_ev[2 * b + 2]));
             ctx->stats.trace_kernel_seconds += ms_t * 1e-3;
             ctx->stats.propagate_kernel_seconds += ms_p * 1e-3;
             ctx->stats.num_trace_launch += 1;

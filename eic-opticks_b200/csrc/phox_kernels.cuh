@@ -293,7 +293,7 @@ PHOX_D void traverse_bvh(Nearest& best, const Scene& sc, float tmin, const float
 // solid 0) whose HomeRec holds its box HB, grown by a pad, and the list of EVERY prim whose padded box overlaps
 // HB grown once more (built in phox_set_geometry; prims with more than kHomeMaxCand neighbours, or whose box is
 // touched by a transformed instance, have no list).  When the ray origin lies in HB, the candidates are tested
-// first (k_wf_home).  If the nearest answer ends before the ray leaves HB
+// first (tail of k_wf_propagate<.., HOME>).  If the nearest answer ends before the ray leaves HB
 // (best.t * 1.000001 < exit distance of HB, the slab expressions of box_hit) the search is over: for any other
 // prim Q some axis k has Q.lo_k > HB.hi_k + pad (or the mirror image), float subtraction and multiplication by
 // idir_k are monotonic, so Q's slab entry is >= HB's slab exit > best.t * 1.0000004 and box_hit(Q) - the test
@@ -636,19 +636,14 @@ struct WaveParams {
     unsigned* count_out;            // device-side length of active_out (zeroed beforehand)
     unsigned* ndraw;                // per slot: uniforms consumed so far
     unsigned* home;                 // per slot: home cell (CSGPrim index or kNoHome), read and kept up by the trace kernels alone
-    unsigned* pending;              // list positions k_wf_home could not settle (null: k_wf_trace takes the whole list)
+    unsigned* pending;              // list positions whose home cell did not settle the ray (null: k_wf_trace takes the whole list)
     unsigned* pending_count;        // device-side length of pending (zeroed beforehand)
     Seq* seq_state;                 // per slot history being built (debug modes)
     Prd* hits;                      // per list position: hit of this bounce
+    Prd* hits_next;                 // HOME: hit records of the next bounce, per position in active_out (the physics kernel reads `hits` while it fills these)
     int bounce;                     // bounces done so far by every photon of active_in
 };
 
-#ifndef PHOX_HOME_HITFIN_INLINE
-#define PHOX_HOME_HITFIN_INLINE 1       // k_wf_home compiles the closest-hit arithmetic in place (value-copy body, see hit_finish_body)
-#endif
-#ifndef PHOX_WF_HOME_MIN_BLOCKS
-#define PHOX_WF_HOME_MIN_BLOCKS 4       // k_wf_home: 64 registers
-#endif
 #ifndef PHOX_WF_TRACE_MIN_BLOCKS
 #define PHOX_WF_TRACE_MIN_BLOCKS 4      // resident 256-thread blocks per SM the trace kernel is compiled for (register cap 65536/(256*N))
 #endif
@@ -730,92 +725,8 @@ PHOX_D void wave_hit_record(Prd& r, const HitInfo& h) {
     r.iindex_identity = h.iindex_identity; r.prim_boundary = h.prim_boundary;
 }
 
-// First pass of a bounce when the geometry has home cells: every live photon tries the candidate list of its home
-// (a handful of box / prim tests, no tree, no stack).  Settled rays get their hit record here; the others - no home
-// yet, origin outside it, nearest candidate hit beyond the home box - are appended to the pending list, which
-// k_wf_trace then walks with full warps.  Splitting the two matters because in one kernel a warp is only as fast as
-// its slowest lane: with 18 % of the rays needing the tree, practically every warp would still pay for it.
-template <bool DEBUG>
-__global__ void __launch_bounds__(kWaveThreads, PHOX_WF_HOME_MIN_BLOCKS) k_wf_home(const __grid_constant__ WaveParams W) {
-    const SimParams& P = W.sim;
-    const unsigned count = *W.count_in;
-    constexpr unsigned kHomeFlush = 3u * kWaveThreads;
-    __shared__ unsigned s_q[4 * kWaveThreads];
-    __shared__ unsigned s_n, s_base;
-    if (threadIdx.x == 0) s_n = 0u;
-    __syncthreads();
-    const unsigned lane = threadIdx.x & 31u;
-    unsigned nray = 0;
-    const unsigned stride = gridDim.x * blockDim.x;
-    const unsigned rounds = (count + stride - 1) / stride;
-    for (unsigned k = 0; k < rounds; k++) {
-        const unsigned a = k * stride + blockIdx.x * blockDim.x + threadIdx.x;
-        bool pending = false;
-        if (a < count) {
-            const unsigned entry = __ldcs(W.active_in + a);
-            const unsigned idx = entry & kListSlotMask;
-            const float4* ph = reinterpret_cast<const float4*>(P.photon + idx);
-            const float4 q0 = __ldcs(ph), q1 = __ldcs(ph + 1);
-            if (!(q0.w < P.max_time)) {                           // the while-condition of the raygen loop fails: photon is final
-                Prd r;
-                wave_no_hit(r);
-                wave_store_hit(W.hits, a, r);
-            } else {
-                unsigned home = __ldcs(W.home + idx);
-                const float tmin = (entry & kListEps0) ? P.tmin0 : P.tmin;
-                const float3 o = f3(q0.x, q0.y, q0.z), d = f3(q1.x, q1.y, q1.z);
-                Nearest best;
-                best.t = P.tmax; best.prim = -1; best.inst = 0; best.n = f3(0.f, 0.f, 0.f);
-                if (home_search(best, P.scene, tmin, o, d, home)) {
-                    const unsigned home_in = home;
-                    home_update(home, P.scene, best.prim);
-                    if (home != home_in) __stcs(W.home + idx, home);
-                    HitInfo h;
-                    {
-                        const Nearest best_c = best;
-                        const float3 o_c = o, d_c = d;
-                        HitInfo h_c;
-#if PHOX_HOME_HITFIN_INLINE
-                        hit_finish_body(h_c, P.scene, best_c, o_c, d_c, ((DEBUG && P.prd != nullptr) || P.lpos != nullptr) ? kHitFphi : 0u);
-#else
-                        hit_finish(h_c, P.scene, best_c, o_c, d_c, ((DEBUG && P.prd != nullptr) || P.lpos != nullptr) ? kHitFphi : 0u);     // a candidate answered: never a miss
-#endif
-                        h = h_c;
-                    }
-                    Prd r;
-                    wave_hit_record(r, h);
-                    if (DEBUG) { if (P.prd && W.bounce < P.max_record) P.prd[(size_t)P.max_record * idx + W.bounce] = r; }
-                    wave_store_hit(W.hits, a, r);
-                    nray++;
-                } else pending = true;
-            }
-        }
-        // pending rays queue up in shared memory and reach the global list in runs of >= kHomeFlush entries: one atomic on
-        // the list length per run (one per warp and round - a quarter of a million per launch - serialises on that one word)
-        const unsigned ballot = __ballot_sync(0xffffffffu, pending);
-        if (ballot) {
-            unsigned base = 0;
-            const int leader = __ffs(ballot) - 1;
-            if ((int)lane == leader) base = atomicAdd(&s_n, (unsigned)__popc(ballot));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (pending) s_q[base + __popc(ballot & ((1u << lane) - 1u))] = a;
-        }
-        __syncthreads();
-        const unsigned queued = s_n;
-        if (queued >= kHomeFlush || (k + 1 == rounds && queued > 0)) {
-            if (threadIdx.x == 0) s_base = atomicAdd(W.pending_count, queued);
-            __syncthreads();
-            for (unsigned i = threadIdx.x; i < queued; i += blockDim.x) W.pending[s_base + i] = s_q[i];
-            __syncthreads();
-            if (threadIdx.x == 0) s_n = 0u;
-        }
-        __syncthreads();
-    }
-    for (int off = 16; off > 0; off >>= 1) nray += __shfl_down_sync(0xffffffffu, nray, off);
-    if (lane == 0 && nray) { atomicAdd(P.counters, (unsigned long long)nray); atomicAdd(P.counters + 2, (unsigned long long)nray); }
-}
-
-// One ray per live photon (W.pending == null) or per entry of the pending list k_wf_home left behind.
+// One ray per live photon (W.pending == null) or per entry of the pending list the physics kernel of the previous bounce
+// left behind (the rays their home cell could not settle).
 template <bool DEBUG>
 __global__ void __launch_bounds__(kTraceThreads, PHOX_WF_TRACE_MIN_BLOCKS) k_wf_trace(const __grid_constant__ WaveParams W) {
     const SimParams& P = W.sim;
@@ -860,18 +771,25 @@ __global__ void __launch_bounds__(kTraceThreads, PHOX_WF_TRACE_MIN_BLOCKS) k_wf_
     if ((threadIdx.x & 31u) == 0 && nray) atomicAdd(P.counters, (unsigned long long)nray);
 }
 
-template <bool DEBUG>
+// HOME: the geometry has home cells (traverse/home_search above).  Each survivor then tries the candidate list of its home
+// right here, with its new position and direction still in registers: a settled ray gets its hit record for the NEXT
+// bounce written from this kernel (W.hits_next, indexed by its position in the next list), the others go to the pending
+// list that k_wf_trace walks before the next physics pass.  The candidate pass costs a few box tests; as a kernel of its
+// own it had to re-read list entry, photon and home (~90 B of DRAM traffic per ray behind a chain of dependent loads).
+template <bool DEBUG, bool HOME>
 __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_propagate(const __grid_constant__ WaveParams W) {
     __shared__ unsigned s_warp[2][kPropThreads / 32];      // double-buffered by chunk parity: two barriers per chunk instead of three
-    __shared__ unsigned s_base[2];
+    __shared__ unsigned s_base[2], s_pbase[2];
     unsigned par = 0;
+    unsigned nhome = 0;
     const SimParams& P = W.sim;
     const unsigned count = *W.count_in;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     for (unsigned base_a = blockIdx.x * blockDim.x; base_a < count; base_a += gridDim.x * blockDim.x) {
         unsigned a = base_a + threadIdx.x;
-        bool survive = false;
+        bool survive = false, settled = false;
         unsigned idx = 0, entry_out = 0;
+        Prd r2;                                             // HOME: hit of the next bounce, when the home cell settles it
         if (a < count) {
 #if PHOX_WF_STREAM
             idx = __ldcs(W.active_in + a) & kListSlotMask;
@@ -930,6 +848,26 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
                 }
                 survive = !(command == FLOW_BREAK) && bounce < P.max_bounce && p.time < P.max_time;
                 entry_out = idx | ((p.obf & P.eps0_mask) ? kListEps0 : 0u);
+                if (HOME && survive) {
+                    unsigned home = __ldcs(W.home + idx);
+                    const float tmin = (p.obf & P.eps0_mask) ? P.tmin0 : P.tmin;
+                    const float3 o = p.pos, d = p.mom;
+                    Nearest best;
+                    best.t = P.tmax; best.prim = -1; best.inst = 0; best.n = f3(0.f, 0.f, 0.f);
+                    if (home_search(best, P.scene, tmin, o, d, home)) {
+                        const unsigned home_in = home;
+                        home_update(home, P.scene, best.prim);
+                        if (home != home_in) __stcs(W.home + idx, home);
+                        const Nearest best_c = best;
+                        const float3 o_c = o, d_c = d;
+                        HitInfo h_c;
+                        hit_finish_body(h_c, P.scene, best_c, o_c, d_c, ((DEBUG && P.prd != nullptr) || P.lpos != nullptr) ? kHitFphi : 0u);     // a candidate answered: never a miss
+                        wave_hit_record(r2, h_c);
+                        if (DEBUG) { if (P.prd && bounce < P.max_record) P.prd[(size_t)P.max_record * idx + bounce] = r2; }
+                        settled = true;
+                        nhome++;
+                    }
+                }
             }
         }
         if (P.lpos && a < count && !survive) {              // lite mode: local position of the photon's last intersect, re-read from
@@ -937,22 +875,41 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
             unsigned pb = hp->prim_boundary;                // the miss program clears it
             P.lpos[idx] = pb == kWaveNoHit ? 0u : pack_lpos(hp->lposcost, hp->lposfphi);
         }
-        unsigned ballot = __ballot_sync(0xffffffffu, survive);
-        // append the survivors of this chunk to the next list, in order within the chunk
-        if (lane == 0) s_warp[par][warp] = __popc(ballot);
+        const unsigned ballot = __ballot_sync(0xffffffffu, survive);
+        const unsigned pballot = HOME ? __ballot_sync(0xffffffffu, survive && !settled) : 0u;
+        // append the survivors of this chunk to the next list, in order within the chunk (HOME: and the unsettled ones
+        // among them to the pending list; the two counts share one word per warp, 16 bits each: a chunk has 256 entries)
+        if (lane == 0) s_warp[par][warp] = __popc(ballot) | (__popc(pballot) << 16);
         __syncthreads();
         if (threadIdx.x == 0) {
-            unsigned tot = 0;
-            for (int w = 0; w < kPropThreads / 32; w++) { unsigned c = s_warp[par][w]; s_warp[par][w] = tot; tot += c; }
+            unsigned tot = 0, ptot = 0;
+            for (int w = 0; w < kPropThreads / 32; w++) {
+                const unsigned c = s_warp[par][w];
+                s_warp[par][w] = tot | (ptot << 16);
+                tot += c & 0xffffu; ptot += c >> 16;
+            }
             s_base[par] = tot ? atomicAdd(W.count_out, tot) : 0u;
+            if (HOME) s_pbase[par] = ptot ? atomicAdd(W.pending_count, ptot) : 0u;
         }
         __syncthreads();
+        if (survive) {
+            const unsigned wo = s_warp[par][warp];
+            const unsigned pos = s_base[par] + (wo & 0xffffu) + __popc(ballot & ((1u << lane) - 1u));
 #if PHOX_WF_STREAM
-        if (survive) __stcs(W.active_out + s_base[par] + s_warp[par][warp] + __popc(ballot & ((1u << lane) - 1u)), entry_out);
+            __stcs(W.active_out + pos, entry_out);
 #else
-        if (survive) W.active_out[s_base[par] + s_warp[par][warp] + __popc(ballot & ((1u << lane) - 1u))] = entry_out;
+            W.active_out[pos] = entry_out;
 #endif
+            if (HOME) {
+                if (settled) wave_store_hit(W.hits_next, pos, r2);
+                else W.pending[s_pbase[par] + (wo >> 16) + __popc(pballot & ((1u << lane) - 1u))] = pos;
+            }
+        }
         par ^= 1u;
+    }
+    if (HOME) {
+        for (int off = 16; off > 0; off >>= 1) nhome += __shfl_down_sync(0xffffffffu, nhome, off);
+        if (lane == 0 && nhome) { atomicAdd(P.counters, (unsigned long long)nhome); atomicAdd(P.counters + 2, (unsigned long long)nhome); }
     }
 }
 

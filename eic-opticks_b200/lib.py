@@ -47,7 +47,7 @@ class Stats(C.Structure):
         ("launch_seconds", C.c_double), ("upload_seconds", C.c_double), ("gather_seconds", C.c_double),
         ("simulate_kernel_seconds", C.c_double), ("compact_kernel_seconds", C.c_double),
         ("trace_kernel_seconds", C.c_double), ("propagate_kernel_seconds", C.c_double), ("num_trace_launch", C.c_uint64),
-        ("num_home_ray", C.c_uint64), ("home_kernel_seconds", C.c_double),
+        ("num_home_ray", C.c_uint64),
     ]
 
 

@@ -190,7 +190,6 @@ typedef struct phox_stats {
     double   propagate_kernel_seconds;  /* sum over the physics kernels of the event */
     uint64_t num_trace_launch;          /* trace kernels that had live photons */
     uint64_t num_home_ray;              /* rays of the event settled by the candidate list of their home cell, without the BVH */
-    double   home_kernel_seconds;       /* profiling: sum over the home-cell kernels of the event (trace_kernel_seconds: the BVH kernels) */
 } phox_stats;
 int phox_get_stats(const phox_context* ctx, phox_stats* st);
 
