@@ -509,7 +509,9 @@ extern "C" int phox_set_geometry(phox_context* ctx, const void* solid_, int64_t 
 
     // Home cells (phox_kernels.cuh, traverse_bvh): for every prim of a solid that is placed exactly once, untransformed
     // (the remainder solid 0 of a CSGFoundry), the list of all prims whose padded box comes within a pad of its box.
-    // A prim has no list when more than kHomeMaxCand prims do, or when the box of a transformed instance does.
+    // A prim has no list when more than kHomeMaxCand prims do, when one of them is not an exact box (the candidate pass
+    // runs inside the physics kernel and is kept free of calls into the general CSG evaluators), or when the box of a
+    // transformed instance does.
     std::vector<float> home((size_t)nprim * 8, 0.f);
     std::vector<int2> cand;
     ctx->num_home = 0;
@@ -523,8 +525,7 @@ extern "C" int phox_set_geometry(phox_context* ctx, const void* solid_, int64_t 
             if (!recs[i].is_identity) { moved.push_back((int)i); continue; }
             for (int k = 0; k < recs[i].num_prim; k++) {
                 int q = recs[i].prim_offset + k;
-                int item = q | (slack[q] > 0.f ? kLeafExactBox : (slack[q] < 0.f ? kLeafSingle : 0));
-                wp.push_back({item, (int)i});
+                wp.push_back({slack[q] > 0.f ? q : (q | kLeafSingle), (int)i});       // flag = not an exact box
             }
         }
         size_t nelig = 0;
@@ -552,7 +553,7 @@ extern "C" int phox_set_geometry(phox_context* ctx, const void* solid_, int64_t 
                 const size_t first = cand.size();
                 for (size_t j = 0; j < wp.size() && ok; j++) {
                     if (!overlaps(&boxes[6 * (size_t)(wp[j].item & kLeafItemMask)])) continue;
-                    if (cand.size() - first == (size_t)kHomeMaxCand) { ok = false; break; }
+                    if (cand.size() - first == (size_t)kHomeMaxCand || (wp[j].item & kLeafSingle)) { ok = false; break; }
                     cand.push_back(make_int2(wp[j].item, wp[j].inst));
                 }
                 if (!ok || cand.size() == first) { cand.resize(first); continue; }

@@ -291,8 +291,8 @@ PHOX_D void traverse_bvh(Nearest& best, const Scene& sc, float tmin, const float
 // light guide), and from inside a box the nearest surface can only belong to a prim whose box reaches into it.
 // `home` names a CSGPrim (of an identity-transform, single-instance solid: in practice the flattened remainder
 // solid 0) whose HomeRec holds its box HB, grown by a pad, and the list of EVERY prim whose padded box overlaps
-// HB grown once more (built in phox_set_geometry; prims with more than kHomeMaxCand neighbours, or whose box is
-// touched by a transformed instance, have no list).  When the ray origin lies in HB, the candidates are tested
+// HB grown once more (built in phox_set_geometry; prims with more than kHomeMaxCand neighbours, with a neighbour that
+// is not an exact box, or whose box is touched by a transformed instance, have no list).  When the ray origin lies in HB, the candidates are tested
 // first (tail of k_wf_propagate<.., HOME>).  If the nearest answer ends before the ray leaves HB
 // (best.t * 1.000001 < exit distance of HB, the slab expressions of box_hit) the search is over: for any other
 // prim Q some axis k has Q.lo_k > HB.hi_k + pad (or the mirror image), float subtraction and multiplication by
@@ -311,20 +311,10 @@ PHOX_D void home_update(unsigned& home, const Scene& sc, int hit_prim) {
     }
 }
 
-// A candidate that is not an exact box: the general prim evaluator, behind a by-value interface so that the one call
-// site of the home pass hands over and takes back plain values.
-__device__ __noinline__ float4 home_cold_candidate(const Scene* sc, int prim_idx, float tmin, float ox, float oy, float oz, float dx, float dy, float dz) {
-    const float4 p0 = __ldg(sc->prim + 4 * prim_idx);
-    const float3 o = f3(ox, oy, oz), d = f3(dx, dy, dz);
-    float4 is = make_float4(0.f, 0.f, 0.f, 0.f);
-    const bool ok = intersect_prim_cold(is, sc->geo.node + 4 * __float_as_int(p0.y), sc->geo, tmin, o, d);
-    if (!ok) is.w = -1.f;                                      // below every tmin: "no report"
-    return is;
-}
-
 // Candidates of `home` against the ray; true when they settle it (best is then the answer of the whole geometry).
-// Box candidates - the common case - only have their distance worked out in the loop; the normal is computed once,
-// for the winner (the same expressions as leaf_box3_idir, which is these two halves back to back).
+// Every candidate is an exact box (phox_set_geometry gives no list to a prim with any other neighbour), so the loop is
+// call-free and runs in registers.  Only distances are worked out in the loop; the normal is computed once, for the
+// winner (the same expressions as leaf_box3_idir, which is these two halves back to back).
 PHOX_D bool home_search(Nearest& best, const Scene& sc, float tmin, const float3& o, const float3& d, unsigned home) {
     if (home == kNoHome) return false;
     const float4* hr = sc.home + 2 * home;
@@ -337,54 +327,27 @@ PHOX_D bool home_search(Nearest& best, const Scene& sc, float tmin, const float3
     const float tz0 = (ha.z - o.z) * idir.z, tz1 = (hb.y - o.z) * idir.z;
     const float t_home = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fmaxf(tz0, tz1));
     const int2* cand = sc.cand + __float_as_int(hb.w);
-    // Everything the loop reads is parked by hand around the one out-of-line call and comes back as NEW values (see
-    // traverse_bvh): box candidates then run in registers alone, instead of out of the spill slots the register
-    // allocator would otherwise give every value that is live across the call.
-    volatile float park[20];
-    float ox = o.x, oy = o.y, oz = o.z, dx = d.x, dy = d.y, dz = d.z, ix = idir.x, iy = idir.y, iz = idir.z, t_home_v = t_home;
-    float bt = best.t, bnx = 0.f, bny = 0.f, bnz = 0.f;
-    int bprim = -1, binst = 0, nn = n;
-    bool bbox = false;                                         // the winner is a box whose normal is still to be computed
-    for (int i = 0; i < nn; i++) {
-        const int2 e = __ldg(cand + i);
-        const int prim_idx = e.x & kLeafItemMask;
-        float t = -1.f, nx = 0.f, ny = 0.f, nz = 0.f;
-        bool ok, isbox = false;
-#if PHOX_EXACT_BOX
-        if (e.x & kLeafExactBox) {
-            const float4* rec = sc.exact + 2 * prim_idx;
-            const float4 q0 = __ldg(rec), tr = __ldg(rec + 1);
-            ok = box3_t(t, q0, tmin, f3(ox + tr.x, oy + tr.y, oz + tr.z), f3(dx, dy, dz), f3(ix, iy, iz));
-            isbox = true;
-        } else
-#endif
-        {
-            park[0] = ox; park[1] = oy; park[2] = oz; park[3] = dx; park[4] = dy; park[5] = dz; park[6] = ix; park[7] = iy; park[8] = iz;
-            park[9] = tmin; park[10] = bt; park[11] = bnx; park[12] = bny; park[13] = bnz; park[14] = __int_as_float(bprim);
-            park[15] = __int_as_float(binst | (bbox ? 0x40000000 : 0)); park[16] = __int_as_float(i); park[17] = __int_as_float(nn); park[18] = t_home_v;
-            park[19] = __int_as_float((int)(cand - sc.cand));
-            const float4 is = home_cold_candidate(&sc, prim_idx, tmin, ox, oy, oz, dx, dy, dz);
-            ox = park[0]; oy = park[1]; oz = park[2]; dx = park[3]; dy = park[4]; dz = park[5]; ix = park[6]; iy = park[7]; iz = park[8];
-            tmin = park[9]; bt = park[10]; bnx = park[11]; bny = park[12]; bnz = park[13]; bprim = __float_as_int(park[14]);
-            binst = __float_as_int(park[15]); bbox = (binst & 0x40000000) != 0; binst &= 0x3fffffff;
-            i = __float_as_int(park[16]); nn = __float_as_int(park[17]); t_home_v = park[18];
-            cand = sc.cand + __float_as_int(park[19]);
-            t = is.w; nx = is.x; ny = is.y; nz = is.z;
-            ok = true;                                         // t = -1 when there was no report
-        }
-        if (ok && t > tmin) {                                  // keep_nearest, on plain values
-            const bool closer = t < bt || (t == bt && (bprim < 0 || e.y < binst || (e.y == binst && prim_idx < bprim)));
-            if (closer) { bt = t; bnx = nx; bny = ny; bnz = nz; bprim = prim_idx; binst = e.y; bbox = isbox; }
+    float bt = best.t;
+    int bprim = -1, binst = 0;
+    for (int i = 0; i < n; i++) {
+        const int2 e = __ldg(cand + i);                        // (prim, instance)
+        const float4* rec = sc.exact + 2 * e.x;
+        const float4 q0 = __ldg(rec), tr = __ldg(rec + 1);
+        float t;
+        if (box3_t(t, q0, tmin, f3(o.x + tr.x, o.y + tr.y, o.z + tr.z), d, idir)) {          // t > tmin
+            // keep_nearest: ties go to the lower (instance, prim) pair
+            const bool closer = t < bt || (t == bt && (bprim < 0 || e.y < binst || (e.y == binst && e.x < bprim)));
+            if (closer) { bt = t; bprim = e.x; binst = e.y; }
         }
     }
-    if (bbox) {
+    float3 nb = f3(0.f, 0.f, 0.f);
+    if (bprim >= 0) {
         const float4* rec = sc.exact + 2 * bprim;
         const float4 q0 = __ldg(rec), tr = __ldg(rec + 1);
-        const float3 nb = box3_normal(q0, f3(ox + tr.x, oy + tr.y, oz + tr.z), f3(dx, dy, dz), bt);
-        bnx = nb.x; bny = nb.y; bnz = nb.z;
+        nb = box3_normal(q0, f3(o.x + tr.x, o.y + tr.y, o.z + tr.z), d, bt);
     }
-    best.t = bt; best.n = f3(bnx, bny, bnz); best.prim = bprim; best.inst = binst;
-    return bt * 1.000001f < t_home_v;
+    best.t = bt; best.n = nb; best.prim = bprim; best.inst = binst;
+    return bt * 1.000001f < t_home;
 }
 
 // validation path: every prim of every instance, no boxes involved

@@ -400,7 +400,7 @@ def test_home_cells_only_cull(name, kw):
         assert home_rays[(mode, ph.ACCEL_BVH_NOHOME)][0] == 0 and home_rays[(mode, ph.ACCEL_BRUTE)][0] == 0
         assert home_rays[(mode, ph.ACCEL_BVH)][1] == home_rays[(mode, ph.ACCEL_BRUTE)][1]          # same rays traced
     print(name, "rays settled by their home cell: %d of %d" % home_rays[(ph.KERNEL_WAVEFRONT, ph.ACCEL_BVH)])
-    if name in ("sipm8x8_scint", "boolean_zoo_torch"):
+    if name == "sipm8x8_scint":
         assert home_rays[(ph.KERNEL_WAVEFRONT, ph.ACCEL_BVH)][0] > 0.3 * home_rays[(ph.KERNEL_WAVEFRONT, ph.ACCEL_BVH)][1]
 
 
