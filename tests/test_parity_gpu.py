@@ -349,17 +349,17 @@ def test_wavefront_form_is_bit_identical_to_persistent_form(name, kw):
     w = workloads.WORKLOADS[name](**kw)
     out = {}
     for mode in (ph.KERNEL_PERSISTENT, ph.KERNEL_WAVEFRONT):
-        for em, extra in ((ph.MODE_MINIMAL, {}), (ph.MODE_DEBUGHEAVY, dict(max_record=12))):
+        for em, extra in ((ph.MODE_MINIMAL, {}), (ph.MODE_DEBUGLITE, dict(max_record=8)), (ph.MODE_DEBUGHEAVY, dict(max_record=12))):
             sim = make_sim(w, event_mode=em, kernel_mode=mode, **extra)
             h = sim.simulate_np(w["gensteps"], 2, w["input_photons"]).copy()
             arrs = {"hit": h}
             if em != ph.MODE_MINIMAL:
-                for k in ("photon", "seq", "record", "prd"):
+                for k in ("photon", "seq", "record") + (("prd",) if em == ph.MODE_DEBUGHEAVY else ()):
                     arrs[k] = sim.get_array(k).copy()
             arrs["num_ray"] = np.array([sim.stats()["num_ray"]])
             out[(mode, em)] = arrs
             sim.close()
-    for em in (ph.MODE_MINIMAL, ph.MODE_DEBUGHEAVY):
+    for em in (ph.MODE_MINIMAL, ph.MODE_DEBUGLITE, ph.MODE_DEBUGHEAVY):
         a, b = out[(ph.KERNEL_PERSISTENT, em)], out[(ph.KERNEL_WAVEFRONT, em)]
         assert a.keys() == b.keys()
         for k in a:
