@@ -296,7 +296,9 @@ def main():
     # per-kernel pass (not part of `value`): CUDA events between the kernels of the bounce loop, on the launch stream
     sim.set_profiling(True)
     prof = dict(trace_kernel_seconds=0.0, propagate_kernel_seconds=0.0, num_trace_launch=0, num_ray=0, num_home_ray=0, simulate_kernel_seconds=0.0)
+    prof_photons = 0
     for k in range(min(args.steps, 3)):
+        prof_photons += cnt_r
         flush.fill_(float(k)); torch.cuda.synchronize(dev)
         step_device(100 + k)
         torch.cuda.synchronize(dev)
@@ -311,34 +313,45 @@ def main():
         bytes_per_photon = 132.0 + 128.0 * f_hit if ip_r is None else 196.0 + 128.0 * f_hit
         loop_s = st_dev["simulate_kernel_seconds"] / max(1, st_dev["num_launch"])
         wave = prof["num_trace_launch"] > 0
-        if wave:
-            # dominant kernel = k_wf_trace.  Algorithmic bytes per live ray: 4 (list entry) + 36 (pos, time, mom, flag word)
-            # read + 32 (quad2 hit record) written = 72 B; one launch processes the photons still alive at that bounce.
-            ray_bytes = 72.0
-            kern_s = prof["trace_kernel_seconds"] / prof["num_trace_launch"]
-            rays_per_launch = prof["num_ray"] / prof["num_trace_launch"]
-            achieved = rays_per_launch * ray_bytes / kern_s / 1e9
-            kernel_name = "k_wf_trace"
-            share = prof["trace_kernel_seconds"] / max(1e-12, prof["simulate_kernel_seconds"])
-        else:
-            kern_s, achieved, kernel_name, share = loop_s, cnt_r * bytes_per_photon / loop_s / 1e9, "k_simulate", st_dev["simulate_kernel_seconds"] / (ms_dev * 1e-3)
-            rays_per_launch, ray_bytes = st_dev["num_ray"] / max(1, st_dev["num_launch"]), None
-        # DRAM traffic per launch of the dominant kernel: bytes per ray from the committed ncu --set full capture x rays per launch here
-        traffic, traffic_src, tj = None, None, None
-        tpath = os.path.join(ROOT, "profiles", "traffic_r1.json")
-        if wave and os.path.exists(tpath) and args.workload == "sipm8x8_scint":
+        traffic_src, tj = None, None
+        tpath = os.path.join(ROOT, "profiles", "traffic_r2.json")
+        if os.path.exists(tpath) and args.workload == "sipm8x8_scint" and args.accel == "bvh":
             with open(tpath) as f:
                 tj = json.load(f)
-            traffic = tj["k_wf_trace"]["dram_bytes_per_ray"] * rays_per_launch
-            traffic_src = "profiles/traffic_r1.json: %.0f DRAM bytes per ray (ncu dram__bytes_read+write of one k_wf_trace launch / its rays) x rays_per_launch" % tj["k_wf_trace"]["dram_bytes_per_ray"]
-        # the other kernel of the bounce loop, k_wf_propagate: 176 algorithmic bytes per live photon (104 read + 72 written)
+            traffic_src = "profiles/traffic_r2.json: ncu dram__bytes_read+write of one launch of the kernel / its live photons, x live photons per launch here"
         second = None
-        if wave and prof["propagate_kernel_seconds"] > 0:
-            prop_s = prof["propagate_kernel_seconds"] / prof["num_trace_launch"]
-            prop_gbs = rays_per_launch * 176.0 / prop_s / 1e9
-            second = {"kernel": "k_wf_propagate", "bound": "hbm", "achieved": prop_gbs, "peak": peak, "unit": "GB/s", "frac": prop_gbs / peak,
-                      "algorithmic_bytes_per_photon": 176.0, "kernel_ms": prop_s * 1e3,
-                      "traffic": (tj["k_wf_propagate"]["dram_bytes_per_ray"] * rays_per_launch) if tj else None}
+        if wave:
+            # Two kernels per bounce.  Algorithmic bytes, from the event's own counts:
+            #  k_wf_propagate (physics + home-cell pass), per live photon: 108 B read (list entry 4, hit record 32, photon 64, draw count 4,
+            #    home 4) + 68 B written (photon 64, draw count 4); per survivor 4 B (next list entry) + 32 B (hit record of the next bounce,
+            #    when its home cell settles the ray) or 4 B (pending-list entry, when it does not)
+            #  k_wf_trace (BVH traversal of the pending rays), per ray: 44 B read (pending entry 4, list entry 4, position/time/direction 32,
+            #    home 4) + 32 B written (hit record)
+            L = prof["num_trace_launch"]
+            live = prof["num_ray"]                                   # live photons summed over the bounces = rays of the event(s)
+            surv = max(0, prof["num_ray"] - prof_photons)            # survivors = the live photons of bounces 1 ..
+            home = prof["num_home_ray"]
+            prop_bytes = 176.0 * live + 8.0 * surv + 28.0 * home
+            trace_rays = live - home
+            trace_bytes = 76.0 * trace_rays
+            prop_s = prof["propagate_kernel_seconds"] / L
+            trace_s = prof["trace_kernel_seconds"] / L
+            loop_prof_s = max(1e-12, prof["simulate_kernel_seconds"])
+            kp = {"kernel": "k_wf_propagate", "bound": "hbm", "achieved": prop_bytes / L / prop_s / 1e9, "peak": peak, "unit": "GB/s",
+                  "kernel_ms": prop_s * 1e3, "algorithmic_bytes_per_photon": prop_bytes / max(1, live), "photons_per_launch": live / L,
+                  "kernel_share_of_bounce_loop": prof["propagate_kernel_seconds"] / loop_prof_s,
+                  "traffic": (tj["k_wf_propagate"]["dram_bytes_per_photon"] * live / L) if tj else None}
+            kt = {"kernel": "k_wf_trace", "bound": "hbm", "achieved": trace_bytes / L / trace_s / 1e9, "peak": peak, "unit": "GB/s",
+                  "kernel_ms": trace_s * 1e3, "algorithmic_bytes_per_ray": 76.0, "rays_per_launch": trace_rays / L,
+                  "kernel_share_of_bounce_loop": prof["trace_kernel_seconds"] / loop_prof_s,
+                  "traffic": (tj["k_wf_trace"]["dram_bytes_per_ray"] * trace_rays / L) if tj else None}
+            for k in (kp, kt):
+                k["frac"] = k["achieved"] / peak
+            dom, second = (kp, kt) if prop_s >= trace_s else (kt, kp)
+        else:
+            dom = {"kernel": "k_simulate", "bound": "hbm", "achieved": cnt_r * bytes_per_photon / loop_s / 1e9, "peak": peak, "unit": "GB/s",
+                   "kernel_ms": loop_s * 1e3, "kernel_share_of_bounce_loop": 1.0, "traffic": None}
+            dom["frac"] = dom["achieved"] / peak
         out = {
             "metric": "photons propagated/sec", "value": value, "unit": "photons/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -352,16 +365,13 @@ def main():
             "e2e": {"value": e2e, "unit": "photons/s", "h2d_bytes_per_step": int(gs_r.nbytes + (ip_r.nbytes if ip_r is not None else 0)),
                     "d2h_bytes_per_step": int(64 * st_e2e["num_hit"] / max(1, args.steps)), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(st_dev["num_kernel"] + st_e2e["num_kernel"]),
-            "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_kind, "traffic": traffic, "traffic_source": traffic_src, "kernel_ms": kern_s * 1e3,
-                         "algorithmic_bytes_per_ray": ray_bytes, "rays_per_launch": rays_per_launch,
-                         "kernel_share_of_bounce_loop": share,
-                         "bounce_loop_ms": loop_s * 1e3, "bounce_loop_share_of_step": st_dev["simulate_kernel_seconds"] / (ms_dev * 1e-3),
-                         "path_algorithmic_bytes_per_photon": bytes_per_photon, "path_achieved_gbs": cnt_r * bytes_per_photon / loop_s / 1e9,
-                         "propagate_kernel_ms": (prof["propagate_kernel_seconds"] / prof["num_trace_launch"] * 1e3) if wave else None,
-                         "second_kernel": second,
-                         "note": "the bounce loop is latency/issue bound, not HBM bound (geometry and tables are cache resident); "
-                                 "ncu traffic and stall breakdown in profiles/"},
+            "roofline": dict(dom, peak_source=peak_kind, traffic_source=traffic_src,
+                             rays_per_launch_all=(prof["num_ray"] / max(1, prof["num_trace_launch"])) if wave else None,
+                             bounce_loop_ms=loop_s * 1e3, bounce_loop_share_of_step=st_dev["simulate_kernel_seconds"] / (ms_dev * 1e-3),
+                             path_algorithmic_bytes_per_photon=bytes_per_photon, path_achieved_gbs=cnt_r * bytes_per_photon / loop_s / 1e9,
+                             second_kernel=second,
+                             note="k_wf_propagate = physics + home-cell candidate pass (HBM / latency bound); k_wf_trace = BVH traversal of the "
+                                  "rays the home cells did not settle (issue / latency bound); ncu traffic and stall breakdown in profiles/"),
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:         # N = 1 only: at N > 1 the other ranks would idle in a barrier behind a CPU loop

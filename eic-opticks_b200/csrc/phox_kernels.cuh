@@ -623,6 +623,9 @@ constexpr int kTraceThreads = PHOX_WF_TRACE_THREADS;
 #define PHOX_WF_PROP_THREADS 256        // block of the physics kernel = run length of the ordered survivor append
 #endif
 constexpr int kPropThreads = PHOX_WF_PROP_THREADS;
+#ifndef PHOX_PROP_PREFETCH
+#define PHOX_PROP_PREFETCH 1            // physics kernel: L2 prefetch of the next chunk's lines (measured, see profiles/r2_summary.md)
+#endif
 #ifndef PHOX_WF_PROP_MIN_BLOCKS
 #define PHOX_WF_PROP_MIN_BLOCKS 4       // 64 registers: the inlined physics body fits without spills (5 blocks = 48 registers: 0.509 vs 0.490 ms per launch)
 #endif
@@ -754,6 +757,13 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     for (unsigned base_a = blockIdx.x * blockDim.x; base_a < count; base_a += gridDim.x * blockDim.x) {
         unsigned a = base_a + threadIdx.x;
+#if PHOX_PROP_PREFETCH
+        // list entry of this thread's photon in the NEXT chunk: it arrives while this chunk's physics runs, and the lines that
+        // chunk will want (hit record, photon, draw count, home) are asked into L2 before the threads meet at the barrier
+        const unsigned a_next = a + gridDim.x * blockDim.x;
+        unsigned entry_next = 0xffffffffu;
+        if (a_next < count) entry_next = __ldcs(W.active_in + a_next);
+#endif
         bool survive = false, settled = false;
         unsigned idx = 0, entry_out = 0;
         Prd r2;                                             // HOME: hit of the next bounce, when the home cell settles it
@@ -842,6 +852,15 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
             unsigned pb = hp->prim_boundary;                // the miss program clears it
             P.lpos[idx] = pb == kWaveNoHit ? 0u : pack_lpos(hp->lposcost, hp->lposfphi);
         }
+#if PHOX_PROP_PREFETCH
+        if (entry_next != 0xffffffffu) {
+            const unsigned idx_next = entry_next & kListSlotMask;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(W.hits + a_next));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(P.photon + idx_next));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(W.ndraw + idx_next));
+            if (HOME) asm volatile("prefetch.global.L2 [%0];" ::"l"(W.home + idx_next));
+        }
+#endif
         const unsigned ballot = __ballot_sync(0xffffffffu, survive);
         const unsigned pballot = HOME ? __ballot_sync(0xffffffffu, survive && !settled) : 0u;
         // append the survivors of this chunk to the next list, in order within the chunk (HOME: and the unsettled ones
