@@ -128,6 +128,7 @@ struct phox_context {
     DevBuf<int2> d_cand;                       // candidate lists of the home cells
     DevBuf<unsigned> d_home_state;             // wavefront form, per slot: home cell of the photon
     DevBuf<unsigned> d_pending, d_pending_count;   // wavefront form: list positions the home cells left to k_wf_trace, and their count per bounce
+    DevBuf<unsigned> d_gs_home;                    // per genstep of the launch: home cell its photons start with
     DevBuf<Prd> d_wave_hits2;                      // second hit buffer: the physics kernel fills the next bounce's records while it reads this bounce's
     int num_home = 0;                          // prims that have a candidate list
     DevBuf<float> d_slack;                     // per CSGPrim: exit-bound slack of prims that are exactly a box (0 = not such a prim)
@@ -228,11 +229,11 @@ extern "C" phox_context* phox_create(int device) {
         ctx->sim_grid[dbg] = per_sm * prop.multiProcessorCount;
         int w[3] = {0, 0, 0};
         if (dbg) {
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[0], k_wf_generate<true>, kWaveThreads, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[0], k_wf_generate<true, true>, kWaveThreads, 0);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[1], k_wf_trace<true>, kTraceThreads, 0);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[2], k_wf_propagate<true, true>, kPropThreads, 0);
         } else {
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[0], k_wf_generate<false>, kWaveThreads, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[0], k_wf_generate<false, true>, kWaveThreads, 0);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[1], k_wf_trace<false>, kTraceThreads, 0);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w[2], k_wf_propagate<false, true>, kPropThreads, 0);
         }
@@ -268,7 +269,7 @@ extern "C" void phox_destroy(phox_context* ctx) {
     ctx->d_record.release(); ctx->d_hit.release(); ctx->d_seq.release(); ctx->d_prd.release();
     ctx->d_block_hits.release(); ctx->d_block_off.release(); ctx->d_counters.release();
     ctx->d_slack.release(); ctx->d_exact.release();
-    ctx->d_home.release(); ctx->d_cand.release(); ctx->d_home_state.release(); ctx->d_pending.release(); ctx->d_pending_count.release(); ctx->d_wave_hits2.release();
+    ctx->d_home.release(); ctx->d_cand.release(); ctx->d_home_state.release(); ctx->d_pending.release(); ctx->d_pending_count.release(); ctx->d_wave_hits2.release(); ctx->d_gs_home.release();
     ctx->d_tag.release(); ctx->d_flat.release(); ctx->d_tagslot.release();
     ctx->d_lpos.release(); ctx->d_hitlite.release(); ctx->d_merged_lite.release();
     ctx->d_merged.release(); ctx->d_merge_in.release(); merge_scratch_free(ctx->merge_scratch);
@@ -828,8 +829,21 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
         };
         CK(cudaEventRecord(ctx->ev[0], ctx->stream));
         W.active_out = ctx->d_active[0].p;
-        if (dbg) k_wf_generate<true><<<grid(0), kWaveThreads, 0, ctx->stream>>>(W);
-        else k_wf_generate<false><<<grid(0), kWaveThreads, 0, ctx->stream>>>(W);
+        if (homes) {           // home cell of each genstep, handed to its photons
+            CK(ctx->d_gs_home.reserve((size_t)std::max(ngs, 1)));
+            k_genstep_home<<<(ngs + 127) / 128, 128, 0, ctx->stream>>>(d_gs, ngs, P.scene.home, ctx->nprim, ctx->d_gs_home.p);
+            W.gs_home = ctx->d_gs_home.p;
+            ctx->stats.num_kernel += 1;
+        }
+        if (home_pass) {
+            W.hits_next = ctx->d_wave_hits.p;                     // bounce 0 reads hit_buf[0]
+            W.pending = ctx->d_pending.p; W.pending_count = ctx->d_pending_count.p;
+            if (dbg) k_wf_generate<true, true><<<grid(0), kWaveThreads, 0, ctx->stream>>>(W);
+            else k_wf_generate<false, true><<<grid(0), kWaveThreads, 0, ctx->stream>>>(W);
+        } else {
+            if (dbg) k_wf_generate<true, false><<<grid(0), kWaveThreads, 0, ctx->stream>>>(W);
+            else k_wf_generate<false, false><<<grid(0), kWaveThreads, 0, ctx->stream>>>(W);
+        }
         CK(cudaGetLastError());
         const bool prof = ctx->profiling;
         if (prof) while (ctx->prof_ev.size() < 2 * (size_t)c.max_bounce + 1) { cudaEvent_t e; CK(cudaEventCreate(&e)); ctx->prof_ev.push_back(e); }
@@ -841,9 +855,9 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
             W.bounce = b;
             // per bounce: k_wf_trace -> k_wf_propagate ; with profiling on, an event before each kernel.
             // With home cells the physics kernel of bounce b - 1 has already written the hit records of the rays their home
-            // settled; the trace kernel takes the rest, the pending list (everything at bounce 0: nobody has a home yet).
+            // settled (for bounce 0: k_wf_generate); the trace kernel takes the rest, the pending list.
             if (prof) CK(cudaEventRecord(ctx->prof_ev[2 * b], ctx->stream));
-            W.pending = (home_pass && b > 0) ? ctx->d_pending.p : nullptr;
+            W.pending = home_pass ? ctx->d_pending.p : nullptr;
             W.pending_count = home_pass ? ctx->d_pending_count.p + b : nullptr;
             if (dbg) k_wf_trace<true><<<grid(1, kTraceThreads), kTraceThreads, 0, ctx->stream>>>(W);
             else k_wf_trace<false><<<grid(1, kTraceThreads), kTraceThreads, 0, ctx->stream>>>(W);

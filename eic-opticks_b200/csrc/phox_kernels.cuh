@@ -602,7 +602,8 @@ struct WaveParams {
     const unsigned* count_in;       // device-side length of active_in
     unsigned* count_out;            // device-side length of active_out (zeroed beforehand)
     unsigned* ndraw;                // per slot: uniforms consumed so far
-    unsigned* home;                 // per slot: home cell (CSGPrim index or kNoHome), read and kept up by the trace kernels alone
+    unsigned* home;                 // per slot: home cell (CSGPrim index or kNoHome)
+    const unsigned* gs_home;        // per genstep: home cell its photons start with (k_genstep_home), or null
     unsigned* pending;              // list positions whose home cell did not settle the ray (null: k_wf_trace takes the whole list)
     unsigned* pending_count;        // device-side length of pending (zeroed beforehand)
     Seq* seq_state;                 // per slot history being built (debug modes)
@@ -633,49 +634,6 @@ constexpr unsigned kListEps0 = 0x80000000u;     // list entry bit: the photon's 
 constexpr unsigned kListSlotMask = 0x7fffffffu; // the trace kernel does not have to read the flag word of the photon record
 constexpr unsigned kWaveNoHit = 0xffffffffu;    // prim_boundary of a list entry whose photon is final (miss or time over)
 
-template <bool DEBUG>
-__global__ void __launch_bounds__(kWaveThreads) k_wf_generate(const __grid_constant__ WaveParams W) {
-    const SimParams& P = W.sim;
-    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < P.num_photon; idx += gridDim.x * blockDim.x) {
-        int lo = 0, hi = P.num_genstep;
-        while (hi - lo > 1) {
-            int mid = (lo + hi) >> 1;
-            if (__ldg(P.gs_prefix + mid) <= (unsigned long long)idx) lo = mid; else hi = mid;
-        }
-        Genstep gs;
-        {
-            const float4* src = reinterpret_cast<const float4*>(P.genstep + lo);
-            float4* dst = reinterpret_cast<float4*>(&gs);
-#pragma unroll
-            for (int k = 0; k < 6; k++) dst[k] = __ldg(src + k);
-        }
-        unsigned long long photon_idx = P.photon_offset + idx;
-        unsigned long long base = P.rng_offset + P.skipahead * (unsigned long long)P.event_index;
-        Philox rng;
-        rng.init(P.seed, photon_idx, base);
-        PhotonState p;
-        generate_photon(p, rng, gs, P.tables, P.input_photon, P.input_base, photon_idx);
-#if PHOX_WF_STREAM
-        p.store_cs(P.photon + idx);
-        __stcs(W.ndraw + idx, rng.consumed(base));
-        __stcs(W.active_out + idx, idx | ((p.obf & P.eps0_mask) ? kListEps0 : 0u));
-        if (W.home) __stcs(W.home + idx, kNoHome);
-#else
-        p.store(P.photon + idx);
-        W.ndraw[idx] = rng.consumed(base);
-        W.active_out[idx] = idx | ((p.obf & P.eps0_mask) ? kListEps0 : 0u);
-        if (W.home) W.home[idx] = kNoHome;
-#endif
-        if (P.lpos) P.lpos[idx] = 0u;
-        if (DEBUG) {
-            Seq seq;
-            seq.seqhis[0] = seq.seqhis[1] = seq.seqbnd[0] = seq.seqbnd[1] = 0ull;
-            if (P.record && 0 < P.max_record) p.store(P.record + (size_t)P.max_record * idx);
-            if (P.seq) { seq_add(seq, 0u, p.flag(), p.boundary()); P.seq[idx] = seq; }
-        }
-    }
-}
-
 // hit record of list position a (streaming store: the physics kernel reads it once)
 PHOX_D void wave_store_hit(Prd* hits, unsigned a, const Prd& r) {
 #if PHOX_WF_STREAM
@@ -693,6 +651,128 @@ PHOX_D void wave_hit_record(Prd& r, const HitInfo& h) {
     r.nx = h.normal.x; r.ny = h.normal.y; r.nz = h.normal.z; r.t = h.t;
     r.lposcost = h.lposcost; r.lposfphi = h.lposfphi;
     r.iindex_identity = h.iindex_identity; r.prim_boundary = h.prim_boundary;
+}
+
+// Home cell a genstep's photons start with: the smallest home box that holds the genstep's position (mid-point of the
+// step for Cerenkov / scintillation gensteps, whose photons are spread along it).  Only a hint - every ray checks for
+// itself that its origin lies in the box of the home it carries - so a genstep near a wall, or a wide torch source, just
+// sends some photons of the first bounce to the BVH.
+__global__ void k_genstep_home(const Genstep* __restrict__ gs, int ngs, const float4* __restrict__ home, int nprim, unsigned* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ngs) return;
+    const Genstep& g = gs[i];
+    const int code = g.gencode();
+    float3 p = f3(g.f[4], g.f[5], g.f[6]);
+    if (code == GS_CERENKOV || code == GS_SCINTILLATION || code == GS_DsG4Scintillation_r4695)
+        p = f3(g.f[4] + 0.5f * g.f[8], g.f[5] + 0.5f * g.f[9], g.f[6] + 0.5f * g.f[10]);
+    unsigned best = kNoHome;
+    float best_vol = CUDART_INF_F;
+    if (code != GS_INPUT_PHOTON) {
+        for (int k = 0; k < nprim; k++) {
+            const float4 ha = __ldg(home + 2 * k), hb = __ldg(home + 2 * k + 1);
+            if (__float_as_int(hb.z) <= 0) continue;
+            if (p.x >= ha.x && p.x <= ha.w && p.y >= ha.y && p.y <= hb.x && p.z >= ha.z && p.z <= hb.y) {
+                const float vol = (ha.w - ha.x) * (hb.x - ha.y) * (hb.y - ha.z);
+                if (vol < best_vol) { best_vol = vol; best = (unsigned)k; }
+            }
+        }
+    }
+    out[i] = best;
+}
+
+// HOME: photons take their genstep's home cell along (k_genstep_home) and try its candidate list at once, exactly like
+// the survivors of a physics pass do (k_wf_propagate): settled rays get the hit record of bounce 0 from here, the rest
+// goes to the pending list of bounce 0.
+template <bool DEBUG, bool HOME>
+__global__ void __launch_bounds__(kWaveThreads) k_wf_generate(const __grid_constant__ WaveParams W) {
+    __shared__ unsigned s_warp[kWaveThreads / 32];
+    __shared__ unsigned s_pbase;
+    const SimParams& P = W.sim;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    unsigned nhome = 0;
+    for (unsigned base_idx = blockIdx.x * blockDim.x; base_idx < P.num_photon; base_idx += gridDim.x * blockDim.x) {
+        const unsigned idx = base_idx + threadIdx.x;
+        bool pend = false;
+        if (idx < P.num_photon) {
+            int lo = 0, hi = P.num_genstep;
+            while (hi - lo > 1) {
+                int mid = (lo + hi) >> 1;
+                if (__ldg(P.gs_prefix + mid) <= (unsigned long long)idx) lo = mid; else hi = mid;
+            }
+            Genstep gs;
+            {
+                const float4* src = reinterpret_cast<const float4*>(P.genstep + lo);
+                float4* dst = reinterpret_cast<float4*>(&gs);
+#pragma unroll
+                for (int k = 0; k < 6; k++) dst[k] = __ldg(src + k);
+            }
+            unsigned long long photon_idx = P.photon_offset + idx;
+            unsigned long long base = P.rng_offset + P.skipahead * (unsigned long long)P.event_index;
+            Philox rng;
+            rng.init(P.seed, photon_idx, base);
+            PhotonState p;
+            generate_photon(p, rng, gs, P.tables, P.input_photon, P.input_base, photon_idx);
+#if PHOX_WF_STREAM
+            p.store_cs(P.photon + idx);
+            __stcs(W.ndraw + idx, rng.consumed(base));
+            __stcs(W.active_out + idx, idx | ((p.obf & P.eps0_mask) ? kListEps0 : 0u));
+#else
+            p.store(P.photon + idx);
+            W.ndraw[idx] = rng.consumed(base);
+            W.active_out[idx] = idx | ((p.obf & P.eps0_mask) ? kListEps0 : 0u);
+#endif
+            if (P.lpos) P.lpos[idx] = 0u;
+            if (DEBUG) {
+                Seq seq;
+                seq.seqhis[0] = seq.seqhis[1] = seq.seqbnd[0] = seq.seqbnd[1] = 0ull;
+                if (P.record && 0 < P.max_record) p.store(P.record + (size_t)P.max_record * idx);
+                if (P.seq) { seq_add(seq, 0u, p.flag(), p.boundary()); P.seq[idx] = seq; }
+            }
+            if (W.home) {
+                unsigned home = W.gs_home ? __ldg(W.gs_home + lo) : kNoHome;
+                if (HOME) {
+                    pend = true;
+                    if (0 < P.max_bounce && p.time < P.max_time) {         // else the first trace kernel writes the no-hit record
+                        const float tmin = (p.obf & P.eps0_mask) ? P.tmin0 : P.tmin;
+                        const float3 o = p.pos, d = p.mom;
+                        Nearest best;
+                        best.t = P.tmax; best.prim = -1; best.inst = 0; best.n = f3(0.f, 0.f, 0.f);
+                        if (home_search(best, P.scene, tmin, o, d, home)) {
+                            home_update(home, P.scene, best.prim);
+                            const Nearest best_c = best;
+                            const float3 o_c = o, d_c = d;
+                            HitInfo h_c;
+                            hit_finish_body(h_c, P.scene, best_c, o_c, d_c, ((DEBUG && P.prd != nullptr) || P.lpos != nullptr) ? kHitFphi : 0u);
+                            Prd r;
+                            wave_hit_record(r, h_c);
+                            if (DEBUG) { if (P.prd && 0 < P.max_record) P.prd[(size_t)P.max_record * idx] = r; }
+                            wave_store_hit(W.hits_next, idx, r);
+                            pend = false;
+                            nhome++;
+                        }
+                    }
+                }
+                __stcs(W.home + idx, home);
+            }
+        }
+        if (HOME) {        // pending list of bounce 0, in slot order within the chunk
+            const unsigned pballot = __ballot_sync(0xffffffffu, pend);
+            if (lane == 0) s_warp[warp] = __popc(pballot);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned ptot = 0;
+                for (int w = 0; w < kWaveThreads / 32; w++) { const unsigned c = s_warp[w]; s_warp[w] = ptot; ptot += c; }
+                s_pbase = ptot ? atomicAdd(W.pending_count, ptot) : 0u;
+            }
+            __syncthreads();
+            if (pend) W.pending[s_pbase + s_warp[warp] + __popc(pballot & ((1u << lane) - 1u))] = idx;
+            __syncthreads();
+        }
+    }
+    if (HOME) {
+        for (int off = 16; off > 0; off >>= 1) nhome += __shfl_down_sync(0xffffffffu, nhome, off);
+        if (lane == 0 && nhome) { atomicAdd(P.counters, (unsigned long long)nhome); atomicAdd(P.counters + 2, (unsigned long long)nhome); }
+    }
 }
 
 // One ray per live photon (W.pending == null) or per entry of the pending list the physics kernel of the previous bounce
