@@ -128,6 +128,10 @@ struct phox_context {
     DevBuf<int2> d_cand;                       // candidate lists of the home cells
     DevBuf<unsigned> d_home_state;             // wavefront form, per slot: home cell of the photon
     DevBuf<unsigned> d_pending, d_pending_count;   // wavefront form: list positions the home cells left to k_wf_trace, and their count per bounce
+    DevBuf<Photon> d_hit_stage[2];                 // phox_get_hits_async: hits of the last two events, copied out while the next event runs
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_stage = nullptr, ev_copied[2] = {nullptr, nullptr};
+    int stage_idx = 0;
     DevBuf<unsigned> d_gs_home;                    // per genstep of the launch: home cell its photons start with
     DevBuf<Prd> d_wave_hits2;                      // second hit buffer: the physics kernel fills the next bounce's records while it reads this bounce's
     int num_home = 0;                          // prims that have a candidate list
@@ -278,6 +282,9 @@ extern "C" void phox_destroy(phox_context* ctx) {
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     for (int k = 0; k < 4; k++) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->ev_stage) cudaEventDestroy(ctx->ev_stage);
+    for (int k = 0; k < 2; k++) { if (ctx->ev_copied[k]) cudaEventDestroy(ctx->ev_copied[k]); ctx->d_hit_stage[k].release(); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -1107,6 +1114,55 @@ extern "C" int phox_get_hits_device(phox_context* ctx, void* d_dst) {
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(d_dst, ctx->d_hit.p, (size_t)ctx->num_hit * 64, cudaMemcpyDeviceToDevice, ctx->stream));
     return PHOX_OK;
+}
+
+// Hits of the last event to host memory WITHOUT blocking the next event: a device-to-device copy into one of two staging
+// buffers on the launch stream, then the device-to-host copy on a second stream.  The caller may start the next
+// phox_simulate at once; phox_hits_wait() returns when every copy posted so far has landed.
+extern "C" int phox_get_hits_async(phox_context* ctx, void* dst) {
+    if (!ctx) return PHOX_E_ARG;
+    if (!ctx->have_event) return ctx->fail(PHOX_E_STATE, "phox_get_hits_async: no event");
+    if (ctx->num_hit == 0) return PHOX_OK;
+    if (!dst) return ctx->fail(PHOX_E_ARG, "phox_get_hits_async: null destination");
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->ev_stage, cudaEventDisableTiming));
+        for (int k = 0; k < 2; k++) CK(cudaEventCreateWithFlags(&ctx->ev_copied[k], cudaEventDisableTiming));
+    }
+    const int k = ctx->stage_idx;
+    CK(cudaEventSynchronize(ctx->ev_copied[k]));                  // the copy that last used this staging buffer (two events ago) is done
+    if ((size_t)ctx->num_hit > ctx->d_hit_stage[k].cap) CK(ctx->d_hit_stage[k].reserve((size_t)ctx->num_hit + (size_t)ctx->num_hit / 4 + 1024));
+    const size_t bytes = (size_t)ctx->num_hit * 64;
+    CK(cudaMemcpyAsync(ctx->d_hit_stage[k].p, ctx->d_hit.p, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_stage, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_stage, 0));
+    CK(cudaMemcpyAsync(dst, ctx->d_hit_stage[k].p, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    CK(cudaEventRecord(ctx->ev_copied[k], ctx->copy_stream));
+    ctx->stage_idx ^= 1;
+    return PHOX_OK;
+}
+
+extern "C" int phox_hits_wait(phox_context* ctx) {
+    if (!ctx) return PHOX_E_ARG;
+    if (!ctx->copy_stream) return PHOX_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    return PHOX_OK;
+}
+
+// page-locked host memory for the hit buffers of a multi-GPU host (any context's device may copy into it)
+extern "C" void* phox_host_alloc(int64_t bytes) {
+    void* p = nullptr;
+    if (bytes <= 0 || cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void phox_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+extern "C" int phox_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
 }
 
 extern "C" int64_t phox_get_array(phox_context* ctx, const char* name, void* dst, int64_t dst_bytes) {

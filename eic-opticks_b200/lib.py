@@ -73,6 +73,11 @@ SYMBOLS = {
     "phox_get_hits": (C.c_int, [C.c_void_p, C.c_void_p]),
     "phox_hits_device": (C.c_void_p, [C.c_void_p]),
     "phox_get_hits_device": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "phox_get_hits_async": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "phox_hits_wait": (C.c_int, [C.c_void_p]),
+    "phox_host_alloc": (C.c_void_p, [C.c_int64]),
+    "phox_host_free": (None, [C.c_void_p]),
+    "phox_device_count": (C.c_int, []),
     "phox_get_array": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
     "phox_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "phox_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),

@@ -173,6 +173,16 @@ int     phox_get_hits_device(phox_context* ctx, void* d_dst);      /* device dst
                                                                       of the NCCL hit gather), async on
                                                                       the context's stream            */
 
+/* Hits to host memory without holding up the next event (the multi-GPU host's gather, include/PhoxMultiGPU.h): the
+ * records are staged on the device (two buffers) and copied out on a second stream, so phox_simulate of the next event
+ * may be called at once.  dst should be page-locked (phox_host_alloc) for the copy to be asynchronous; it must stay
+ * valid until phox_hits_wait() - which returns once every copy posted so far has landed - or the second-next call. */
+int   phox_get_hits_async(phox_context* ctx, void* dst_sphoton);
+int   phox_hits_wait(phox_context* ctx);
+void* phox_host_alloc(int64_t bytes);     /* page-locked, usable from every device; NULL on failure */
+void  phox_host_free(void* p);
+int   phox_device_count(void);            /* CUDA devices visible to this process (0 = none: no CPU path) */
+
 /* Named arrays of the last event, when the event mode keeps them:
  * "photon" (64 B/photon), "record" (64 B * max_record), "seq" (32 B), "prd" (32 B * max_record),
  * "tag" (stag, 32 B: 4-bit consumption tag of each of the first 64 tagged random draws, sysrap/stag.h) and "flat"

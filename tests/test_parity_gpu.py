@@ -730,6 +730,42 @@ def test_cxx_torch_driver_matches_python_path(tmp_path):
         assert want > 50 and len(open(out).read().strip().split("\n")) == want
 
 
+@pytest.mark.parametrize("name,kw", [("sipm8x8_scint", dict(num_photon=200000, photons_per_genstep=500)), ("pmt_wall_torch", dict(num_photon=60000, nx=20, ny=20))])
+def test_cxx_multi_gpu_host_equals_single_gpu(tmp_path, name, kw):
+    """apps/PhoxMultiGPU.cpp on include/PhoxMultiGPU.h: one thread + context per rank, genstep ranges with absolute photon
+    offsets (input photons: photon ranges), hits into one pinned buffer at the prefix offsets of the ranks' counts while the
+    next event runs.  The bytes must be those of one context simulating the whole event.  On a 1-GPU box the ranks share
+    device 0 (--devices 0,0,0), which exercises the same host logic."""
+    import subprocess
+    import torch
+    from eic_opticks_b200 import foundry as F
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "eic-opticks_b200", "apps", "PhoxMultiGPU")
+    assert os.path.exists(exe), "run __graft_entry__.build()"
+    w = workloads.WORKLOADS[name](**kw)
+    g = w["geom"]
+    F.save_geometry(g, str(tmp_path / "geom"))
+    np.save(tmp_path / "gs.npy", np.ascontiguousarray(w["gensteps"], dtype=np.float32))
+    args = [exe, "-g", str(tmp_path / "geom"), "-G", str(tmp_path / "gs.npy"), "--events", "3", "--max-bounce", str(w["config"].get("max_bounce", 31))]
+    if w["input_photons"] is not None:
+        np.save(tmp_path / "ip.npy", np.ascontiguousarray(w["input_photons"], dtype=np.float32))
+        args += ["-I", str(tmp_path / "ip.npy")]
+    sim = make_sim(w)
+    want = sim.simulate_np(w["gensteps"], 2, w["input_photons"]).copy()          # the app writes the hits of its last event, id 2
+    sim.close()
+    assert len(want) > 100
+    ndev = torch.cuda.device_count()
+    layouts = ["0", "0,0,0"] + ([",".join(str(d) for d in range(ndev))] if ndev > 1 else [])
+    for devs in layouts:
+        out = tmp_path / ("hits_%s.npy" % devs.replace(",", "_"))
+        r = subprocess.run(args + ["--devices", devs, "-o", str(out)], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, (r.stdout, r.stderr)
+        got = np.load(out)
+        assert got.shape == want.shape, (devs, got.shape, want.shape)
+        assert got.tobytes() == want.tobytes(), devs
+        assert "Opticks: NumHits:  %d" % len(want) in r.stdout
+
+
 def test_oracle_texture_emulation_vs_hardware():
     """the CPU oracle's restatement of CUDA linear texture filtering (8-bit fraction, lerp form) against the
     B200 texture unit on a dispersive boundary table at random fractional wavelengths"""
