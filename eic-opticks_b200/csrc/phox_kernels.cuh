@@ -624,6 +624,9 @@ constexpr int kTraceThreads = PHOX_WF_TRACE_THREADS;
 #define PHOX_WF_PROP_THREADS 256        // block of the physics kernel = run length of the ordered survivor append
 #endif
 constexpr int kPropThreads = PHOX_WF_PROP_THREADS;
+#ifndef PHOX_APPEND_SORT
+#define PHOX_APPEND_SORT 0              // experiment: survivors grouped by the boundary they meet next (measured and rejected, profiles/r2_summary.md)
+#endif
 #ifndef PHOX_PROP_PREFETCH
 #define PHOX_PROP_PREFETCH 1            // physics kernel: L2 prefetch of the next chunk's lines (measured, see profiles/r2_summary.md)
 #endif
@@ -830,6 +833,9 @@ template <bool DEBUG, bool HOME>
 __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_propagate(const __grid_constant__ WaveParams W) {
     __shared__ unsigned s_warp[2][kPropThreads / 32];      // double-buffered by chunk parity: two barriers per chunk instead of three
     __shared__ unsigned s_base[2], s_pbase[2];
+#if PHOX_APPEND_SORT
+    __shared__ unsigned s_cls[2][8][kPropThreads / 32];
+#endif
     unsigned par = 0;
     unsigned nhome = 0;
     const SimParams& P = W.sim;
@@ -941,6 +947,41 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
             if (HOME) asm volatile("prefetch.global.L2 [%0];" ::"l"(W.home + idx_next));
         }
 #endif
+#if PHOX_APPEND_SORT
+        // EXPERIMENT (profiles/r2_summary.md, "re-sorting by boundary"): survivors of the chunk are appended grouped by the
+        // boundary they will meet next (known for the rays their home cell settled; the pending ones form the last group),
+        // so that the warps of the next physics pass see fewer different surface types.  Stable within a group.
+        const unsigned ballot = __ballot_sync(0xffffffffu, survive);
+        const unsigned pballot = HOME ? __ballot_sync(0xffffffffu, survive && !settled) : 0u;
+        const unsigned key = (HOME && settled) ? min(r2.prim_boundary & 0xffffu, 6u) : 7u;
+        unsigned my_class_ballot = 0u;
+#pragma unroll
+        for (unsigned c = 0; c < 8u; c++) {
+            const unsigned bc = __ballot_sync(0xffffffffu, survive && key == c);
+            if (key == c) my_class_ballot = bc;
+            if (lane == 0) s_cls[par][c][warp] = __popc(bc);
+        }
+        if (lane == 0) s_warp[par][warp] = __popc(pballot) << 16;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned tot = 0, ptot = 0;
+            for (int c = 0; c < 8; c++)
+                for (int w = 0; w < kPropThreads / 32; w++) { const unsigned n = s_cls[par][c][w]; s_cls[par][c][w] = tot; tot += n; }
+            for (int w = 0; w < kPropThreads / 32; w++) { const unsigned n = s_warp[par][w] >> 16; s_warp[par][w] = ptot << 16; ptot += n; }
+            s_base[par] = tot ? atomicAdd(W.count_out, tot) : 0u;
+            if (HOME) s_pbase[par] = ptot ? atomicAdd(W.pending_count, ptot) : 0u;
+        }
+        __syncthreads();
+        if (survive) {
+            const unsigned wo = s_warp[par][warp];
+            const unsigned pos = s_base[par] + s_cls[par][key][warp] + __popc(my_class_ballot & ((1u << lane) - 1u));
+            __stcs(W.active_out + pos, entry_out);
+            if (HOME) {
+                if (settled) wave_store_hit(W.hits_next, pos, r2);
+                else W.pending[s_pbase[par] + (wo >> 16) + __popc(pballot & ((1u << lane) - 1u))] = pos;
+            }
+        }
+#else
         const unsigned ballot = __ballot_sync(0xffffffffu, survive);
         const unsigned pballot = HOME ? __ballot_sync(0xffffffffu, survive && !settled) : 0u;
         // append the survivors of this chunk to the next list, in order within the chunk (HOME: and the unsettled ones
@@ -971,6 +1012,7 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
                 else W.pending[s_pbase[par] + (wo >> 16) + __popc(pballot & ((1u << lane) - 1u))] = pos;
             }
         }
+#endif
         par ^= 1u;
     }
     if (HOME) {
