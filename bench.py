@@ -204,9 +204,34 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     # weak scaling: the global event has world * photons; rank r takes its contiguous genstep share
-    w = workloads.WORKLOADS[args.workload](num_photon=args.photons * world)
+    big_file = None
+    if args.workload == "pmt_wall_torch" and args.photons > 32_000_000:
+        # BASELINE config 4 at its stated size (1 G photons / 8 GPUs = 125 M per rank): the photon-file contents of this rank's
+        # photon range are drawn on the device with torch (same disc source: r = R u1, phi = 2 pi u2, straight down, 420 nm, zero
+        # flags) - the host Philox restatement of src/torch.cpp needs a minute per rank at this size.  Synthetic either way.
+        from eic_opticks_b200 import gensteps as G
+        w = workloads.WORKLOADS[args.workload](num_photon=1000)
+        hx, hy = w["geom"]["half"]
+        gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
+        u = torch.rand((args.photons, 2), generator=gen, device=dev, dtype=torch.float32)
+        r, phi = (min(hx, hy) - 600.0) * u[:, 0], 6.283185307179586 * u[:, 1]
+        big_file = torch.zeros((args.photons, 4, 4), dtype=torch.float32, device=dev)
+        big_file[:, 0, 0] = r * torch.cos(phi); big_file[:, 0, 1] = r * torch.sin(phi); big_file[:, 0, 2] = 1500.0
+        big_file[:, 1, 2] = -1.0
+        big_file[:, 2, 0] = torch.sin(phi); big_file[:, 2, 1] = -torch.cos(phi); big_file[:, 2, 3] = 420.0
+        del u, r, phi
+        big_host = torch.empty((args.photons, 4, 4), dtype=torch.float32).pin_memory()      # the ONE host copy (8 GB per rank at 125 M photons)
+        big_host.copy_(big_file)
+        gs_r, ip_r, off_r, cnt_r = G.input_photon_genstep(args.photons), big_host.numpy(), rank * args.photons, args.photons
+    elif world > 1 and args.workload in ("pmt_wall_torch", "sphere_leak_torch"):
+        # input-photon workloads: every rank makes its own photon-range of the global event (its own Philox seed) instead of the
+        # whole array - at BASELINE config 4's size (1 G photons) that array is 64 GB per process
+        w = workloads.WORKLOADS[args.workload](num_photon=args.photons, seed=rank)
+        gs_r, ip_r, off_r, cnt_r = w["gensteps"], w["input_photons"], rank * args.photons, args.photons
+    else:
+        w = workloads.WORKLOADS[args.workload](num_photon=args.photons * world)
+        gs_r, ip_r, off_r, cnt_r = parallel.shard_event(w["gensteps"], rank, world, w["input_photons"])
     g = w["geom"]
-    gs_r, ip_r, off_r, cnt_r = parallel.shard_event(w["gensteps"], rank, world, w["input_photons"])
     kmode = {"auto": 0, "persistent": 1, "wavefront": 2}[args.kernel_mode]
     sim = ph.Simulator.Create(g["foundry"], g["bnd"], g["optical"], g["icdf"], device=local_rank, event_mode=ph.MODE_MINIMAL, kernel_mode=kmode, **w["config"])
     if args.max_slot > 0:
@@ -217,10 +242,12 @@ def main():
     sim.set_stream(stream.cuda_stream)
 
     d_gs = torch.from_numpy(gs_r).to(dev)
-    d_ip = torch.from_numpy(ip_r).to(dev) if ip_r is not None else None
+    d_ip = (big_file if big_file is not None else torch.from_numpy(ip_r).to(dev)) if ip_r is not None else None
     h_gs = torch.from_numpy(gs_r).pin_memory()
-    h_ip = torch.from_numpy(ip_r).pin_memory() if ip_r is not None else None
-    h_hits = torch.empty((max(cnt_r, 1), 4, 4), dtype=torch.float32).pin_memory()
+    h_ip = (big_host if big_file is not None else torch.from_numpy(ip_r).pin_memory()) if ip_r is not None else None
+    # pinned destination of the e2e hits: every photon could be a hit, except at the 125 M-photon size where a quarter is plenty
+    # (11.6 % of the PMT-wall photons are detected) and 8 ranks x 8 GB of pinned memory would not be
+    h_hits = torch.empty((max(cnt_r if big_file is None else cnt_r // 4, 1), 4, 4), dtype=torch.float32).pin_memory()
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)     # 256 MB > 126 MB L2
 
     # N > 1: every event's hits end up on rank 0 (the reference hands hits to one host process).  The gather of event k is posted

@@ -127,7 +127,7 @@ def _rotate_uz(d, u):
     return d
 
 
-def torch_photons(t, num_photons=0, seed=0):
+def torch_photons(t, num_photons=0, seed=0, _offset=0):
     """generate_photons (src/torch.cpp:8-30) for the disc type the shipped configs use:
     one Philox stream (seed, subsequence 0, offset 0), two uniforms per photon."""
     n = num_photons or t["numphoton"]
@@ -136,7 +136,13 @@ def torch_photons(t, num_photons=0, seed=0):
     if ty != TORCH_TYPES["disc"]:
         raise NotImplementedError("host torch generation covers the disc type of the shipped configs")
     f = np.float32
-    uu = curand_uniform_stream(seed, 0, 0, 2 * n).reshape(n, 2)
+    chunk = 8_000_000
+    if n > chunk:           # big arrays in pieces of the same stream (offset = 2 uniforms per photon): same numbers, bounded scratch
+        out = np.empty((n, 4, 4), dtype=f)
+        for s0 in range(0, n, chunk):
+            out[s0:s0 + chunk] = torch_photons(t, min(chunk, n - s0), seed, _offset=2 * s0)
+        return out
+    uu = curand_uniform_stream(seed, 0, _offset, 2 * n).reshape(n, 2)
     zen, azi = t.get("zenith", (0.0, 1.0)), t.get("azimuth", (0.0, 1.0))
     u_zenith = f(zen[0]) + uu[:, 0] * f(zen[1] - zen[0])
     u_azimuth = f(azi[0]) + uu[:, 1] * f(azi[1] - azi[0])

@@ -74,25 +74,25 @@ def raindrop_cerenkov(num_photon=10_000_000, photons_per_genstep=1000, seed=SEED
     return dict(name="raindrop_cerenkov", geom=geom, gensteps=np.ascontiguousarray(gs), input_photons=None, config=dict(), num_photon=int(counts.sum()))
 
 
-def sphere_leak_torch(num_photon=1_000_000):
+def sphere_leak_torch(num_photon=1_000_000, seed=0):
     """BASELINE config 1: config/sphere_leak.json torch (disc r 0.1 at the origin, mom (0,0.3,1),
     420 nm) scaled to 1e6 photons, generated on the host and fed as input photons like
     GPUPhotonSource does (src/GPUPhotonSourceMinimal.h:57-88)."""
     geom = GEO.sphere_leak()
     t = dict(pos=[0.0, 0.0, 0.0], time=0.0, mom=G._normalize_f32([0.0, 0.3, 1.0]), pol=[1.0, 0.0, 0.0], wavelength=420.0, radius=0.1,
              numphoton=num_photon, type="disc")
-    ph = G.torch_photons(t, num_photon, seed=0)
+    ph = G.torch_photons(t, num_photon, seed=seed)
     return dict(name="sphere_leak_torch", geom=geom, gensteps=G.input_photon_genstep(num_photon), input_photons=ph, config=dict(), num_photon=num_photon)
 
 
-def pmt_wall_torch(num_photon=10_000_000, nx=100, ny=100):
+def pmt_wall_torch(num_photon=10_000_000, nx=100, ny=100, seed=0):
     """BASELINE config 4 (scaled per launch): instanced PMT wall, photons from a wide disc above it,
     supplied as an input-photon array like GPUPhotonFileSource (src/GPUPhotonFileSource.h:51-87)."""
     geom = GEO.pmt_wall(nx, ny)
     hx, hy = geom["half"]
     t = dict(pos=[0.0, 0.0, 1500.0], time=0.0, mom=[0.0, 0.0, -1.0], pol=[1.0, 0.0, 0.0], wavelength=420.0, radius=float(min(hx, hy) - 600.0),
              numphoton=num_photon, type="disc")
-    ph = G.torch_photons(t, num_photon, seed=0)
+    ph = G.torch_photons(t, num_photon, seed=seed)
     pu = ph.view(np.uint32)
     pu[:, 3, :] = 0                                   # file-source photons carry zero flags
     return dict(name="pmt_wall_torch", geom=geom, gensteps=G.input_photon_genstep(num_photon), input_photons=ph, config=dict(), num_photon=num_photon)
