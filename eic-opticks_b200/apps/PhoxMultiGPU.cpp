@@ -86,7 +86,7 @@ int main(int argc, char** argv) {
         });
         int64_t photons = 0;
         for (int64_t i = 0; i < ngs; i++) { uint32_t n; std::memcpy(&n, gs.data.data() + i * 96 + 12, 4); photons += n; }
-        mg.submit(gs.data.data(), ngs, nip ? ip.data.data() : nullptr, nip, 0);      // warm-up: buffers reach their size
+        for (int k = 0; k < 2; k++) mg.submit(gs.data.data(), ngs, nip ? ip.data.data() : nullptr, nip, k);      // warm-up: both hit buffers and both staging buffers reach their size
         mg.wait();
         const auto t0 = std::chrono::steady_clock::now();
         int64_t nhit = 0;
