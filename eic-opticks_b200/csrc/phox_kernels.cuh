@@ -558,10 +558,6 @@ __global__ void __launch_bounds__(kSimThreads, PHOX_SIM_MIN_BLOCKS) k_simulate(c
                         tg.tag = P.tag + 4 * (size_t)idx; tg.flat = P.flat + 64 * (size_t)idx; tg.slot = tag_slot;
                         command = propagate_t<true>(p, rng, h, P.tables, P.burn != 0, &tg);
                         tag_slot = tg.slot;
-                    } else if (DEBUG) {
-                        // the debug instantiations of both loop forms share ONE compiled physics body: the inlined value-copy body was
-                        // seen to contract one a*b+c differently between k_simulate<true> and k_wf_propagate<true> (1 ulp, 1 photon in 40 000)
-                        command = propagate_t<false>(p, rng, h, P.tables, P.burn != 0, nullptr);
                     } else {
                         command = propagate(p, rng, h, P.tables, P.burn != 0);
                     }
@@ -888,8 +884,6 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
                     tg.tag = P.tag + 4 * (size_t)idx; tg.flat = P.flat + 64 * (size_t)idx; tg.slot = P.tagslot[idx];
                     command = propagate_t<true>(p, rng, h, P.tables, P.burn != 0, &tg);
                     P.tagslot[idx] = tg.slot;
-                } else if (DEBUG) {
-                    command = propagate_t<false>(p, rng, h, P.tables, P.burn != 0, nullptr);       // one body for the debug kernels of both loop forms, see k_simulate
                 } else {
 #if PHOX_WF_PROP_INLINE
                     command = propagate_body<false>(p, rng, h, P.tables, P.burn != 0, nullptr);

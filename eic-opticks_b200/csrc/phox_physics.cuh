@@ -394,6 +394,49 @@ PHOX_D void marsaglia_direction(float3& dir, Philox& rng) {
     dir = f3(a * u, a * v, 2.f * b - 1.f);
 }
 
+// Lambertian reflection about the geometric normal flipped against the incident direction (qsim::reflect_diffuse).
+// Every product and sum is spelled out with the round-to-nearest intrinsics, which the compiler never fuses: written with
+// plain operators, this block was seen to get a different a*b+c contraction in k_wf_propagate<false, ..> than in the other
+// kernels (scripts/form_consistency.py: last-bit differences in mom / pol of exactly the photons that took this branch).
+// Pinned like this it is the arithmetic of the -fmad=false build in every kernel of every build.
+PHOX_D float dot_rn(const float3& a, const float3& b) { return __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z)); }
+PHOX_D void diffuse_reflect(float3& mom_io, float3& pol_io, const float3& normal, Philox& rng) {
+    const float3 old_mom = mom_io, old_pol = pol_io;
+    float3 mom = old_mom;
+    const float orient = dot_rn(old_mom, normal) > 0.f ? -1.f : 1.f;
+    float ndotv, u;
+    int count = 0;
+    do {
+        count++;
+        {   // marsaglia_direction
+            float mu, mv, mb;
+            do {
+                const float u0 = rng.uniform();
+                const float u1 = rng.uniform();
+                mu = __fadd_rn(__fmul_rn(2.f, u0), -1.f);
+                mv = __fadd_rn(__fmul_rn(2.f, u1), -1.f);
+                mb = __fadd_rn(__fmul_rn(mu, mu), __fmul_rn(mv, mv));
+            } while (mb > 1.f);
+            const float ma = __fmul_rn(2.f, sqrtf(__fadd_rn(1.f, -mb)));
+            mom = f3(__fmul_rn(ma, mu), __fmul_rn(ma, mv), __fadd_rn(__fmul_rn(2.f, mb), -1.f));
+        }
+        ndotv = __fmul_rn(dot_rn(mom, normal), orient);
+        if (ndotv < 0.f) {
+            mom = f3(__fmul_rn(-1.f, mom.x), __fmul_rn(-1.f, mom.y), __fmul_rn(-1.f, mom.z));
+            ndotv = __fmul_rn(-1.f, ndotv);
+        }
+        u = rng.uniform();
+    } while (!(u < ndotv) && (count < 1024));
+    const float3 diff = f3(__fadd_rn(mom.x, -old_mom.x), __fadd_rn(mom.y, -old_mom.y), __fadd_rn(mom.z, -old_mom.z));
+    const float inv = 1.0f / sqrtf(dot_rn(diff, diff));
+    const float3 facet_normal = f3(__fmul_rn(diff.x, inv), __fmul_rn(diff.y, inv), __fmul_rn(diff.z, inv));
+    const float two_edotn = __fmul_rn(2.f, dot_rn(old_pol, facet_normal));
+    mom_io = mom;
+    pol_io = f3(__fadd_rn(__fmul_rn(-1.f, old_pol.x), __fmul_rn(two_edotn, facet_normal.x)),
+                __fadd_rn(__fmul_rn(-1.f, old_pol.y), __fmul_rn(two_edotn, facet_normal.y)),
+                __fadd_rn(__fmul_rn(-1.f, old_pol.z), __fmul_rn(two_edotn, facet_normal.z)));
+}
+
 template <bool TAG>
 PHOX_D void rayleigh_scatter(PhotonState& p, Philox& rng, Tagr* tg) {
     float3 direction, polarization;
@@ -584,24 +627,7 @@ PHOX_D int propagate_core(PhotonState& p, Philox& rng, const HitInfo& h, const T
             } else {
                 flag = u_surface < absorb + detect + diffuse ? F_SURFACE_DREFLECT : F_SURFACE_SREFLECT;
                 if (flag == F_SURFACE_DREFLECT) {
-                    // Lambertian about the geometric normal flipped against the incident direction
-                    float3 old_mom = p.mom;
-                    const float orient = dot(old_mom, normal) > 0.f ? -1.f : 1.f;
-                    float ndotv, u;
-                    int count = 0;
-                    do {
-                        count++;
-                        marsaglia_direction(p.mom, rng);
-                        ndotv = dot(p.mom, normal) * orient;
-                        if (ndotv < 0.f) {
-                            p.mom = -1.f * p.mom;
-                            ndotv = -1.f * ndotv;
-                        }
-                        u = rng.uniform();
-                    } while (!(u < ndotv) && (count < 1024));
-                    float3 facet_normal = normalize(p.mom - old_mom);
-                    const float EdotN = dot(p.pol, facet_normal);
-                    p.pol = -1.f * (p.pol) + 2.f * EdotN * facet_normal;
+                    diffuse_reflect(p.mom, p.pol, normal, rng);
                 } else {
                     const float PdotN = dot(p.mom, normal);
                     p.mom = p.mom - 2.f * PdotN * normal;

@@ -296,3 +296,51 @@ def halfspace_zoo():
         fd.add_prim(shape, b, F.rotate_z(15.0 * k) @ F.translate(*c), mesh_idx=k + 2, name=name)
     fd.end_solid()
     return _finish(fd, bt, extra=dict(shape_centers=np.array(centers, dtype=np.float32), shape_names=[s[0] for s in shapes]))
+
+
+def box_maze():
+    """Stress geometry for the home cells and the exact-box paths (not a reference file): blocks of boxes that TOUCH (coincident
+    faces, edges and corners: every face hit is a tie between two or more prims), boxes nested three deep, a thin layer across
+    a whole block, pitches that are exact in float32 and pitches that are not; glass of two indices, a mirror skin, a
+    half-reflecting skin and a detecting skin, all in water inside an absorbing rock box."""
+    bt = T.BoundaryTable()
+    en = [1.55, 6.2]
+    bt.add_material(T.Material("Rock"))
+    bt.add_material(T.Material("Water", RINDEX=(en, [1.333, 1.35]), ABSLENGTH=(en, [5000.0, 4000.0]), RAYLEIGH=(en, [3000.0, 1500.0])))
+    bt.add_material(T.Material("GlassA", RINDEX=(en, [1.48, 1.52]), ABSLENGTH=(en, [800.0, 600.0])))
+    bt.add_material(T.Material("GlassB", RINDEX=(en, [1.70, 1.80]), ABSLENGTH=(en, [300.0, 200.0]), RAYLEIGH=(en, [500.0, 300.0])))
+    bt.add_surface(T.implicit_surface("Implicit_RINDEX_NoRINDEX_water_rock"))
+    bt.add_surface(T.Surface("MirrorSkin", REFLECTIVITY=(en, [0.97, 0.97]), polished=True))
+    bt.add_surface(T.Surface("RoughSkin", REFLECTIVITY=(en, [0.6, 0.6]), polished=False))
+    bt.add_surface(T.Surface("SensorSkin", EFFICIENCY=(en, [0.7, 0.7])))
+    b_water = bt.boundary("Rock", "Implicit_RINDEX_NoRINDEX_water_rock", "Implicit_RINDEX_NoRINDEX_water_rock", "Water")
+    kinds = [bt.boundary("Water", "", "", "GlassA"), bt.boundary("Water", "", "", "GlassB"), bt.boundary("Water", "MirrorSkin", "MirrorSkin", "GlassA"),
+             bt.boundary("Water", "RoughSkin", "RoughSkin", "GlassB"), bt.boundary("Water", "SensorSkin", "SensorSkin", "GlassA")]
+    fd = F.Foundry()
+    fd.begin_solid("r0")
+    fd.add_prim(F.box3(640, 640, 640), bt.boundary("Rock", "", "", "Rock"), name="Rock")
+    fd.add_prim(F.box3(600, 600, 600), b_water, name="Water")
+    centers = []
+    k = 0
+    # block 1: 4 x 4 x 2 touching boxes, pitch 25 (exact in float32)
+    for i in range(4):
+        for j in range(4):
+            for l in range(2):
+                c = (-150.0 + 25.0 * i, -150.0 + 25.0 * j, -40.0 + 25.0 * l)
+                fd.add_prim(F.box3(25.0, 25.0, 25.0), kinds[k % len(kinds)], F.translate(*c), name="touch%d" % k)
+                centers.append(c); k += 1
+    # a thin layer lying on block 1 (its bottom face is the top face of 16 boxes)
+    fd.add_prim(F.box3(100.0, 100.0, 0.7), kinds[1], F.translate(-112.5, -112.5, -2.15), name="layer")
+    # block 2: 5 x 3 touching boxes, pitch 17.3 (not exact in float32: faces coincide only up to rounding)
+    for i in range(5):
+        for j in range(3):
+            c = (60.0 + 17.3 * i, -120.1 + 17.3 * j, 33.3)
+            fd.add_prim(F.box3(17.3, 17.3, 40.0), kinds[(k + 2) % len(kinds)], F.translate(*c), name="pitch%d" % k)
+            centers.append(c); k += 1
+    # nested three deep, sharing one face plane (x = 50) and one corner
+    fd.add_prim(F.box3(100.0, 100.0, 100.0), kinds[0], F.translate(0.0, 150.0, 100.0), name="outer")
+    fd.add_prim(F.box3(60.0, 60.0, 60.0), bt.boundary("GlassA", "", "", "GlassB"), F.translate(20.0, 150.0, 100.0), name="middle")
+    fd.add_prim(F.box3(20.0, 20.0, 20.0), bt.boundary("GlassB", "SensorSkin", "SensorSkin", "GlassA"), F.translate(40.0, 170.0, 120.0), name="inner")
+    centers += [(0.0, 150.0, 100.0), (20.0, 150.0, 100.0), (40.0, 170.0, 120.0)]
+    fd.end_solid()
+    return _finish(fd, bt, extra=dict(box_centers=np.array(centers, dtype=np.float32)))

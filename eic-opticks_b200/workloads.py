@@ -205,6 +205,51 @@ def halfspace_zoo_torch(num_photon=30_000):
     return dict(name="halfspace_zoo_torch", geom=geom, gensteps=G.torch_genstep(t, num_photon), input_photons=None, config=dict(), num_photon=num_photon)
 
 
-ARM_WORKLOADS = dict(far_wall_torch=far_wall_torch, torch_shapes=torch_shapes, carrier_photons=carrier_photons, pmt_wall_sensor_a=pmt_wall_sensor_a,
+def box_maze_photons(num_photon=40_000, seed=11):
+    """input photons aimed at what makes box geometry awkward: starts exactly ON faces, edges and corners of touching boxes,
+    axis-parallel directions (1 / d = inf), directions lying IN a face plane, plus isotropic photons from inside the boxes"""
+    geom = GEO.box_maze()
+    rng = np.random.default_rng(seed)
+    cen = geom["box_centers"]
+    n = num_photon // 4 * 4
+    q = n // 4
+    pos = np.zeros((n, 3), dtype=np.float32); mom = np.zeros((n, 3), dtype=np.float32)
+    pick = cen[rng.integers(0, len(cen), size=n)]
+    # 1: isotropic, from random points around box centres (inside boxes and in the water between blocks)
+    pos[:q] = pick[:q] + rng.uniform(-14.0, 14.0, size=(q, 3))
+    v = rng.normal(size=(q, 3)); mom[:q] = v / np.linalg.norm(v, axis=1)[:, None]
+    # 2: axis-parallel directions from random points
+    pos[q:2 * q] = pick[q:2 * q] + rng.uniform(-14.0, 14.0, size=(q, 3))
+    ax = rng.integers(0, 3, size=q); sg = rng.choice([-1.0, 1.0], size=q)
+    mom[q + np.arange(q), ax] = sg
+    # 3: starts exactly on a face / edge / corner of a 25 mm box of block 1 (coordinates that are face values), random directions
+    c1 = cen[rng.integers(0, 32, size=q)]
+    off = rng.uniform(-12.5, 12.5, size=(q, 3))
+    snap = rng.integers(1, 8, size=q)                       # bit k: axis k sits on a face
+    for a in range(3):
+        on = (snap >> a) & 1 == 1
+        off[on, a] = rng.choice([-12.5, 12.5], size=int(on.sum()))
+    pos[2 * q:3 * q] = c1 + off
+    v = rng.normal(size=(q, 3)); mom[2 * q:3 * q] = v / np.linalg.norm(v, axis=1)[:, None]
+    # 4: starts on a face, direction IN that face plane (grazing along coincident faces), half of them axis-parallel
+    c2 = cen[rng.integers(0, 32, size=q)]
+    off = rng.uniform(-12.5, 12.5, size=(q, 3))
+    fa = rng.integers(0, 3, size=q)
+    off[np.arange(q), fa] = rng.choice([-12.5, 12.5], size=q)
+    pos[3 * q:] = c2 + off
+    v = rng.normal(size=(q, 3)); v[np.arange(q), fa] = 0.0
+    axp = rng.random(q) < 0.5
+    oth = (fa + 1 + rng.integers(0, 2, size=q)) % 3
+    v[axp] = 0.0; v[np.nonzero(axp)[0], oth[axp]] = rng.choice([-1.0, 1.0], size=int(axp.sum()))
+    mom[3 * q:] = v / np.linalg.norm(v, axis=1)[:, None]
+    ph = np.zeros((n, 4, 4), dtype=np.float32)
+    ph[:, 0, :3] = pos; ph[:, 0, 3] = 0.0
+    ph[:, 1, :3] = mom
+    pol = np.cross(mom, np.array([0.3, -0.5, 0.81], dtype=np.float32)); pol /= np.linalg.norm(pol, axis=1)[:, None]
+    ph[:, 2, :3] = pol; ph[:, 2, 3] = rng.uniform(300.0, 600.0, size=n)
+    return dict(name="box_maze_photons", geom=geom, gensteps=G.input_photon_genstep(n), input_photons=np.ascontiguousarray(ph), config=dict(), num_photon=n)
+
+
+ARM_WORKLOADS = dict(box_maze_photons=box_maze_photons, far_wall_torch=far_wall_torch, torch_shapes=torch_shapes, carrier_photons=carrier_photons, pmt_wall_sensor_a=pmt_wall_sensor_a,
                      halfspace_zoo_torch=halfspace_zoo_torch)
 WORKLOADS.update(ARM_WORKLOADS)

@@ -32,7 +32,8 @@ CASES = [("sipm8x8_scint", dict(num_photon=30000, photons_per_genstep=100)),
          ("sphere_leak_torch", dict(num_photon=10000)),
          ("pmt_wall_torch", dict(num_photon=30000, nx=20, ny=20)),
          ("boolean_zoo_torch", dict(num_photon=40000)),
-         ("scintillator_tank", dict(num_photon=30000, photons_per_genstep=100))]      # re-emission, Rayleigh, dispersive tables
+         ("scintillator_tank", dict(num_photon=30000, photons_per_genstep=100)),      # re-emission, Rayleigh, dispersive tables
+         ("box_maze_photons", dict(num_photon=40000))]      # touching / nested boxes, starts on faces and edges, axis-parallel and in-plane rays
 
 
 def make_sim(w, **cfg):
@@ -51,8 +52,15 @@ def rel_err(a, b):
 # the sphere_leak billiard, is then amplified by 31 specular bounces; flat-faced geometry stays at 1e-5.  The bound that
 # holds everywhere is the one of the nofma pair: 0.
 MAX_FLOAT_ERR = {"sipm8x8_scint": 1e-4, "raindrop_cerenkov": 1e-6, "sphere_leak_torch": 3e-2, "pmt_wall_torch": 3e-2,
-                 "boolean_zoo_torch": 5e-2, "scintillator_tank": 1e-2}
+                 "boolean_zoo_torch": 5e-2, "scintillator_tank": 1e-2,
+                 # the maze is made of ties: two photons can part at a shared face and still collect the same flags and boundaries (neighbouring
+                 # boxes of one kind), so "matching history" does not mean "same path" there: quantile bound only (the nofma pair is bit-identical)
+                 "box_maze_photons": None}
 MIN_SAME = 0.9995            # measured: >= 0.99973 on every workload, both RNG modes
+# ... except the box maze, which is MADE of ties: every face of its touching boxes is shared by two to eight prims, a third of its
+# photons start exactly on faces / edges / corners or travel inside a face plane, so which prim answers hangs on the last bit of t
+# far more often (measured 0.99898; with FMA contraction off on both sides it is 1.0 like everywhere else, see the nofma test)
+MIN_SAME_BY = {"box_maze_photons": 0.998}
 
 
 def check_against(name, p, seq, ref_p, ref_seq, min_same=MIN_SAME, float_q=0.9995, max_err=None, q_tol=1e-4):
@@ -82,7 +90,7 @@ def test_photon_by_photon_vs_reference_headers(name, kw, variant):
         p, seq = sim.get_array("photon"), sim.get_array("seq")
         # the production build of the reference keeps no seq array: photons that part and end on the same final flags cannot be
         # told from matching ones there, so the max over "matching" photons is only asserted where histories are compared
-        frac = check_against("%s/%s/accel%d" % (name, variant, accel), p, seq, ref["photon"], ref["seq"],
+        frac = check_against("%s/%s/accel%d" % (name, variant, accel), p, seq, ref["photon"], ref["seq"], min_same=MIN_SAME_BY.get(name, MIN_SAME),
                              max_err=MAX_FLOAT_ERR[name] if variant == "debugtag" else None,
                              q_tol=5e-4 if name.startswith("sphere_leak") else 1e-4)
         # hits = stable compaction of the photon array
@@ -95,7 +103,7 @@ def test_photon_by_photon_vs_reference_headers(name, kw, variant):
             ns = 4 if name.startswith("sphere_leak") else rec.shape[1]          # step records: first bounces of the billiard
             rr = np.abs(rec[same][:, :ns, :3, :] - ref["record"][same][:, :ns, :3, :]) / np.maximum(1.0, np.abs(ref["record"][same][:, :ns, :3, :]))
             assert np.quantile(rr, 0.9995) < 1e-4
-            assert rr.max() <= MAX_FLOAT_ERR[name]
+            assert MAX_FLOAT_ERR[name] is None or rr.max() <= MAX_FLOAT_ERR[name]
             assert (prd.view(np.uint32)[same][:, :, 1, 2:] == ref["prd"].view(np.uint32)[same][:, :, 1, 2:]).mean() > 0.9999   # identity, prim|boundary
         print(name, variant, accel, "identical fraction %.5f" % frac, "hits", len(hits), "rays", sim.stats()["num_ray"], ref["nray"])
     sim.close()
@@ -118,7 +126,7 @@ def test_nofma_builds_are_bit_identical_to_reference_headers(tmp_path):
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     rep = json.load(open(out))
-    assert len(rep["entries"]) == (6 + 5) * 2 * 2 - 2        # the six workloads and the five arm workloads of tests/_parity.py (carrier: production only)
+    assert len(rep["entries"]) == (6 + 6) * 2 * 2 - 2        # the six workloads and the six arm workloads of tests/_parity.py (carrier: production only)
     for e in rep["entries"]:
         tag = (e["workload"], e["rng_mode"], e["accel"])
         assert e["identical_integer_data"] == e["photons"], tag
@@ -274,7 +282,7 @@ def test_photon_by_photon_vs_cpu_oracle(name, kw):
     # dispersive tables: the oracle's emulation of the texture filter matches the hardware bit for bit on 97.4 % of
     # fetches (see test_oracle_texture_emulation_vs_hardware); the others move lengths by up to 1/256 of a table step
     fq = 0.98 if name == "scintillator_tank" else 0.9995
-    check_against(name + "/oracle", p, seq, orc["photon"], orc["seq"], min_same=0.99 if name == "scintillator_tank" else 0.995, float_q=fq,
+    check_against(name + "/oracle", p, seq, orc["photon"], orc["seq"], min_same=0.99 if name in ("scintillator_tank", "box_maze_photons") else 0.995, float_q=fq,
                   q_tol=5e-3 if name.startswith("sphere_leak") else 1e-4)      # host libm (sinf, logf ...) differs from CUDA's by ulps: the billiard amplifies them
     assert abs(len(hits) - orc["nhit"]) <= max(5, 0.005 * len(p))
     sim.close()
@@ -344,27 +352,43 @@ def test_multi_launch_slicing_equals_single_launch():
 
 @pytest.mark.parametrize("name,kw", CASES)
 def test_wavefront_form_is_bit_identical_to_persistent_form(name, kw):
-    """The two forms of the bounce loop (include/phox.h PHOX_KERNEL_*) call the same compiled trace/propagate
-    bodies and re-create each photon's Philox stream from its draw count, so every output byte must agree."""
+    """The two forms of the bounce loop (include/phox.h PHOX_KERNEL_*), and the production and debug instantiations of each,
+    compile the same physics / generation / intersect bodies into different kernels.  nvcc fuses a*b+c per compilation
+    context, so their agreement is checked, not assumed: every output byte must be the same - hits of the production
+    kernels (Minimal), photon arrays of the production kernels (HitPhoton) against those of the debug kernels (DebugLite,
+    DebugHeavy), records / seq / prd between the forms.  (scripts/form_consistency.py is the same check at 1 M photons.)"""
     w = workloads.WORKLOADS[name](**kw)
     out = {}
+    modes = ((ph.MODE_MINIMAL, {}), (ph.MODE_HITPHOTON, {}), (ph.MODE_DEBUGLITE, dict(max_record=8)), (ph.MODE_DEBUGHEAVY, dict(max_record=12)))
     for mode in (ph.KERNEL_PERSISTENT, ph.KERNEL_WAVEFRONT):
-        for em, extra in ((ph.MODE_MINIMAL, {}), (ph.MODE_DEBUGLITE, dict(max_record=8)), (ph.MODE_DEBUGHEAVY, dict(max_record=12))):
+        for em, extra in modes:
             sim = make_sim(w, event_mode=em, kernel_mode=mode, **extra)
             h = sim.simulate_np(w["gensteps"], 2, w["input_photons"]).copy()
             arrs = {"hit": h}
             if em != ph.MODE_MINIMAL:
-                for k in ("photon", "seq", "record") + (("prd",) if em == ph.MODE_DEBUGHEAVY else ()):
+                names = {ph.MODE_HITPHOTON: ("photon",), ph.MODE_DEBUGLITE: ("photon", "seq", "record"), ph.MODE_DEBUGHEAVY: ("photon", "seq", "record", "prd")}[em]
+                for k in names:
                     arrs[k] = sim.get_array(k).copy()
             arrs["num_ray"] = np.array([sim.stats()["num_ray"]])
             out[(mode, em)] = arrs
             sim.close()
-    for em in (ph.MODE_MINIMAL, ph.MODE_DEBUGLITE, ph.MODE_DEBUGHEAVY):
+    for em, _ in modes:
         a, b = out[(ph.KERNEL_PERSISTENT, em)], out[(ph.KERNEL_WAVEFRONT, em)]
         assert a.keys() == b.keys()
         for k in a:
             assert a[k].shape == b[k].shape, (name, k, a[k].shape, b[k].shape)
             assert a[k].tobytes() == b[k].tobytes(), (name, em, k)
+    for mode in (ph.KERNEL_PERSISTENT, ph.KERNEL_WAVEFRONT):           # production kernels against debug kernels
+        prod, lite, heavy = out[(mode, ph.MODE_HITPHOTON)], out[(mode, ph.MODE_DEBUGLITE)], out[(mode, ph.MODE_DEBUGHEAVY)]
+        assert prod["photon"].tobytes() == lite["photon"].tobytes(), (name, mode, "photon")
+        assert prod["hit"].tobytes() == lite["hit"].tobytes() == out[(mode, ph.MODE_MINIMAL)]["hit"].tobytes(), (name, mode, "hit")
+        # DebugHeavy runs the tag-recording physics body (propagate_t<true>: every tagged draw is also written to the tag / flat
+        # arrays), a second compiled body whose multiply-adds are fused differently: same integer data and histories, floats equal
+        # to a few last bits
+        pu, hu = prod["photon"].view(np.uint32), heavy["photon"].view(np.uint32)
+        assert (pu[:, 3, :] == hu[:, 3, :]).all() and (pu[:, 1, 3] == hu[:, 1, 3]).all(), (name, mode, "DebugHeavy integer data")
+        assert (lite["seq"] == heavy["seq"]).all(), (name, mode, "DebugHeavy seq")
+        assert rel_err(heavy["photon"], prod["photon"]).max() < 2e-5, (name, mode, rel_err(heavy["photon"], prod["photon"]).max())
     assert len(out[(ph.KERNEL_WAVEFRONT, ph.MODE_MINIMAL)]["hit"]) > 0
 
 
@@ -402,6 +426,8 @@ def test_home_cells_only_cull(name, kw):
     print(name, "rays settled by their home cell: %d of %d" % home_rays[(ph.KERNEL_WAVEFRONT, ph.ACCEL_BVH)])
     if name == "sipm8x8_scint":
         assert home_rays[(ph.KERNEL_WAVEFRONT, ph.ACCEL_BVH)][0] > 0.3 * home_rays[(ph.KERNEL_WAVEFRONT, ph.ACCEL_BVH)][1]
+    if name == "box_maze_photons":
+        assert home_rays[(ph.KERNEL_WAVEFRONT, ph.ACCEL_BVH)][0] > 0.05 * home_rays[(ph.KERNEL_WAVEFRONT, ph.ACCEL_BVH)][1]
 
 
 def test_wavefront_form_with_launch_slicing_and_time_cut():
