@@ -21,7 +21,8 @@ placement with the inverse), G4Scintillation's trapezoid integral of the emissio
 
 Covered beyond plain placements: <assembly> imprints, instancing by repeated subtree digests (stree::factorize, FREQ_CUT 500).
 Not covered (asserts, like the reference does for phi segments u4/U4Solid.h:555-561): phi segments of tubs / sphere,
-trap, polyhedra, torus, cut tubs, replicas, NIST materials by name.
+polyhedra, torus, cut tubs, replicas, NIST materials by name.  <trap> (G4Trap) IS translated - to a convexpolyhedron -
+although the reference's U4Solid has no conversion for it: tests/geom/pfrich_min_FINAL.gdml needs it.
 """
 import ast
 import math
@@ -244,6 +245,34 @@ class GDML:
             pl.append([0, 0, 1, hz]); pl.append([0, 0, -1, hz])
             xm, ym = max(x1, x2), max(y1, y2)
             return F.convexpolyhedron(pl, [-xm, -ym, -hz, xm, ym, hz])
+        if tag == "trap":
+            # G4Trap (G4GDMLReadSolids::TrapRead halves z, y1, x1, x2, y2, x3, x4): 8 vertices as G4Trap::MakePlanes lays them out,
+            # 6 outward planes -> convexpolyhedron.  (u4/U4Solid.h has no G4Trap: the reference cannot convert these itself;
+            # needed for tests/geom/pfrich_min_FINAL.gdml.)
+            dz = g("z") * lu / 2
+            th, phi = g("theta") * au, g("phi") * au
+            dy1, dx1, dx2, ta1 = g("y1") * lu / 2, g("x1") * lu / 2, g("x2") * lu / 2, math.tan(g("alpha1") * au)
+            dy2, dx3, dx4, ta2 = g("y2") * lu / 2, g("x3") * lu / 2, g("x4") * lu / 2, math.tan(g("alpha2") * au)
+            tc, ts = math.tan(th) * math.cos(phi), math.tan(th) * math.sin(phi)
+            pt = np.array([[-dz * tc - dy1 * ta1 - dx1, -dz * ts - dy1, -dz], [-dz * tc - dy1 * ta1 + dx1, -dz * ts - dy1, -dz],
+                           [-dz * tc + dy1 * ta1 - dx2, -dz * ts + dy1, -dz], [-dz * tc + dy1 * ta1 + dx2, -dz * ts + dy1, -dz],
+                           [dz * tc - dy2 * ta2 - dx3, dz * ts - dy2, dz], [dz * tc - dy2 * ta2 + dx3, dz * ts - dy2, dz],
+                           [dz * tc + dy2 * ta2 - dx4, dz * ts + dy2, dz], [dz * tc + dy2 * ta2 + dx4, dz * ts + dy2, dz]])
+            cen = pt.mean(axis=0)
+            pl = []
+            for quad in ((0, 1, 3, 2), (4, 5, 7, 6), (0, 4, 5, 1), (2, 3, 7, 6), (0, 2, 6, 4), (1, 5, 7, 3)):
+                a, b, c, d = pt[list(quad)]
+                n = np.cross(c - a, d - b)                     # diagonals: robust for a face that degenerates to a triangle
+                assert np.linalg.norm(n) > 0, "degenerate trap face"
+                n = n / np.linalg.norm(n)
+                fc = (a + b + c + d) / 4
+                if np.dot(n, fc - cen) < 0:
+                    n = -n
+                dist = float(np.dot(n, fc))
+                assert max(abs(np.dot(n, v) - dist) for v in (a, b, c, d)) < 1e-6 * max(1.0, np.abs(pt).max()), "G4Trap face is not planar"
+                pl.append([n[0], n[1], n[2], dist])
+            lo, hi = pt.min(axis=0), pt.max(axis=0)
+            return F.convexpolyhedron(pl, [lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]])
         if tag == "polycone":
             assert g("deltaphi", 2 * math.pi / au) * au >= 2 * math.pi - 1e-9 and g("startphi") == 0, \
                 "polycone phi segments need the experimental phicut of u4/U4Polycone.h:331-346 and are not translated"

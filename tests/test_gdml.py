@@ -40,7 +40,7 @@ def test_translation_of_reference_gdml_matches_hand_built(fname, builder):
         assert len(t["sensitive_prims"]) == 64
 
 
-@pytest.mark.parametrize("fname", ["raindrop.gdml", "basic_detector.gdml", "opticks_raindrop_with_scintillation.gdml"])
+@pytest.mark.parametrize("fname", ["raindrop.gdml", "basic_detector.gdml", "opticks_raindrop_with_scintillation.gdml", "pfrich_min_FINAL.gdml"])
 def test_other_reference_gdml_files_translate(fname):
     path = os.path.join(REF_GEOM, fname)
     if not os.path.exists(path):
@@ -48,6 +48,38 @@ def test_other_reference_gdml_files_translate(fname):
     t = gdml.translate(path)
     assert len(t["foundry"]["prim"]) >= 4 and t["bnd"].shape[0] == len(t["bnd_names"])
     assert t["bnd_names"][0].split("/")[0] == t["bnd_names"][0].split("/")[3]           # world: omat == imat
+
+
+def test_trap_becomes_a_convexpolyhedron_through_its_eight_vertices(tmp_path):
+    """<trap> (G4Trap; tests/geom/pfrich_min_FINAL.gdml has eleven): six outward planes, each of the eight G4Trap vertices
+    (G4Trap::MakePlanes layout from the halved GDML lengths) on exactly three of them and inside the rest"""
+    import math
+    z, th, phi, y1, x1, x2, a1, y2, x3, x4, a2 = 60.0, 0.2, 0.3, 40.0, 30.0, 36.0, 0.1, 28.0, 21.0, 25.2, 0.1      # top = 0.7 x bottom: planar side faces, as G4Trap demands
+    gd = tmp_path / "trap.gdml"
+    gd.write_text('''<?xml version="1.0"?><gdml><define><matrix name="RI" coldim="2" values="1.55*eV 1.5 6.2*eV 1.5"/></define><materials>
+<material name="Vac"><D value="1e-25"/><property name="RINDEX" ref="RI"/></material><material name="Gl"><D value="2.2"/><property name="RINDEX" ref="RI"/></material></materials>
+<solids><box name="w" x="500" y="500" z="500" lunit="mm"/>
+<trap name="t" z="%g" theta="%g" phi="%g" y1="%g" x1="%g" x2="%g" alpha1="%g" y2="%g" x3="%g" x4="%g" alpha2="%g" lunit="mm" aunit="rad"/></solids>
+<structure><volume name="tv"><materialref ref="Gl"/><solidref ref="t"/></volume>
+<volume name="wv"><materialref ref="Vac"/><solidref ref="w"/><physvol name="tp"><volumeref ref="tv"/></physvol></volume></structure>
+<setup name="Default" version="1.0"><world ref="wv"/></setup></gdml>''' % (z, th, phi, y1, x1, x2, a1, y2, x3, x4, a2))
+    t = gdml.translate(str(gd))
+    plan = t["foundry"]["plan"].reshape(-1, 4).astype(np.float64)
+    assert len(plan) == 6
+    dz, tc, ts = z / 2, math.tan(th) * math.cos(phi), math.tan(th) * math.sin(phi)
+    verts = []
+    for sz, dy, dxa, dxb, ta in ((-1, y1 / 2, x1 / 2, x2 / 2, math.tan(a1)), (1, y2 / 2, x3 / 2, x4 / 2, math.tan(a2))):
+        for sy, dx in ((-1, dxa), (1, dxb)):
+            for sx in (-1, 1):
+                verts.append([sz * dz * tc + sy * dy * ta + sx * dx, sz * dz * ts + sy * dy, sz * dz])
+    verts = np.array(verts)
+    d = verts @ plan[:, :3].T - plan[:, 3]                 # signed distance of every vertex to every plane
+    assert (d < 1e-4).all()                                # inside or on
+    assert ((np.abs(d) < 1e-4).sum(axis=1) == 3).all()     # each vertex is the corner of three faces
+    assert np.allclose(np.linalg.norm(plan[:, :3], axis=1), 1.0, atol=1e-6)
+    prim = t["foundry"]["prim"].reshape(-1, 16)
+    tp = prim[-1]
+    assert np.allclose(tp[8:11], verts.min(axis=0), atol=1e-4) and np.allclose(tp[11:14], verts.max(axis=0), atol=1e-4)
 
 
 def test_mini_detector_translation():
