@@ -344,3 +344,16 @@ def box_maze():
     centers += [(0.0, 150.0, 100.0), (20.0, 150.0, 100.0), (40.0, 170.0, 120.0)]
     fd.end_solid()
     return _finish(fd, bt, extra=dict(box_centers=np.array(centers, dtype=np.float32)))
+
+
+def pfrich(path=None):
+    """The pfRICH detector the reference ships as tests/geom/pfrich_min_FINAL.gdml (aerogel radiator, nitrogen vessel, inner and outer
+    mirrors, 64 sensor pyramids, absorbing edges; 103 prims, 39 boundaries), as translated by gdml.py and kept in
+    tests/golden/pfrich_min_geometry.npz (tests/golden/make_pfrich_fixture.py) - the GPU box has no copy of the reference."""
+    import os
+    if path is None:
+        path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "pfrich_min_geometry.npz")
+    z = np.load(path)
+    fd = {k: z[k] for k in ("solid", "prim", "node", "tran", "itra", "plan", "inst")}
+    return dict(foundry=fd, bnd=z["bnd"], optical=z["optical"], icdf=None, bnd_names=[str(n) for n in z["bnd_names"]],
+                prim_names=[str(n) for n in z["prim_names"]], sensitive_prims=z["sensitive_prims"])

@@ -250,6 +250,24 @@ def box_maze_photons(num_photon=40_000, seed=11):
     return dict(name="box_maze_photons", geom=geom, gensteps=G.input_photon_genstep(n), input_photons=np.ascontiguousarray(ph), config=dict(), num_photon=n)
 
 
-ARM_WORKLOADS = dict(box_maze_photons=box_maze_photons, far_wall_torch=far_wall_torch, torch_shapes=torch_shapes, carrier_photons=carrier_photons, pmt_wall_sensor_a=pmt_wall_sensor_a,
+def pfrich_photons(num_photon=100_000, seed=3):
+    """Cherenkov-like photons in the reference's own pfRICH geometry (geometries.pfrich): born in the aerogel annulus, heading down
+    the vessel within 0.1 - 0.4 rad of +z, 300 - 600 nm; they cross the aerogel face, fly through the nitrogen, bounce off the
+    inner / outer mirrors and end on the sensor pyramids or the absorbing edges"""
+    geom = GEO.pfrich()
+    rng = np.random.default_rng(seed)
+    n = num_photon
+    r = np.sqrt(rng.uniform(135.0 ** 2, 585.0 ** 2, size=n)); a = rng.uniform(0, 2 * np.pi, size=n)
+    ph = np.zeros((n, 4, 4), dtype=np.float32)
+    ph[:, 0, 0] = r * np.cos(a); ph[:, 0, 1] = r * np.sin(a); ph[:, 0, 2] = rng.uniform(-236.0, -216.0, size=n)
+    th = rng.uniform(0.1, 0.4, size=n); az = rng.uniform(0, 2 * np.pi, size=n)
+    mom = np.stack([np.sin(th) * np.cos(az), np.sin(th) * np.sin(az), np.cos(th)], axis=1)
+    ph[:, 1, :3] = mom
+    pol = np.cross(mom, np.array([0.0, 0.0, 1.0])); pol /= np.linalg.norm(pol, axis=1)[:, None]
+    ph[:, 2, :3] = pol; ph[:, 2, 3] = rng.uniform(300.0, 600.0, size=n)
+    return dict(name="pfrich_photons", geom=geom, gensteps=G.input_photon_genstep(n), input_photons=np.ascontiguousarray(ph), config=dict(), num_photon=n)
+
+
+ARM_WORKLOADS = dict(box_maze_photons=box_maze_photons, pfrich_photons=pfrich_photons, far_wall_torch=far_wall_torch, torch_shapes=torch_shapes, carrier_photons=carrier_photons, pmt_wall_sensor_a=pmt_wall_sensor_a,
                      halfspace_zoo_torch=halfspace_zoo_torch)
 WORKLOADS.update(ARM_WORKLOADS)

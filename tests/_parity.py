@@ -37,7 +37,9 @@ ARM_CASES = [("far_wall_torch", dict(num_photon=20000)),
              ("pmt_wall_sensor_a", dict(num_photon=30000)),
              ("halfspace_zoo_torch", dict(num_photon=30000)),
              # touching / nested boxes, photons starting on faces, edges and corners, axis-parallel and in-plane directions: ties everywhere
-             ("box_maze_photons", dict(num_photon=40000))]
+             ("box_maze_photons", dict(num_photon=40000)),
+             # the pfRICH geometry the reference ships (tests/geom/pfrich_min_FINAL.gdml through gdml.py, tests/golden/pfrich_min_geometry.npz)
+             ("pfrich_photons", dict(num_photon=40000))]
 
 FLAG_NAMES = {1: "CK", 2: "SI", 4: "TO", 8: "AB", 16: "RE", 32: "SC", 64: "SD", 128: "SA", 256: "DR", 512: "SR", 1024: "BR", 2048: "BT", 0: "--"}
 

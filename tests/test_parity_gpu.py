@@ -126,7 +126,7 @@ def test_nofma_builds_are_bit_identical_to_reference_headers(tmp_path):
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     rep = json.load(open(out))
-    assert len(rep["entries"]) == (6 + 6) * 2 * 2 - 2        # the six workloads and the six arm workloads of tests/_parity.py (carrier: production only)
+    assert len(rep["entries"]) == (6 + 7) * 2 * 2 - 2        # the six workloads and the seven arm workloads of tests/_parity.py (carrier: production only)
     for e in rep["entries"]:
         tag = (e["workload"], e["rng_mode"], e["accel"])
         assert e["identical_integer_data"] == e["photons"], tag
@@ -271,6 +271,37 @@ def test_halfspace_cut_solids():
         assert len(hits) > 100
 
 
+def test_pfrich_the_detector_geometry_the_reference_ships():
+    """tests/geom/pfrich_min_FINAL.gdml (aerogel, nitrogen vessel, inner / outer mirrors, 64 sensor pyramids, absorbing edges: tubes,
+    cones, booleans, G4Trap as convexpolyhedron; 103 prims, 39 boundaries) translated by gdml.py and carried as
+    tests/golden/pfrich_min_geometry.npz: geometry queries BVH = brute force = the reference's intersect headers, then Cherenkov-like
+    photons from the aerogel against the reference's device headers, photon by photon"""
+    w = workloads.pfrich_photons(num_photon=1000)
+    g = w["geom"]
+    sim = make_sim(w)
+    rng = np.random.default_rng(12)
+    n = 200000
+    o = (rng.uniform(-1, 1, (n, 3)) * np.array([640.0, 640.0, 240.0])).astype(np.float32)
+    d = rng.normal(size=(n, 3)); d = (d / np.linalg.norm(d, axis=1)[:, None]).astype(np.float32)
+    a = sim.intersect(o, d, 0.05, ph.ACCEL_BVH)
+    b = sim.intersect(o, d, 0.05, ph.ACCEL_BRUTE)
+    assert a.tobytes() == b.tobytes()
+    r = RefGPU("debugtag").intersect(g, o, d, 0.05)
+    bu, ru = b.view(np.uint32), r.view(np.uint32)
+    same = (bu[:, 1, 2:] == ru[:, 1, 2:]).all(axis=1)
+    assert same.mean() > 0.9995, same.mean()
+    prim = bu[:, 1, 3] >> 16
+    assert len(np.unique(prim[bu[:, 1, 3] != 0xffffffff])) > 80                     # rays reach most of the 103 prims
+    err = np.abs(b[same, 0, 3] - r[same, 0, 3]) / np.maximum(1, np.abs(r[same, 0, 3]))
+    assert np.quantile(err, 0.999) < 1e-4
+    sim.close()
+    w, ref, got = _arm("pfrich_photons", dict(num_photon=40000))
+    for p, seq, rec, prd, hits, nray in got:
+        frac = check_against("pfrich", p, seq, ref["photon"], ref["seq"], min_same=0.999, max_err=None)
+        assert len(hits) > 4000 and nray == ref["nray"] or frac < 1.0
+        print("pfrich identical fraction %.5f hits %d rays %d (reference %d)" % (frac, len(hits), nray, ref["nray"]))
+
+
 @pytest.mark.parametrize("name,kw", CASES)
 def test_photon_by_photon_vs_cpu_oracle(name, kw):
     kw = dict(kw); kw["num_photon"] = min(kw["num_photon"], 10000)
@@ -393,7 +424,7 @@ def test_wavefront_form_is_bit_identical_to_persistent_form(name, kw):
 
 
 HOME_CASES = CASES + [("far_wall_torch", dict(num_photon=20000)), ("halfspace_zoo_torch", dict(num_photon=20000)),
-                      ("pmt_wall_sensor_a", dict(num_photon=20000))]
+                      ("pmt_wall_sensor_a", dict(num_photon=20000)), ("pfrich_photons", dict(num_photon=30000))]
 
 
 @pytest.mark.parametrize("name,kw", HOME_CASES)
