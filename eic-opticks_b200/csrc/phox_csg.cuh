@@ -136,18 +136,16 @@ PHOX_D bool box3_t(float& t_out, const float4& q0, float tmin, const float3& ro,
     float t_near = fmaxf(fmaxf(nr.x, nr.y), nr.z);
     float t_far = fminf(fminf(fr.x, fr.y), fr.z);
 
-    bool along_x = rd.x != 0.f && rd.y == 0.f && rd.z == 0.f;
-    bool along_y = rd.x == 0.f && rd.y != 0.f && rd.z == 0.f;
-    bool along_z = rd.x == 0.f && rd.y == 0.f && rd.z != 0.f;
-    bool in_x = ro.x > bmin.x && ro.x < bmax.x;
-    bool in_y = ro.y > bmin.y && ro.y < bmax.y;
-    bool in_z = ro.z > bmin.z && ro.z < bmax.z;
-
+    // axis-parallel rays (two zero components) are decided by the origin's position in the other two slabs; everything else by
+    // the slab distances.  The rare case is kept off the common path (same decisions as csg_intersect_leaf_box3.h:100-125).
+    const int nzero = (rd.x == 0.f) + (rd.y == 0.f) + (rd.z == 0.f);
     bool has;
-    if (along_x) has = in_y && in_z;
-    else if (along_y) has = in_x && in_z;
-    else if (along_z) has = in_x && in_y;
-    else has = (t_far > t_near && t_far > 0.f);
+    if (nzero == 2) {
+        bool in_x = ro.x > bmin.x && ro.x < bmax.x;
+        bool in_y = ro.y > bmin.y && ro.y < bmax.y;
+        bool in_z = ro.z > bmin.z && ro.z < bmax.z;
+        has = rd.x != 0.f ? (in_y && in_z) : (rd.y != 0.f ? (in_x && in_z) : (in_x && in_y));
+    } else has = (t_far > t_near && t_far > 0.f);
     if (!has) return false;
     float t = tmin < t_near ? t_near : (tmin < t_far ? t_far : tmin);
     t_out = t;

@@ -394,7 +394,10 @@ PHOX_D bool hit_finish_core(HitInfo& h, const Scene& sc, const Nearest& best, co
         n = xform_normal(r0, r1, r2, best.n);       // object -> world uses the inverse-transpose
     }
     float3 lpos = oo + best.t * dd;
-    h.normal = (flags & kHitRawNormal) ? n : normalize(n);        // the simulate raygen normalises every normal (CSGOptiX7.cu:470-471)
+    // the simulate raygen normalises every normal (CSGOptiX7.cu:470-471): n * (1 / sqrt(n.n)).  A box face normal has n.n == 1
+    // exactly, for which that expression returns n bit for bit (1 / sqrt(1) = 1, x * 1 = x): skip the square root and the division
+    const float nn = dot(n, n);
+    h.normal = ((flags & kHitRawNormal) || nn == 1.f) ? n : n * (1.0f / sqrtf(nn));
     h.t = best.t;
     h.lposcost = lpos.z / sqrtf(dot(lpos, lpos));
     h.lposfphi = (flags & kHitFphi) ? (atan2f(lpos.y, lpos.x) + kPi) / (2.0f * kPi) : 0.f;
