@@ -126,9 +126,10 @@ PHOX_D bool leaf_box3(float4& is, const float4& q0, float tmin, const float3& ro
 
 // The box leaf in two halves, so that a caller with several boxes to compare (the home-cell pass) can settle the
 // nearest distance first and work out one normal, for the winner.  box3_t: does the ray meet the box beyond tmin, and where.
-PHOX_D bool box3_t(float& t_out, const float4& q0, float tmin, const float3& ro, const float3& rd, const float3& idir) {
-    float3 bmin = f3(-q0.x / 2.f, -q0.y / 2.f, -q0.z / 2.f);
-    float3 bmax = f3(q0.x / 2.f, q0.y / 2.f, q0.z / 2.f);
+// (half = the three full sizes / 2, an exact operation, so a caller may hold the halves ready made)
+PHOX_D bool box3_t_half(float& t_out, const float3& half, float tmin, const float3& ro, const float3& rd, const float3& idir) {
+    float3 bmin = f3(-half.x, -half.y, -half.z);
+    float3 bmax = half;
     float3 t0 = f3((bmin.x - ro.x) * idir.x, (bmin.y - ro.y) * idir.y, (bmin.z - ro.z) * idir.z);
     float3 t1 = f3((bmax.x - ro.x) * idir.x, (bmax.y - ro.y) * idir.y, (bmax.z - ro.z) * idir.z);
     float3 nr = f3(fminf(t0.x, t1.x), fminf(t0.y, t1.y), fminf(t0.z, t1.z));
@@ -151,10 +152,13 @@ PHOX_D bool box3_t(float& t_out, const float4& q0, float tmin, const float3& ro,
     t_out = t;
     return t > tmin;
 }
+PHOX_D bool box3_t(float& t_out, const float4& q0, float tmin, const float3& ro, const float3& rd, const float3& idir) {
+    return box3_t_half(t_out, f3(q0.x / 2.f, q0.y / 2.f, q0.z / 2.f), tmin, ro, rd, idir);
+}
 // ... and the face normal at distance t along the ray
-PHOX_D float3 box3_normal(const float4& q0, const float3& ro, const float3& rd, float t) {
-    float3 bmin = f3(-q0.x / 2.f, -q0.y / 2.f, -q0.z / 2.f);
-    float3 bmax = f3(q0.x / 2.f, q0.y / 2.f, q0.z / 2.f);
+PHOX_D float3 box3_normal_half(const float3& half, const float3& ro, const float3& rd, float t) {
+    float3 bmin = f3(-half.x, -half.y, -half.z);
+    float3 bmax = half;
     float3 p = f3(ro.x + t * rd.x - 0.f, ro.y + t * rd.y - 0.f, ro.z + t * rd.z - 0.f);
     float3 pa = f3(fabsf(p.x) / (bmax.x - bmin.x), fabsf(p.y) / (bmax.y - bmin.y), fabsf(p.z) / (bmax.z - bmin.z));
     float3 n = f3(0.f, 0.f, 0.f);
@@ -162,6 +166,9 @@ PHOX_D float3 box3_normal(const float4& q0, const float3& ro, const float3& rd, 
     else if (pa.y >= pa.x && pa.y >= pa.z) n.y = copysignf(1.f, p.y);
     else if (pa.z >= pa.x && pa.z >= pa.y) n.z = copysignf(1.f, p.z);
     return n;
+}
+PHOX_D float3 box3_normal(const float4& q0, const float3& ro, const float3& rd, float t) {
+    return box3_normal_half(f3(q0.x / 2.f, q0.y / 2.f, q0.z / 2.f), ro, rd, t);
 }
 
 PHOX_D bool leaf_box3_idir(float4& is, const float4& q0, float tmin, const float3& ro, const float3& rd, const float3& idir) {

@@ -100,6 +100,8 @@ struct phox_context {
     unsigned nx = 0, ny = 0;
     float nm0 = 60.f, nms = 1.f;
     unsigned hd_factor = 0;
+    float inv_ny = 0.f;
+    unsigned y_fast = 0;
 
     // event
     DevBuf<Genstep> d_genstep;
@@ -125,7 +127,7 @@ struct phox_context {
     MergeScratch merge_scratch;
     DevBuf<float4> d_exact;                    // per CSGPrim: (sizes ; translation) of prims that are exactly a box
     DevBuf<float4> d_home;                     // per CSGPrim: HomeRec (box, candidate count, offset), see traverse_bvh
-    DevBuf<int2> d_cand;                       // candidate lists of the home cells
+    DevBuf<float4> d_cand;                     // candidate lists of the home cells, two float4 per candidate
     DevBuf<unsigned> d_home_state;             // wavefront form, per slot: home cell of the photon
     DevBuf<unsigned> d_pending, d_pending_count;   // wavefront form: list positions the home cells left to k_wf_trace, and their count per bounce
     DevBuf<Photon> d_hit_stage[2];                 // phox_get_hits_async: hits of the last two events, copied out while the next event runs
@@ -521,7 +523,7 @@ extern "C" int phox_set_geometry(phox_context* ctx, const void* solid_, int64_t 
     // runs inside the physics kernel and is kept free of calls into the general CSG evaluators), or when the box of a
     // transformed instance does.
     std::vector<float> home((size_t)nprim * 8, 0.f);
-    std::vector<int2> cand;
+    std::vector<float4> cand;                            // two float4 per candidate: half sizes | prim, translation | instance (home_search)
     ctx->num_home = 0;
     {
         std::vector<int> solid_inst_count((size_t)nsolid, 0), solid_inst((size_t)nsolid, -1);
@@ -559,15 +561,33 @@ extern "C" int phox_set_geometry(phox_context* ctx, const void* solid_, int64_t 
                 bool ok = true;
                 for (size_t j = 0; j < moved.size() && ok; j++) ok = !overlaps(&boxes[6 * (size_t)(nprim + moved[j])]);
                 const size_t first = cand.size();
+                // wp is in ascending (instance, prim) order and so are the lists: the first of several equal distances is
+                // the one keep_nearest would keep, and the candidate loop needs no tie rule of its own
                 for (size_t j = 0; j < wp.size() && ok; j++) {
-                    if (!overlaps(&boxes[6 * (size_t)(wp[j].item & kLeafItemMask)])) continue;
-                    if (cand.size() - first == (size_t)kHomeMaxCand || (wp[j].item & kLeafSingle)) { ok = false; break; }
-                    cand.push_back(make_int2(wp[j].item, wp[j].inst));
+                    const int q = wp[j].item & kLeafItemMask;
+                    if (!overlaps(&boxes[6 * (size_t)q])) continue;
+                    const float* e = &exact[8 * (size_t)q];
+                    if (!(wp[j].item & kLeafSingle)) {
+                        // An exact box that holds this home's outer box with another pad to spare (the world volume, mother
+                        // volumes) can only answer with its exit face, and that lies beyond the exit from the home box by
+                        // more than the 1e-6 relative margin of the settle test (each of its exit-side slab distances exceeds
+                        // the home box's by >= 2 pads = 4e-5 relative, against < 1e-6 of rounding): whenever the candidates
+                        // settle a ray, such a prim is strictly farther than their answer.  It is left off the list.
+                        bool encloses = true;
+                        for (int a = 0; a < 3; a++) {
+                            const float tlo = -e[4 + a] - 0.5f * e[a], thi = -e[4 + a] + 0.5f * e[a];
+                            if (!(tlo <= out_lo[a] - hp && thi >= out_hi[a] + hp)) encloses = false;
+                        }
+                        if (encloses) continue;
+                    }
+                    if ((cand.size() - first) / 2 == (size_t)kHomeMaxCand || (wp[j].item & kLeafSingle)) { ok = false; break; }
+                    cand.push_back(make_float4(0.5f * e[0], 0.5f * e[1], 0.5f * e[2], __builtin_bit_cast(float, q)));
+                    cand.push_back(make_float4(e[4], e[5], e[6], __builtin_bit_cast(float, wp[j].inst)));
                 }
                 if (!ok || cand.size() == first) { cand.resize(first); continue; }
                 float* h = &home[8 * (size_t)p];
                 h[0] = in_lo[0]; h[1] = in_lo[1]; h[2] = in_lo[2]; h[3] = in_hi[0]; h[4] = in_hi[1]; h[5] = in_hi[2];
-                int cnt = (int)(cand.size() - first), off = (int)first;
+                int cnt = (int)(cand.size() - first) / 2, off = (int)first;
                 std::memcpy(&h[6], &cnt, 4); std::memcpy(&h[7], &off, 4);
                 ctx->num_home++;
             }
@@ -576,7 +596,7 @@ extern "C" int phox_set_geometry(phox_context* ctx, const void* solid_, int64_t 
     CK(ctx->d_home.reserve(std::max<size_t>(2, (size_t)nprim * 2)));
     CK(cudaMemcpyAsync(ctx->d_home.p, home.data(), (size_t)nprim * 8 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     CK(ctx->d_cand.reserve(std::max<size_t>(1, cand.size())));
-    if (!cand.empty()) CK(cudaMemcpyAsync(ctx->d_cand.p, cand.data(), cand.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+    if (!cand.empty()) CK(cudaMemcpyAsync(ctx->d_cand.p, cand.data(), cand.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
 
     CK(ctx->d_inst.reserve((size_t)ninst));
     CK(ctx->d_boxes.reserve(boxes.size()));
@@ -657,6 +677,18 @@ extern "C" int phox_set_tables(phox_context* ctx, const float* bnd, int64_t nbnd
     free_tables(ctx);
     ctx->nx = (unsigned)nwl; ctx->ny = (unsigned)(nbnd * 8);
     ctx->nm0 = domain_low; ctx->nms = domain_step;
+    {   // bnd_y (phox_physics.cuh): the reciprocal form of (iy + 0.5) / ny is used only when it gives the bits of the division for every row
+        const float c = (float)ctx->ny;
+        volatile float inv = 1.0f / c;
+        bool same = true;
+        for (unsigned iy = 0; iy < ctx->ny && same; iy++) {
+            const float a = (float)iy + 0.5f;
+            volatile float q = a * inv;
+            const float fast = std::fmaf(std::fmaf(-q, c, a), inv, q);
+            same = fast == a / c;
+        }
+        ctx->inv_ny = inv; ctx->y_fast = same ? 1u : 0u;
+    }
     CK(make_tex(&ctx->bnd_array, &ctx->bnd_tex, bnd, (size_t)nwl, (size_t)nbnd * 8, 4));
     if (icdf) {
         CK(make_tex(&ctx->icdf_array, &ctx->icdf_tex, icdf, (size_t)icdf_nx, (size_t)icdf_ny, 1));
@@ -769,6 +801,7 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
     P.scene.home = (c.accel == PHOX_ACCEL_BVH && ctx->num_home > 0) ? ctx->d_home.p : nullptr; P.scene.cand = ctx->d_cand.p;
     P.tables.bnd_tex = ctx->bnd_tex; P.tables.icdf_tex = ctx->icdf_tex; P.tables.optical = ctx->d_optical.p;
     P.tables.nx = ctx->nx; P.tables.ny = ctx->ny; P.tables.nm0 = ctx->nm0; P.tables.nms = ctx->nms; P.tables.hd_factor = ctx->hd_factor;
+    P.tables.inv_ny = ctx->inv_ny; P.tables.y_fast = ctx->y_fast;
     P.genstep = d_gs; P.gs_prefix = d_prefix; P.num_genstep = ngs;
     P.input_photon = d_input; P.input_base = input_base; P.photon_offset = photon_offset;
     P.num_photon = (unsigned)n; P.event_index = event_id;
@@ -1376,6 +1409,7 @@ extern "C" int phox_boundary_lookup(phox_context* ctx, const float* nm, const ui
     Tables tb;
     tb.bnd_tex = ctx->bnd_tex; tb.icdf_tex = ctx->icdf_tex; tb.optical = ctx->d_optical.p;
     tb.nx = ctx->nx; tb.ny = ctx->ny; tb.nm0 = ctx->nm0; tb.nms = ctx->nms; tb.hd_factor = ctx->hd_factor;
+    tb.inv_ny = ctx->inv_ny; tb.y_fast = ctx->y_fast;
     k_boundary_lookup<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(tb, b_nm.p, b_line.p, b_k.p, (unsigned)n, b_out.p);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(dst, b_out.p, n * 16, cudaMemcpyDeviceToHost, ctx->stream));

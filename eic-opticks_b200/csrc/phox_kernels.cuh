@@ -62,7 +62,7 @@ struct Scene {
     int tlas_root;                  // node index of the instance tree
     int accel;                      // PHOX_ACCEL_*
     const float4* home;             // 2 x float4 per CSGPrim (HomeRec, see traverse_bvh); null = home cells off
-    const int2* cand;               // candidate lists of the home cells: (leaf item with its flag bits, instance)
+    const float4* cand;             // candidate lists of the home cells, two float4 per candidate: half sizes | prim, translation | instance
 };
 
 struct SimParams {
@@ -326,25 +326,23 @@ PHOX_D bool home_search(Nearest& best, const Scene& sc, float tmin, const float3
     const float ty0 = (ha.y - o.y) * idir.y, ty1 = (hb.x - o.y) * idir.y;
     const float tz0 = (ha.z - o.z) * idir.z, tz1 = (hb.y - o.z) * idir.z;
     const float t_home = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fmaxf(tz0, tz1));
-    const int2* cand = sc.cand + __float_as_int(hb.w);
+    const float4* cand = sc.cand + __float_as_int(hb.w);      // records of this home's candidates, in ascending (instance, prim) order
     float bt = best.t;
-    int bprim = -1, binst = 0;
+    int bi = -1;
     for (int i = 0; i < n; i++) {
-        const int2 e = __ldg(cand + i);                        // (prim, instance)
-        const float4* rec = sc.exact + 2 * e.x;
-        const float4 q0 = __ldg(rec), tr = __ldg(rec + 1);
+        const float4 hs = __ldg(cand + 2 * i), tr = __ldg(cand + 2 * i + 1);
         float t;
-        if (box3_t(t, q0, tmin, f3(o.x + tr.x, o.y + tr.y, o.z + tr.z), d, idir)) {          // t > tmin
-            // keep_nearest: ties go to the lower (instance, prim) pair
-            const bool closer = t < bt || (t == bt && (bprim < 0 || e.y < binst || (e.y == binst && e.x < bprim)));
-            if (closer) { bt = t; bprim = e.x; binst = e.y; }
+        if (box3_t_half(t, f3(hs.x, hs.y, hs.z), tmin, f3(o.x + tr.x, o.y + tr.y, o.z + tr.z), d, idir)) {          // t > tmin
+            // keep_nearest, whose ties go to the lower (instance, prim) pair: in list order that is the earlier candidate
+            if (t < bt || (t == bt && bi < 0)) { bt = t; bi = i; }
         }
     }
     float3 nb = f3(0.f, 0.f, 0.f);
-    if (bprim >= 0) {
-        const float4* rec = sc.exact + 2 * bprim;
-        const float4 q0 = __ldg(rec), tr = __ldg(rec + 1);
-        nb = box3_normal(q0, f3(o.x + tr.x, o.y + tr.y, o.z + tr.z), d, bt);
+    int bprim = -1, binst = 0;
+    if (bi >= 0) {
+        const float4 hs = __ldg(cand + 2 * bi), tr = __ldg(cand + 2 * bi + 1);
+        bprim = __float_as_int(hs.w); binst = __float_as_int(tr.w);
+        nb = box3_normal_half(f3(hs.x, hs.y, hs.z), f3(o.x + tr.x, o.y + tr.y, o.z + tr.z), d, bt);
     }
     best.t = bt; best.n = nb; best.prim = bprim; best.inst = binst;
     return bt * 1.000001f < t_home;

@@ -11,9 +11,11 @@
 // (z,w) = subsequence; the four 32-bit outputs of a block are handed out in x,y,z,w order and an
 // element offset n selects block n/4, lane n%4; a uniform is  u32 * 2^-32 + 2^-33  in (0,1].
 //
-// Instead of the 64-byte curandStatePhilox4_32_10 the stream caches TWO consecutive blocks (8
-// outputs) plus the block counter and a position, so that the refill (10 Philox rounds) can be done
-// at points where the warp is converged (align()) instead of inside divergent physics branches.
+// Instead of the 64-byte curandStatePhilox4_32_10 the stream caches ONE block (4 outputs), lazily: a block is only
+// worked out when a draw that is actually USED falls into it.  The as-built reference (DEBUG_TAG) burns 3 - 7 of the
+// 6 - 10 draws of a bounce; skip() steps over those without generating anything, and draw2_ahead() - the two draws
+// every bounce starts with - refills at points where the whole warp is converged, so that a typical bounce costs two
+// warp-level block computations (it was 3.3 with the former eager two-block cache, profiles/r2_summary.md).
 #pragma once
 #include <stdint.h>
 #include <cuda_runtime.h>
@@ -21,11 +23,13 @@
 namespace phox {
 
 struct Philox {
-    uint4    a, b;       // outputs of blocks `blk` and `blk + 1`
-    uint32_t blk_lo, blk_hi;
+    uint4    a;          // outputs of block `blk + cblk`
+    uint32_t blk_lo, blk_hi;     // block of the element offset the stream was created with
     uint32_t sub_lo, sub_hi;
     uint32_t key_lo, key_hi;
-    uint32_t pos;        // next draw, 0..7 into (a,b); 8 = both blocks used up
+    uint32_t rel;        // next draw, counted from the first output of block `blk`
+    uint32_t cblk;       // which block `a` holds, relative to blk (rel >> 2 of its draws); kNone = nothing cached yet
+    static constexpr uint32_t kNone = 0xffffffffu;
 
     // Out of line on purpose: uniform() is expanded at ~30 draw sites and each would otherwise carry its own
     // copy of the 10 rounds; the simulate kernel is instruction-fetch bound (profiles/), so code size matters.
@@ -42,13 +46,13 @@ struct Philox {
         return make_uint4(c0, c1, c2, c3);
     }
 
-    // a <- b, b <- the block after it
-    __device__ __forceinline__ void advance() {
-        blk_lo += 1u;
-        if (blk_lo == 0u) blk_hi += 1u;         // carry into the subsequence words cannot happen for < 2^66 draws
-        uint32_t nlo = blk_lo + 1u, nhi = blk_hi + (nlo == 0u ? 1u : 0u);
-        a = b;
-        b = block(nlo, nhi, sub_lo, sub_hi, key_lo, key_hi);
+    // a <- the block the next draw falls into
+    __device__ __forceinline__ void fill() {
+        const uint32_t b = rel >> 2;
+        const uint32_t lo = blk_lo + b;
+        const uint32_t hi = blk_hi + (lo < blk_lo ? 1u : 0u);      // carry into the subsequence words cannot happen for < 2^66 draws
+        a = block(lo, hi, sub_lo, sub_hi, key_lo, key_hi);
+        cblk = b;
     }
 
     // seed / subsequence / element offset (offset already includes any per-event skipahead)
@@ -57,38 +61,57 @@ struct Philox {
         sub_lo = (uint32_t)subsequence; sub_hi = (uint32_t)(subsequence >> 32);
         uint64_t blk = element_offset >> 2;
         blk_lo = (uint32_t)blk; blk_hi = (uint32_t)(blk >> 32);
-        pos = (uint32_t)(element_offset & 3u);
-        a = block(blk_lo, blk_hi, sub_lo, sub_hi, key_lo, key_hi);
-        uint32_t nlo = blk_lo + 1u, nhi = blk_hi + (nlo == 0u ? 1u : 0u);
-        b = block(nlo, nhi, sub_lo, sub_hi, key_lo, key_hi);
+        rel = (uint32_t)(element_offset & 3u);
+        cblk = kNone;
+        a = make_uint4(0u, 0u, 0u, 0u);
     }
 
-    // Call where the warp is converged (top of a bounce, before the surface/boundary draws): afterwards
-    // at least 5 draws are cached, so the 4 + 2 draws of a typical bounce never refill inside divergent
-    // code.  Has no effect on the sequence of numbers handed out.
+    // Call where the warp is converged: the block of the next draw is worked out here if it is not cached yet.
+    // Has no effect on the sequence of numbers handed out.
     __device__ __forceinline__ void align() {
-        if (pos >= 4u) { advance(); pos -= 4u; }
+        if ((rel >> 2) != cblk) fill();
+    }
+
+    // draws whose value nobody reads (the burns of the DEBUG_TAG consumption pattern): nothing is generated
+    __device__ __forceinline__ void skip(uint32_t n) { rel += n; }
+
+    __device__ __forceinline__ uint32_t pick(uint32_t r) const {
+        const uint32_t p = r & 3u;
+        return p == 0u ? a.x : p == 1u ? a.y : p == 2u ? a.z : a.w;
     }
 
     __device__ __forceinline__ uint32_t next_u32() {
-        if (pos == 8u) { advance(); pos = 4u; }
-        uint32_t p = pos;
-        uint32_t r = p < 4u ? (p == 0u ? a.x : p == 1u ? a.y : p == 2u ? a.z : a.w)
-                            : (p == 4u ? b.x : p == 5u ? b.y : p == 6u ? b.z : b.w);
-        pos = p + 1u;
+        if ((rel >> 2) != cblk) fill();
+        const uint32_t r = pick(rel);
+        rel += 1u;
         return r;
     }
 
-    // uniforms handed out so far, counted from element offset `base` (lets a stream be parked as 4 bytes
+    // uniforms handed out (or skipped) so far, counted from element offset `base` (lets a stream be parked as 4 bytes
     // and re-created with init(seed, subsequence, base + consumed))
     __device__ __forceinline__ uint32_t consumed(uint64_t base) const {
         uint64_t blk = ((uint64_t)blk_hi << 32) | blk_lo;
-        return (uint32_t)(blk * 4ull + pos - base);
+        return (uint32_t)(blk * 4ull + rel - base);
     }
 
-    // curand_uniform : (0,1]
-    __device__ __forceinline__ float uniform() {
-        return next_u32() * 2.3283064365386963e-10f + (2.3283064365386963e-10f / 2.0f);
+    static __device__ __forceinline__ float to_uniform(uint32_t x) {       // curand_uniform : (0,1]
+        return x * 2.3283064365386963e-10f + (2.3283064365386963e-10f / 2.0f);
+    }
+    __device__ __forceinline__ float uniform() { return to_uniform(next_u32()); }
+
+    // u0 = uniform(); u1 = uniform(); and the block of the draw AFTER them is cached on return.  Both refills sit at
+    // warp-converged points (every lane of a bounce comes through here), the second one only for the lanes whose next
+    // two draws leave the block of the first.
+    __device__ __forceinline__ void draw2_ahead(float& u0, float& u1) {
+        if ((rel >> 2) != cblk) fill();
+        const uint32_t x0 = pick(rel);
+        const uint32_t r1 = rel + 1u;
+        const bool same = (r1 >> 2) == cblk;
+        uint32_t x1 = pick(r1);                  // valid when `same`
+        rel += 2u;
+        if ((rel >> 2) != cblk) fill();          // r1 & 3 == 0 (then it holds draw r1 in .x) or rel & 3 == 0
+        if (!same) x1 = a.x;
+        u0 = to_uniform(x0); u1 = to_uniform(x1);
     }
 };
 

@@ -31,6 +31,8 @@ struct Tables {
     unsigned nx, ny;
     float nm0, nms;                 // wavelength of sample 0, step
     unsigned hd_factor;
+    float inv_ny;                   // 1 / float(ny), correctly rounded
+    unsigned y_fast;                // 1: bnd_y's reciprocal form was checked against the division for every iy < ny
 };
 
 struct PhotonState {                // sphoton in registers
@@ -126,12 +128,27 @@ struct Tagr {
 };
 
 // ---- tables ----------------------------------------------------------------------------------
-PHOX_D float4 bnd_lookup(const Tables& tb, float nm, unsigned line, unsigned k) {
+// qbnd::boundary_lookup (qudarap/qbnd.h:103-132) in two halves: the x coordinate depends on the wavelength only, so a
+// bounce works it out once for its three or four fetches; the y coordinate is (iy + 0.5) / ny, for which phox_set_tables
+// checks over every iy < ny that the three-instruction form below (one product with the correctly rounded reciprocal and
+// one exact-residual correction) returns the bits of the IEEE division, and otherwise leaves y_fast at 0.
+PHOX_D float bnd_x(const Tables& tb, float nm) {
     float fx = (nm - tb.nm0) / tb.nms;
-    float x = (fx + 0.5f) / float(tb.nx);
-    unsigned iy = 2u * line + k;
-    float y = (float(iy) + 0.5f) / float(tb.ny);
-    return tex2D<float4>(tb.bnd_tex, x, y);
+    return (fx + 0.5f) / float(tb.nx);
+}
+PHOX_D float bnd_y(const Tables& tb, unsigned iy) {
+    const float a = float(iy) + 0.5f, c = float(tb.ny);
+    if (tb.y_fast) {
+        const float q = __fmul_rn(a, tb.inv_ny);
+        return __fmaf_rn(__fmaf_rn(-q, c, a), tb.inv_ny, q);
+    }
+    return a / c;
+}
+PHOX_D float4 bnd_fetch(const Tables& tb, float x, unsigned line, unsigned k) {
+    return tex2D<float4>(tb.bnd_tex, x, bnd_y(tb, 2u * line + k));
+}
+PHOX_D float4 bnd_lookup(const Tables& tb, float nm, unsigned line, unsigned k) {
+    return bnd_fetch(tb, bnd_x(tb, nm), line, k);
 }
 
 PHOX_D float icdf_wavelength(const Tables& tb, float u0) {       // qscint::wavelength
@@ -437,8 +454,16 @@ PHOX_D void diffuse_reflect(float3& mom_io, float3& pol_io, const float3& normal
                 __fadd_rn(__fmul_rn(-1.f, old_pol.z), __fmul_rn(two_edotn, facet_normal.z)));
 }
 
+// Rayleigh scattering (qsim::rayleigh_scatter), plain operators like the reference so that nvcc fuses what it fuses there.
+// ONE compiled body for every kernel (out of line, on private copies handed over by address: nothing of the caller's state gets
+// its address taken): inlined, the persistent and the wavefront kernel were seen to fuse the a*b + c*d terms of the polarisation
+// differently once the code around this block changed (scripts/form_diff.py on sphere_leak: last-bit differences in pol of exactly
+// the BULK_SCATTER photons).  The path is cold on detector geometries; the call costs nothing where it is not taken.
+struct ScatterIO { float3 mom, pol; };
 template <bool TAG>
-PHOX_D void rayleigh_scatter(PhotonState& p, Philox& rng, Tagr* tg) {
+__device__ __noinline__ void rayleigh_scatter_cold(ScatterIO* io, Philox* rng_io, Tagr* tg) {
+    const float3 mom = io->mom, pol = io->pol;
+    Philox rng = *rng_io;
     float3 direction, polarization;
     bool looping = true;
     do {
@@ -450,9 +475,9 @@ PHOX_D void rayleigh_scatter(PhotonState& p, Philox& rng, Tagr* tg) {
         float sinPhi, cosPhi;
         sincosf(2.f * kPi * u2, &sinPhi, &cosPhi);
         direction = f3(sinTheta * cosPhi, sinTheta * sinPhi, cosTheta);
-        rotate_uz(direction, p.mom);
-        float constant = -dot(direction, p.pol);
-        polarization = f3(p.pol.x + constant * direction.x, p.pol.y + constant * direction.y, p.pol.z + constant * direction.z);
+        rotate_uz(direction, mom);
+        float constant = -dot(direction, pol);
+        polarization = f3(pol.x + constant * direction.x, pol.y + constant * direction.y, pol.z + constant * direction.z);
         if (dot(polarization, polarization) == 0.f) {
             sincosf(2.f * kPi * u3, &sinPhi, &cosPhi);
             polarization = f3(cosPhi, sinPhi, 0.f);
@@ -461,12 +486,22 @@ PHOX_D void rayleigh_scatter(PhotonState& p, Philox& rng, Tagr* tg) {
             if (u3 < 0.5f) polarization = -polarization;
         }
         polarization = normalize(polarization);
-        float doCosTheta = dot(polarization, p.pol);
+        float doCosTheta = dot(polarization, pol);
         float doCosTheta2 = doCosTheta * doCosTheta;
         looping = doCosTheta2 < u4;
     } while (looping);
-    p.mom = direction;
-    p.pol = polarization;
+    io->mom = direction;
+    io->pol = polarization;
+    *rng_io = rng;
+}
+template <bool TAG>
+PHOX_D void rayleigh_scatter(PhotonState& p, Philox& rng, Tagr* tg) {
+    ScatterIO io;
+    io.mom = p.mom; io.pol = p.pol;
+    Philox rc = rng;
+    rayleigh_scatter_cold<TAG>(&io, &rc, tg);
+    p.mom = io.mom; p.pol = io.pol;
+    rng = rc;
 }
 
 // One bounce: the photon has a ray hit `h` (normal normalised, world frame).  Returns the flow
@@ -489,8 +524,9 @@ PHOX_D int propagate_core(PhotonState& p, Philox& rng, const HitInfo& h, const T
     const int m1_line = cosTheta > 0.f ? line + SP_IMAT : line + SP_OMAT;
     const int m2_line = cosTheta > 0.f ? line + SP_OMAT : line + SP_IMAT;
     const int su_line = cosTheta > 0.f ? line + SP_ISUR : line + SP_OSUR;
-    const float4 material1 = bnd_lookup(tb, p.wavelength, m1_line, 0);
-    const float group_velocity = bnd_lookup(tb, p.wavelength, m1_line, 1).x;
+    const float bx = bnd_x(tb, p.wavelength);       // every fetch of this bounce happens before the wavelength can change (re-emission ends it)
+    const float4 material1 = bnd_fetch(tb, bx, m1_line, 0);
+    const float group_velocity = bnd_fetch(tb, bx, m1_line, 1).x;
 
     unsigned flag = 0u;
     int command;
@@ -499,13 +535,14 @@ PHOX_D int propagate_core(PhotonState& p, Philox& rng, const HitInfo& h, const T
     {
         const float absorption_length = material1.y, scattering_length = material1.z, reemission_prob = material1.w;
         const float distance_to_boundary = h.t;
-        rng.align();
         if (burn) {
-            float u_to_sci = rng.uniform(), u_to_bnd = rng.uniform();
-            if (TAG) { tg->add(TAG_to_sci, u_to_sci); tg->add(TAG_to_bnd, u_to_bnd); }
+            if (TAG) {
+                float u_to_sci = rng.uniform(), u_to_bnd = rng.uniform();
+                tg->add(TAG_to_sci, u_to_sci); tg->add(TAG_to_bnd, u_to_bnd);
+            } else rng.skip(2u);                                 // burns: stepped over, never generated
         }
-        float u_scattering = rng.uniform();
-        float u_absorption = rng.uniform();
+        float u_scattering, u_absorption;
+        rng.draw2_ahead(u_scattering, u_absorption);             // warp-converged refills; the block of the next draw is cached on return
         if (TAG) { tg->add(TAG_to_sca, u_scattering); tg->add(TAG_to_abs, u_absorption); }
         float scattering_distance = -scattering_length * logf(u_scattering);
         float absorption_distance = -absorption_length * logf(u_absorption);
@@ -551,13 +588,12 @@ PHOX_D int propagate_core(PhotonState& p, Philox& rng, const HitInfo& h, const T
     }
 
     if (command == FLOW_BOUNDARY) {
-        rng.align();
         const unsigned ems = __ldg(tb.optical + su_line).y;
         bool at_surface = false;
         if (ems == EMS_NoSurface) {
             // ---- propagate_at_boundary : Fresnel reflect / refract ----
             const float n1 = material1.x;
-            const float n2 = bnd_lookup(tb, p.wavelength, m2_line, 0).x;
+            const float n2 = bnd_fetch(tb, bx, m2_line, 0).x;
             const float eta = n1 / n2;
             const float _c1 = -dot(p.mom, normal);
             const float3 on = _c1 < 0.f ? -normal : normal;          // oriented against the incident direction
@@ -580,8 +616,8 @@ PHOX_D int propagate_core(PhotonState& p, Philox& rng, const HitInfo& h, const T
             const float TransCoeff = (tir || n1c1 == 0.f) ? 0.f : n2c2 * dot2(E2_t, E2_t) / n1c1;
 
             if (burn) {
-                const float u_boundary_burn = rng.uniform();
-                if (TAG) tg->add(TAG_at_burn_sf_sd, u_boundary_burn);
+                if (TAG) { const float u_boundary_burn = rng.uniform(); tg->add(TAG_at_burn_sf_sd, u_boundary_burn); }
+                else rng.skip(1u);
             }
             const float u_reflect = rng.uniform();
             if (TAG) tg->add(TAG_at_ref, u_reflect);
@@ -595,8 +631,10 @@ PHOX_D int propagate_core(PhotonState& p, Philox& rng, const HitInfo& h, const T
                                    : TT.x * A_trans + TT.y * A_paral);
             flag = reflect ? F_BOUNDARY_REFLECT : F_BOUNDARY_TRANSMIT;
             if (burn && reflect) {
-                const float a0 = rng.uniform(), a1 = rng.uniform(), a2 = rng.uniform(), a3 = rng.uniform();
-                if (TAG) { tg->add(TAG_to_sci, a0); tg->add(TAG_to_bnd, a1); tg->add(TAG_to_sca, a2); tg->add(TAG_to_abs, a3); }
+                if (TAG) {
+                    const float a0 = rng.uniform(), a1 = rng.uniform(), a2 = rng.uniform(), a3 = rng.uniform();
+                    tg->add(TAG_to_sci, a0); tg->add(TAG_to_bnd, a1); tg->add(TAG_to_sca, a2); tg->add(TAG_to_abs, a3);
+                } else rng.skip(4u);
             }
             command = FLOW_CONTINUE;
         } else if (ems == EMS_Surface) {
@@ -604,7 +642,7 @@ PHOX_D int propagate_core(PhotonState& p, Philox& rng, const HitInfo& h, const T
         } else if (h.lposcost < 0.f) {
             at_surface = true;
         } else if (ems == EMS_SensorA) {
-            rng.uniform();
+            rng.skip(1u);
             flag = F_SURFACE_DETECT;
             command = FLOW_BREAK;
         }
@@ -613,13 +651,13 @@ PHOX_D int propagate_core(PhotonState& p, Philox& rng, const HitInfo& h, const T
 
         if (at_surface) {
             // ---- propagate_at_surface ----
-            const float4 surface = bnd_lookup(tb, p.wavelength, su_line, 0);     // detect, absorb, specular, diffuse
+            const float4 surface = bnd_fetch(tb, bx, su_line, 0);     // detect, absorb, specular, diffuse
             const float detect = surface.x, absorb = surface.y, diffuse = surface.w;
             float u_surface = rng.uniform();
             if (TAG) tg->add(TAG_at_burn_sf_sd, u_surface);
             if (burn) {
-                const float u_surface_burn = rng.uniform();
-                if (TAG) tg->add(TAG_sf_burn, u_surface_burn);
+                if (TAG) { const float u_surface_burn = rng.uniform(); tg->add(TAG_sf_burn, u_surface_burn); }
+                else rng.skip(1u);
             }
             command = u_surface < absorb + detect ? FLOW_BREAK : FLOW_CONTINUE;
             if (command == FLOW_BREAK) {
