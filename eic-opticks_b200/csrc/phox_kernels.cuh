@@ -627,6 +627,9 @@ constexpr int kPropThreads = PHOX_WF_PROP_THREADS;
 #ifndef PHOX_PROP_PREFETCH
 #define PHOX_PROP_PREFETCH 1            // physics kernel: L2 prefetch of the next chunk's lines (measured, see profiles/r2_summary.md)
 #endif
+#ifndef PHOX_PROP_STAGE
+#define PHOX_PROP_STAGE 0               // physics kernel: the next chunk's hit record / photon / draw count / home come in by cp.async while this chunk computes
+#endif
 #ifndef PHOX_WF_PROP_MIN_BLOCKS
 #define PHOX_WF_PROP_MIN_BLOCKS 4       // 64 registers: the inlined physics body fits without spills (5 blocks = 48 registers: 0.509 vs 0.490 ms per launch)
 #endif
@@ -637,9 +640,8 @@ constexpr unsigned kWaveNoHit = 0xffffffffu;    // prim_boundary of a list entry
 // hit record of list position a (streaming store: the physics kernel reads it once)
 PHOX_D void wave_store_hit(Prd* hits, unsigned a, const Prd& r) {
 #if PHOX_WF_STREAM
-    float4* hp = reinterpret_cast<float4*>(hits + a);
-    __stcs(hp, make_float4(r.nx, r.ny, r.nz, r.t));
-    __stcs(hp + 1, make_float4(r.lposcost, r.lposfphi, __uint_as_float(r.iindex_identity), __uint_as_float(r.prim_boundary)));
+    stcs256(hits + a, make_float4(r.nx, r.ny, r.nz, r.t),
+            make_float4(r.lposcost, r.lposfphi, __uint_as_float(r.iindex_identity), __uint_as_float(r.prim_boundary)));
 #else
     hits[a] = r;
 #endif
@@ -788,7 +790,8 @@ __global__ void __launch_bounds__(kTraceThreads, PHOX_WF_TRACE_MIN_BLOCKS) k_wf_
         const unsigned entry = __ldcs(W.active_in + a);
         const unsigned idx = entry & kListSlotMask;
         const float4* ph = reinterpret_cast<const float4*>(P.photon + idx);
-        float4 q0 = __ldcs(ph), q1 = __ldcs(ph + 1);
+        float4 q0, q1;
+        ldcs256(ph, q0, q1);
         Prd r;
         wave_no_hit(r);
         if (q0.w < P.max_time) {                                // else the while-condition of the raygen loop fails: photon is final
@@ -838,25 +841,65 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
     const SimParams& P = W.sim;
     const unsigned count = *W.count_in;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+#if PHOX_PROP_STAGE
+    // Staging: what a thread needs at the head of its NEXT chunk (hit record, photon, draw count, home: 104 B behind the
+    // dependent load of the list entry) is copied into shared memory by cp.async while the current chunk computes, each
+    // thread into its own column - so the head of a chunk costs a shared-memory read instead of two DRAM round trips, no
+    // registers are held across the physics, and nobody but the copying thread reads a column (no barrier: wait_group).
+    __shared__ float4 s_ph[4][kPropThreads];
+    __shared__ float4 s_hit[2][kPropThreads];
+    __shared__ unsigned s_nd[kPropThreads], s_hm[kPropThreads];
+    auto stage = [&](unsigned a_s, unsigned entry_s) {
+        const unsigned idx_s = entry_s & kListSlotMask;
+        const float4* hp = reinterpret_cast<const float4*>(W.hits + a_s);
+        const float4* pp = reinterpret_cast<const float4*>(P.photon + idx_s);
+#pragma unroll
+        for (int k = 0; k < 2; k++)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(&s_hit[k][threadIdx.x])), "l"(hp + k) : "memory");
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(&s_ph[k][threadIdx.x])), "l"(pp + k) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(&s_nd[threadIdx.x])), "l"(W.ndraw + idx_s) : "memory");
+        if (HOME) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(&s_hm[threadIdx.x])), "l"(W.home + idx_s) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    unsigned entry_cur = 0xffffffffu;
+    {
+        const unsigned a0 = blockIdx.x * blockDim.x + threadIdx.x;
+        if (a0 < count) { entry_cur = __ldcs(W.active_in + a0); stage(a0, entry_cur); }
+    }
+#endif
     for (unsigned base_a = blockIdx.x * blockDim.x; base_a < count; base_a += gridDim.x * blockDim.x) {
         unsigned a = base_a + threadIdx.x;
-#if PHOX_PROP_PREFETCH
-        // list entry of this thread's photon in the NEXT chunk: it arrives while this chunk's physics runs, and the lines that
-        // chunk will want (hit record, photon, draw count, home) are asked into L2 before the threads meet at the barrier
+#if PHOX_PROP_PREFETCH || PHOX_PROP_STAGE
+        // list entry of this thread's photon in the NEXT chunk: it arrives while this chunk's physics runs (then the data it
+        // points to are staged; without staging: asked into L2 before the threads meet at the barrier)
         const unsigned a_next = a + gridDim.x * blockDim.x;
         unsigned entry_next = 0xffffffffu;
         if (a_next < count) entry_next = __ldcs(W.active_in + a_next);
 #endif
-        bool survive = false, settled = false;
-        unsigned idx = 0, entry_out = 0;
+        bool survive = false, settled = false, have = false;
+        unsigned idx = 0, entry_out = 0, home = kNoHome;
+        int bounce = W.bounce + 1;
         Prd r2;                                             // HOME: hit of the next bounce, when the home cell settles it
+        PhotonState p;
         if (a < count) {
-#if PHOX_WF_STREAM
+#if PHOX_PROP_STAGE
+            idx = entry_cur & kListSlotMask;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            Prd r;
+            {
+                const float4 h0 = s_hit[0][threadIdx.x], h1 = s_hit[1][threadIdx.x];
+                r.nx = h0.x; r.ny = h0.y; r.nz = h0.z; r.t = h0.w; r.lposcost = h1.x; r.lposfphi = h1.y;
+                r.iindex_identity = __float_as_uint(h1.z); r.prim_boundary = __float_as_uint(h1.w);
+            }
+            if (HOME) home = s_hm[threadIdx.x];
+#elif PHOX_WF_STREAM
             idx = __ldcs(W.active_in + a) & kListSlotMask;
             Prd r;
             {
-                const float4* hp = reinterpret_cast<const float4*>(W.hits + a);
-                float4 h0 = __ldcs(hp), h1 = __ldcs(hp + 1);
+                float4 h0, h1;
+                ldcs256(W.hits + a, h0, h1);
                 r.nx = h0.x; r.ny = h0.y; r.nz = h0.z; r.t = h0.w; r.lposcost = h1.x; r.lposfphi = h1.y;
                 r.iindex_identity = __float_as_uint(h1.z); r.prim_boundary = __float_as_uint(h1.w);
             }
@@ -865,8 +908,17 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
             Prd r = W.hits[a];
 #endif
             if (r.prim_boundary != kWaveNoHit) {            // a miss (or time over) leaves the photon as it is: final
-                PhotonState p;
-#if PHOX_WF_STREAM
+                have = true;
+#if PHOX_PROP_STAGE
+                {
+                    const float4 qa = s_ph[0][threadIdx.x], qb = s_ph[1][threadIdx.x], qc = s_ph[2][threadIdx.x], qd = s_ph[3][threadIdx.x];
+                    p.pos = f3(qa.x, qa.y, qa.z); p.time = qa.w;
+                    p.mom = f3(qb.x, qb.y, qb.z); p.hitcount_iindex = __float_as_uint(qb.w);
+                    p.pol = f3(qc.x, qc.y, qc.z); p.wavelength = qc.w;
+                    p.obf = __float_as_uint(qd.x); p.identity = __float_as_uint(qd.y); p.index = __float_as_uint(qd.z); p.flagmask = __float_as_uint(qd.w);
+                }
+                unsigned nd = s_nd[threadIdx.x];
+#elif PHOX_WF_STREAM
                 p.load_cs(P.photon + idx);
                 unsigned nd = __ldcs(W.ndraw + idx);
 #else
@@ -892,7 +944,6 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
                     command = propagate(p, rng, h, P.tables, P.burn != 0);
 #endif
                 }
-                int bounce = W.bounce + 1;
 #if PHOX_WF_STREAM
                 p.store_cs(P.photon + idx);
                 __stcs(W.ndraw + idx, rng.consumed(base));
@@ -906,8 +957,19 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
                 }
                 survive = !(command == FLOW_BREAK) && bounce < P.max_bounce && p.time < P.max_time;
                 entry_out = idx | ((p.obf & P.eps0_mask) ? kListEps0 : 0u);
+            }
+        }
+#if PHOX_PROP_STAGE
+        // this chunk's columns are in registers: the next chunk's copies may start (they land during the candidate pass and the append)
+        entry_cur = entry_next;
+        if (entry_next != 0xffffffffu) stage(a_next, entry_next);
+#endif
+        {
+            {
                 if (HOME && survive) {
-                    unsigned home = __ldcs(W.home + idx);
+#if !PHOX_PROP_STAGE
+                    home = __ldcs(W.home + idx);
+#endif
                     const float tmin = (p.obf & P.eps0_mask) ? P.tmin0 : P.tmin;
                     const float3 o = p.pos, d = p.mom;
                     Nearest best;
@@ -933,7 +995,7 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
             unsigned pb = hp->prim_boundary;                // the miss program clears it
             P.lpos[idx] = pb == kWaveNoHit ? 0u : pack_lpos(hp->lposcost, hp->lposfphi);
         }
-#if PHOX_PROP_PREFETCH
+#if PHOX_PROP_PREFETCH && !PHOX_PROP_STAGE
         if (entry_next != 0xffffffffu) {
             const unsigned idx_next = entry_next & kListSlotMask;
             asm volatile("prefetch.global.L2 [%0];" ::"l"(W.hits + a_next));

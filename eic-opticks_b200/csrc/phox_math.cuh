@@ -49,6 +49,19 @@ PHOX_D void rotate_uz(float3& d, const float3& u) {
     }
 }
 
+// 256-bit streaming accesses (sm_100: LDG.E.EF.256 / STG.E.EF.256; the address must be 32 B aligned).  The per-photon records
+// are 64 B (sphoton) and 32 B (quad2) per lane at a 64 / 32 B stride: with 128-bit accesses every 32 B sector passes the L1 data
+// pipe twice, and that pipe - not DRAM, not the issue slots - was the busiest unit of the physics kernel (l1tex lsu
+// wavefronts 45 % of peak, profiles/r2_summary.md).
+PHOX_D void ldcs256(const void* p, float4& a, float4& b) {
+    asm volatile("ld.global.cs.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p) : "memory");
+}
+PHOX_D void stcs256(void* p, const float4& a, const float4& b) {
+    asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+}
+
 // point / direction through an inverse transform, row-vector convention (sysrap/sqat4.h:45-52)
 PHOX_D float3 xform(const float4& r0, const float4& r1, const float4& r2, const float4& r3, const float3& v, float w) {
     float3 o;

@@ -33,7 +33,7 @@ struct Philox {
 
     // Out of line on purpose: uniform() is expanded at ~30 draw sites and each would otherwise carry its own
     // copy of the 10 rounds; the simulate kernel is instruction-fetch bound (profiles/), so code size matters.
-    static __device__ __noinline__ uint4 block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+    static __device__ __forceinline__ uint4 block_inline(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
         constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
         for (int r = 0; r < 10; r++) {
@@ -45,6 +45,9 @@ struct Philox {
         }
         return make_uint4(c0, c1, c2, c3);
     }
+    static __device__ __noinline__ uint4 block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+        return block_inline(c0, c1, c2, c3, k0, k1);
+    }
 
     // a <- the block the next draw falls into
     __device__ __forceinline__ void fill() {
@@ -52,6 +55,18 @@ struct Philox {
         const uint32_t lo = blk_lo + b;
         const uint32_t hi = blk_hi + (lo < blk_lo ? 1u : 0u);      // carry into the subsequence words cannot happen for < 2^66 draws
         a = block(lo, hi, sub_lo, sub_hi, key_lo, key_hi);
+        cblk = b;
+    }
+
+    // The same with the ten rounds compiled in place.  A call is a scoreboard boundary: the caller waits for every load and
+    // texture fetch in flight before it branches, and the first refill of a bounce sits right behind the material fetches
+    // (profiles/r2_summary.md: 8.9 % of the physics kernel's stall samples were on that one CALL).  In place, the rounds
+    // run while the fetches travel.
+    __device__ __forceinline__ void fill_inline() {
+        const uint32_t b = rel >> 2;
+        const uint32_t lo = blk_lo + b;
+        const uint32_t hi = blk_hi + (lo < blk_lo ? 1u : 0u);
+        a = block_inline(lo, hi, sub_lo, sub_hi, key_lo, key_hi);
         cblk = b;
     }
 
@@ -103,7 +118,7 @@ struct Philox {
     // warp-converged points (every lane of a bounce comes through here), the second one only for the lanes whose next
     // two draws leave the block of the first.
     __device__ __forceinline__ void draw2_ahead(float& u0, float& u1) {
-        if ((rel >> 2) != cblk) fill();
+        if ((rel >> 2) != cblk) fill_inline();
         const uint32_t x0 = pick(rel);
         const uint32_t r1 = rel + 1u;
         const bool same = (r1 >> 2) == cblk;

@@ -76,7 +76,8 @@ struct PhotonState {                // sphoton in registers
     // stream evict-first keeps L1/L2 for what is re-used (BVH nodes, tables, local-memory frames)
     PHOX_D void load_cs(const Photon* src) {
         const float4* s = reinterpret_cast<const float4*>(src);
-        float4 a = __ldcs(s), b = __ldcs(s + 1), c = __ldcs(s + 2), d = __ldcs(s + 3);
+        float4 a, b, c, d;
+        ldcs256(s, a, b); ldcs256(s + 2, c, d);
         pos = f3(a.x, a.y, a.z); time = a.w;
         mom = f3(b.x, b.y, b.z); hitcount_iindex = __float_as_uint(b.w);
         pol = f3(c.x, c.y, c.z); wavelength = c.w;
@@ -84,10 +85,9 @@ struct PhotonState {                // sphoton in registers
     }
     PHOX_D void store_cs(Photon* dst) const {
         float4* o = reinterpret_cast<float4*>(dst);
-        __stcs(o + 0, make_float4(pos.x, pos.y, pos.z, time));
-        __stcs(o + 1, make_float4(mom.x, mom.y, mom.z, __uint_as_float(hitcount_iindex)));
-        __stcs(o + 2, make_float4(pol.x, pol.y, pol.z, wavelength));
-        __stcs(o + 3, make_float4(__uint_as_float(obf), __uint_as_float(identity), __uint_as_float(index), __uint_as_float(flagmask)));
+        stcs256(o, make_float4(pos.x, pos.y, pos.z, time), make_float4(mom.x, mom.y, mom.z, __uint_as_float(hitcount_iindex)));
+        stcs256(o + 2, make_float4(pol.x, pol.y, pol.z, wavelength),
+                make_float4(__uint_as_float(obf), __uint_as_float(identity), __uint_as_float(index), __uint_as_float(flagmask)));
     }
     PHOX_D void store(Photon* dst) const {
         float4* o = reinterpret_cast<float4*>(dst);
