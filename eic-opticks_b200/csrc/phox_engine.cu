@@ -844,7 +844,7 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
         // wavefront: generate, then per bounce a trace kernel and a physics kernel over the live list;
         // list lengths stay on the device, so there is no host synchronisation inside the loop
         CK(ctx->d_active[0].reserve((size_t)n)); CK(ctx->d_active[1].reserve((size_t)n));
-        CK(ctx->d_ndraw.reserve((size_t)n)); CK(ctx->d_wave_hits.reserve((size_t)n));
+        CK(ctx->d_wave_hits.reserve((size_t)n));                  // (the draw counts travel in the index word of the photon records)
         const bool homes = P.scene.home != nullptr;
         const bool home_pass = homes && !c.propagate_refine;       // PropagateRefine re-traces from 0.99 t: those rays take the tree
         if (homes) CK(ctx->d_home_state.reserve((size_t)n));
@@ -861,7 +861,7 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
         WaveParams W;
         std::memset(&W, 0, sizeof(W));
         W.sim = P;
-        W.ndraw = ctx->d_ndraw.p; W.hits = ctx->d_wave_hits.p;
+        W.ndraw = nullptr; W.hits = ctx->d_wave_hits.p;
         W.home = P.scene.home ? ctx->d_home_state.p : nullptr;
         const int d = dbg ? 1 : 0;
         auto grid = [&](int k, int threads = kWaveThreads) {

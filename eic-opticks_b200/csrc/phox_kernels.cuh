@@ -598,7 +598,7 @@ struct WaveParams {
     unsigned* active_out;           // survivors (next bounce)
     const unsigned* count_in;       // device-side length of active_in
     unsigned* count_out;            // device-side length of active_out (zeroed beforehand)
-    unsigned* ndraw;                // per slot: uniforms consumed so far
+    unsigned* ndraw;                // (unused since the draw count travels in the index word of the live photon records)
     unsigned* home;                 // per slot: home cell (CSGPrim index or kNoHome)
     const unsigned* gs_home;        // per genstep: home cell its photons start with (k_genstep_home), or null
     unsigned* pending;              // list positions whose home cell did not settle the ray (null: k_wf_trace takes the whole list)
@@ -714,15 +714,20 @@ __global__ void __launch_bounds__(kWaveThreads) k_wf_generate(const __grid_const
             rng.init(P.seed, photon_idx, base);
             PhotonState p;
             generate_photon(p, rng, gs, P.tables, P.input_photon, P.input_base, photon_idx);
+            // A live photon's record carries its draw count in the `index` word (the index itself is photon_offset + slot, put
+            // back by whichever physics pass writes the record for the last time): one scattered 4 B load and store less per bounce.
+            {
+                const unsigned true_index = p.index;
+                if (P.max_bounce > 0) p.index = rng.consumed(base);
 #if PHOX_WF_STREAM
-            p.store_cs(P.photon + idx);
-            __stcs(W.ndraw + idx, rng.consumed(base));
-            __stcs(W.active_out + idx, idx | ((p.obf & P.eps0_mask) ? kListEps0 : 0u));
+                p.store_cs(P.photon + idx);
+                __stcs(W.active_out + idx, idx | ((p.obf & P.eps0_mask) ? kListEps0 : 0u));
 #else
-            p.store(P.photon + idx);
-            W.ndraw[idx] = rng.consumed(base);
-            W.active_out[idx] = idx | ((p.obf & P.eps0_mask) ? kListEps0 : 0u);
+                p.store(P.photon + idx);
+                W.active_out[idx] = idx | ((p.obf & P.eps0_mask) ? kListEps0 : 0u);
 #endif
+                p.index = true_index;
+            }
             if (P.lpos) P.lpos[idx] = 0u;
             if (DEBUG) {
                 Seq seq;
@@ -848,7 +853,7 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
     // registers are held across the physics, and nobody but the copying thread reads a column (no barrier: wait_group).
     __shared__ float4 s_ph[4][kPropThreads];
     __shared__ float4 s_hit[2][kPropThreads];
-    __shared__ unsigned s_nd[kPropThreads], s_hm[kPropThreads];
+    __shared__ unsigned s_hm[kPropThreads];
     auto stage = [&](unsigned a_s, unsigned entry_s) {
         const unsigned idx_s = entry_s & kListSlotMask;
         const float4* hp = reinterpret_cast<const float4*>(W.hits + a_s);
@@ -859,7 +864,6 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
 #pragma unroll
         for (int k = 0; k < 4; k++)
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(&s_ph[k][threadIdx.x])), "l"(pp + k) : "memory");
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(&s_nd[threadIdx.x])), "l"(W.ndraw + idx_s) : "memory");
         if (HOME) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(&s_hm[threadIdx.x])), "l"(W.home + idx_s) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -917,14 +921,13 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
                     p.pol = f3(qc.x, qc.y, qc.z); p.wavelength = qc.w;
                     p.obf = __float_as_uint(qd.x); p.identity = __float_as_uint(qd.y); p.index = __float_as_uint(qd.z); p.flagmask = __float_as_uint(qd.w);
                 }
-                unsigned nd = s_nd[threadIdx.x];
 #elif PHOX_WF_STREAM
                 p.load_cs(P.photon + idx);
-                unsigned nd = __ldcs(W.ndraw + idx);
 #else
                 p.load_rw(P.photon + idx);
-                unsigned nd = W.ndraw[idx];
 #endif
+                const unsigned nd = p.index;                 // draw count parked in the index word (k_wf_generate)
+                p.index = (unsigned)(P.photon_offset + idx);
                 unsigned long long base = P.rng_offset + P.skipahead * (unsigned long long)P.event_index;
                 Philox rng;
                 rng.init(P.seed, P.photon_offset + idx, base + nd);
@@ -944,19 +947,20 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
                     command = propagate(p, rng, h, P.tables, P.burn != 0);
 #endif
                 }
-#if PHOX_WF_STREAM
-                p.store_cs(P.photon + idx);
-                __stcs(W.ndraw + idx, rng.consumed(base));
-#else
-                p.store(P.photon + idx);
-                W.ndraw[idx] = rng.consumed(base);
-#endif
                 if (DEBUG) {
                     if (P.record && bounce < P.max_record) p.store(P.record + (size_t)P.max_record * idx + bounce);
                     if (P.seq) { Seq seq = P.seq[idx]; seq_add(seq, (unsigned)bounce, p.flag(), p.boundary()); P.seq[idx] = seq; }
                 }
                 survive = !(command == FLOW_BREAK) && bounce < P.max_bounce && p.time < P.max_time;
                 entry_out = idx | ((p.obf & P.eps0_mask) ? kListEps0 : 0u);
+                if (survive) p.index = rng.consumed(base);   // still alive: the index word parks the draw count again
+#if PHOX_WF_STREAM
+                p.store_cs(P.photon + idx);
+#else
+                p.store(P.photon + idx);
+#endif
+            } else {
+                P.photon[idx].index = (unsigned)(P.photon_offset + idx);    // final as it is, but for the draw count parked in its index word
             }
         }
 #if PHOX_PROP_STAGE
@@ -1000,7 +1004,6 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
             const unsigned idx_next = entry_next & kListSlotMask;
             asm volatile("prefetch.global.L2 [%0];" ::"l"(W.hits + a_next));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(P.photon + idx_next));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(W.ndraw + idx_next));
             if (HOME) asm volatile("prefetch.global.L2 [%0];" ::"l"(W.home + idx_next));
         }
 #endif
