@@ -128,7 +128,7 @@ struct phox_context {
     DevBuf<float4> d_exact;                    // per CSGPrim: (sizes ; translation) of prims that are exactly a box
     DevBuf<float4> d_home;                     // per CSGPrim: HomeRec (box, candidate count, offset), see traverse_bvh
     DevBuf<float4> d_cand;                     // candidate lists of the home cells, two float4 per candidate
-    DevBuf<unsigned> d_home_state;             // wavefront form, per slot: home cell of the photon
+    DevBuf<unsigned> d_home_state[2];          // wavefront form, per list position (double-buffered like the lists): home cell of the photon
     DevBuf<unsigned> d_pending, d_pending_count;   // wavefront form: list positions the home cells left to k_wf_trace, and their count per bounce
     DevBuf<Photon> d_hit_stage[2];                 // phox_get_hits_async: hits of the last two events, copied out while the next event runs
     cudaStream_t copy_stream = nullptr;
@@ -275,7 +275,7 @@ extern "C" void phox_destroy(phox_context* ctx) {
     ctx->d_record.release(); ctx->d_hit.release(); ctx->d_seq.release(); ctx->d_prd.release();
     ctx->d_block_hits.release(); ctx->d_block_off.release(); ctx->d_counters.release();
     ctx->d_slack.release(); ctx->d_exact.release();
-    ctx->d_home.release(); ctx->d_cand.release(); ctx->d_home_state.release(); ctx->d_pending.release(); ctx->d_pending_count.release(); ctx->d_wave_hits2.release(); ctx->d_gs_home.release();
+    ctx->d_home.release(); ctx->d_cand.release(); ctx->d_home_state[0].release(); ctx->d_home_state[1].release(); ctx->d_pending.release(); ctx->d_pending_count.release(); ctx->d_wave_hits2.release(); ctx->d_gs_home.release();
     ctx->d_tag.release(); ctx->d_flat.release(); ctx->d_tagslot.release();
     ctx->d_lpos.release(); ctx->d_hitlite.release(); ctx->d_merged_lite.release();
     ctx->d_merged.release(); ctx->d_merge_in.release(); merge_scratch_free(ctx->merge_scratch);
@@ -847,8 +847,8 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
         CK(ctx->d_wave_hits.reserve((size_t)n));                  // (the draw counts travel in the index word of the photon records)
         const bool homes = P.scene.home != nullptr;
         const bool home_pass = homes && !c.propagate_refine;       // PropagateRefine re-traces from 0.99 t: those rays take the tree
-        if (homes) CK(ctx->d_home_state.reserve((size_t)n));
         if (home_pass) {
+            CK(ctx->d_home_state[0].reserve((size_t)n)); CK(ctx->d_home_state[1].reserve((size_t)n));
             CK(ctx->d_wave_hits2.reserve((size_t)n));
             CK(ctx->d_pending.reserve((size_t)n));
             CK(ctx->d_pending_count.reserve((size_t)c.max_bounce + 2));
@@ -862,14 +862,14 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
         std::memset(&W, 0, sizeof(W));
         W.sim = P;
         W.ndraw = nullptr; W.hits = ctx->d_wave_hits.p;
-        W.home = P.scene.home ? ctx->d_home_state.p : nullptr;
+        W.home = nullptr; W.home_next = home_pass ? ctx->d_home_state[0].p : nullptr;     // k_wf_generate fills the list of bounce 0
         const int d = dbg ? 1 : 0;
         auto grid = [&](int k, int threads = kWaveThreads) {
             return (unsigned)std::max<int64_t>(1, std::min<int64_t>(ctx->wave_grid[k][d], (n + threads - 1) / threads));
         };
         CK(cudaEventRecord(ctx->ev[0], ctx->stream));
         W.active_out = ctx->d_active[0].p;
-        if (homes) {           // home cell of each genstep, handed to its photons
+        if (home_pass) {       // home cell of each genstep, handed to its photons
             CK(ctx->d_gs_home.reserve((size_t)std::max(ngs, 1)));
             k_genstep_home<<<(ngs + 127) / 128, 128, 0, ctx->stream>>>(d_gs, ngs, P.scene.home, ctx->nprim, ctx->d_gs_home.p);
             W.gs_home = ctx->d_gs_home.p;
@@ -890,6 +890,7 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
         Prd* hit_buf[2] = {ctx->d_wave_hits.p, home_pass ? ctx->d_wave_hits2.p : ctx->d_wave_hits.p};
         for (int b = 0; b < c.max_bounce; b++) {
             W.active_in = ctx->d_active[b & 1].p; W.active_out = ctx->d_active[(b + 1) & 1].p;
+            W.home = home_pass ? ctx->d_home_state[b & 1].p : nullptr; W.home_next = home_pass ? ctx->d_home_state[(b + 1) & 1].p : nullptr;
             W.count_in = ctx->d_wave_count.p + b; W.count_out = ctx->d_wave_count.p + b + 1;
             W.hits = hit_buf[b & 1]; W.hits_next = hit_buf[(b + 1) & 1];
             W.bounce = b;

@@ -599,7 +599,8 @@ struct WaveParams {
     const unsigned* count_in;       // device-side length of active_in
     unsigned* count_out;            // device-side length of active_out (zeroed beforehand)
     unsigned* ndraw;                // (unused since the draw count travels in the index word of the live photon records)
-    unsigned* home;                 // per slot: home cell (CSGPrim index or kNoHome)
+    unsigned* home;                 // per position of active_in: home cell of that photon (CSGPrim index or kNoHome); null = no home pass
+    unsigned* home_next;            // ... of active_out (the home travels with the list entry: coalesced, no per-slot array)
     const unsigned* gs_home;        // per genstep: home cell its photons start with (k_genstep_home), or null
     unsigned* pending;              // list positions whose home cell did not settle the ray (null: k_wf_trace takes the whole list)
     unsigned* pending_count;        // device-side length of pending (zeroed beforehand)
@@ -735,7 +736,7 @@ __global__ void __launch_bounds__(kWaveThreads) k_wf_generate(const __grid_const
                 if (P.record && 0 < P.max_record) p.store(P.record + (size_t)P.max_record * idx);
                 if (P.seq) { seq_add(seq, 0u, p.flag(), p.boundary()); P.seq[idx] = seq; }
             }
-            if (W.home) {
+            if (W.home_next) {
                 unsigned home = W.gs_home ? __ldg(W.gs_home + lo) : kNoHome;
                 if (HOME) {
                     pend = true;
@@ -759,7 +760,7 @@ __global__ void __launch_bounds__(kWaveThreads) k_wf_generate(const __grid_const
                         }
                     }
                 }
-                __stcs(W.home + idx, home);
+                __stcs(W.home_next + idx, home);
             }
         }
         if (HOME) {        // pending list of bounce 0, in slot order within the chunk
@@ -800,7 +801,7 @@ __global__ void __launch_bounds__(kTraceThreads, PHOX_WF_TRACE_MIN_BLOCKS) k_wf_
         Prd r;
         wave_no_hit(r);
         if (q0.w < P.max_time) {                                // else the while-condition of the raygen loop fails: photon is final
-            const unsigned home_in = W.home ? __ldcs(W.home + idx) : kNoHome;
+            const unsigned home_in = W.home ? __ldcs(W.home + a) : kNoHome;
             unsigned home = home_in;
             float tmin = (entry & kListEps0) ? P.tmin0 : P.tmin;   // the list entry carries (last flag & PropagateEpsilon0Mask) != 0
             float3 o = f3(q0.x, q0.y, q0.z), d = f3(q1.x, q1.y, q1.z);
@@ -817,7 +818,7 @@ __global__ void __launch_bounds__(kTraceThreads, PHOX_WF_TRACE_MIN_BLOCKS) k_wf_
                 if (!(t_add > P.refine_distance)) break;
                 from = o + t_add * d;
             }
-            if (home != home_in) __stcs(W.home + idx, home);
+            if (W.home && home != home_in) W.home[a] = home;
             if (ok) {
                 wave_hit_record(r, h);
                 if (DEBUG) { if (P.prd && W.bounce < P.max_record) P.prd[(size_t)P.max_record * idx + W.bounce] = r; }
@@ -864,7 +865,7 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
 #pragma unroll
         for (int k = 0; k < 4; k++)
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(&s_ph[k][threadIdx.x])), "l"(pp + k) : "memory");
-        if (HOME) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(&s_hm[threadIdx.x])), "l"(W.home + idx_s) : "memory");
+        if (HOME) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(&s_hm[threadIdx.x])), "l"(W.home + a_s) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     unsigned entry_cur = 0xffffffffu;
@@ -972,16 +973,14 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
             {
                 if (HOME && survive) {
 #if !PHOX_PROP_STAGE
-                    home = __ldcs(W.home + idx);
+                    home = __ldcs(W.home + a);
 #endif
                     const float tmin = (p.obf & P.eps0_mask) ? P.tmin0 : P.tmin;
                     const float3 o = p.pos, d = p.mom;
                     Nearest best;
                     best.t = P.tmax; best.prim = -1; best.inst = 0; best.n = f3(0.f, 0.f, 0.f);
                     if (home_search(best, P.scene, tmin, o, d, home)) {
-                        const unsigned home_in = home;
                         home_update(home, P.scene, best.prim);
-                        if (home != home_in) __stcs(W.home + idx, home);
                         const Nearest best_c = best;
                         const float3 o_c = o, d_c = d;
                         HitInfo h_c;
@@ -1004,7 +1003,6 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
             const unsigned idx_next = entry_next & kListSlotMask;
             asm volatile("prefetch.global.L2 [%0];" ::"l"(W.hits + a_next));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(P.photon + idx_next));
-            if (HOME) asm volatile("prefetch.global.L2 [%0];" ::"l"(W.home + idx_next));
         }
 #endif
 #if PHOX_APPEND_SORT
@@ -1037,6 +1035,7 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
             const unsigned pos = s_base[par] + s_cls[par][key][warp] + __popc(my_class_ballot & ((1u << lane) - 1u));
             __stcs(W.active_out + pos, entry_out);
             if (HOME) {
+                __stcs(W.home_next + pos, home);
                 if (settled) wave_store_hit(W.hits_next, pos, r2);
                 else W.pending[s_pbase[par] + (wo >> 16) + __popc(pballot & ((1u << lane) - 1u))] = pos;
             }
@@ -1068,6 +1067,7 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
             W.active_out[pos] = entry_out;
 #endif
             if (HOME) {
+                __stcs(W.home_next + pos, home);
                 if (settled) wave_store_hit(W.hits_next, pos, r2);
                 else W.pending[s_pbase[par] + (wo >> 16) + __popc(pballot & ((1u << lane) - 1u))] = pos;
             }
