@@ -912,6 +912,9 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
             idx = W.active_in[a] & kListSlotMask;
             Prd r = W.hits[a];
 #endif
+#if !PHOX_PROP_STAGE
+            if (HOME) home = __ldcs(W.home + a);            // coalesced, asked for with the hit record: back long before the candidate pass wants it
+#endif
             if (r.prim_boundary != kWaveNoHit) {            // a miss (or time over) leaves the photon as it is: final
                 have = true;
 #if PHOX_PROP_STAGE
@@ -972,9 +975,6 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
         {
             {
                 if (HOME && survive) {
-#if !PHOX_PROP_STAGE
-                    home = __ldcs(W.home + a);
-#endif
                     const float tmin = (p.obf & P.eps0_mask) ? P.tmin0 : P.tmin;
                     const float3 o = p.pos, d = p.mom;
                     Nearest best;

@@ -527,6 +527,11 @@ PHOX_D int propagate_core(PhotonState& p, Philox& rng, const HitInfo& h, const T
     const float bx = bnd_x(tb, p.wavelength);       // every fetch of this bounce happens before the wavelength can change (re-emission ends it)
     const float4 material1 = bnd_fetch(tb, bx, m1_line, 0);
     const float group_velocity = bnd_fetch(tb, bx, m1_line, 1).x;
+    // The fetch the boundary step will want - the far side's refractive index without a surface, the surface row with one - is
+    // issued here, next to the material fetches, so that it travels during the bulk step instead of being waited for behind
+    // it (7.9 % of the physics kernel's stall samples sat on that wait).  Same texel, same coordinates: same bits.
+    const unsigned ems = __ldg(tb.optical + su_line).y;
+    const float4 second = bnd_fetch(tb, bx, ems == EMS_NoSurface ? m2_line : su_line, 0);
 
     unsigned flag = 0u;
     int command;
@@ -588,12 +593,11 @@ PHOX_D int propagate_core(PhotonState& p, Philox& rng, const HitInfo& h, const T
     }
 
     if (command == FLOW_BOUNDARY) {
-        const unsigned ems = __ldg(tb.optical + su_line).y;
         bool at_surface = false;
         if (ems == EMS_NoSurface) {
             // ---- propagate_at_boundary : Fresnel reflect / refract ----
             const float n1 = material1.x;
-            const float n2 = bnd_fetch(tb, bx, m2_line, 0).x;
+            const float n2 = second.x;
             const float eta = n1 / n2;
             const float _c1 = -dot(p.mom, normal);
             const float3 on = _c1 < 0.f ? -normal : normal;          // oriented against the incident direction
@@ -651,7 +655,7 @@ PHOX_D int propagate_core(PhotonState& p, Philox& rng, const HitInfo& h, const T
 
         if (at_surface) {
             // ---- propagate_at_surface ----
-            const float4 surface = bnd_fetch(tb, bx, su_line, 0);     // detect, absorb, specular, diffuse
+            const float4 surface = second;                            // detect, absorb, specular, diffuse (ems != NoSurface: the surface row)
             const float detect = surface.x, absorb = surface.y, diffuse = surface.w;
             float u_surface = rng.uniform();
             if (TAG) tg->add(TAG_at_burn_sf_sd, u_surface);
