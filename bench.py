@@ -14,10 +14,11 @@ synthetic gensteps.  Default workload = the configuration the north_star target 
             (phox_simulate_device), timed with CUDA events on the launch stream, max over ranks
     e2e     same metric through the public host-buffer API (Simulator.simulate_np): gensteps in
             pinned host memory -> H2D -> simulate -> hits D2H, every step
-    roofline  HBM roofline of the dominant kernel (k_wf_trace, ~2/3 of the bounce loop): 72 algorithmic
-            bytes per live ray x rays per launch / average launch duration, from CUDA events the
-            library records between the kernels on the launch stream (a separate pass of <= 3 steps
-            with phox_set_profiling on, right after the timed region).  The path-level figure of
+    roofline  HBM roofline of the dominant kernel (k_wf_propagate, ~3/4 of the bounce loop, on the bench
+            workload): its algorithmic bytes from the event's own counts (168 B per live photon + 12 B
+            per survivor + 28 B per ray its home cell settles) / average launch
+            duration, from CUDA events the library records between the kernels on the launch stream (a
+            separate pass of <= 3 steps with phox_set_profiling on, right after the timed region).  The path-level figure of
             SURVEY 8(d), 132 + 128 f_hit bytes per photon over the whole bounce loop, is reported
             beside it (path_*)
     cpu_baseline  the CPU oracle (a port, NOT Geant4 and NOT the OptiX build - neither installs
@@ -341,24 +342,25 @@ def main():
         loop_s = st_dev["simulate_kernel_seconds"] / max(1, st_dev["num_launch"])
         wave = prof["num_trace_launch"] > 0
         traffic_src, tj = None, None
-        tpath = os.path.join(ROOT, "profiles", "traffic_r2.json")
+        tpath = os.path.join(ROOT, "profiles", "traffic_r2b.json")
         if os.path.exists(tpath) and args.workload == "sipm8x8_scint" and args.accel == "bvh":
             with open(tpath) as f:
                 tj = json.load(f)
-            traffic_src = "profiles/traffic_r2.json: ncu dram__bytes_read+write of one launch of the kernel / its live photons, x live photons per launch here"
+            traffic_src = "profiles/traffic_r2b.json: ncu dram__bytes_read+write of one launch of the kernel / its live photons, x live photons per launch here"
         second = None
         if wave:
             # Two kernels per bounce.  Algorithmic bytes, from the event's own counts:
-            #  k_wf_propagate (physics + home-cell pass), per live photon: 108 B read (list entry 4, hit record 32, photon 64, draw count 4,
-            #    home 4) + 68 B written (photon 64, draw count 4); per survivor 4 B (next list entry) + 32 B (hit record of the next bounce,
-            #    when its home cell settles the ray) or 4 B (pending-list entry, when it does not)
+            #  k_wf_propagate (physics + home-cell pass), per live photon: 104 B read (list entry 4, hit record 32, photon 64 - the draw
+            #    count travels in its index word -, home 4) + 64 B written (photon); per survivor 8 B (next list entry + its home) + 32 B
+            #    (hit record of the next bounce, when its home cell settles the ray) or 4 B (pending-list entry, when it does not).
+            #    Without home cells: 100 B read + 64 B written per live photon, 4 B per survivor.
             #  k_wf_trace (BVH traversal of the pending rays), per ray: 44 B read (pending entry 4, list entry 4, position/time/direction 32,
             #    home 4) + 32 B written (hit record)
             L = prof["num_trace_launch"]
             live = prof["num_ray"]                                   # live photons summed over the bounces = rays of the event(s)
             surv = max(0, prof["num_ray"] - prof_photons)            # survivors = the live photons of bounces 1 ..
             home = prof["num_home_ray"]
-            prop_bytes = 176.0 * live + 8.0 * surv + 28.0 * home
+            prop_bytes = (168.0 * live + 12.0 * surv + 28.0 * home) if home > 0 else (164.0 * live + 4.0 * surv)
             trace_rays = live - home
             trace_bytes = 76.0 * trace_rays
             prop_s = prof["propagate_kernel_seconds"] / L
