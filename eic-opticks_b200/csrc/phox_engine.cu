@@ -888,12 +888,32 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
         const bool prof = ctx->profiling;
         if (prof) while (ctx->prof_ev.size() < 2 * (size_t)c.max_bounce + 1) { cudaEvent_t e; CK(cudaEventCreate(&e)); ctx->prof_ev.push_back(e); }
         Prd* hit_buf[2] = {ctx->d_wave_hits.p, home_pass ? ctx->d_wave_hits2.p : ctx->d_wave_hits.p};
+        // The loop ends early once the list has run empty (short histories: one or two bounces on a PMT wall or in a water box, of
+        // max_bounce = 32).  The host must not hold the device up inside the loop, so every kLiveCheck bounces the BVH kernel posts the
+        // list length it starts from into a pinned host word (a plain store over PCIe: no copy, no event, no gap in the stream), and
+        // the host reads the word of the batch BEFORE the one it queued last.
+        constexpr int kLiveCheck = 4;
+        constexpr unsigned kLiveUnknown = 0xffffffffu;
+        volatile unsigned* h_live = reinterpret_cast<volatile unsigned*>(ctx->h_counters + 7);       // two pinned words, one per batch in flight
+        int launched = 0;
         for (int b = 0; b < c.max_bounce; b++) {
             W.active_in = ctx->d_active[b & 1].p; W.active_out = ctx->d_active[(b + 1) & 1].p;
             W.home = home_pass ? ctx->d_home_state[b & 1].p : nullptr; W.home_next = home_pass ? ctx->d_home_state[(b + 1) & 1].p : nullptr;
             W.count_in = ctx->d_wave_count.p + b; W.count_out = ctx->d_wave_count.p + b + 1;
             W.hits = hit_buf[b & 1]; W.hits_next = hit_buf[(b + 1) & 1];
             W.bounce = b;
+            W.live_report = nullptr;
+            if (b > 0 && b % kLiveCheck == 0) {
+                const int k = b / kLiveCheck;
+                if (k >= 2) {                                   // the word of batch k - 1 (posted by the BVH kernel of bounce b - kLiveCheck)
+                    unsigned v;
+                    for (unsigned spin = 0; (v = h_live[(k - 1) & 1]) == kLiveUnknown; spin++)
+                        if ((spin & 0xfffffu) == 0xfffffu && cudaStreamQuery(ctx->stream) != cudaErrorNotReady) break;      // a dead stream must not hang the host
+                    if (v == 0u) break;                         // nothing was alive when batch k - 1 began: batch k - 1 ran on empty lists, the rest is not launched
+                }
+                h_live[k & 1] = kLiveUnknown;
+                W.live_report = const_cast<unsigned*>(h_live + (k & 1));
+            }
             // per bounce: k_wf_trace -> k_wf_propagate ; with profiling on, an event before each kernel.
             // With home cells the physics kernel of bounce b - 1 has already written the hit records of the rays their home
             // settled (for bounce 0: k_wf_generate); the trace kernel takes the rest, the pending list.
@@ -913,10 +933,11 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
                 else k_wf_propagate<false, false><<<grid(2, kPropThreads), kPropThreads, 0, ctx->stream>>>(W);
             }
             if (prof && b == c.max_bounce - 1) CK(cudaEventRecord(ctx->prof_ev[2 * b + 2], ctx->stream));
+            launched = b + 1;
         }
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-        ctx->stats.num_kernel += 1 + 2 * (uint64_t)c.max_bounce;
+        ctx->stats.num_kernel += 1 + 2 * (uint64_t)launched;
     }
     k_hit_count<<<nblock, T, 0, ctx->stream>>>(ctx->d_photon.p, (unsigned)n, c.hit_mask, ctx->d_block_hits.p);
     CK(cudaGetLastError());

@@ -608,6 +608,7 @@ struct WaveParams {
     Prd* hits;                      // per list position: hit of this bounce
     Prd* hits_next;                 // HOME: hit records of the next bounce, per position in active_out (the physics kernel reads `hits` while it fills these)
     int bounce;                     // bounces done so far by every photon of active_in
+    unsigned* live_report;          // pinned host word that k_wf_trace posts the length of active_in to (null: not this bounce)
 };
 
 #ifndef PHOX_WF_TRACE_MIN_BLOCKS
@@ -789,6 +790,10 @@ template <bool DEBUG>
 __global__ void __launch_bounds__(kTraceThreads, PHOX_WF_TRACE_MIN_BLOCKS) k_wf_trace(const __grid_constant__ WaveParams W) {
     const SimParams& P = W.sim;
     const unsigned count = W.pending ? *W.pending_count : *W.count_in;
+    if (W.live_report != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {         // lets the host stop launching once the list is empty (phox_engine.cu)
+        *reinterpret_cast<volatile unsigned*>(W.live_report) = *W.count_in;
+        __threadfence_system();
+    }
     unsigned nray = 0;
     const unsigned stride = gridDim.x * blockDim.x;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
@@ -1110,30 +1115,44 @@ __global__ void __launch_bounds__(kHitTile) k_hit_count(const Photon* __restrict
     if (threadIdx.x == 0) block_hits[blockIdx.x] = (unsigned)n;
 }
 
-// exclusive scan of block_hits[n] -> block_off[n], total -> total_out[0] (single block, any n)
-__global__ void k_hit_offsets(const unsigned* __restrict__ block_hits, int n, unsigned long long* __restrict__ block_off,
-                              unsigned long long* __restrict__ total_out) {
-    __shared__ unsigned long long s[1024];
-    __shared__ unsigned long long carry;
-    if (threadIdx.x == 0) carry = 0ull;
+// exclusive scan of block_hits[n] -> block_off[n], total -> total_out[0] (single block of 1024 threads, any n): each of the 32 warps
+// owns a contiguous segment, sums it with coalesced 32-wide loads, the 32 segment sums are scanned once, then each warp walks its
+// segment again with a shuffle scan per 32 entries and a running carry - two block barriers in all.
+// (The former version scanned 1024 entries at a time with 20 barriers each: 170 us for the 97 k tiles of a 12.5 M-photon event.)
+__global__ void __launch_bounds__(1024) k_hit_offsets(const unsigned* __restrict__ block_hits, int n, unsigned long long* __restrict__ block_off,
+                                                       unsigned long long* __restrict__ total_out) {
+    __shared__ unsigned long long s_warp[32];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const int per = ((n + 31) / 32 + 31) / 32 * 32;               // segment length, a multiple of 32
+    const int lo = min(n, (int)warp * per), hi = min(n, lo + per);
+    unsigned long long sum = 0ull;
+    for (int i = lo + (int)lane; i < hi; i += 32) sum += block_hits[i];
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    if (lane == 0) s_warp[warp] = sum;
     __syncthreads();
-    for (int base = 0; base < n; base += 1024) {
-        int i = base + threadIdx.x;
-        unsigned long long v = i < n ? block_hits[i] : 0ull;
-        s[threadIdx.x] = v;
-        __syncthreads();
-        for (int off = 1; off < 1024; off <<= 1) {
-            unsigned long long t = threadIdx.x >= off ? s[threadIdx.x - off] : 0ull;
-            __syncthreads();
-            s[threadIdx.x] += t;
-            __syncthreads();
+    if (warp == 0) {
+        const unsigned long long w = s_warp[lane];
+        unsigned long long winc = w;
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, winc, off);
+            if ((int)lane >= off) winc += t;
         }
-        if (i < n) block_off[i] = carry + s[threadIdx.x] - v;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry += s[1023];
-        __syncthreads();
+        s_warp[lane] = winc - w;                                   // exclusive offset of each warp's segment
+        if (lane == 31u) total_out[0] = winc;
     }
-    if (threadIdx.x == 0) total_out[0] = carry;
+    __syncthreads();
+    unsigned long long carry = s_warp[warp];
+    for (int base = lo; base < hi; base += 32) {
+        const int i = base + (int)lane;
+        const unsigned v = i < hi ? block_hits[i] : 0u;
+        unsigned inc = v;
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, inc, off);
+            if ((int)lane >= off) inc += t;
+        }
+        if (i < hi) block_off[i] = carry + inc - v;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
 }
 
 // block b re-reads the flagmasks of its photons and copies the hits, in order, to
