@@ -629,9 +629,6 @@ constexpr int kPropThreads = PHOX_WF_PROP_THREADS;
 #ifndef PHOX_PROP_PREFETCH
 #define PHOX_PROP_PREFETCH 1            // physics kernel: L2 prefetch of the next chunk's lines (measured, see profiles/r2_summary.md)
 #endif
-#ifndef PHOX_GEN_INLINE
-#define PHOX_GEN_INLINE 1               // k_wf_generate: the generators compiled in place (the out-of-line body kept photon, stream and genstep in local memory)
-#endif
 #ifndef PHOX_PROP_STAGE
 #define PHOX_PROP_STAGE 0               // physics kernel: the next chunk's hit record / photon / draw count / home come in by cp.async while this chunk computes
 #endif
@@ -718,11 +715,7 @@ __global__ void __launch_bounds__(kWaveThreads) k_wf_generate(const __grid_const
             Philox rng;
             rng.init(P.seed, photon_idx, base);
             PhotonState p;
-#if PHOX_GEN_INLINE
-            generate_photon_body(p, rng, gs, P.tables, P.input_photon, P.input_base, photon_idx);      // in place: photon, stream and genstep stay in registers
-#else
             generate_photon(p, rng, gs, P.tables, P.input_photon, P.input_base, photon_idx);
-#endif
             // A live photon's record carries its draw count in the `index` word (the index itself is photon_offset + slot, put
             // back by whichever physics pass writes the record for the last time): one scattered 4 B load and store less per bounce.
             {

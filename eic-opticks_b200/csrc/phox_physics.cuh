@@ -376,7 +376,7 @@ PHOX_D void generate_carrier(PhotonState& p, const Genstep& gs, unsigned long lo
 
 // qsim::generate_photon : input photons are indexed by the absolute photon id like the reference
 // out of line: runs once per photon, must not sit in the instruction stream of the bounce loop
-PHOX_D void generate_photon_core(PhotonState& p, Philox& rng, const Genstep& gs, const Tables& tb,
+__device__ __noinline__ void generate_photon(PhotonState& p, Philox& rng, const Genstep& gs, const Tables& tb,
                             const Photon* input_photon, unsigned long long input_base, unsigned long long photon_id) {
     switch (gs.gencode()) {
         case GS_CARRIER: generate_carrier(p, gs, photon_id); break;
@@ -395,22 +395,6 @@ PHOX_D void generate_photon_core(PhotonState& p, Philox& rng, const Genstep& gs,
             break;
     }
     p.set_index(photon_id);
-}
-// value copies in, value copies out (see propagate_body): the same expression graph - hence the same FMA contraction - whether it
-// is compiled into k_wf_generate or into the out-of-line body the persistent kernel calls
-PHOX_D void generate_photon_body(PhotonState& p_io, Philox& rng_io, const Genstep& gs_in, const Tables& tb,
-                            const Photon* input_photon, unsigned long long input_base, unsigned long long photon_id) {
-    PhotonState p;
-    Philox rng = rng_io;
-    const Genstep gs = gs_in;
-    generate_photon_core(p, rng, gs, tb, input_photon, input_base, photon_id);
-    p_io = p;
-    rng_io = rng;
-}
-// out of line for the persistent kernel: runs once per photon, must not sit in the instruction stream of its bounce loop
-__device__ __noinline__ void generate_photon(PhotonState& p, Philox& rng, const Genstep& gs, const Tables& tb,
-                            const Photon* input_photon, unsigned long long input_base, unsigned long long photon_id) {
-    generate_photon_body(p, rng, gs, tb, input_photon, input_base, photon_id);
 }
 
 // ---- bulk + surface physics --------------------------------------------------------------------
