@@ -167,12 +167,14 @@ struct phox_context {
 #define PHOX_KERNEL_AUTO_CHOICE PHOX_KERNEL_WAVEFRONT
 #endif
 
-// PHOX_KERNEL_AUTO: photons per launch from which the wavefront form is picked.  Long histories (the 8x8 crystals: 20 bounces per
-// photon) pay off from 250 k photons; when the previous launch of this context averaged fewer than 6 bounces per photon the live
-// list collapses after a few bounces and the persistent kernel stays ahead up to ~2 M photons (profiles/r1_summary.md, small events).
+// PHOX_KERNEL_AUTO: photons per launch from which the wavefront form is picked, by the bounces per photon of the context's previous
+// launch.  Long histories (the 8x8 crystals: 20 bounces per photon) pay off from 250 k photons, histories of a few bounces (tank 4,
+// boolean zoo 3) from 400 k now that the loop stops launching once the list is empty, histories of one or two bounces (raindrop,
+// PMT wall) only from 2 M photons: the persistent kernel has no per-bounce launches at all (scripts/small_events2.py, profiles/r2_summary.md).
 static const int64_t kAutoWavefrontMinPhotons = 250000;
-static const int64_t kAutoWavefrontMinPhotonsShort = 2000000;
-static const double kAutoShortHistory = 6.0;
+static const int64_t kAutoWavefrontMinPhotonsShort = 400000;
+static const int64_t kAutoWavefrontMinPhotonsVeryShort = 2000000;
+static const double kAutoShortHistory = 6.0, kAutoVeryShortHistory = 2.5;
 
 extern "C" void phox_default_config(phox_config* c) {
     if (!c) return;
@@ -825,8 +827,10 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
     // AUTO: the wavefront form wins once a launch fills the machine several times over; below that its ~65 kernels each
     // run a single under-filled wave and the one persistent kernel is up to 2x quicker (profiles/r1_summary.md, small events)
     if (n > 0x7fffffffll) return ctx->fail(PHOX_E_NOMEM, "launch of more than 2^31 photons: lower max_slot");
-    const int64_t auto_min = (ctx->last_bounces_per_photon > 0. && ctx->last_bounces_per_photon < kAutoShortHistory) ? kAutoWavefrontMinPhotonsShort
-                                                                                                                     : kAutoWavefrontMinPhotons;
+    const double bpp = ctx->last_bounces_per_photon;
+    const int64_t auto_min = !(bpp > 0.) ? kAutoWavefrontMinPhotons
+                             : bpp < kAutoVeryShortHistory ? kAutoWavefrontMinPhotonsVeryShort
+                             : bpp < kAutoShortHistory ? kAutoWavefrontMinPhotonsShort : kAutoWavefrontMinPhotons;
     const bool wavefront = (c.kernel_mode == PHOX_KERNEL_AUTO ? (n < auto_min ? PHOX_KERNEL_PERSISTENT : PHOX_KERNEL_AUTO_CHOICE)
                                                               : c.kernel_mode) == PHOX_KERNEL_WAVEFRONT;
     if (!wavefront) {
