@@ -476,6 +476,33 @@ def test_wavefront_form_with_launch_slicing_and_time_cut():
         assert a.shape == b.shape and a.tobytes() == b.tobytes()
 
 
+def max_bounce_cfg(w):
+    return w["config"].get("max_bounce", 32)
+
+
+def test_bounce_loop_stops_once_the_list_is_empty():
+    """The wavefront form stops launching bounce kernels once no photon is alive (the BVH kernel posts the list length to a pinned
+    host word every 4 bounces, the host reads one batch behind): a one-bounce workload runs 8 to 12 of its 32 bounce pairs, a
+    long-history workload all of them, and neither changes a byte of output against the persistent form."""
+    for name, kw, short in (("raindrop_cerenkov", dict(num_photon=300000), True), ("sipm8x8_scint", dict(num_photon=60000, photons_per_genstep=100), False)):
+        w = workloads.WORKLOADS[name](**kw)
+        out = {}
+        for mode in (ph.KERNEL_PERSISTENT, ph.KERNEL_WAVEFRONT):
+            sim = make_sim(w, event_mode=ph.MODE_HITPHOTON, kernel_mode=mode, max_bounce=max_bounce_cfg(w))
+            h = sim.simulate_np(w["gensteps"], 1, w["input_photons"]).copy()
+            out[mode] = (h, sim.get_array("photon").copy(), sim.stats())
+            sim.close()
+        a, b = out[ph.KERNEL_PERSISTENT], out[ph.KERNEL_WAVEFRONT]
+        assert a[0].tobytes() == b[0].tobytes() and a[1].tobytes() == b[1].tobytes(), name
+        assert a[2]["num_ray"] == b[2]["num_ray"], name
+        max_bounce = max_bounce_cfg(w)
+        full = 2 * max_bounce + 5                                  # generate + a kernel pair per bounce + hit selection (+ genstep home)
+        if short:
+            assert b[2]["num_kernel"] <= 2 * 12 + 6, (name, b[2]["num_kernel"])
+        else:
+            assert full - 2 <= b[2]["num_kernel"] <= full + 2, (name, b[2]["num_kernel"], full)
+
+
 @pytest.mark.parametrize("name,kw", [CASES[0], CASES[3]])
 def test_rank_sharding_concatenates_to_single_gpu_result(name, kw):
     w = workloads.WORKLOADS[name](**dict(kw, num_photon=24000))
