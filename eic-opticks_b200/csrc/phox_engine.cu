@@ -18,6 +18,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -137,6 +138,7 @@ struct phox_context {
     DevBuf<unsigned> d_gs_home;                    // per genstep of the launch: home cell its photons start with
     DevBuf<Prd> d_wave_hits2;                      // second hit buffer: the physics kernel fills the next bounce's records while it reads this bounce's
     int num_home = 0;                          // prims that have a candidate list
+    unsigned tail_photons = 131072;            // PHOX_KERNEL_AUTO: live photons at or below which the persistent kernel finishes a wavefront event (env PHOX_TAIL_PHOTONS, 0 = never)
     DevBuf<float> d_slack;                     // per CSGPrim: exit-bound slack of prims that are exactly a box (0 = not such a prim)
     DevBuf<unsigned long long> d_counters;     // [0] rays, [1] hit total of the launch, [2] rays settled by their home cell, [3] work counter, [4-5] genstep info
     unsigned long long* h_counters = nullptr;  // pinned mirror
@@ -218,6 +220,7 @@ extern "C" phox_context* phox_create(int device) {
     e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     ctx->stream = ctx->own_stream;
     for (int k = 0; k < 4 && e == cudaSuccess; k++) e = cudaEventCreate(&ctx->ev[k]);
+    if (const char* t = getenv("PHOX_TAIL_PHOTONS")) ctx->tail_photons = (unsigned)strtoul(t, nullptr, 10);
     if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_counters, 8 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = ctx->d_counters.reserve(8);
     if (e != cudaSuccess) {
@@ -823,6 +826,7 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
     P.refine_distance = c.refine_distance; P.eps0_mask = c.epsilon0_mask; P.hit_mask = c.hit_mask; P.refine = c.propagate_refine;
     P.seed = c.rng_seed; P.rng_offset = c.rng_offset; P.skipahead = c.skipahead_event_offset;
     P.burn = c.rng_mode == PHOX_RNG_DEBUG_TAG ? 1 : 0;
+    P.resume_list = nullptr; P.resume_count = nullptr; P.resume_bounce = 0;
 
     // AUTO: the wavefront form wins once a launch fills the machine several times over; below that its ~65 kernels each
     // run a single under-filled wave and the one persistent kernel is up to 2x quicker (profiles/r1_summary.md, small events)
@@ -914,6 +918,18 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
                     for (unsigned spin = 0; (v = h_live[(k - 1) & 1]) == kLiveUnknown; spin++)
                         if ((spin & 0xfffffu) == 0xfffffu && cudaStreamQuery(ctx->stream) != cudaErrorNotReady) break;      // a dead stream must not hang the host
                     if (v == 0u) break;                         // nothing was alive when batch k - 1 began: batch k - 1 ran on empty lists, the rest is not launched
+                    // PHOX_KERNEL_AUTO, production modes: a list of a few thousand photons costs every bounce the latency of one ray through
+                    // the tree TWICE over plus two launches (tank: 28 % of the event in such launches, profiles/r2_summary.md).  The rest of
+                    // the histories goes to the persistent kernel - same bodies, same bytes - which has no launch boundary between bounces.
+                    if (v <= ctx->tail_photons && c.kernel_mode == PHOX_KERNEL_AUTO && !dbg && !lite && !prof) {
+                        SimParams R = P;
+                        R.resume_list = ctx->d_active[b & 1].p; R.resume_count = ctx->d_wave_count.p + b; R.resume_bounce = b;
+                        CK(cudaMemsetAsync(ctx->d_counters.p + 3, 0, sizeof(unsigned long long), ctx->stream));
+                        const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->sim_grid[0], ((int64_t)v + kSimThreads - 1) / kSimThreads));
+                        k_simulate<false><<<blocks, kSimThreads, 0, ctx->stream>>>(R);
+                        ctx->stats.num_kernel += 1;
+                        break;
+                    }
                 }
                 h_live[k & 1] = kLiveUnknown;
                 W.live_report = const_cast<unsigned*>(h_live + (k & 1));

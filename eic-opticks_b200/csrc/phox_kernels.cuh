@@ -95,6 +95,11 @@ struct SimParams {
     unsigned eps0_mask, hit_mask, refine;
     unsigned long long seed, rng_offset, skipahead;
     int burn;
+    // persistent kernel as the FINISHER of a wavefront event (PHOX_KERNEL_AUTO, phox_engine.cu): instead of generating photons it takes
+    // the photons of a live list over - record in `photon`, draw count in its index word - and runs each to the end of its history
+    const unsigned* resume_list;            // null: generate
+    const unsigned* resume_count;           // device-side length of resume_list
+    int resume_bounce;                      // bounces every photon of the list has done
 };
 
 struct Nearest {
@@ -465,6 +470,9 @@ PHOX_D unsigned pack_lpos(float lposcost, float lposfphi) {
 // finished, so lanes do not idle while the longest history of the warp runs out (bounce counts are
 // long-tailed: 1 .. max_bounce).  A photon's result depends only on its absolute index (RNG
 // subsequence), never on which lane ran it, so this reordering cannot change any output.
+constexpr unsigned kListEps0 = 0x80000000u;     // list entry bit: the photon's last flag is in PropagateEpsilon0Mask (-> tmin0), so that
+constexpr unsigned kListSlotMask = 0x7fffffffu; // the trace kernel does not have to read the flag word of the photon record
+constexpr unsigned kWaveNoHit = 0xffffffffu;    // prim_boundary of a list entry whose photon is final (miss or time over)
 constexpr int kSimThreads = 128;
 constexpr int kRefillMin = 8;        // refill when at least this many lanes of the warp are idle
 
@@ -481,6 +489,7 @@ __global__ void __launch_bounds__(kSimThreads, PHOX_SIM_MIN_BLOCKS) k_simulate(c
     unsigned tag_slot = 0u;              // DebugHeavy: tagged draws of this photon so far
     unsigned last_lpos = 0u;             // lite mode: packed lposcost/lposfphi of the last trace (0 after a miss, like the miss program)
     const unsigned hit_flags = ((DEBUG && P.prd != nullptr) || P.lpos != nullptr) ? kHitFphi : 0u;
+    const unsigned work_n = P.resume_list ? *P.resume_count : P.num_photon;
 
     while (true) {
         unsigned need = __ballot_sync(0xffffffffu, !active);
@@ -489,8 +498,21 @@ __global__ void __launch_bounds__(kSimThreads, PHOX_SIM_MIN_BLOCKS) k_simulate(c
             int leader = __ffs(need) - 1;
             if ((int)lane == leader) base = atomicAdd(P.work_counter, (unsigned)__popc(need));
             base = __shfl_sync(0xffffffffu, base, leader);
-            if (base + (unsigned)__popc(need) >= P.num_photon) exhausted = true;
+            if (base + (unsigned)__popc(need) >= work_n) exhausted = true;
             unsigned mine = base + (unsigned)__popc(need & lt_mask);
+            if (!DEBUG && P.resume_list != nullptr) {
+                if (!active && mine < work_n) {              // take a live photon of the wavefront loop over (production modes only)
+                    idx = P.resume_list[mine] & kListSlotMask;
+                    p.load(P.photon + idx);
+                    const unsigned nd = p.index;             // draw count parked in the index word
+                    p.index = (unsigned)(P.photon_offset + idx);
+                    rng.init(P.seed, P.photon_offset + idx, P.rng_offset + P.skipahead * (unsigned long long)P.event_index + nd);
+                    bounce = P.resume_bounce;
+                    active = true;
+                    last_lpos = 0u;
+                    tag_slot = 0u;
+                }
+            } else
             if (!active && mine < P.num_photon) {
                 idx = mine;
                 // seed : which genstep owns slot idx (binary search in the numphoton prefix sum)
@@ -635,9 +657,6 @@ constexpr int kPropThreads = PHOX_WF_PROP_THREADS;
 #ifndef PHOX_WF_PROP_MIN_BLOCKS
 #define PHOX_WF_PROP_MIN_BLOCKS 4       // 64 registers: the inlined physics body fits without spills (5 blocks = 48 registers: 0.509 vs 0.490 ms per launch)
 #endif
-constexpr unsigned kListEps0 = 0x80000000u;     // list entry bit: the photon's last flag is in PropagateEpsilon0Mask (-> tmin0), so that
-constexpr unsigned kListSlotMask = 0x7fffffffu; // the trace kernel does not have to read the flag word of the photon record
-constexpr unsigned kWaveNoHit = 0xffffffffu;    // prim_boundary of a list entry whose photon is final (miss or time over)
 
 // hit record of list position a (streaming store: the physics kernel reads it once)
 PHOX_D void wave_store_hit(Prd* hits, unsigned a, const Prd& r) {

@@ -503,6 +503,25 @@ def test_bounce_loop_stops_once_the_list_is_empty():
             assert full - 2 <= b[2]["num_kernel"] <= full + 2, (name, b[2]["num_kernel"], full)
 
 
+def test_auto_mode_hands_the_tail_of_an_event_to_the_persistent_kernel():
+    """PHOX_KERNEL_AUTO: once the posted list length is at or below the tail threshold, the rest of the histories runs in the persistent
+    kernel (resume mode: photon records and parked draw counts taken over from the live list).  Same bytes as the pure wavefront and
+    the pure persistent form, fewer kernels than the pure wavefront form."""
+    for name, kw in (("scintillator_tank", dict(num_photon=400000, photons_per_genstep=100)), ("pmt_wall_torch", dict(num_photon=300000, nx=20, ny=20))):
+        w = workloads.WORKLOADS[name](**kw)
+        out = {}
+        for mode in (ph.KERNEL_PERSISTENT, ph.KERNEL_WAVEFRONT, ph.KERNEL_AUTO):
+            sim = make_sim(w, event_mode=ph.MODE_HITPHOTON, kernel_mode=mode)
+            h = sim.simulate_np(w["gensteps"], 1, w["input_photons"]).copy()
+            out[mode] = (h, sim.get_array("photon").copy(), sim.stats())
+            sim.close()
+        ref = out[ph.KERNEL_PERSISTENT]
+        for mode in (ph.KERNEL_WAVEFRONT, ph.KERNEL_AUTO):
+            assert out[mode][0].tobytes() == ref[0].tobytes() and out[mode][1].tobytes() == ref[1].tobytes(), (name, mode)
+            assert out[mode][2]["num_ray"] == ref[2]["num_ray"], (name, mode)
+        assert 10 < out[ph.KERNEL_AUTO][2]["num_kernel"] < out[ph.KERNEL_WAVEFRONT][2]["num_kernel"], (name, out[ph.KERNEL_AUTO][2]["num_kernel"], out[ph.KERNEL_WAVEFRONT][2]["num_kernel"])
+
+
 @pytest.mark.parametrize("name,kw", [CASES[0], CASES[3]])
 def test_rank_sharding_concatenates_to_single_gpu_result(name, kw):
     w = workloads.WORKLOADS[name](**dict(kw, num_photon=24000))
