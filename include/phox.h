@@ -51,8 +51,10 @@ enum {
 /* How the bounce loop is scheduled on the GPU.  Both forms call the same trace and propagate code and
  * give bit-identical results. */
 enum {
-    PHOX_KERNEL_AUTO = 0,       /* by launch size: persistent below 250 k photons (2 M when the previous launch
-                                   averaged < 6 bounces per photon), wavefront above; results do not depend on it */
+    PHOX_KERNEL_AUTO = 0,       /* by launch size: persistent below 250 k photons (400 k when the previous launch
+                                   averaged < 6 bounces per photon, 2 M below 2.5), wavefront above - and, in the
+                                   production event modes, the persistent kernel takes the live list over once it
+                                   holds <= 131072 photons (env PHOX_TAIL_PHOTONS, 0 = never); results do not depend on it */
     PHOX_KERNEL_PERSISTENT = 1, /* one fused kernel, persistent warps that refill idle lanes                  */
     PHOX_KERNEL_WAVEFRONT = 2   /* per bounce: trace kernel + physics kernel over the list of live photons    */
 };
