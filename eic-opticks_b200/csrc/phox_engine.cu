@@ -941,6 +941,7 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
             W.pending = home_pass ? ctx->d_pending.p : nullptr;
             W.pending_count = home_pass ? ctx->d_pending_count.p + b : nullptr;
             if (dbg) k_wf_trace<true><<<grid(1, kTraceThreads), kTraceThreads, 0, ctx->stream>>>(W);
+            else if (home_pass) k_wf_trace<false, true><<<grid(1, kTraceThreads), kTraceThreads, 0, ctx->stream>>>(W);      // box-dominated geometry: hit_finish in place
             else k_wf_trace<false><<<grid(1, kTraceThreads), kTraceThreads, 0, ctx->stream>>>(W);
             if (prof) CK(cudaEventRecord(ctx->prof_ev[2 * b + 1], ctx->stream));
             W.pending = home_pass ? ctx->d_pending.p : nullptr;

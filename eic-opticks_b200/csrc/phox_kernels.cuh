@@ -429,17 +429,18 @@ __device__ __noinline__ bool hit_finish(HitInfo& h, const Scene& sc, const Neare
 // program sets boundary 0xffff).  Inline form: the traversal is compiled into the calling kernel, where the scene
 // pointers are kernel parameters (constant bank) instead of loads through a reference.  The boxes only cull; hit
 // distances and normals come from the out-of-line prim evaluators and hit_finish.
+template <bool HITFIN_INLINE = (PHOX_HITFIN_INLINE != 0)>
 PHOX_D bool trace_inline(HitInfo& h, const Scene& sc, const float3& o, const float3& d, float tmin, float tmax, unsigned flags, unsigned& home) {
     Nearest best;
     best.t = tmax; best.prim = -1; best.inst = 0; best.n = f3(0.f, 0.f, 0.f);
     if (sc.accel == 0) traverse_bvh(best, sc, tmin, o, d);
     else traverse_brute(best, sc, tmin, o, d);
     home_update(home, sc, best.prim);
-#if PHOX_HITFIN_INLINE
-    return hit_finish_body(h, sc, best, o, d, flags);
-#else
+    // hit_finish compiled in place or called: a value-copy body either way, the same bits.  In place the BVH kernel is 3 - 5 % quicker on
+    // geometries of boxes and single-leaf prims and 5 % slower on the boolean-tree ones (zoo, pfRICH: the tree evaluator's register
+    // pressure); the engine takes the in-place instance for geometries with home cells (profiles/r2_summary.md)
+    if (HITFIN_INLINE) return hit_finish_body(h, sc, best, o, d, flags);
     return hit_finish(h, sc, best, o, d, flags);
-#endif
 }
 
 // out-of-line form for kernels with several trace sites (persistent kernel, geometry queries)
@@ -805,7 +806,7 @@ __global__ void __launch_bounds__(kWaveThreads) k_wf_generate(const __grid_const
 
 // One ray per live photon (W.pending == null) or per entry of the pending list the physics kernel of the previous bounce
 // left behind (the rays their home cell could not settle).
-template <bool DEBUG>
+template <bool DEBUG, bool HITFIN_INLINE = false>
 __global__ void __launch_bounds__(kTraceThreads, PHOX_WF_TRACE_MIN_BLOCKS) k_wf_trace(const __grid_constant__ WaveParams W) {
     const SimParams& P = W.sim;
     const unsigned count = W.pending ? *W.pending_count : *W.count_in;
@@ -834,7 +835,7 @@ __global__ void __launch_bounds__(kTraceThreads, PHOX_WF_TRACE_MIN_BLOCKS) k_wf_
             float3 from = o;
             float t_add = 0.f;
             for (int pass = 0;; pass++) {                       // one inlined trace site; pass 1 = PropagateRefine re-trace from 0.99 t
-                ok = trace_inline(h, P.scene, from, d, tmin, P.tmax, ((DEBUG && P.prd != nullptr) || P.lpos != nullptr) ? kHitFphi : 0u, home);
+                ok = trace_inline<HITFIN_INLINE || (PHOX_HITFIN_INLINE != 0)>(h, P.scene, from, d, tmin, P.tmax, ((DEBUG && P.prd != nullptr) || P.lpos != nullptr) ? kHitFphi : 0u, home);
                 nray++;
                 if (pass == 1) { h.t += t_add; break; }
                 if (!P.refine) break;
