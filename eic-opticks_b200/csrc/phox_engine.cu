@@ -138,6 +138,7 @@ struct phox_context {
     DevBuf<unsigned> d_gs_home;                    // per genstep of the launch: home cell its photons start with
     DevBuf<Prd> d_wave_hits2;                      // second hit buffer: the physics kernel fills the next bounce's records while it reads this bounce's
     int num_home = 0;                          // prims that have a candidate list
+    int max_prim_nodes = 1;                    // largest CSGPrim of the geometry, in nodes (picks the BVH kernel instance, see run_launch)
     unsigned tail_photons = 131072;            // PHOX_KERNEL_AUTO: live photons at or below which the persistent kernel finishes a wavefront event (env PHOX_TAIL_PHOTONS, 0 = never)
     DevBuf<float> d_slack;                     // per CSGPrim: exit-bound slack of prims that are exactly a box (0 = not such a prim)
     DevBuf<unsigned long long> d_counters;     // [0] rays, [1] hit total of the launch, [2] rays settled by their home cell, [3] work counter, [4-5] genstep info
@@ -428,6 +429,8 @@ extern "C" int phox_set_geometry(phox_context* ctx, const void* solid_, int64_t 
     // Prims that ARE their box (a single un-complemented box3 leaf, no rotation): from inside such a prim the hit
     // is the exit face, so the traversal may drop it once a nearer hit is known (phox_kernels.cuh, exit bound).
     // slack = distance by which the padded box must be shrunk to lie inside the true box with a pad to spare.
+    ctx->max_prim_nodes = 1;
+    for (int64_t p = 0; p < nprim; p++) ctx->max_prim_nodes = std::max(ctx->max_prim_nodes, prim[p].num_node());
     std::vector<float> slack((size_t)nprim, 0.f);
     std::vector<float> exact((size_t)nprim * 8, 0.f);
     const Node* hnode = (const Node*)node_;
@@ -941,7 +944,7 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
             W.pending = home_pass ? ctx->d_pending.p : nullptr;
             W.pending_count = home_pass ? ctx->d_pending_count.p + b : nullptr;
             if (dbg) k_wf_trace<true><<<grid(1, kTraceThreads), kTraceThreads, 0, ctx->stream>>>(W);
-            else if (home_pass) k_wf_trace<false, true><<<grid(1, kTraceThreads), kTraceThreads, 0, ctx->stream>>>(W);      // box-dominated geometry: hit_finish in place
+            else if (ctx->max_prim_nodes <= 3) k_wf_trace<false, true><<<grid(1, kTraceThreads), kTraceThreads, 0, ctx->stream>>>(W);      // no boolean tree beyond one operator: hit_finish in place
             else k_wf_trace<false><<<grid(1, kTraceThreads), kTraceThreads, 0, ctx->stream>>>(W);
             if (prof) CK(cudaEventRecord(ctx->prof_ev[2 * b + 1], ctx->stream));
             W.pending = home_pass ? ctx->d_pending.p : nullptr;

@@ -438,7 +438,7 @@ PHOX_D bool trace_inline(HitInfo& h, const Scene& sc, const float3& o, const flo
     home_update(home, sc, best.prim);
     // hit_finish compiled in place or called: a value-copy body either way, the same bits.  In place the BVH kernel is 3 - 5 % quicker on
     // geometries of boxes and single-leaf prims and 5 % slower on the boolean-tree ones (zoo, pfRICH: the tree evaluator's register
-    // pressure); the engine takes the in-place instance for geometries with home cells (profiles/r2_summary.md)
+    // pressure); the engine takes the in-place instance for geometries without a boolean tree beyond one operator (profiles/r2_summary.md)
     if (HITFIN_INLINE) return hit_finish_body(h, sc, best, o, d, flags);
     return hit_finish(h, sc, best, o, d, flags);
 }
