@@ -522,13 +522,7 @@ __global__ void __launch_bounds__(kSimThreads, PHOX_SIM_MIN_BLOCKS) k_simulate(c
                     int mid = (lo + hi) >> 1;
                     if (__ldg(P.gs_prefix + mid) <= (unsigned long long)idx) lo = mid; else hi = mid;
                 }
-                Genstep gs;
-                {
-                    const float4* src = reinterpret_cast<const float4*>(P.genstep + lo);
-                    float4* dst = reinterpret_cast<float4*>(&gs);
-#pragma unroll
-                    for (int k = 0; k < 6; k++) dst[k] = __ldg(src + k);
-                }
+                const Genstep& gs = P.genstep[lo];          // read where it lies (see k_wf_generate)
                 unsigned long long photon_idx = P.photon_offset + idx;
                 rng.init(P.seed, photon_idx, P.rng_offset + P.skipahead * (unsigned long long)P.event_index);
                 generate_photon(p, rng, gs, P.tables, P.input_photon, P.input_base, photon_idx);
@@ -723,13 +717,7 @@ __global__ void __launch_bounds__(kWaveThreads) k_wf_generate(const __grid_const
                 int mid = (lo + hi) >> 1;
                 if (__ldg(P.gs_prefix + mid) <= (unsigned long long)idx) lo = mid; else hi = mid;
             }
-            Genstep gs;
-            {
-                const float4* src = reinterpret_cast<const float4*>(P.genstep + lo);
-                float4* dst = reinterpret_cast<float4*>(&gs);
-#pragma unroll
-                for (int k = 0; k < 6; k++) dst[k] = __ldg(src + k);
-            }
+            const Genstep& gs = P.genstep[lo];          // read where it lies (the out-of-line generators take it by reference: a local copy would sit in the frame)
             unsigned long long photon_idx = P.photon_offset + idx;
             unsigned long long base = P.rng_offset + P.skipahead * (unsigned long long)P.event_index;
             Philox rng;
