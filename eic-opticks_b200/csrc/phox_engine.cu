@@ -102,7 +102,7 @@ struct phox_context {
     float nm0 = 60.f, nms = 1.f;
     unsigned hd_factor = 0;
     float inv_ny = 0.f;
-    unsigned y_fast = 0;
+    unsigned y_fast = 0, need_lposcost = 1;
 
     // event
     DevBuf<Genstep> d_genstep;
@@ -704,6 +704,11 @@ extern "C" int phox_set_tables(phox_context* ctx, const float* bnd, int64_t nbnd
     }
     CK(ctx->d_optical.reserve((size_t)nbnd * 4));
     CK(cudaMemcpy(ctx->d_optical.p, optical, (size_t)nbnd * 4 * 16, cudaMemcpyHostToDevice));
+    ctx->need_lposcost = 0;                           // optical[row] = (index, ems, ..): propagate() reads HitInfo::lposcost only behind a SURFACE row
+    for (int64_t r = 0; r < nbnd * 4; r++) {          // (osur / isur) whose ems is neither NoSurface nor Surface (qsim.h:2296-2312)
+        const unsigned ems = (unsigned)optical[4 * r + 1];
+        if ((r % 4 == SP_OSUR || r % 4 == SP_ISUR) && ems != EMS_NoSurface && ems != EMS_Surface) ctx->need_lposcost = 1;
+    }
     ctx->have_tables = true;
     return PHOX_OK;
 }
@@ -809,7 +814,7 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
     P.scene.home = (c.accel == PHOX_ACCEL_BVH && ctx->num_home > 0) ? ctx->d_home.p : nullptr; P.scene.cand = ctx->d_cand.p;
     P.tables.bnd_tex = ctx->bnd_tex; P.tables.icdf_tex = ctx->icdf_tex; P.tables.optical = ctx->d_optical.p;
     P.tables.nx = ctx->nx; P.tables.ny = ctx->ny; P.tables.nm0 = ctx->nm0; P.tables.nms = ctx->nms; P.tables.hd_factor = ctx->hd_factor;
-    P.tables.inv_ny = ctx->inv_ny; P.tables.y_fast = ctx->y_fast;
+    P.tables.inv_ny = ctx->inv_ny; P.tables.y_fast = ctx->y_fast; P.tables.need_lposcost = ctx->need_lposcost;
     P.genstep = d_gs; P.gs_prefix = d_prefix; P.num_genstep = ngs;
     P.input_photon = d_input; P.input_base = input_base; P.photon_offset = photon_offset;
     P.num_photon = (unsigned)n; P.event_index = event_id;
@@ -1455,7 +1460,7 @@ extern "C" int phox_boundary_lookup(phox_context* ctx, const float* nm, const ui
     Tables tb;
     tb.bnd_tex = ctx->bnd_tex; tb.icdf_tex = ctx->icdf_tex; tb.optical = ctx->d_optical.p;
     tb.nx = ctx->nx; tb.ny = ctx->ny; tb.nm0 = ctx->nm0; tb.nms = ctx->nms; tb.hd_factor = ctx->hd_factor;
-    tb.inv_ny = ctx->inv_ny; tb.y_fast = ctx->y_fast;
+    tb.inv_ny = ctx->inv_ny; tb.y_fast = ctx->y_fast; tb.need_lposcost = ctx->need_lposcost;
     k_boundary_lookup<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(tb, b_nm.p, b_line.p, b_k.p, (unsigned)n, b_out.p);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(dst, b_out.p, n * 16, cudaMemcpyDeviceToHost, ctx->stream));

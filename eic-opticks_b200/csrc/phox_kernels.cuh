@@ -102,6 +102,14 @@ struct SimParams {
     int resume_bounce;                      // bounces every photon of the list has done
 };
 
+constexpr unsigned kHitFphi = 1u;          // fill lposfphi (only the prd debug array and simtrace read it); implies kHitCost
+constexpr unsigned kHitCost = 4u;          // fill lposcost: the physics reads it only behind a surface row whose ems is neither NoSurface nor Surface (sensor_A ...), see hit_flags_of
+// which optional parts of the hit record this launch needs: lposfphi for the prd debug array and the lite hits, lposcost also when
+// the optical table has a row whose ems sends the physics to the lposcost test (qsim.h:2296-2312); a square root and a division per ray otherwise saved
+PHOX_D unsigned hit_flags_of(const SimParams& P, bool debug) {
+    return (((debug && P.prd != nullptr) || P.lpos != nullptr) ? kHitFphi : 0u) | (P.tables.need_lposcost ? kHitCost : 0u);
+}
+
 struct Nearest {
     float t;
     float3 n;                       // object-frame normal
@@ -379,7 +387,6 @@ __device__ __noinline__ void traverse_brute(Nearest& best, const Scene& sc, floa
 // the IS program's local-position terms, :919-934).  Out of line: every float that reaches the physics is computed by
 // ONE compiled body (this function and intersect_prim_cold), whatever kernel ran the traversal around it - that is
 // what keeps the persistent and the wavefront form, and the debug and production kernels, bit-identical.
-constexpr unsigned kHitFphi = 1u;          // fill lposfphi (only the prd debug array and simtrace read it)
 constexpr unsigned kHitRawNormal = 2u;     // leave the normal as the closest-hit program delivers it (simtrace); the simulate raygen normalises
 PHOX_D bool hit_finish_core(HitInfo& h, const Scene& sc, const Nearest& best, const float3& o, const float3& d, unsigned flags) {
     if (best.prim < 0) {
@@ -402,7 +409,7 @@ PHOX_D bool hit_finish_core(HitInfo& h, const Scene& sc, const Nearest& best, co
     const float nn = dot(n, n);
     h.normal = ((flags & kHitRawNormal) || nn == 1.f) ? n : n * (1.0f / sqrtf(nn));
     h.t = best.t;
-    h.lposcost = lpos.z / sqrtf(dot(lpos, lpos));
+    h.lposcost = (flags & (kHitFphi | kHitCost)) ? lpos.z / sqrtf(dot(lpos, lpos)) : 0.f;
     h.lposfphi = (flags & kHitFphi) ? (atan2f(lpos.y, lpos.x) + kPi) / (2.0f * kPi) : 0.f;
     h.iindex_identity = (((unsigned)best.inst & 0xffffu) << 16) | ((unsigned)meta.y & 0xffffu);
     float4 p0 = __ldg(sc.prim + 4 * best.prim);
@@ -489,7 +496,7 @@ __global__ void __launch_bounds__(kSimThreads, PHOX_SIM_MIN_BLOCKS) k_simulate(c
     Seq seq;
     unsigned tag_slot = 0u;              // DebugHeavy: tagged draws of this photon so far
     unsigned last_lpos = 0u;             // lite mode: packed lposcost/lposfphi of the last trace (0 after a miss, like the miss program)
-    const unsigned hit_flags = ((DEBUG && P.prd != nullptr) || P.lpos != nullptr) ? kHitFphi : 0u;
+    const unsigned hit_flags = hit_flags_of(P, DEBUG);
     const unsigned work_n = P.resume_list ? *P.resume_count : P.num_photon;
 
     while (true) {
@@ -759,7 +766,7 @@ __global__ void __launch_bounds__(kWaveThreads) k_wf_generate(const __grid_const
                             const Nearest best_c = best;
                             const float3 o_c = o, d_c = d;
                             HitInfo h_c;
-                            hit_finish_body(h_c, P.scene, best_c, o_c, d_c, ((DEBUG && P.prd != nullptr) || P.lpos != nullptr) ? kHitFphi : 0u);
+                            hit_finish_body(h_c, P.scene, best_c, o_c, d_c, hit_flags_of(P, DEBUG));
                             Prd r;
                             wave_hit_record(r, h_c);
                             if (DEBUG) { if (P.prd && 0 < P.max_record) P.prd[(size_t)P.max_record * idx] = r; }
@@ -823,7 +830,7 @@ __global__ void __launch_bounds__(kTraceThreads, PHOX_WF_TRACE_MIN_BLOCKS) k_wf_
             float3 from = o;
             float t_add = 0.f;
             for (int pass = 0;; pass++) {                       // one inlined trace site; pass 1 = PropagateRefine re-trace from 0.99 t
-                ok = trace_inline<HITFIN_INLINE || (PHOX_HITFIN_INLINE != 0)>(h, P.scene, from, d, tmin, P.tmax, ((DEBUG && P.prd != nullptr) || P.lpos != nullptr) ? kHitFphi : 0u, home);
+                ok = trace_inline<HITFIN_INLINE || (PHOX_HITFIN_INLINE != 0)>(h, P.scene, from, d, tmin, P.tmax, hit_flags_of(P, DEBUG), home);
                 nray++;
                 if (pass == 1) { h.t += t_add; break; }
                 if (!P.refine) break;
@@ -997,7 +1004,7 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
                         const Nearest best_c = best;
                         const float3 o_c = o, d_c = d;
                         HitInfo h_c;
-                        hit_finish_body(h_c, P.scene, best_c, o_c, d_c, ((DEBUG && P.prd != nullptr) || P.lpos != nullptr) ? kHitFphi : 0u);     // a candidate answered: never a miss
+                        hit_finish_body(h_c, P.scene, best_c, o_c, d_c, hit_flags_of(P, DEBUG));     // a candidate answered: never a miss
                         wave_hit_record(r2, h_c);
                         if (DEBUG) { if (P.prd && bounce < P.max_record) P.prd[(size_t)P.max_record * idx + bounce] = r2; }
                         settled = true;

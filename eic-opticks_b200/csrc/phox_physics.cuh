@@ -33,6 +33,7 @@ struct Tables {
     unsigned hd_factor;
     float inv_ny;                   // 1 / float(ny), correctly rounded
     unsigned y_fast;                // 1: bnd_y's reciprocal form was checked against the division for every iy < ny
+    unsigned need_lposcost;         // 1: some optical row has ems >= 2, i.e. propagate() may read HitInfo::lposcost
 };
 
 struct PhotonState {                // sphoton in registers
