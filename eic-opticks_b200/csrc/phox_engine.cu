@@ -128,6 +128,7 @@ struct phox_context {
     MergeScratch merge_scratch;
     DevBuf<float4> d_exact;                    // per CSGPrim: (sizes ; translation) of prims that are exactly a box
     DevBuf<float4> d_home;                     // per CSGPrim: HomeRec (box, candidate count, offset), see traverse_bvh
+    DevBuf<unsigned> d_prim_pb;                // per CSGPrim: prim/boundary word of the hit record (hit_finish_core)
     DevBuf<float4> d_cand;                     // candidate lists of the home cells, two float4 per candidate
     DevBuf<unsigned> d_home_state[2];          // wavefront form, per list position (double-buffered like the lists): home cell of the photon
     DevBuf<unsigned> d_pending, d_pending_count;   // wavefront form: list positions the home cells left to k_wf_trace, and their count per bounce
@@ -281,7 +282,7 @@ extern "C" void phox_destroy(phox_context* ctx) {
     ctx->d_record.release(); ctx->d_hit.release(); ctx->d_seq.release(); ctx->d_prd.release();
     ctx->d_block_hits.release(); ctx->d_block_off.release(); ctx->d_counters.release();
     ctx->d_slack.release(); ctx->d_exact.release();
-    ctx->d_home.release(); ctx->d_cand.release(); ctx->d_home_state[0].release(); ctx->d_home_state[1].release(); ctx->d_pending.release(); ctx->d_pending_count.release(); ctx->d_wave_hits2.release(); ctx->d_gs_home.release();
+    ctx->d_home.release(); ctx->d_cand.release(); ctx->d_prim_pb.release(); ctx->d_home_state[0].release(); ctx->d_home_state[1].release(); ctx->d_pending.release(); ctx->d_pending_count.release(); ctx->d_wave_hits2.release(); ctx->d_gs_home.release();
     ctx->d_tag.release(); ctx->d_flat.release(); ctx->d_tagslot.release();
     ctx->d_lpos.release(); ctx->d_hitlite.release(); ctx->d_merged_lite.release();
     ctx->d_merged.release(); ctx->d_merge_in.release(); merge_scratch_free(ctx->merge_scratch);
@@ -431,6 +432,19 @@ extern "C" int phox_set_geometry(phox_context* ctx, const void* solid_, int64_t 
     // slack = distance by which the padded box must be shrunk to lie inside the true box with a pad to spare.
     ctx->max_prim_nodes = 1;
     for (int64_t p = 0; p < nprim; p++) ctx->max_prim_nodes = std::max(ctx->max_prim_nodes, prim[p].num_node());
+    {
+        std::vector<unsigned> pb((size_t)nprim, 0u);
+        const Node* nodes_h = (const Node*)node_;
+        for (int64_t p = 0; p < nprim; p++) {
+            const int no = prim[p].node_offset();
+            const unsigned boundary = (no >= 0 && no < nnode) ? nodes_h[no].u[6] : 0u;         // node q1.z
+            const unsigned gpi = prim[p].u[15];                                                 // prim q3.w
+            pb[p] = ((gpi & 0xffffu) << 16) | (boundary & 0xffffu);
+        }
+        CK(ctx->d_prim_pb.reserve(std::max<size_t>(1, (size_t)nprim)));
+        CK(cudaMemcpyAsync(ctx->d_prim_pb.p, pb.data(), (size_t)nprim * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     std::vector<float> slack((size_t)nprim, 0.f);
     std::vector<float> exact((size_t)nprim * 8, 0.f);
     const Node* hnode = (const Node*)node_;
@@ -808,7 +822,7 @@ static int run_launch(phox_context* ctx, const Genstep* d_gs, const unsigned lon
     SimParams P;
     std::memset(&P, 0, sizeof(P));
     P.scene.geo.node = ctx->d_node.p; P.scene.geo.plan = ctx->d_plan.p; P.scene.geo.itra = ctx->d_itra.p;
-    P.scene.prim = ctx->d_prim.p; P.scene.exact = ctx->d_exact.p; P.scene.nodes = ctx->d_bvh.p; P.scene.inst = ctx->d_inst.p;
+    P.scene.prim = ctx->d_prim.p; P.scene.exact = ctx->d_exact.p; P.scene.nodes = ctx->d_bvh.p; P.scene.inst = ctx->d_inst.p; P.scene.prim_pb = ctx->d_prim_pb.p;
     P.scene.ninst = ctx->ninst; P.scene.tlas_root = ctx->tlas_root;
     P.scene.accel = c.accel == PHOX_ACCEL_BVH_NOHOME ? PHOX_ACCEL_BVH : c.accel;
     P.scene.home = (c.accel == PHOX_ACCEL_BVH && ctx->num_home > 0) ? ctx->d_home.p : nullptr; P.scene.cand = ctx->d_cand.p;
@@ -1303,7 +1317,7 @@ extern "C" int phox_intersect(phox_context* ctx, const float* ray_o_tmin, const 
     CK(cudaMemcpyAsync(d_d, ray_d, (size_t)nray * 16, cudaMemcpyHostToDevice, ctx->stream));
     Scene sc;
     sc.geo.node = ctx->d_node.p; sc.geo.plan = ctx->d_plan.p; sc.geo.itra = ctx->d_itra.p;
-    sc.prim = ctx->d_prim.p; sc.exact = ctx->d_exact.p; sc.nodes = ctx->d_bvh.p; sc.inst = ctx->d_inst.p;
+    sc.prim = ctx->d_prim.p; sc.exact = ctx->d_exact.p; sc.nodes = ctx->d_bvh.p; sc.inst = ctx->d_inst.p; sc.prim_pb = ctx->d_prim_pb.p;
     sc.ninst = ctx->ninst; sc.tlas_root = ctx->tlas_root; sc.accel = accel == PHOX_ACCEL_BVH_NOHOME ? PHOX_ACCEL_BVH : accel;
     sc.home = nullptr; sc.cand = nullptr;            // single rays carry no home
     const int T = 128;
@@ -1353,7 +1367,7 @@ extern "C" int64_t phox_simtrace(phox_context* ctx, const void* genstep, int64_t
         SimtraceParams S;
         std::memset(&S, 0, sizeof(S));
         S.scene.geo.node = ctx->d_node.p; S.scene.geo.plan = ctx->d_plan.p; S.scene.geo.itra = ctx->d_itra.p;
-        S.scene.prim = ctx->d_prim.p; S.scene.exact = ctx->d_exact.p; S.scene.nodes = ctx->d_bvh.p; S.scene.inst = ctx->d_inst.p;
+        S.scene.prim = ctx->d_prim.p; S.scene.exact = ctx->d_exact.p; S.scene.nodes = ctx->d_bvh.p; S.scene.inst = ctx->d_inst.p; S.scene.prim_pb = ctx->d_prim_pb.p;
         S.scene.ninst = ctx->ninst; S.scene.tlas_root = ctx->tlas_root; S.scene.accel = c.accel == PHOX_ACCEL_BVH_NOHOME ? PHOX_ACCEL_BVH : c.accel;
         S.scene.home = nullptr; S.scene.cand = nullptr;
         S.genstep = d_gs; S.gs_prefix = d_prefix; S.num_genstep = (int)num_genstep;

@@ -63,6 +63,7 @@ struct Scene {
     int accel;                      // PHOX_ACCEL_*
     const float4* home;             // 2 x float4 per CSGPrim (HomeRec, see traverse_bvh); null = home cells off
     const float4* cand;             // candidate lists of the home cells, two float4 per candidate: half sizes | prim, translation | instance
+    const unsigned* prim_pb;        // per CSGPrim: the prd word (global prim index & 0xffff) << 16 | (boundary of its root node & 0xffff)
 };
 
 struct SimParams {
@@ -412,10 +413,8 @@ PHOX_D bool hit_finish_core(HitInfo& h, const Scene& sc, const Nearest& best, co
     h.lposcost = (flags & (kHitFphi | kHitCost)) ? lpos.z / sqrtf(dot(lpos, lpos)) : 0.f;
     h.lposfphi = (flags & kHitFphi) ? (atan2f(lpos.y, lpos.x) + kPi) / (2.0f * kPi) : 0.f;
     h.iindex_identity = (((unsigned)best.inst & 0xffffu) << 16) | ((unsigned)meta.y & 0xffffu);
-    float4 p0 = __ldg(sc.prim + 4 * best.prim);
-    unsigned boundary = __float_as_uint(__ldg(sc.geo.node + 4 * __float_as_int(p0.y) + 1).z);
-    unsigned gpi = __float_as_uint(__ldg(sc.prim + 4 * best.prim + 3).w);
-    h.prim_boundary = ((gpi & 0xffffu) << 16) | (boundary & 0xffffu);
+    // (global prim index << 16 | boundary of the prim's root node, put together per prim by phox_set_geometry: one load instead of prim -> node -> prim)
+    h.prim_boundary = __ldg(sc.prim_pb + best.prim);
     return true;
 }
 
