@@ -15,8 +15,8 @@ synthetic gensteps.  Default workload = the configuration the north_star target 
     e2e     same metric through the public host-buffer API (Simulator.simulate_np): gensteps in
             pinned host memory -> H2D -> simulate -> hits D2H, every step
     roofline  HBM roofline of the dominant kernel (k_wf_propagate, ~3/4 of the bounce loop, on the bench
-            workload): its algorithmic bytes from the event's own counts (168 B per live photon + 12 B
-            per survivor + 28 B per ray its home cell settles) / average launch
+            workload): its algorithmic bytes from the event's own counts (168 B per live photon + 16 B
+            per survivor + 24 B per ray its home cell settles) / average launch
             duration, from CUDA events the library records between the kernels on the launch stream (a
             separate pass of <= 3 steps with phox_set_profiling on, right after the timed region).  The path-level figure of
             SURVEY 8(d), 132 + 128 f_hit bytes per photon over the whole bounce loop, is reported
@@ -352,7 +352,7 @@ def main():
             # Two kernels per bounce.  Algorithmic bytes, from the event's own counts:
             #  k_wf_propagate (physics + home-cell pass), per live photon: 104 B read (list entry 4, hit record 32, photon 64 - the draw
             #    count travels in its index word -, home 4) + 64 B written (photon); per survivor 8 B (next list entry + its home) + 32 B
-            #    (hit record of the next bounce, when its home cell settles the ray) or 4 B (pending-list entry, when it does not).
+            #    (hit record of the next bounce, when its home cell settles the ray) or 8 B (pending-list entry: list position + list entry, when it does not).
             #    Without home cells: 100 B read + 64 B written per live photon, 4 B per survivor.
             #  k_wf_trace (BVH traversal of the pending rays), per ray: 44 B read (pending entry 4, list entry 4, position/time/direction 32,
             #    home 4) + 32 B written (hit record)
@@ -360,7 +360,7 @@ def main():
             live = prof["num_ray"]                                   # live photons summed over the bounces = rays of the event(s)
             surv = max(0, prof["num_ray"] - prof_photons)            # survivors = the live photons of bounces 1 ..
             home = prof["num_home_ray"]
-            prop_bytes = (168.0 * live + 12.0 * surv + 28.0 * home) if home > 0 else (164.0 * live + 4.0 * surv)
+            prop_bytes = (168.0 * live + 16.0 * surv + 24.0 * home) if home > 0 else (164.0 * live + 4.0 * surv)
             trace_rays = live - home
             trace_bytes = 76.0 * trace_rays
             prop_s = prof["propagate_kernel_seconds"] / L

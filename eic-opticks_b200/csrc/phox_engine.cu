@@ -131,7 +131,7 @@ struct phox_context {
     DevBuf<unsigned> d_prim_pb;                // per CSGPrim: prim/boundary word of the hit record (hit_finish_core)
     DevBuf<float4> d_cand;                     // candidate lists of the home cells, two float4 per candidate
     DevBuf<unsigned> d_home_state[2];          // wavefront form, per list position (double-buffered like the lists): home cell of the photon
-    DevBuf<unsigned> d_pending, d_pending_count;   // wavefront form: list positions the home cells left to k_wf_trace, and their count per bounce
+    DevBuf<uint2> d_pending; DevBuf<unsigned> d_pending_count;   // wavefront form: list positions the home cells left to k_wf_trace, and their count per bounce
     DevBuf<Photon> d_hit_stage[2];                 // phox_get_hits_async: hits of the last two events, copied out while the next event runs
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_stage = nullptr, ev_copied[2] = {nullptr, nullptr};

@@ -625,7 +625,8 @@ struct WaveParams {
     unsigned* home;                 // per position of active_in: home cell of that photon (CSGPrim index or kNoHome); null = no home pass
     unsigned* home_next;            // ... of active_out (the home travels with the list entry: coalesced, no per-slot array)
     const unsigned* gs_home;        // per genstep: home cell its photons start with (k_genstep_home), or null
-    unsigned* pending;              // list positions whose home cell did not settle the ray (null: k_wf_trace takes the whole list)
+    uint2* pending;                 // (list position, list entry) of the rays their home cell did not settle (null: k_wf_trace takes the whole list); the entry
+                                    // rides along so that the BVH kernel goes from the pending entry straight to the photon record, one scattered load less
     unsigned* pending_count;        // device-side length of pending (zeroed beforehand)
     Seq* seq_state;                 // per slot history being built (debug modes)
     Prd* hits;                      // per list position: hit of this bounce
@@ -717,6 +718,7 @@ __global__ void __launch_bounds__(kWaveThreads) k_wf_generate(const __grid_const
     for (unsigned base_idx = blockIdx.x * blockDim.x; base_idx < P.num_photon; base_idx += gridDim.x * blockDim.x) {
         const unsigned idx = base_idx + threadIdx.x;
         bool pend = false;
+        unsigned entry0 = 0u;                  // this slot's entry of the first list
         if (idx < P.num_photon) {
             int lo = 0, hi = P.num_genstep;
             while (hi - lo > 1) {
@@ -735,12 +737,13 @@ __global__ void __launch_bounds__(kWaveThreads) k_wf_generate(const __grid_const
             {
                 const unsigned true_index = p.index;
                 if (P.max_bounce > 0) p.index = rng.consumed(base);
+                entry0 = idx | ((p.obf & P.eps0_mask) ? kListEps0 : 0u);
 #if PHOX_WF_STREAM
                 p.store_cs(P.photon + idx);
-                __stcs(W.active_out + idx, idx | ((p.obf & P.eps0_mask) ? kListEps0 : 0u));
+                __stcs(W.active_out + idx, entry0);
 #else
                 p.store(P.photon + idx);
-                W.active_out[idx] = idx | ((p.obf & P.eps0_mask) ? kListEps0 : 0u);
+                W.active_out[idx] = entry0;
 #endif
                 p.index = true_index;
             }
@@ -788,7 +791,7 @@ __global__ void __launch_bounds__(kWaveThreads) k_wf_generate(const __grid_const
                 s_pbase = ptot ? atomicAdd(W.pending_count, ptot) : 0u;
             }
             __syncthreads();
-            if (pend) W.pending[s_pbase + s_warp[warp] + __popc(pballot & ((1u << lane) - 1u))] = idx;
+            if (pend) W.pending[s_pbase + s_warp[warp] + __popc(pballot & ((1u << lane) - 1u))] = make_uint2(idx, entry0);
             __syncthreads();
         }
     }
@@ -811,8 +814,9 @@ __global__ void __launch_bounds__(kTraceThreads, PHOX_WF_TRACE_MIN_BLOCKS) k_wf_
     unsigned nray = 0;
     const unsigned stride = gridDim.x * blockDim.x;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
-        const unsigned a = W.pending ? __ldcs(W.pending + i) : i;
-        const unsigned entry = __ldcs(W.active_in + a);
+        unsigned a = i, entry;
+        if (W.pending) { const uint2 pe = __ldcs(W.pending + i); a = pe.x; entry = pe.y; }
+        else entry = __ldcs(W.active_in + a);
         const unsigned idx = entry & kListSlotMask;
         const float4* ph = reinterpret_cast<const float4*>(P.photon + idx);
         float4 q0, q1;
@@ -1056,7 +1060,7 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
             if (HOME) {
                 __stcs(W.home_next + pos, home);
                 if (settled) wave_store_hit(W.hits_next, pos, r2);
-                else W.pending[s_pbase[par] + (wo >> 16) + __popc(pballot & ((1u << lane) - 1u))] = pos;
+                else W.pending[s_pbase[par] + (wo >> 16) + __popc(pballot & ((1u << lane) - 1u))] = make_uint2(pos, entry_out);
             }
         }
 #else
@@ -1088,7 +1092,7 @@ __global__ void __launch_bounds__(kPropThreads, PHOX_WF_PROP_MIN_BLOCKS) k_wf_pr
             if (HOME) {
                 __stcs(W.home_next + pos, home);
                 if (settled) wave_store_hit(W.hits_next, pos, r2);
-                else W.pending[s_pbase[par] + (wo >> 16) + __popc(pballot & ((1u << lane) - 1u))] = pos;
+                else W.pending[s_pbase[par] + (wo >> 16) + __popc(pballot & ((1u << lane) - 1u))] = make_uint2(pos, entry_out);
             }
         }
 #endif
